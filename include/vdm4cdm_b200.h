@@ -1,0 +1,154 @@
+/*
+ * vdm4cdm_b200 -- C ABI of the B200 (sm_100a) hot path of cfpark00/vdm4cdm.
+ *
+ * Every entry point is extern "C", takes plain device pointers + sizes + an explicit
+ * cudaStream_t (passed as void*), allocates nothing on the device (cuFFT plans excepted,
+ * see vdm_pk_*), returns 0 on success or a negative VDM_E_* code, and leaves a
+ * thread-local message retrievable with vdm_last_error_string().  There is no CPU
+ * fallback: on a machine without an sm_100 GPU the compute entry points fail.
+ *
+ * The reference (pure Python) reaches these operations through PyTorch; each entry
+ * point cites the reference interface it stands in for (paths relative to the
+ * reference checkout; "mltools" lines are the ones recoverable from the traceback in
+ * model_test.ipynb:678-692).
+ *
+ * Tensor layouts
+ *   activations : NDHWC, bf16, shape [B][D][H][W][C]           ("channels-last 3d")
+ *   conv weights: [T][Cout_pad][Cin] bf16, Cin contiguous      (T taps, Cout_pad % 16 == 0)
+ *   latent z    : [B][D][H][W] fp32 (the reference's (B,1,D,H,W))
+ *   chan stats  : double [B][C][2] = (sum, sum of squares) over the D*H*W voxels
+ */
+#ifndef VDM4CDM_B200_H
+#define VDM4CDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VDM_API __attribute__((visibility("default")))
+#else
+#define VDM_API
+#endif
+
+#define VDM_OK 0
+#define VDM_E_BADARG (-1)
+#define VDM_E_UNSUPPORTED (-2)
+#define VDM_E_CUDA (-3)
+#define VDM_E_CUFFT (-4)
+#define VDM_E_DRIVER (-5)
+
+#define VDM_MAX_TAPS 27
+
+/* ---- library ------------------------------------------------------------------- */
+VDM_API int vdm_version(void);                       /* 10000*major + 100*minor + patch */
+VDM_API const char* vdm_last_error_string(void);     /* thread-local, never NULL */
+/* 0 if device `dev` is an sm_100 part this library can run on, else VDM_E_UNSUPPORTED. */
+VDM_API int vdm_device_supported(int dev);
+
+/* ---- conv3d as implicit GEMM on tcgen05 ------------------------------------------
+ * Stands in for every torch.nn.Conv3d executed by mltools' CUNet (forward: cuDNN conv3d
+ * fprop; with transposed/flipped weights the same entry point is the dgrad), reached from
+ * CUNet.forward (networks.py:259-265) -> ResNetBlock.forward (blocks.py:129-132).
+ */
+typedef struct VdmConvDesc {
+  int32_t batch, depth, height, width;   /* B, D, H, W of input == output grid (stride 1, "same") */
+  int32_t c_in;                          /* input channels, multiple of 16 */
+  int32_t c_out;                         /* real output channels written */
+  int32_t c_out_pad;                     /* rows per tap in the weight tensor, multiple of 16, <= 256 */
+  int32_t n_taps;                        /* 1..27 */
+  int8_t tap_offset[VDM_MAX_TAPS][3];    /* (dd, dh, dw) read offset of each tap, each in [-1, 1] */
+  int32_t circular;                      /* 0: zero padding (TMA out-of-bounds fill). 1: unsupported yet */
+  int32_t out_fp32;                      /* 0: y is bf16 NDHWC; 1: y is fp32 NDHWC */
+} VdmConvDesc;
+
+typedef struct VdmConvEpilogue {
+  const float* chan_add;        /* fp32 [n_steps?][B][c_out] bias + conditioning projection, or NULL */
+  const int32_t* step_ptr;      /* device int: row block of chan_add to use (CUDA-graph replay), or NULL */
+  int64_t chan_add_step_stride; /* elements between consecutive steps of chan_add */
+  const void* residual;         /* bf16 NDHWC [B][D][H][W][c_out] added to the output, or NULL */
+  const void* residual_half;    /* bf16 NDHWC on the (D/2,H/2,W/2) grid, nearest-upsampled add, or NULL */
+  double* stats;                /* double [B][c_out][2], atomically accumulated (sum, sumsq), or NULL */
+} VdmConvEpilogue;
+
+VDM_API int vdm_conv3d_fwd(const VdmConvDesc* desc, const void* x, const void* w, void* y,
+                   const VdmConvEpilogue* epi, void* stream);
+
+/* wgrad: dw[t][co][ci] (fp32, c_out_pad rows) += sum_voxels x[v + off_t][ci] * dy[v][co].
+ * Also accumulates dbias[co] += sum_v dy[v][co] when dbias != NULL.  Stands in for cuDNN
+ * conv3d backward-filter reached through autograd of the same Conv3d modules. */
+VDM_API int vdm_conv3d_wgrad(const VdmConvDesc* desc, const void* x, const void* dy, float* dw,
+                     float* dbias, void* stream);
+
+/* ---- fused elementwise passes (ATen group_norm / silu / dropout / avg_pool3d / interpolate /
+ *      cat in the reference's ResNetBlock / ResNetDown; blocks.py:129-170) ------------------- */
+
+/* stats[b][c] = (sum, sumsq) of x over voxels; stats must be zeroed by the caller. */
+VDM_API int vdm_channel_stats(const void* x, int batch, int64_t voxels, int channels, double* stats,
+                      void* stream);
+
+/* y = dropout(silu(groupnorm(x))) ; statistics come from `stats` (sum,sumsq per channel).
+ * dropout_p == 0 disables dropout; otherwise keep-mask = Philox(seed, layer_tag, element). */
+VDM_API int vdm_gn_silu(const void* x, void* y, int batch, int64_t voxels, int channels, int groups,
+                const double* stats, const float* gamma, const float* beta, float eps,
+                float dropout_p, uint64_t seed, uint32_t layer_tag, void* stream);
+
+/* 2x2x2 average pooling; also accumulates the channel stats of the output when stats != NULL. */
+VDM_API int vdm_avgpool2(const void* x, void* y, int batch, int depth, int height, int width, int channels,
+                 double* stats, void* stream);
+
+/* y = concat(nearest_upsample_x2(coarse), skip) along channels; (depth,height,width) is the
+ * fine grid.  Accumulates channel stats of y when stats != NULL. */
+VDM_API int vdm_upsample_concat(const void* coarse, const void* skip, void* y, int batch, int depth,
+                        int height, int width, int c_coarse, int c_skip, double* stats,
+                        void* stream);
+
+/* Pack the network input: out[b][v][0] = z, out[b][v][1..n_cond] = cond planes, rest 0.
+ * z: fp32 [B][V]; cond: fp32 [B][n_cond][V] (NCDHW) or NULL; out: bf16 [B][V][c_pad]. */
+VDM_API int vdm_pack_input(const float* z, const float* cond, void* out, int batch, int64_t voxels,
+                   int n_cond, int c_pad, void* stream);
+
+/* ---- fused VDM ancestral-sampler update ------------------------------------------------
+ * VDM.sample_zs_given_zt (vdm_model.py:370-378): mean = alpha_s/alpha_t*(zt - c*sigma_t*eps_hat),
+ * z_s = mean + sigma_s*sqrt(c)*N(0,1).  coef[step] = (w_z, w_eps, noise_scale, out_scale):
+ *   z_out = out_scale * (w_z * z + w_eps * eps_hat + noise_scale * noise)
+ * noise = Philox4x32-10 + Box-Muller keyed by (seed, realisation_id[b], draw, element), or
+ * `noise_in` (fp32 [B][V]) when it is not NULL (injected noise, parity tests).
+ * When packed_out != NULL also rewrites channel 0.. of the packed network input for the next
+ * step (see vdm_pack_input).  step_ptr == NULL means step 0 of coef / draw = draw_base. */
+VDM_API int vdm_sampler_step(const float* z, const float* eps_hat, float* z_out, int batch, int64_t voxels,
+                     const float* coef, const int32_t* step_ptr, uint64_t seed,
+                     const int32_t* realisation_id, int32_t draw_base, const float* noise_in,
+                     const float* cond, int n_cond, void* packed_out, int c_pad, void* stream);
+
+/* out[b][v] = N(0,1) noise of draw `draw` (the definition used by vdm_sampler_step). */
+VDM_API int vdm_philox_normal(float* out, int batch, int64_t voxels, uint64_t seed,
+                      const int32_t* realisation_id, int32_t draw, void* stream);
+
+/* step counter helper for CUDA-graph replay: *counter += 1 on the stream. */
+VDM_API int vdm_increment(int32_t* counter, void* stream);
+
+/* ---- P(k) / r(k): cuFFT R2C + k-shell binning ---------------------------------------------
+ * power() at src/utils.py:16-83 (and pk :85-102, get_ccs :110-128).  `fields` is fp32
+ * [n_fields][batch][chan][n0][n1][n2] (n0 == 1 for 2-D inputs); for every field the spectrum is
+ * the batch mean of the channel sum of Re(X conj(X2)), binned by ceil(|k|) with Hermitian
+ * weights.  Outputs are per field and per bin 1..kmax (kmax = min(n)//2):
+ *   k_mean, p_mean : double [n_fields][kmax];  n_modes : int64 [n_fields][kmax].
+ * fields2 == NULL computes the auto spectrum.  `work` is a caller-owned complex64 scratch of
+ * vdm_pk_work_bytes(...) bytes.  cuFFT plans are cached inside the library per (dims, count). */
+VDM_API size_t vdm_pk_work_bytes(int n_fields, int batch, int chan, int n0, int n1, int n2, int cross);
+VDM_API int vdm_pk(const float* fields, const float* fields2, int n_fields, int batch, int chan, int n0,
+           int n1, int n2, void* work, size_t work_bytes, double* k_mean, double* p_mean,
+           int64_t* n_modes, void* stream);
+/* One pass over two transforms: P11, P22 and P12 together (get_ccs without the four FFTs). */
+VDM_API int vdm_pk_cross3(const float* fields1, const float* fields2, int n_fields, int batch, int chan,
+                  int n0, int n1, int n2, void* work, size_t work_bytes, double* k_mean,
+                  double* p11, double* p22, double* p12, int64_t* n_modes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDM4CDM_B200_H */

@@ -1,0 +1,89 @@
+"""ctypes binding of ``libvdm4cdm_b200.so`` (the C ABI declared in ``include/vdm4cdm_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+``RuntimeError`` is raised.  ``lib()`` only loads the library (possible on a CPU-only box, used by
+the symbol-export test); every compute entry point needs an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int8, c_int32, c_int64, c_size_t, \
+    c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvdm4cdm_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "vdm4cdm_b200.h")
+MAX_TAPS = 27
+
+
+class ConvDesc(Structure):
+    _fields_ = [
+        ("batch", c_int32), ("depth", c_int32), ("height", c_int32), ("width", c_int32),
+        ("c_in", c_int32), ("c_out", c_int32), ("c_out_pad", c_int32), ("n_taps", c_int32),
+        ("tap_offset", (c_int8 * 3) * MAX_TAPS),
+        ("circular", c_int32), ("out_fp32", c_int32),
+    ]
+
+
+class ConvEpilogue(Structure):
+    _fields_ = [
+        ("chan_add", c_void_p), ("step_ptr", c_void_p), ("chan_add_step_stride", c_int64),
+        ("residual", c_void_p), ("residual_half", c_void_p), ("stats", c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    "vdm_version": (c_int, []),
+    "vdm_last_error_string": (c_char_p, []),
+    "vdm_device_supported": (c_int, [c_int]),
+    "vdm_conv3d_fwd": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(ConvEpilogue), c_void_p]),
+    "vdm_conv3d_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vdm_channel_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "vdm_gn_silu": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                            c_float, c_float, c_uint64, c_uint32, c_void_p]),
+    "vdm_avgpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vdm_upsample_concat": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p]),
+    "vdm_pack_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "vdm_sampler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_uint64,
+                                 c_void_p, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "vdm_philox_normal": (c_int, [c_void_p, c_int, c_int64, c_uint64, c_void_p, c_int32, c_void_p]),
+    "vdm_increment": (c_int, [c_void_p, c_void_p]),
+    "vdm_pk_work_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "vdm_pk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                       c_void_p, c_void_p, c_void_p]),
+    "vdm_pk_cross3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def declared_symbols(header_path: str = HEADER_PATH):
+    """Names of every function the public header declares (used by the export test)."""
+    text = open(header_path).read()
+    return sorted(set(re.findall(r"VDM_API[^;(]*?\b(vdm_\w+)\s*\(", text)))
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C vdm4cdm_b200/csrc`). vdm4cdm_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError here == the library is stale
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vdm_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,111 @@
+// Shared helpers for the vdm4cdm_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/vdm4cdm_b200.h"
+
+namespace vdm {
+
+void set_error(const char* fmt, ...);
+
+#define VDM_CHECK_ARG(cond, ...)                \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::vdm::set_error(__VA_ARGS__);            \
+      return VDM_E_BADARG;                      \
+    }                                           \
+  } while (0)
+
+#define VDM_CHECK_CUDA(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::vdm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                       \
+      return VDM_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
+#define VDM_CHECK_LAUNCH() VDM_CHECK_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller: the noise definition of oracle/philox_ref.py.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+constexpr uint32_t kStreamTagNoise = 0x56444D34u;    // 'VDM4'
+constexpr uint32_t kStreamTagDropout = 0x44524F50u;  // 'DROP'
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
+    const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += kPhiloxW0;
+    k.y += kPhiloxW1;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float philox_unit(uint32_t w) {
+  return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
+}
+
+// Four N(0,1) values for element group g (elements 4g..4g+3) of (realisation, draw).
+__device__ __forceinline__ float4 philox_normal4(uint32_t group, uint32_t draw, uint32_t realisation,
+                                                 uint64_t seed) {
+  const uint4 w = philox4x32_10(make_uint4(group, draw, realisation, kStreamTagNoise),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float u0 = philox_unit(w.x), u1 = philox_unit(w.y), u2 = philox_unit(w.z), u3 = philox_unit(w.w);
+  const float ra = sqrtf(-2.0f * logf(u0));
+  const float rb = sqrtf(-2.0f * logf(u2));
+  float s1, c1, s3, c3;
+  sincosf(6.283185307179586f * u1, &s1, &c1);
+  sincosf(6.283185307179586f * u3, &s3, &c3);
+  return make_float4(ra * s1, ra * c1, rb * s3, rb * c3);
+}
+
+// ---------------------------------------------------------------------------------------
+// bf16 <-> fp32 vector helpers (8 bf16 = one 16-byte access)
+// ---------------------------------------------------------------------------------------
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace vdm
