@@ -13,9 +13,12 @@
  * model_test.ipynb:678-692).
  *
  * Tensor layouts
- *   activations : NDHWC, bf16, shape [B][D][H][W][C]           ("channels-last 3d")
- *   conv weights: [T][Cout_pad][Cin] bf16, Cin contiguous      (T taps, Cout_pad % 16 == 0)
- *   latent z    : [B][D][H][W] fp32 (the reference's (B,1,D,H,W))
+ *   activations : "channel-planar" bf16 [B][C/8][D][H][W][8]: 8 channels (16 bytes) per voxel and
+ *                 plane.  Buffers may hold more planes than one tensor uses (x_planes / *_plane0
+ *                 below), which makes channel concatenation a matter of where producers write.
+ *   conv weights: bf16 [tap][Cin/8][Cout_pad][8]  (element (tap, ci, co) at
+ *                 ((tap*Cin/8 + ci/8)*Cout_pad + co)*8 + ci%8), Cout_pad % 16 == 0
+ *   latent z    : fp32 [B][D][H][W] (the reference's (B,1,D,H,W))
  *   chan stats  : double [B][C][2] = (sum, sum of squares) over the D*H*W voxels
  */
 #ifndef VDM4CDM_B200_H
@@ -56,59 +59,70 @@ VDM_API int vdm_device_supported(int dev);
  */
 typedef struct VdmConvDesc {
   int32_t batch, depth, height, width;   /* B, D, H, W of input == output grid (stride 1, "same") */
-  int32_t c_in;                          /* input channels, multiple of 16 */
-  int32_t c_out;                         /* real output channels written */
-  int32_t c_out_pad;                     /* rows per tap in the weight tensor, multiple of 16, <= 256 */
+  int32_t c_in;                          /* input channels read, multiple of 16 */
+  int32_t c_out;                         /* real output channels written (multiple of 8 unless out_fp32) */
+  int32_t c_out_pad;                     /* rows per (tap, plane) in the weight tensor, multiple of 16, <= 256 */
   int32_t n_taps;                        /* 1..27 */
   int8_t tap_offset[VDM_MAX_TAPS][3];    /* (dd, dh, dw) read offset of each tap, each in [-1, 1] */
   int32_t circular;                      /* 0: zero padding (TMA out-of-bounds fill). 1: unsupported yet */
-  int32_t out_fp32;                      /* 0: y is bf16 NDHWC; 1: y is fp32 NDHWC */
+  int32_t out_fp32;                      /* 0: y is bf16 channel-planar; 1: y is fp32 [B][c_out][D][H][W] */
+  int32_t x_planes, x_plane0;            /* planes per sample of the x buffer (0: c_in/8), first plane read */
+  int32_t y_planes, y_plane0;            /* same for y (bf16 output only) */
+  int32_t r_planes, r_plane0;            /* same for the residual */
 } VdmConvDesc;
 
 typedef struct VdmConvEpilogue {
-  const float* chan_add;        /* fp32 [n_steps?][B][c_out] bias + conditioning projection, or NULL */
+  const float* chan_add;        /* fp32 [n_steps][B][c_out] bias + conditioning projection, or NULL */
   const int32_t* step_ptr;      /* device int: row block of chan_add to use (CUDA-graph replay), or NULL */
   int64_t chan_add_step_stride; /* elements between consecutive steps of chan_add */
-  const void* residual;         /* bf16 NDHWC [B][D][H][W][c_out] added to the output, or NULL */
-  const void* residual_half;    /* bf16 NDHWC on the (D/2,H/2,W/2) grid, nearest-upsampled add, or NULL */
-  double* stats;                /* double [B][c_out][2], atomically accumulated (sum, sumsq), or NULL */
+  const void* residual;         /* bf16 channel-planar, same grid, c_out channels, added to the output, or NULL */
+  double* stats;                /* double [B][stats_channels][2], atomically accumulated (sum, sumsq), or NULL */
+  int32_t stats_channels;       /* channels per sample of the stats buffer (0: c_out) */
+  int32_t stats_c0;             /* first stats channel this conv's output maps to */
 } VdmConvEpilogue;
 
-VDM_API int vdm_conv3d_fwd(const VdmConvDesc* desc, const void* x, const void* w, void* y,
-                   const VdmConvEpilogue* epi, void* stream);
+/* y = conv(x, w) [+ chan_add[b][co]] [+ residual]; also the dgrad when w holds the flipped,
+ * transposed filter. */
+VDM_API int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w, void* y,
+               const VdmConvEpilogue* epi, void* stream);
 
-/* wgrad: dw[t][co][ci] (fp32, c_out_pad rows) += sum_voxels x[v + off_t][ci] * dy[v][co].
- * Also accumulates dbias[co] += sum_v dy[v][co] when dbias != NULL.  Stands in for cuDNN
- * conv3d backward-filter reached through autograd of the same Conv3d modules. */
-VDM_API int vdm_conv3d_wgrad(const VdmConvDesc* desc, const void* x, const void* dy, float* dw,
-                     float* dbias, void* stream);
+/* Tuning / bring-up knobs (0 = automatic): key 0 swap LBO/SBO roles, 1 force MT, 2 force KC, 3 force n_split. */
+VDM_API int vdm_debug_set(int key, int value);
 
 /* ---- fused elementwise passes (ATen group_norm / silu / dropout / avg_pool3d / interpolate /
  *      cat in the reference's ResNetBlock / ResNetDown; blocks.py:129-170) ------------------- */
 
-/* stats[b][c] = (sum, sumsq) of x over voxels; stats must be zeroed by the caller. */
-VDM_API int vdm_channel_stats(const void* x, int batch, int64_t voxels, int channels, double* stats,
-                      void* stream);
+/* View of `channels` consecutive channels inside a channel-planar buffer: plane (b, p) of the view
+ * starts at data + ((b*planes + plane0 + p) * voxels) * 16 bytes. */
+typedef struct VdmTensor {
+  void* data;
+  int32_t planes;   /* planes per sample of the whole buffer */
+  int32_t plane0;   /* first plane of this view */
+} VdmTensor;
 
-/* y = dropout(silu(groupnorm(x))) ; statistics come from `stats` (sum,sumsq per channel).
+/* stats[b][stats_c0 + c] += (sum, sumsq) of x over voxels; stats must be zeroed by the caller. */
+VDM_API int vdm_channel_stats(const VdmTensor* x, int batch, int64_t voxels, int channels, double* stats,
+                      int stats_channels, int stats_c0, void* stream);
+
+/* y = dropout(silu(groupnorm(x))) ; statistics come from `stats` (double [B][channels][2]).
  * dropout_p == 0 disables dropout; otherwise keep-mask = Philox(seed, layer_tag, element). */
-VDM_API int vdm_gn_silu(const void* x, void* y, int batch, int64_t voxels, int channels, int groups,
+VDM_API int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
                 const double* stats, const float* gamma, const float* beta, float eps,
                 float dropout_p, uint64_t seed, uint32_t layer_tag, void* stream);
 
-/* 2x2x2 average pooling; also accumulates the channel stats of the output when stats != NULL. */
-VDM_API int vdm_avgpool2(const void* x, void* y, int batch, int depth, int height, int width, int channels,
-                 double* stats, void* stream);
+/* 2x2x2 average pooling of a (depth,height,width) grid; accumulates channel stats of y when stats != NULL. */
+VDM_API int vdm_avgpool2(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
+                 int channels, double* stats, int stats_channels, int stats_c0, void* stream);
 
-/* y = concat(nearest_upsample_x2(coarse), skip) along channels; (depth,height,width) is the
- * fine grid.  Accumulates channel stats of y when stats != NULL. */
-VDM_API int vdm_upsample_concat(const void* coarse, const void* skip, void* y, int batch, int depth,
-                        int height, int width, int c_coarse, int c_skip, double* stats,
-                        void* stream);
+/* y = nearest_upsample_x2(coarse); (depth,height,width) is the fine grid.  Writing into a plane
+ * window of a wider buffer is how channel concatenation with the skip tensor happens.
+ * Accumulates channel stats of y when stats != NULL. */
+VDM_API int vdm_upsample2(const VdmTensor* coarse, const VdmTensor* y, int batch, int depth, int height, int width,
+                  int channels, double* stats, int stats_channels, int stats_c0, void* stream);
 
-/* Pack the network input: out[b][v][0] = z, out[b][v][1..n_cond] = cond planes, rest 0.
- * z: fp32 [B][V]; cond: fp32 [B][n_cond][V] (NCDHW) or NULL; out: bf16 [B][V][c_pad]. */
-VDM_API int vdm_pack_input(const float* z, const float* cond, void* out, int batch, int64_t voxels,
+/* Pack the network input: plane 0 of out = (z, cond_1..cond_n, 0...) per voxel, planes 1.. = 0.
+ * z: fp32 [B][V]; cond: fp32 [B][n_cond][V] (NCDHW) or NULL; out: c_pad/8 planes; n_cond <= 7. */
+VDM_API int vdm_pack_input(const float* z, const float* cond, const VdmTensor* out, int batch, int64_t voxels,
                    int n_cond, int c_pad, void* stream);
 
 /* ---- fused VDM ancestral-sampler update ------------------------------------------------
@@ -117,12 +131,13 @@ VDM_API int vdm_pack_input(const float* z, const float* cond, void* out, int bat
  *   z_out = out_scale * (w_z * z + w_eps * eps_hat + noise_scale * noise)
  * noise = Philox4x32-10 + Box-Muller keyed by (seed, realisation_id[b], draw, element), or
  * `noise_in` (fp32 [B][V]) when it is not NULL (injected noise, parity tests).
- * When packed_out != NULL also rewrites channel 0.. of the packed network input for the next
- * step (see vdm_pack_input).  step_ptr == NULL means step 0 of coef / draw = draw_base. */
+ * When packed_out != NULL (plane 0 of sample 0 of a packed network input with `packed_planes`
+ * planes per sample, see vdm_pack_input) also rewrites that plane for the next step.
+ * step_ptr == NULL means step 0 of coef / draw = draw_base. */
 VDM_API int vdm_sampler_step(const float* z, const float* eps_hat, float* z_out, int batch, int64_t voxels,
                      const float* coef, const int32_t* step_ptr, uint64_t seed,
                      const int32_t* realisation_id, int32_t draw_base, const float* noise_in,
-                     const float* cond, int n_cond, void* packed_out, int c_pad, void* stream);
+                     const float* cond, int n_cond, void* packed_out, int packed_planes, void* stream);
 
 /* out[b][v] = N(0,1) noise of draw `draw` (the definition used by vdm_sampler_step). */
 VDM_API int vdm_philox_normal(float* out, int batch, int64_t voxels, uint64_t seed,

@@ -1,0 +1,152 @@
+"""GPU parity of vdm_conv3d (tcgen05 implicit GEMM on halo tiles) against torch's conv3d.
+
+Integer-valued inputs make every product and partial sum exact in fp32, so the comparison with the
+fp32 reference is BIT-EXACT after the same bf16 rounding; random-normal inputs are checked to the
+bf16 tolerance named by BASELINE.json's north_star (1e-2 relative).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from vdm4cdm_b200 import ops
+    return ops
+
+
+def _int_tensor(shape, lo, hi, gen, device):
+    return torch.randint(lo, hi + 1, shape, generator=gen, device="cpu").float().to(device)
+
+
+def _reference(x, w, chan_add=None, residual=None):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    k = w.shape[-1]
+    y = F.conv3d(x.double(), w.double(), padding=k // 2).float()
+    if chan_add is not None:
+        y = y + chan_add[:, :, None, None, None]
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+CASES = [
+    # B, Cin, Cout, D, H, W, k
+    (1, 16, 16, 4, 16, 8, 3),
+    (1, 32, 32, 8, 16, 16, 3),
+    (2, 32, 32, 6, 20, 12, 3),      # ragged: H, W not multiples of the 16x8 tile, D not of MT
+    (1, 64, 64, 8, 16, 16, 3),
+    (1, 96, 32, 4, 16, 16, 3),      # concat-shaped input (KC=32, 3 chunks)
+    (1, 32, 64, 5, 9, 7, 3),        # tiny odd grid
+    (1, 256, 256, 4, 16, 8, 3),     # coarse level: output channels split over CTAs
+    (1, 384, 128, 2, 16, 8, 3),
+    (1, 96, 32, 4, 16, 16, 1),      # 1x1x1 skip conv
+    (3, 16, 32, 3, 8, 8, 3),        # H < tile height
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv3d_exact_integers(case):
+    ops = _ops()
+    b, ci, co, d, h, w, k = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1234 + ci + co)
+    x = _int_tensor((b, ci, d, h, w), -2, 2, g, dev)
+    wt = _int_tensor((co, ci, k, k, k), -1, 1, g, dev)
+    ref = _reference(x, wt).to(torch.bfloat16).float()
+    taps = ops.TAPS_3X3X3 if k == 3 else ops.TAPS_1X1X1
+    y = ops.conv3d(ops.to_planar(x), ops.pack_conv_weight(wt), co, taps=taps)
+    torch.cuda.synchronize()
+    got = ops.from_planar(y, co)
+    bad = (got != ref).sum().item()
+    assert bad == 0, f"{bad} of {ref.numel()} outputs differ; max |diff| = {(got - ref).abs().max().item()}"
+
+
+def test_conv3d_epilogue_bias_residual_stats_and_windows():
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(7)
+    b, ci, co, d, h, w = 2, 32, 32, 6, 16, 16
+    x = _int_tensor((b, ci, d, h, w), -2, 2, g, dev)
+    wt = _int_tensor((co, ci, 3, 3, 3), -1, 1, g, dev)
+    cadd = _int_tensor((b, co), -3, 3, g, dev)
+    res = _int_tensor((b, co, d, h, w), -4, 4, g, dev)
+    ref = _reference(x, wt, cadd, res).to(torch.bfloat16).float()
+    # x lives in planes 2..5 of a 7-plane buffer, the output goes to planes 1..4 of a 6-plane buffer,
+    # the residual sits at plane 3 of an 8-plane buffer, stats at channel 8 of a 48-channel table
+    xbuf = torch.zeros((b, 7, d, h, w, 8), dtype=torch.bfloat16, device=dev)
+    xbuf[:, 2:6] = ops.to_planar(x)
+    rbuf = torch.zeros((b, 8, d, h, w, 8), dtype=torch.bfloat16, device=dev)
+    rbuf[:, 3:7] = ops.to_planar(res)
+    ybuf = torch.full((b, 6, d, h, w, 8), 77.0, dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros((b, 48, 2), dtype=torch.float64, device=dev)
+    ops.conv3d(xbuf, ops.pack_conv_weight(wt), co, x_plane0=2, c_in=ci, out=ybuf, out_plane0=1, chan_add=cadd,
+               residual=rbuf, residual_plane0=3, stats=stats, stats_c0=8)
+    torch.cuda.synchronize()
+    got = ops.from_planar(ybuf[:, 1:5].contiguous(), co)
+    assert (got != ref).sum().item() == 0, f"max |diff| = {(got - ref).abs().max().item()}"
+    assert (ybuf[:, 0].float() == 77.0).all() and (ybuf[:, 5].float() == 77.0).all(), "wrote outside the plane window"
+    s1 = ref.double().sum(dim=(2, 3, 4))
+    s2 = (ref.double() ** 2).sum(dim=(2, 3, 4))
+    assert torch.allclose(stats[:, 8:40, 0], s1, rtol=1e-6, atol=1e-3), (stats[:, 8:40, 0] - s1).abs().max()
+    assert torch.allclose(stats[:, 8:40, 1], s2, rtol=1e-6, atol=1e-3), (stats[:, 8:40, 1] - s2).abs().max()
+    assert stats[:, :8].abs().sum().item() == 0 and stats[:, 40:].abs().sum().item() == 0
+
+
+def test_conv3d_fp32_single_channel_output():
+    """conv_out of the UNet: C -> 1, fp32 NCDHW result."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    b, ci, d, h, w = 2, 32, 5, 16, 24
+    x = _int_tensor((b, ci, d, h, w), -2, 2, g, dev)
+    wt = _int_tensor((1, ci, 3, 3, 3), -1, 1, g, dev)
+    cadd = _int_tensor((b, 1), -3, 3, g, dev)
+    ref = _reference(x, wt, cadd)
+    y = ops.conv3d(ops.to_planar(x), ops.pack_conv_weight(wt), 1, out_fp32=True, chan_add=cadd)
+    torch.cuda.synchronize()
+    assert (y != ref).sum().item() == 0, f"max |diff| = {(y - ref).abs().max().item()}"
+
+
+@pytest.mark.parametrize("case", [(1, 32, 32, 16, 32, 32), (1, 128, 128, 8, 16, 16), (2, 64, 32, 8, 24, 16)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv3d_random_normal_bf16_tolerance(case):
+    ops = _ops()
+    b, ci, co, d, h, w = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn((b, ci, d, h, w), generator=g).to(dev)
+    wt = (torch.randn((co, ci, 3, 3, 3), generator=g) / (27 * ci) ** 0.5).to(dev)
+    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    ref = _reference(xb, wb)
+    got = ops.from_planar(ops.conv3d(ops.to_planar(x), ops.pack_conv_weight(wt), co), co)
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, f"relative max error {err}"   # bf16 output rounding: 2^-8 relative
+
+
+def test_conv3d_dgrad_weight_packing():
+    """dgrad = the same kernel run with the flipped, transposed filter."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    b, ci, co, d, h, w = 1, 32, 64, 4, 16, 8
+    wt = _int_tensor((co, ci, 3, 3, 3), -1, 1, g, dev)
+    dy = _int_tensor((b, co, d, h, w), -2, 2, g, dev)
+    x = torch.zeros((b, ci, d, h, w), device=dev, requires_grad=True)
+    F.conv3d(x, wt, padding=1).backward(dy)
+    ref = x.grad.to(torch.bfloat16).float()
+    got = ops.from_planar(ops.conv3d(ops.to_planar(dy), ops.pack_conv_weight(wt, transpose_flip=True), ci), ci)
+    torch.cuda.synchronize()
+    assert (got != ref).sum().item() == 0, f"max |diff| = {(got - ref).abs().max().item()}"
+
+
+def test_conv3d_rejects_bad_arguments():
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    x = torch.zeros((1, 1, 4, 16, 8, 8), dtype=torch.bfloat16, device=dev)   # 8 channels: not a multiple of 16
+    w = torch.zeros((27, 1, 16, 8), dtype=torch.bfloat16, device=dev)
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        ops.conv3d(x, w, 16)

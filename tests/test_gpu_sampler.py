@@ -1,0 +1,93 @@
+"""GPU parity of the fused sampler update and its counter-based noise against the CPU oracle
+(oracle/philox_ref.py, oracle/vdm_ref.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from vdm4cdm_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("n", [4, 37, 4096, 32 ** 3 + 3])
+def test_philox_normal_matches_oracle(n):
+    from oracle import philox_ref
+    ops = _ops()
+    seed, draw = 0x1234_5678_9ABC_DEF0, 7
+    rid = torch.tensor([0, 5, 1 << 20], dtype=torch.int32, device="cuda:0")
+    got = ops.philox_normal((3, n), seed, draw, rid).cpu().numpy()
+    for i, r in enumerate([0, 5, 1 << 20]):
+        want = philox_ref.normal_field(seed, r, draw, n)
+        # same Philox words bit for bit; logf/sincosf differ from numpy's by a few ulp
+        np.testing.assert_allclose(got[i], want, rtol=0, atol=2e-6)
+    # moments of a large draw
+    if n > 30000:
+        assert abs(got.mean()) < 0.01 and abs(got.std() - 1.0) < 0.01
+
+
+def test_sampler_step_injected_noise_matches_oracle_formula():
+    """z_s = alpha_s/alpha_t (z_t - c sigma_t eps_hat) + sigma_s sqrt(c) eps  (vdm_model.py:370-378)."""
+    from oracle.vdm_ref import VDM
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    shape = (2, 1, 6, 10, 14)
+    z = torch.randn(shape, generator=g)
+    eps = torch.randn(shape, generator=g)
+    noise = torch.randn(shape, generator=g)
+
+    class Net(torch.nn.Module):
+        shape = (1, 6, 10, 14)
+
+        def forward(self, zt, t=None, **kw):
+            return eps
+
+    vdm = VDM(Net())
+    t, s = 0.62, 0.58
+    want = vdm.sample_zs_given_zt(z, t, s, noise=noise)
+    gt, gs = torch.tensor(-13.3 + 26.6 * t, dtype=torch.float64), torch.tensor(-13.3 + 26.6 * s, dtype=torch.float64)
+    c = -torch.expm1(gs - gt)
+    a_t, a_s = torch.sigmoid(-gt).sqrt(), torch.sigmoid(-gs).sqrt()
+    s_t, s_s = torch.sigmoid(gt).sqrt(), torch.sigmoid(gs).sqrt()
+    coef = torch.tensor([[a_s / a_t, -a_s / a_t * c * s_t, s_s * c.sqrt(), 1.0]], dtype=torch.float32, device=dev)
+    got = ops.sampler_step(z.to(dev), eps.to(dev), coef, noise=noise.to(dev)).cpu()
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (got - want).abs().max()
+
+
+def test_sampler_step_philox_noise_steps_and_packed_output():
+    from oracle import philox_ref
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    b, d, h, w = 2, 4, 6, 10
+    n = d * h * w
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn((b, 1, d, h, w), generator=g).to(dev)
+    eps = torch.randn((b, 1, d, h, w), generator=g).to(dev)
+    cond = torch.randn((b, 1, d, h, w), generator=g).to(dev)
+    coef = torch.tensor([[1.0, 0.0, 0.0, 1.0], [0.5, -0.25, 2.0, 1.5], [0.9, 0.1, 0.0, 1.0]], dtype=torch.float32,
+                        device=dev)
+    step = torch.tensor([1], dtype=torch.int32, device=dev)
+    rid = torch.tensor([3, 11], dtype=torch.int32, device=dev)
+    packed = ops.pack_input(z, cond, 16)
+    seed = 2024
+    out = ops.sampler_step(z, eps, coef, step_ptr=step, seed=seed, realisation_id=rid, draw_base=1, cond=cond,
+                           packed_out=packed)
+    torch.cuda.synchronize()
+    for i, r in enumerate([3, 11]):
+        nz = torch.from_numpy(philox_ref.normal_field(seed, r, 1 + 1, n)).reshape(1, d, h, w)
+        want = 1.5 * (0.5 * z[i].cpu() - 0.25 * eps[i].cpu() + 2.0 * nz)
+        assert torch.allclose(out[i].cpu(), want, rtol=1e-5, atol=1e-5), (out[i].cpu() - want).abs().max()
+    dense = ops.from_planar(packed)
+    assert torch.equal(dense[:, 0:1], out.to(torch.bfloat16).float()), "plane 0 must carry the new latent"
+    assert torch.equal(dense[:, 1:2], cond.to(torch.bfloat16).float())
+    assert dense[:, 2:].abs().sum().item() == 0
+    # noise_scale == 0 (last step) must not touch the RNG path and stays deterministic
+    step.fill_(2)
+    o2 = ops.sampler_step(z, eps, coef, step_ptr=step, seed=seed)
+    assert torch.allclose(o2, 0.9 * z + 0.1 * eps, rtol=1e-6, atol=1e-6)
+    ops.increment(step)
+    torch.cuda.synchronize()
+    assert step.item() == 3

@@ -24,29 +24,38 @@ class ConvDesc(Structure):
         ("c_in", c_int32), ("c_out", c_int32), ("c_out_pad", c_int32), ("n_taps", c_int32),
         ("tap_offset", (c_int8 * 3) * MAX_TAPS),
         ("circular", c_int32), ("out_fp32", c_int32),
+        ("x_planes", c_int32), ("x_plane0", c_int32),
+        ("y_planes", c_int32), ("y_plane0", c_int32),
+        ("r_planes", c_int32), ("r_plane0", c_int32),
     ]
 
 
 class ConvEpilogue(Structure):
     _fields_ = [
         ("chan_add", c_void_p), ("step_ptr", c_void_p), ("chan_add_step_stride", c_int64),
-        ("residual", c_void_p), ("residual_half", c_void_p), ("stats", c_void_p),
+        ("residual", c_void_p), ("stats", c_void_p), ("stats_channels", c_int32), ("stats_c0", c_int32),
     ]
 
+
+class Tensor(Structure):
+    """VdmTensor: a window of planes inside a channel-planar buffer."""
+    _fields_ = [("data", c_void_p), ("planes", c_int32), ("plane0", c_int32)]
+
+
+_T = POINTER(Tensor)
 
 _SIGNATURES = {
     "vdm_version": (c_int, []),
     "vdm_last_error_string": (c_char_p, []),
     "vdm_device_supported": (c_int, [c_int]),
-    "vdm_conv3d_fwd": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(ConvEpilogue), c_void_p]),
-    "vdm_conv3d_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "vdm_channel_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
-    "vdm_gn_silu": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+    "vdm_conv3d": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(ConvEpilogue), c_void_p]),
+    "vdm_debug_set": (c_int, [c_int, c_int]),
+    "vdm_channel_stats": (c_int, [_T, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_gn_silu": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             c_float, c_float, c_uint64, c_uint32, c_void_p]),
-    "vdm_avgpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "vdm_upsample_concat": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                    c_void_p, c_void_p]),
-    "vdm_pack_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "vdm_avgpool2": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_upsample2": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_pack_input": (c_int, [c_void_p, c_void_p, _T, c_int, c_int64, c_int, c_int, c_void_p]),
     "vdm_sampler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_uint64,
                                  c_void_p, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "vdm_philox_normal": (c_int, [c_void_p, c_int, c_int64, c_uint64, c_void_p, c_int32, c_void_p]),

@@ -1,0 +1,591 @@
+// Conv3d ("same", stride 1, up to 27 taps) as an implicit GEMM on the 5th-gen tensor cores, fed from
+// ONE halo tile per (output tile, channel chunk) instead of one tile per filter tap.
+//
+// Stands in for the cuDNN conv3d fprop (and, with flipped/transposed weights, dgrad) launched by
+// every torch.nn.Conv3d of mltools' CUNet (networks.py:259-265 -> blocks.py:129-132, recovered in
+// model_test.ipynb:684-692).
+//
+// Data layout ("channel-planar", 8 channels = 16 B per voxel and plane):
+//     activations  bf16 [B][C/8][D][H][W][8]          weights  bf16 [tap][Cin/8][Cout_pad][8]
+// Why: tcgen05.mma's un-swizzled K-major operand is a grid of 8-row x 16-byte core matrices whose
+// rows are 16 B apart, 8-row groups SBO apart and K-neighbours LBO apart.  With the planar layout a
+// halo box (MT+2, 18, 10) of one channel plane sits in shared memory as [d'][h'][w'][16 B], so
+//   * 8 consecutive voxels along w are one core matrix,
+//   * the 16 h-rows of a 16x8 output tile are 16 row groups at SBO = 10*16 B,
+//   * the second half of K=16 is the next plane at LBO = plane stride,
+//   * and a filter tap (dd,dh,dw) is nothing but a START-ADDRESS OFFSET of the descriptor.
+// All 27 taps therefore read the same shared-memory bytes: L2->SM traffic per output voxel drops
+// from 27x (per-tap im2col loads, what cuDNN/CUTLASS implicit GEMM do) to (MT+2)/MT*18/16*10/8 ~ 2.1x.
+// (Descriptor semantics verified on hardware by tools/probe_umma.cu, profiles/r01_probe_umma.txt.)
+//
+// Pipeline per persistent CTA (7 warps):
+//   warp 0  A producer : one 5-D TMA load per (tile, channel chunk) -> halo stage (2 stages);
+//                        out-of-range voxels are zero-filled by the TMA unit == Conv3d zero padding
+//   warp 2  B producer : weights of one (chunk, tap): KC/8 bulk copies -> ring of B stages
+//   warp 1  MMA issuer : for chunk, tap, sub-tile s < MT, k16: tcgen05.mma M=128 N=n_cta K=16 into
+//                        accumulator s (TMEM, fp32); 2 accumulator sets so the epilogue of tile i
+//                        overlaps the main loop of tile i+1
+//   warps 3-6 epilogue : tcgen05.ld -> + bias/conditioning row + residual -> bf16 planar (or fp32
+//                        NCDHW) store, per-channel (sum, sumsq) GroupNorm statistics by warp-shuffle
+//                        transpose reduction, flushed once per tile with fp64 atomics.
+//
+// Roofline: tensor-bound; algorithmic FLOPs = 2 * taps * Cin * Cout * B*D*H*W.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vdm {
+
+constexpr int kConvThreads = 224;  // 7 warps
+constexpr int kMaxBStages = 16;
+constexpr int kTileH = 16, kTileW = 8;
+
+struct ConvKernelParams {
+  int B, D, H, W;
+  int c_out;                 // real output channels
+  int n_cta, n_split;        // UMMA N per CTA, CTAs sharing one spatial tile
+  int n_pad;                 // rows per (tap, plane) of the weight tensor
+  int n_taps, pad;
+  int8_t tap[VDM_MAX_TAPS][3];
+  int MT, KC, k_chunks;
+  int Hd, Hh, Wh;            // halo box (voxels)
+  int tiles_w, tiles_h, tiles_d, n_tiles;
+  int a_stage_bytes, b_stage_bytes, nsb;
+  int plane_bytes;           // Hd*Hh*Wh*16
+  int tmem_cols;
+  int x_planes, x_plane0, c_in8;
+  const __nv_bfloat16* w;
+  // epilogue
+  void* y;
+  int y_planes, y_plane0, out_fp32;
+  const float* chan_add;
+  const int32_t* step_ptr;
+  long long chan_add_step_stride;
+  const __nv_bfloat16* residual;
+  int r_planes, r_plane0;
+  double* stats;
+  int stats_channels, stats_c0;
+  int swap_lbo_sbo;          // debug: exchange the LBO/SBO roles
+};
+
+struct ConvShared {
+  uint64_t a_full[2], a_empty[2];
+  uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  float stat_sum[4][256];
+  float stat_sq[4][256];
+};
+
+// Transpose-reduce 16 per-row values over the 32 lanes of a warp: afterwards lane l (even) holds
+// the column (l >> 1) total in v[0].
+__device__ __forceinline__ void warp_column_sums16(float (&v)[16]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool hi = lane & 16;
+    const float send = hi ? v[i] : v[i + 8];
+    const float keep = hi ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(full, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 8;
+    const float send = hi ? v[i] : v[i + 4];
+    const float keep = hi ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(full, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 4;
+    const float send = hi ? v[i] : v[i + 2];
+    const float keep = hi ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(full, send, 4);
+  }
+  {
+    const bool hi = lane & 2;
+    const float send = hi ? v[0] : v[1];
+    const float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(full, send, 2);
+  }
+  v[0] += __shfl_xor_sync(full, v[0], 1);
+}
+
+struct TileCoord {
+  int b, d0, h0, w0, ns;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int tile) {
+  TileCoord t;
+  t.ns = tile % p.n_split; tile /= p.n_split;
+  t.w0 = (tile % p.tiles_w) * kTileW; tile /= p.tiles_w;
+  t.h0 = (tile % p.tiles_h) * kTileH; tile /= p.tiles_h;
+  t.d0 = (tile % p.tiles_d) * p.MT;
+  t.b = tile / p.tiles_d;
+  return t;
+}
+
+// Un-swizzled K-major descriptor: rows 16 B apart inside a core matrix, `sbo` between 8-row groups,
+// `lbo` between the two K core matrices of one K=16 MMA (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t make_planar_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + 2 * (size_t)p.a_stage_bytes;
+  ConvShared* sh = reinterpret_cast<ConvShared*>(b_smem + (size_t)p.nsb * p.b_stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_x);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&sh->a_full[s], 1);
+      ptx::mbar_init(&sh->a_empty[s], 1);
+      ptx::mbar_init(&sh->tmem_full[s], 1);
+      ptx::mbar_init(&sh->tmem_empty[s], 128);
+    }
+    for (int s = 0; s < p.nsb; ++s) {
+      ptx::mbar_init(&sh->b_full[s], 1);
+      ptx::mbar_init(&sh->b_empty[s], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (warp >= 3) {
+    for (int i = threadIdx.x - 96; i < 4 * 256; i += 128) {
+      (&sh->stat_sum[0][0])[i] = 0.f;
+      (&sh->stat_sq[0][0])[i] = 0.f;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  const int planes_per_chunk = p.KC >> 3;
+
+  if (warp == 0) {
+    // ===================== A producer: halo tiles =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+          const int s = it & 1;
+          ptx::mbar_wait(&sh->a_empty[s], ((it >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes_per_chunk * p.plane_bytes));
+          ptx::tma_load_5d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], 0, t.w0 - p.pad,
+                           t.h0 - p.pad, t.d0 - p.pad, t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== B producer: weights of one (chunk, tap) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t plane_copy_bytes = (uint32_t)p.n_cta * 16u;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int tap = 0; tap < p.n_taps; ++tap, ++it) {
+            const int s = it % p.nsb;
+            ptx::mbar_wait(&sh->b_empty[s], ((it / p.nsb) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk);
+            uint8_t* dst = b_smem + (size_t)s * p.b_stage_bytes;
+            const __nv_bfloat16* src =
+                p.w + (((size_t)tap * p.c_in8 + (size_t)kc * planes_per_chunk) * p.n_pad + (size_t)t.ns * p.n_cta) * 8;
+            for (int pl = 0; pl < planes_per_chunk; ++pl)
+              ptx::bulk_load(dst + (size_t)pl * plane_copy_bytes, src + (size_t)pl * p.n_pad * 8, plane_copy_bytes,
+                             &sh->b_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)p.n_cta);
+    const uint32_t a_k = (uint32_t)p.plane_bytes, a_m = (uint32_t)p.Wh * 16u;
+    const uint32_t b_k = (uint32_t)p.n_cta * 16u, b_m = 128u;
+    const uint32_t a_lbo = p.swap_lbo_sbo ? a_m : a_k, a_sbo = p.swap_lbo_sbo ? a_k : a_m;
+    const uint32_t b_lbo = p.swap_lbo_sbo ? b_m : b_k, b_sbo = p.swap_lbo_sbo ? b_k : b_m;
+    uint32_t ita = 0, itb = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t acc = ti & 1;
+      ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem0 = tmem_base + acc * (uint32_t)(p.MT * p.n_cta);
+      for (int kc = 0; kc < p.k_chunks; ++kc, ++ita) {
+        const int sa = ita & 1;
+        ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
+        const uint32_t a_base = ptx::smem_u32(a_smem + (size_t)sa * p.a_stage_bytes);
+        for (int tap = 0; tap < p.n_taps; ++tap, ++itb) {
+          const int sb = itb % p.nsb;
+          ptx::mbar_wait(&sh->b_full[sb], (itb / p.nsb) & 1);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t b_base = ptx::smem_u32(b_smem + (size_t)sb * p.b_stage_bytes);
+            const int dd = p.tap[tap][0] + p.pad, dh = p.tap[tap][1] + p.pad, dw = p.tap[tap][2] + p.pad;
+            for (int s = 0; s < p.MT; ++s) {
+              const uint32_t a_tap = a_base + (uint32_t)((((s + dd) * p.Hh + dh) * p.Wh + dw) * 16);
+              for (int j = 0; j < (p.KC >> 4); ++j) {
+                const uint64_t a_desc = make_planar_desc(a_tap + (uint32_t)(2 * j) * a_k, a_lbo, a_sbo);
+                const uint64_t b_desc = make_planar_desc(b_base + (uint32_t)(2 * j) * b_k, b_lbo, b_sbo);
+                ptx::umma_bf16(d_tmem0 + (uint32_t)(s * p.n_cta), a_desc, b_desc, idesc,
+                               (kc > 0 || tap > 0 || j > 0) ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit(&sh->b_empty[sb]);
+            if (tap == p.n_taps - 1) {
+              ptx::umma_commit(&sh->a_empty[sa]);
+              if (kc == p.k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, 128 TMEM lanes) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;                  // tile row == TMEM lane
+    const int lh = r >> 3, lw = r & 7;
+    const int n_chunks = p.n_cta >> 4;
+    const long long V = (long long)p.D * p.H * p.W;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      const TileCoord t = decode_tile(p, tile);
+      const int h = t.h0 + lh, w = t.w0 + lw;
+      const bool hw_ok = (h < p.H) && (w < p.W);
+      const int cbase = t.ns * p.n_cta;
+      const uint32_t acc = ti & 1;
+      ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
+      ptx::tc_fence_after();
+      const float* cadd = nullptr;
+      if (p.chan_add) {
+        const long long step = p.step_ptr ? (long long)(*p.step_ptr) : 0ll;
+        cadd = p.chan_add + step * p.chan_add_step_stride + (long long)t.b * p.c_out;
+      }
+      for (int s = 0; s < p.MT; ++s) {
+        const int d = t.d0 + s;
+        const bool valid = hw_ok && (d < p.D);
+        const long long vox = ((long long)d * p.H + h) * p.W + w;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + s) * p.n_cta);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          uint32_t raw[16];
+          ptx::tmem_ld16(taddr + (uint32_t)(ch * 16), raw);
+          ptx::tmem_ld_wait();
+          const int c0 = cbase + ch * 16;
+          if (c0 >= p.c_out) continue;  // padded output channels (warp-uniform)
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(raw[j]);
+          const bool full16 = (c0 + 16 <= p.c_out);
+          if (cadd) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full16 || c0 + j < p.c_out) f[j] += __ldg(cadd + c0 + j);
+          }
+          if (p.out_fp32) {
+            if (valid) {
+              float* yp = static_cast<float*>(p.y) + ((long long)t.b * p.c_out + c0) * V + vox;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (full16 || c0 + j < p.c_out) yp[(long long)j * V] = f[j];
+            }
+            continue;
+          }
+          // bf16 planar output: two planes of 8 channels (c_out % 8 == 0 is checked on the host)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int c = c0 + half * 8;
+            if (c >= p.c_out) break;
+            float g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = f[half * 8 + j];
+            if (p.residual && valid) {
+              const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual) +
+                                 ((long long)t.b * p.r_planes + p.r_plane0 + (c >> 3)) * V + vox;
+              float rr[8];
+              unpack8(*rp, rr);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) g[j] += rr[j];
+            }
+            const bf16x8 packed = pack8(g);
+            if (valid) {
+              bf16x8* yp = reinterpret_cast<bf16x8*>(p.y) + ((long long)t.b * p.y_planes + p.y_plane0 + (c >> 3)) * V + vox;
+              *yp = packed;
+            }
+            unpack8(packed, g);  // statistics describe the stored (rounded) tensor
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[half * 8 + j] = valid ? g[j] : 0.f;
+          }
+          if (p.stats) {
+            float s1[16], s2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = (full16 || c0 + j < p.c_out) ? f[j] : 0.f;
+              s1[j] = x;
+              s2[j] = x * x;
+            }
+            warp_column_sums16(s1);
+            warp_column_sums16(s2);
+            if ((lane & 1) == 0) {
+              const int c = ch * 16 + (lane >> 1);
+              sh->stat_sum[q][c] += s1[0];
+              sh->stat_sq[q][c] += s2[0];
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator set are complete (wait::ld above): hand it back
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&sh->tmem_empty[acc]);
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = threadIdx.x - 96; c < p.n_cta; c += 128) {
+          if (cbase + c < p.c_out) {
+            const float s1 = sh->stat_sum[0][c] + sh->stat_sum[1][c] + sh->stat_sum[2][c] + sh->stat_sum[3][c];
+            const float s2 = sh->stat_sq[0][c] + sh->stat_sq[1][c] + sh->stat_sq[2][c] + sh->stat_sq[3][c];
+            double* dst = p.stats + ((long long)t.b * p.stats_channels + p.stats_c0 + cbase + c) * 2;
+            atomicAdd(dst, (double)s1);
+            atomicAdd(dst + 1, (double)s2);
+          }
+          sh->stat_sum[0][c] = sh->stat_sum[1][c] = sh->stat_sum[2][c] = sh->stat_sum[3][c] = 0.f;
+          sh->stat_sq[0][c] = sh->stat_sq[1][c] = sh->stat_sq[2][c] = sh->stat_sq[3][c] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }();
+  return fn;
+}
+
+static int num_sms() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return kNumSMs;
+    return v;
+  }();
+  return n;
+}
+
+static int g_debug_swap_lbo_sbo = 0;
+static int g_debug_force_mt = 0, g_debug_force_kc = 0, g_debug_force_nsplit = 0;
+
+}  // namespace vdm
+
+using namespace vdm;
+
+extern "C" int vdm_debug_set(int key, int value) {
+  switch (key) {
+    case 0: g_debug_swap_lbo_sbo = value; return VDM_OK;
+    case 1: g_debug_force_mt = value; return VDM_OK;
+    case 2: g_debug_force_kc = value; return VDM_OK;
+    case 3: g_debug_force_nsplit = value; return VDM_OK;
+    default: set_error("vdm_debug_set: unknown key %d", key); return VDM_E_BADARG;
+  }
+}
+
+extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w, void* y,
+                          const VdmConvEpilogue* epi, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VDM_CHECK_ARG(desc && x && w && y, "vdm_conv3d: NULL pointer argument");
+  const VdmConvDesc& d = *desc;
+  VDM_CHECK_ARG(d.batch >= 1 && d.depth >= 1 && d.height >= 1 && d.width >= 1, "vdm_conv3d: bad grid");
+  VDM_CHECK_ARG(d.c_in >= 16 && d.c_in % 16 == 0, "vdm_conv3d: c_in=%d must be a multiple of 16", d.c_in);
+  VDM_CHECK_ARG(d.c_out_pad >= 16 && d.c_out_pad % 16 == 0 && d.c_out_pad <= 256,
+                "vdm_conv3d: c_out_pad=%d must be a multiple of 16 in [16,256]", d.c_out_pad);
+  VDM_CHECK_ARG(d.c_out >= 1 && d.c_out <= d.c_out_pad, "vdm_conv3d: c_out=%d vs c_out_pad=%d", d.c_out, d.c_out_pad);
+  VDM_CHECK_ARG(d.out_fp32 || d.c_out % 8 == 0, "vdm_conv3d: bf16 planar output needs c_out %% 8 == 0 (got %d)", d.c_out);
+  VDM_CHECK_ARG(d.n_taps >= 1 && d.n_taps <= VDM_MAX_TAPS, "vdm_conv3d: n_taps=%d", d.n_taps);
+  if (d.circular) {
+    set_error("vdm_conv3d: circular padding is not implemented");
+    return VDM_E_UNSUPPORTED;
+  }
+  const int x_planes = d.x_planes > 0 ? d.x_planes : d.c_in / 8;
+  const int y_planes = d.y_planes > 0 ? d.y_planes : (d.c_out + 7) / 8;
+  VDM_CHECK_ARG(d.x_plane0 >= 0 && d.x_plane0 + d.c_in / 8 <= x_planes, "vdm_conv3d: x plane window out of range");
+  VDM_CHECK_ARG(d.out_fp32 || (d.y_plane0 >= 0 && d.y_plane0 + d.c_out / 8 <= y_planes),
+                "vdm_conv3d: y plane window out of range");
+  VDM_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "vdm_conv3d: pointers must be 16-byte aligned");
+  VDM_CHECK_ARG((long long)d.batch * x_planes < (1ll << 31), "vdm_conv3d: too many planes");
+  auto encode = get_encode_fn();
+  if (!encode) {
+    set_error("vdm_conv3d: cuTensorMapEncodeTiled is not available from the driver");
+    return VDM_E_DRIVER;
+  }
+
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d.batch; p.D = d.depth; p.H = d.height; p.W = d.width;
+  p.c_out = d.c_out; p.n_pad = d.c_out_pad; p.n_taps = d.n_taps;
+  int pad = 0;
+  for (int t = 0; t < d.n_taps; ++t)
+    for (int k = 0; k < 3; ++k) {
+      VDM_CHECK_ARG(d.tap_offset[t][k] >= -1 && d.tap_offset[t][k] <= 1, "vdm_conv3d: tap offset out of range");
+      p.tap[t][k] = d.tap_offset[t][k];
+      if (d.tap_offset[t][k] != 0) pad = 1;
+    }
+  p.pad = pad;
+  p.c_in8 = d.c_in / 8;
+  p.x_planes = x_planes; p.x_plane0 = d.x_plane0;
+
+  // ---- tiling ----
+  p.tiles_w = ceil_div(d.width, kTileW);
+  p.tiles_h = ceil_div(d.height, kTileH);
+  // Pick (n_split, MT) with a small cost model: a CTA tile costs max(tensor time, L2->SM time) and the
+  // grid runs in ceil(tiles / SMs) waves.  n_split shares one spatial tile between CTAs that each
+  // compute c_out_pad / n_split output channels (more CTAs for the coarse levels); MT d-slices
+  // per tile amortise the halo and the weight stream (fewer, fatter tiles).
+  int n_split = 1, mt = 1;
+  {
+    double best = -1.0;
+    const int sms = num_sms();
+    for (int ns = 1; ns <= 8; ns *= 2) {
+      if (d.c_out_pad % (ns * 16) != 0) break;
+      const int ncta = d.c_out_pad / ns;
+      if (ns > 1 && ncta < 32) break;
+      int mt_max = 256 / ncta;
+      if (mt_max > 4) mt_max = 4;
+      if (mt_max > d.depth) mt_max = d.depth;
+      for (int m = 1; m <= mt_max; ++m) {
+        const long long tiles = (long long)p.tiles_w * p.tiles_h * ceil_div(d.depth, m) * d.batch * ns;
+        const long long waves = (tiles + sms - 1) / sms;
+        const double active = (double)(tiles < sms ? tiles : sms);
+        const double mma_cyc = (double)d.n_taps * (d.c_in / 16) * m * (ncta / 2 > 24 ? ncta / 2 : 24);
+        const double bytes = (double)(m + 2 * pad) * (kTileH + 2 * pad) * (kTileW + 2 * pad) * d.c_in * 2.0 +
+                             (double)d.n_taps * d.c_in * ncta * 2.0;
+        double bw = 5500.0 / active;  // L2 -> SM bytes per cycle per SM when `active` SMs pull at once
+        if (bw > 64.0) bw = 64.0;
+        const double cyc = (mma_cyc > bytes / bw ? mma_cyc : bytes / bw) + 2000.0;  // + per-tile fixed cost
+        const double total = (double)waves * cyc;
+        if (best < 0.0 || total < best * 0.999) {
+          best = total;
+          n_split = ns;
+          mt = m;
+        }
+      }
+    }
+  }
+  if (g_debug_force_nsplit > 0) n_split = g_debug_force_nsplit;
+  VDM_CHECK_ARG(d.c_out_pad % (n_split * 16) == 0, "vdm_conv3d: n_split=%d does not divide c_out_pad=%d", n_split,
+                d.c_out_pad);
+  p.n_split = n_split;
+  p.n_cta = d.c_out_pad / n_split;
+  if (g_debug_force_mt > 0) mt = g_debug_force_mt;
+  VDM_CHECK_ARG(mt >= 1 && 2 * mt * p.n_cta <= 512, "vdm_conv3d: MT=%d does not fit TMEM with N=%d", mt, p.n_cta);
+  p.MT = mt;
+  p.tiles_d = ceil_div(d.depth, mt);
+  const long long n_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * d.batch * n_split;
+  VDM_CHECK_ARG(n_tiles < (1ll << 31), "vdm_conv3d: too many tiles");
+  p.n_tiles = (int)n_tiles;
+  p.Hd = mt + 2 * pad; p.Hh = kTileH + 2 * pad; p.Wh = kTileW + 2 * pad;
+  p.plane_bytes = p.Hd * p.Hh * p.Wh * 16;
+
+  // ---- shared memory plan: 2 halo stages + a ring of weight stages ----
+  const int smem_budget = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - 256;
+  int kc = 0, nsb = 0;
+  const int kc_options[3] = {64, 32, 16};
+  for (int o = 0; o < 3; ++o) {
+    const int c = kc_options[o];
+    if (g_debug_force_kc > 0 && c != g_debug_force_kc) continue;
+    if (d.c_in % c != 0) continue;
+    const int a_stage = ((c / 8) * p.plane_bytes + 127) & ~127;
+    const int b_stage = c * p.n_cta * 2;
+    const int room = smem_budget - 2 * a_stage;
+    if (room < 2 * b_stage) continue;
+    kc = c;
+    nsb = room / b_stage;
+    if (nsb > kMaxBStages) nsb = kMaxBStages;
+    p.a_stage_bytes = a_stage;
+    p.b_stage_bytes = b_stage;
+    break;
+  }
+  VDM_CHECK_ARG(kc > 0, "vdm_conv3d: no channel-chunk size fits shared memory (c_in=%d, N=%d, MT=%d)", d.c_in, p.n_cta, mt);
+  p.KC = kc; p.k_chunks = d.c_in / kc; p.nsb = nsb;
+  VDM_CHECK_ARG(p.plane_bytes <= 0x3FFF * 16, "vdm_conv3d: halo plane too large for the descriptor stride field");
+  int cols = 32;
+  while (cols < 2 * mt * p.n_cta) cols <<= 1;
+  p.tmem_cols = cols;
+  p.w = static_cast<const __nv_bfloat16*>(w);
+  p.y = y; p.y_planes = y_planes; p.y_plane0 = d.y_plane0; p.out_fp32 = d.out_fp32;
+  if (epi) {
+    p.chan_add = epi->chan_add;
+    p.step_ptr = epi->step_ptr;
+    p.chan_add_step_stride = epi->chan_add_step_stride;
+    p.residual = static_cast<const __nv_bfloat16*>(epi->residual);
+    p.r_planes = d.r_planes > 0 ? d.r_planes : d.c_out / 8;
+    p.r_plane0 = d.r_plane0;
+    p.stats = epi->stats;
+    p.stats_channels = epi->stats_channels > 0 ? epi->stats_channels : d.c_out;
+    p.stats_c0 = epi->stats_c0;
+  }
+  VDM_CHECK_ARG(!(p.stats && d.out_fp32), "vdm_conv3d: stats are only produced for bf16 outputs");
+  VDM_CHECK_ARG(!(p.residual && d.out_fp32), "vdm_conv3d: residual is only supported for bf16 outputs");
+  p.swap_lbo_sbo = g_debug_swap_lbo_sbo;
+
+  // activations: 5-D (8ch, W, H, D, B*planes), box (8, Wh, Hh, Hd, KC/8); out-of-bounds -> zeros
+  CUtensorMap tmx;
+  {
+    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
+    cuuint64_t gdim[5] = {8, (cuuint64_t)d.width, (cuuint64_t)d.height, (cuuint64_t)d.depth,
+                          (cuuint64_t)d.batch * x_planes};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.Wh, (cuuint32_t)p.Hh, (cuuint32_t)p.Hd, (cuuint32_t)(kc / 8)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+  }
+
+  const size_t smem_bytes = 2 * (size_t)p.a_stage_bytes + (size_t)p.nsb * p.b_stage_bytes + sizeof(ConvShared) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_planar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  conv3d_planar_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, p);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}

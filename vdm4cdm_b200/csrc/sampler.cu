@@ -4,7 +4,7 @@
 // recovered in model_test.ipynb:681):  mean = alpha_s/alpha_t*(zt - c*sigma_t*pred_noise);
 // z_s = mean + sigma_s*sqrt(c)*randn.  The reference issues ~6 elementwise launches plus
 // torch.randn_like per step; this is one pass: 4 B (z) + 4 B (eps_hat) read, 4 B written per
-// voxel, optionally + c_pad*2 B for the packed bf16 network input of the next step.
+// voxel, optionally + 16 B for plane 0 of the packed bf16 network input of the next step.
 #include "common.cuh"
 
 namespace vdm {
@@ -15,7 +15,7 @@ sampler_step_kernel(const float* __restrict__ z, const float* __restrict__ eps_h
                     int64_t voxels, const float* __restrict__ coef, const int32_t* __restrict__ step_ptr,
                     uint64_t seed, const int32_t* __restrict__ realisation_id, int32_t draw_base,
                     const float* __restrict__ noise_in, const float* __restrict__ cond, int n_cond,
-                    __nv_bfloat16* __restrict__ packed_out, int c_pad) {
+                    bf16x8* __restrict__ packed_out, int packed_planes) {
   const int b = blockIdx.y;
   const int step = step_ptr ? *step_ptr : 0;
   const float4 cf = *reinterpret_cast<const float4*>(coef + 4 * (int64_t)step);
@@ -62,22 +62,17 @@ sampler_step_kernel(const float* __restrict__ z, const float* __restrict__ eps_h
         if (e0 + i < voxels) ob[e0 + i] = out[i];
     }
     if (packed_out) {
-      // rewrite the whole c_pad-channel row (32 B for c_pad = 16): full-sector stores
+      // plane 0 of the packed network input: (z, cond_1..cond_n, 0...) as 8 bf16 = one 16-byte store per voxel
+      bf16x8* plane0 = packed_out + (int64_t)b * packed_planes * voxels;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int64_t v = e0 + i;
         if (v >= voxels) break;
-        __nv_bfloat16* row = packed_out + ((int64_t)b * voxels + v) * c_pad;
-        for (int c0 = 0; c0 < c_pad; c0 += 8) {
-          float f[8];
+        float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            f[j] = (c == 0) ? out[i]
-                            : (c <= n_cond ? cond[((int64_t)b * n_cond + (c - 1)) * voxels + v] : 0.f);
-          }
-          *reinterpret_cast<bf16x8*>(row + c0) = pack8(f);
-        }
+        for (int j = 0; j < 8; ++j)
+          f[j] = (j == 0) ? out[i] : (j <= n_cond ? cond[((int64_t)b * n_cond + (j - 1)) * voxels + v] : 0.f);
+        plane0[v] = pack8(f);
       }
     }
   }
@@ -100,24 +95,22 @@ philox_normal_kernel(float* __restrict__ out, int64_t voxels, uint64_t seed,
   }
 }
 
-// z fp32 + cond fp32 planes -> bf16 [B][V][c_pad]
+// z fp32 + cond fp32 planes -> channel-planar bf16: plane 0 = (z, cond_1..cond_n, 0...), other planes 0
 __global__ void __launch_bounds__(256)
-pack_input_kernel(const float* __restrict__ z, const float* __restrict__ cond, __nv_bfloat16* __restrict__ out,
-                  int64_t voxels, int n_cond, int c_pad) {
+pack_input_kernel(const float* __restrict__ z, const float* __restrict__ cond, VdmTensor out, int planes,
+                  int64_t voxels, int n_cond) {
   const int b = blockIdx.y;
+  bf16x8* ob = reinterpret_cast<bf16x8*>(out.data) + ((int64_t)b * out.planes + out.plane0) * voxels;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < voxels;
        v += (int64_t)gridDim.x * blockDim.x) {
-    __nv_bfloat16* row = out + ((int64_t)b * voxels + v) * c_pad;
-    for (int c0 = 0; c0 < c_pad; c0 += 8) {
-      float f[8];
+    float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        f[j] = (c == 0) ? z[(int64_t)b * voxels + v]
-                        : (c <= n_cond ? cond[((int64_t)b * n_cond + (c - 1)) * voxels + v] : 0.f);
-      }
-      *reinterpret_cast<bf16x8*>(row + c0) = pack8(f);
-    }
+    for (int j = 0; j < 8; ++j)
+      f[j] = (j == 0) ? z[(int64_t)b * voxels + v]
+                      : (j <= n_cond ? cond[((int64_t)b * n_cond + (j - 1)) * voxels + v] : 0.f);
+    ob[v] = pack8(f);
+    const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pl = 1; pl < planes; ++pl) ob[(int64_t)pl * voxels + v] = pack8(zero);
   }
 }
 
@@ -134,20 +127,20 @@ static inline dim3 grid_for(int64_t work_items, int batch, int threads) {
 extern "C" int vdm_sampler_step(const float* z, const float* eps_hat, float* z_out, int batch, int64_t voxels,
                                 const float* coef, const int32_t* step_ptr, uint64_t seed,
                                 const int32_t* realisation_id, int32_t draw_base, const float* noise_in,
-                                const float* cond, int n_cond, void* packed_out, int c_pad, void* stream) {
+                                const float* cond, int n_cond, void* packed_out, int packed_planes, void* stream) {
   VDM_CHECK_ARG(z && eps_hat && z_out && coef, "vdm_sampler_step: NULL pointer argument");
   VDM_CHECK_ARG(batch >= 1 && batch <= 65535 && voxels >= 1, "vdm_sampler_step: bad shape (%d, %lld)", batch,
                 (long long)voxels);
   VDM_CHECK_ARG(voxels <= ((int64_t)1 << 34), "vdm_sampler_step: field too large for the 32-bit Philox group index");
   if (packed_out) {
-    VDM_CHECK_ARG(c_pad >= 8 && c_pad % 8 == 0 && n_cond + 1 <= c_pad, "vdm_sampler_step: bad c_pad %d / n_cond %d",
-                  c_pad, n_cond);
+    VDM_CHECK_ARG(packed_planes >= 1 && n_cond >= 0 && n_cond + 1 <= 8, "vdm_sampler_step: bad packed_planes %d / n_cond %d",
+                  packed_planes, n_cond);
     VDM_CHECK_ARG(n_cond == 0 || cond, "vdm_sampler_step: cond is NULL with n_cond=%d", n_cond);
   }
   const dim3 grid = vdm::grid_for((voxels + 3) / 4, batch, 256);
   vdm::sampler_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       z, eps_hat, z_out, voxels, coef, step_ptr, seed, realisation_id, draw_base, noise_in, cond, n_cond,
-      static_cast<__nv_bfloat16*>(packed_out), c_pad);
+      static_cast<vdm::bf16x8*>(packed_out), packed_planes);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
 }
@@ -161,15 +154,15 @@ extern "C" int vdm_philox_normal(float* out, int batch, int64_t voxels, uint64_t
   return VDM_OK;
 }
 
-extern "C" int vdm_pack_input(const float* z, const float* cond, void* out, int batch, int64_t voxels, int n_cond,
-                              int c_pad, void* stream) {
-  VDM_CHECK_ARG(z && out && batch >= 1 && batch <= 65535 && voxels >= 1, "vdm_pack_input: bad argument");
-  VDM_CHECK_ARG(c_pad >= 8 && c_pad % 8 == 0 && n_cond + 1 <= c_pad, "vdm_pack_input: bad c_pad %d / n_cond %d",
-                c_pad, n_cond);
+extern "C" int vdm_pack_input(const float* z, const float* cond, const VdmTensor* out, int batch, int64_t voxels,
+                              int n_cond, int c_pad, void* stream) {
+  VDM_CHECK_ARG(z && out && out->data && batch >= 1 && batch <= 65535 && voxels >= 1, "vdm_pack_input: bad argument");
+  VDM_CHECK_ARG(c_pad >= 8 && c_pad % 8 == 0 && n_cond >= 0 && n_cond + 1 <= 8 && out->plane0 >= 0 &&
+                    out->planes >= out->plane0 + c_pad / 8,
+                "vdm_pack_input: bad c_pad %d / n_cond %d / plane window", c_pad, n_cond);
   VDM_CHECK_ARG(n_cond == 0 || cond, "vdm_pack_input: cond is NULL with n_cond=%d", n_cond);
   const dim3 grid = vdm::grid_for(voxels, batch, 256);
-  vdm::pack_input_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, cond, static_cast<__nv_bfloat16*>(out), voxels,
-                                                                n_cond, c_pad);
+  vdm::pack_input_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, cond, *out, c_pad / 8, voxels, n_cond);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
 }

@@ -1,0 +1,325 @@
+"""Torch-tensor front end of the C ABI (``include/vdm4cdm_b200.h``): every function here checks
+shapes/dtypes, hands raw device pointers and the current CUDA stream to ``libvdm4cdm_b200.so`` and
+raises ``RuntimeError`` on failure.  There is no PyTorch fallback for any of them.
+
+Channel-planar activations are torch bf16 tensors of shape ``[B, P, D, H, W, 8]`` (P planes of 8
+channels); a *view* ``(buf, plane0, channels)`` addresses ``channels`` consecutive channels of a
+wider buffer, which is how channel concatenation is expressed without copies.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _C
+
+TAPS_3X3X3 = tuple((kd - 1, kh - 1, kw - 1) for kd in range(3) for kh in range(3) for kw in range(3))
+TAPS_1X1X1 = ((0, 0, 0),)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(cond: bool, msg: str) -> None:
+    if not cond:
+        raise ValueError(msg)
+
+
+def _planar_ok(t: torch.Tensor, name: str) -> None:
+    _need(t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 6 and t.shape[-1] == 8 and t.is_contiguous(),
+          f"{name}: expected a contiguous CUDA bf16 [B,P,D,H,W,8] tensor, got {tuple(t.shape)} {t.dtype} {t.device}")
+
+
+def _view(t: torch.Tensor, plane0: int) -> _C.Tensor:
+    return _C.Tensor(t.data_ptr(), t.shape[1], plane0)
+
+
+# ---- layout helpers (host-side glue; run on whatever device the tensor lives on) -------------------
+def to_planar(x: torch.Tensor, pad_to: int = 8) -> torch.Tensor:
+    """(B, C, D, H, W) any float dtype -> bf16 [B, ceil(C/pad_to)*pad_to/8, D, H, W, 8] (zero padded)."""
+    b, c, d, h, w = x.shape
+    cp = -(-c // pad_to) * pad_to
+    if cp != c:
+        x = torch.cat([x, x.new_zeros(b, cp - c, d, h, w)], dim=1)
+    return x.reshape(b, cp // 8, 8, d, h, w).permute(0, 1, 3, 4, 5, 2).contiguous().to(torch.bfloat16)
+
+
+def from_planar(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    """bf16 [B, P, D, H, W, 8] -> fp32 (B, C, D, H, W)."""
+    b, p, d, h, w, _ = x.shape
+    y = x.permute(0, 1, 5, 2, 3, 4).reshape(b, p * 8, d, h, w).float()
+    return y if channels is None else y[:, :channels]
+
+
+def pack_conv_weight(w: torch.Tensor, c_in_pad: Optional[int] = None, c_out_pad: Optional[int] = None,
+                     transpose_flip: bool = False) -> torch.Tensor:
+    """torch Conv3d weight (Cout, Cin, kd, kh, kw) -> bf16 [taps][Cin_pad/8][Cout_pad][8].
+
+    ``transpose_flip=True`` packs the dgrad filter: roles of Cin/Cout exchanged and taps mirrored.
+    Tap order matches ``TAPS_3X3X3`` / ``TAPS_1X1X1``.
+    """
+    if transpose_flip:
+        w = w.transpose(0, 1).flip(2, 3, 4)
+    co, ci, kd, kh, kw = w.shape
+    cip = -(-ci // 16) * 16 if c_in_pad is None else c_in_pad
+    cop = -(-co // 16) * 16 if c_out_pad is None else c_out_pad
+    t = w.permute(2, 3, 4, 1, 0).reshape(kd * kh * kw, ci, co).float()
+    full = t.new_zeros(kd * kh * kw, cip, cop)
+    full[:, :ci, :co] = t
+    return full.reshape(kd * kh * kw, cip // 8, 8, cop).permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
+
+
+# ---- conv ------------------------------------------------------------------------------------------
+def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequence[Tuple[int, int, int]] = TAPS_3X3X3,
+           x_plane0: int = 0, c_in: Optional[int] = None, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
+           out_fp32: bool = False, chan_add: Optional[torch.Tensor] = None, step_ptr: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, residual_plane0: int = 0, stats: Optional[torch.Tensor] = None,
+           stats_c0: int = 0) -> torch.Tensor:
+    """``vdm_conv3d``: y = conv(x, w) [+ chan_add[b, co]] [+ residual], optional GroupNorm statistics.
+
+    x: planar buffer; the conv reads ``c_in`` channels starting at plane ``x_plane0``.
+    w_packed: ``pack_conv_weight`` output, shape [taps, c_in/8, c_out_pad, 8].
+    out: planar buffer written at plane ``out_plane0`` (allocated when None); with ``out_fp32`` the
+    result is fp32 (B, c_out, D, H, W) instead.
+    chan_add: fp32 [B, c_out] or [steps, B, c_out] (then ``step_ptr`` selects the row block on device).
+    stats: double [B, Cs, 2], accumulated at channel ``stats_c0``.
+    """
+    _planar_ok(x, "conv3d x")
+    b, xp, d, h, w_, _ = x.shape
+    n_taps, cin8, c_out_pad, eight = w_packed.shape
+    _need(w_packed.is_cuda and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous() and eight == 8,
+          "conv3d: w_packed must be a contiguous CUDA bf16 [taps, Cin/8, Cout_pad, 8] tensor")
+    c_in = cin8 * 8 if c_in is None else c_in
+    _need(c_in == cin8 * 8, f"conv3d: weight packs {cin8 * 8} input channels, c_in={c_in}")
+    _need(n_taps == len(taps), f"conv3d: weight has {n_taps} taps, {len(taps)} offsets given")
+    desc = _C.ConvDesc()
+    desc.batch, desc.depth, desc.height, desc.width = b, d, h, w_
+    desc.c_in, desc.c_out, desc.c_out_pad, desc.n_taps = c_in, c_out, c_out_pad, n_taps
+    for i, t in enumerate(taps):
+        for k in range(3):
+            desc.tap_offset[i][k] = t[k]
+    desc.circular = 0
+    desc.out_fp32 = 1 if out_fp32 else 0
+    desc.x_planes, desc.x_plane0 = xp, x_plane0
+    if out is None:
+        if out_fp32:
+            out = torch.empty((b, c_out, d, h, w_), dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty((b, c_out // 8, d, h, w_, 8), dtype=torch.bfloat16, device=x.device)
+    if out_fp32:
+        _need(out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (b, c_out, d, h, w_),
+              "conv3d: fp32 output must be contiguous (B, c_out, D, H, W)")
+    else:
+        _planar_ok(out, "conv3d out")
+        _need(tuple(out.shape[2:5]) == (d, h, w_) and out.shape[0] == b, "conv3d: out grid mismatch")
+        desc.y_planes, desc.y_plane0 = out.shape[1], out_plane0
+    epi = _C.ConvEpilogue()
+    if chan_add is not None:
+        _need(chan_add.is_cuda and chan_add.dtype == torch.float32 and chan_add.is_contiguous() and
+              chan_add.shape[-1] == c_out and chan_add.shape[-2] == b, "conv3d: chan_add must be fp32 [..., B, c_out]")
+        epi.chan_add = chan_add.data_ptr()
+        epi.chan_add_step_stride = b * c_out
+        if step_ptr is not None:
+            _need(step_ptr.is_cuda and step_ptr.dtype == torch.int32, "conv3d: step_ptr must be a CUDA int32 tensor")
+            epi.step_ptr = step_ptr.data_ptr()
+    if residual is not None:
+        _planar_ok(residual, "conv3d residual")
+        _need(tuple(residual.shape[2:5]) == (d, h, w_) and residual.shape[0] == b, "conv3d: residual grid mismatch")
+        epi.residual = residual.data_ptr()
+        desc.r_planes, desc.r_plane0 = residual.shape[1], residual_plane0
+    if stats is not None:
+        _need(stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous() and stats.dim() == 3 and
+              stats.shape[0] == b and stats.shape[2] == 2, "conv3d: stats must be double [B, C, 2]")
+        epi.stats = stats.data_ptr()
+        epi.stats_channels = stats.shape[1]
+        epi.stats_c0 = stats_c0
+    rc = _C.lib().vdm_conv3d(ctypes.byref(desc), x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), ctypes.byref(epi),
+                             _stream())
+    _C.check(rc, "vdm_conv3d")
+    return out
+
+
+# ---- elementwise ---------------------------------------------------------------------------------
+def channel_stats(x: torch.Tensor, channels: int, x_plane0: int = 0, stats: Optional[torch.Tensor] = None,
+                  stats_c0: int = 0) -> torch.Tensor:
+    _planar_ok(x, "channel_stats x")
+    b = x.shape[0]
+    voxels = x.shape[2] * x.shape[3] * x.shape[4]
+    if stats is None:
+        stats = torch.zeros((b, channels, 2), dtype=torch.float64, device=x.device)
+    v = _view(x, x_plane0)
+    rc = _C.lib().vdm_channel_stats(ctypes.byref(v), b, voxels, channels, stats.data_ptr(), stats.shape[1], stats_c0,
+                                    _stream())
+    _C.check(rc, "vdm_channel_stats")
+    return stats
+
+
+def gn_silu(x: torch.Tensor, channels: int, groups: int, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+            eps: float = 1e-5, *, x_plane0: int = 0, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
+            dropout_p: float = 0.0, seed: int = 0, layer_tag: int = 0) -> torch.Tensor:
+    _planar_ok(x, "gn_silu x")
+    b = x.shape[0]
+    voxels = x.shape[2] * x.shape[3] * x.shape[4]
+    _need(stats.dtype == torch.float64 and tuple(stats.shape) == (b, channels, 2) and stats.is_contiguous(),
+          "gn_silu: stats must be double [B, channels, 2]")
+    _need(gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == channels and
+          beta.numel() == channels and gamma.is_cuda and beta.is_cuda, "gn_silu: gamma/beta must be CUDA fp32 [channels]")
+    if out is None:
+        out = torch.empty((b, channels // 8) + tuple(x.shape[2:]), dtype=torch.bfloat16, device=x.device)
+    _planar_ok(out, "gn_silu out")
+    vx, vy = _view(x, x_plane0), _view(out, out_plane0)
+    rc = _C.lib().vdm_gn_silu(ctypes.byref(vx), ctypes.byref(vy), b, voxels, channels, groups, stats.data_ptr(),
+                              gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, layer_tag, _stream())
+    _C.check(rc, "vdm_gn_silu")
+    return out
+
+
+def avgpool2(x: torch.Tensor, channels: int, *, x_plane0: int = 0, out: Optional[torch.Tensor] = None,
+             out_plane0: int = 0, stats: Optional[torch.Tensor] = None, stats_c0: int = 0) -> torch.Tensor:
+    _planar_ok(x, "avgpool2 x")
+    b, _, d, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty((b, channels // 8, d // 2, h // 2, w // 2, 8), dtype=torch.bfloat16, device=x.device)
+    _planar_ok(out, "avgpool2 out")
+    vx, vy = _view(x, x_plane0), _view(out, out_plane0)
+    rc = _C.lib().vdm_avgpool2(ctypes.byref(vx), ctypes.byref(vy), b, d, h, w, channels, _ptr(stats),
+                               0 if stats is None else stats.shape[1], stats_c0, _stream())
+    _C.check(rc, "vdm_avgpool2")
+    return out
+
+
+def upsample2(coarse: torch.Tensor, channels: int, out: torch.Tensor, *, coarse_plane0: int = 0, out_plane0: int = 0,
+              stats: Optional[torch.Tensor] = None, stats_c0: int = 0) -> torch.Tensor:
+    _planar_ok(coarse, "upsample2 coarse")
+    _planar_ok(out, "upsample2 out")
+    b, _, d, h, w, _ = out.shape
+    _need(tuple(coarse.shape[2:5]) == (d // 2, h // 2, w // 2), "upsample2: coarse grid must be half the fine grid")
+    vx, vy = _view(coarse, coarse_plane0), _view(out, out_plane0)
+    rc = _C.lib().vdm_upsample2(ctypes.byref(vx), ctypes.byref(vy), b, d, h, w, channels, _ptr(stats),
+                                0 if stats is None else stats.shape[1], stats_c0, _stream())
+    _C.check(rc, "vdm_upsample2")
+    return out
+
+
+def pack_input(z: torch.Tensor, cond: Optional[torch.Tensor], c_pad: int = 16,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """z: fp32 (B, 1, D, H, W) or (B, D, H, W); cond: fp32 (B, n_cond, D, H, W) -> planar [B, c_pad/8, D, H, W, 8]."""
+    _need(z.is_cuda and z.dtype == torch.float32 and z.is_contiguous(), "pack_input: z must be contiguous CUDA fp32")
+    if z.dim() == 5:
+        _need(z.shape[1] == 1, "pack_input: z must have one channel")
+        b, _, d, h, w = z.shape
+    else:
+        b, d, h, w = z.shape
+    n_cond = 0
+    if cond is not None:
+        _need(cond.is_cuda and cond.dtype == torch.float32 and cond.is_contiguous() and cond.dim() == 5 and
+              tuple(cond.shape[2:]) == (d, h, w) and cond.shape[0] == b, "pack_input: cond must be fp32 (B, n, D, H, W)")
+        n_cond = cond.shape[1]
+    if out is None:
+        out = torch.empty((b, c_pad // 8, d, h, w, 8), dtype=torch.bfloat16, device=z.device)
+    _planar_ok(out, "pack_input out")
+    vo = _view(out, 0)
+    rc = _C.lib().vdm_pack_input(z.data_ptr(), _ptr(cond), ctypes.byref(vo), b, d * h * w, n_cond, c_pad, _stream())
+    _C.check(rc, "vdm_pack_input")
+    return out
+
+
+# ---- sampler ---------------------------------------------------------------------------------------
+def sampler_step(z: torch.Tensor, eps_hat: torch.Tensor, coef: torch.Tensor, *, out: Optional[torch.Tensor] = None,
+                 step_ptr: Optional[torch.Tensor] = None, seed: int = 0, realisation_id: Optional[torch.Tensor] = None,
+                 draw_base: int = 1, noise: Optional[torch.Tensor] = None, cond: Optional[torch.Tensor] = None,
+                 packed_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``vdm_sampler_step``: z_out = out_scale * (w_z z + w_eps eps_hat + noise_scale N(0,1)).
+
+    coef: fp32 [steps, 4] = (w_z, w_eps, noise_scale, out_scale); ``step_ptr`` (device int32) picks the row.
+    """
+    _need(z.is_cuda and z.dtype == torch.float32 and z.is_contiguous(), "sampler_step: z must be contiguous CUDA fp32")
+    _need(eps_hat.dtype == torch.float32 and eps_hat.is_contiguous() and eps_hat.numel() == z.numel(),
+          "sampler_step: eps_hat must be fp32 with z's shape")
+    _need(coef.is_cuda and coef.dtype == torch.float32 and coef.is_contiguous() and coef.shape[-1] == 4,
+          "sampler_step: coef must be fp32 [steps, 4]")
+    b = z.shape[0]
+    voxels = z.numel() // b
+    if out is None:
+        out = torch.empty_like(z)
+    n_cond = 0 if cond is None else cond.shape[1]
+    packed_planes = 0 if packed_out is None else packed_out.shape[1]
+    if noise is not None:
+        _need(noise.dtype == torch.float32 and noise.is_contiguous() and noise.numel() == z.numel(),
+              "sampler_step: injected noise must be fp32 with z's shape")
+    rc = _C.lib().vdm_sampler_step(z.data_ptr(), eps_hat.data_ptr(), out.data_ptr(), b, voxels, coef.data_ptr(),
+                                   _ptr(step_ptr), seed, _ptr(realisation_id), draw_base, _ptr(noise), _ptr(cond),
+                                   n_cond, _ptr(packed_out), packed_planes, _stream())
+    _C.check(rc, "vdm_sampler_step")
+    return out
+
+
+def philox_normal(shape, seed: int, draw: int, realisation_id: Optional[torch.Tensor] = None,
+                  device="cuda") -> torch.Tensor:
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    b = shape[0]
+    rc = _C.lib().vdm_philox_normal(out.data_ptr(), b, out.numel() // b, seed, _ptr(realisation_id), draw, _stream())
+    _C.check(rc, "vdm_philox_normal")
+    return out
+
+
+def increment(counter: torch.Tensor) -> None:
+    _C.check(_C.lib().vdm_increment(counter.data_ptr(), _stream()), "vdm_increment")
+
+
+# ---- P(k) --------------------------------------------------------------------------------------------
+def _pk_shape(fields: torch.Tensor):
+    _need(fields.is_cuda and fields.dtype == torch.float32 and fields.is_contiguous() and fields.dim() in (5, 6),
+          "pk: fields must be contiguous CUDA fp32 [F, B, C, (n0,) n1, n2]")
+    if fields.dim() == 5:
+        f, b, c, n1, n2 = fields.shape
+        n0 = 1
+    else:
+        f, b, c, n0, n1, n2 = fields.shape
+    return f, b, c, n0, n1, n2
+
+
+def pk_fields(fields: torch.Tensor, fields2: Optional[torch.Tensor] = None):
+    """``vdm_pk``: per field f: power(fields[f], fields2[f]) of src/utils.py:16-83.
+    fields: fp32 [F, B, C, n0, n1, n2] (3-D) or [F, B, C, n1, n2] (2-D).  Returns (k, P, N) as
+    (double [F, kmax], double [F, kmax], int64 [F, kmax])."""
+    f, b, c, n0, n1, n2 = _pk_shape(fields)
+    if fields2 is not None:
+        _need(fields2.shape == fields.shape and fields2.dtype == torch.float32 and fields2.is_contiguous(),
+              "pk: fields2 must match fields")
+    lib = _C.lib()
+    nbytes = lib.vdm_pk_work_bytes(f, b, c, n0, n1, n2, 0 if fields2 is None else 1)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=fields.device)
+    kmax = (min(n1, n2) if n0 == 1 else min(n0, n1, n2)) // 2
+    k = torch.empty((f, kmax), dtype=torch.float64, device=fields.device)
+    p = torch.empty_like(k)
+    n = torch.empty((f, kmax), dtype=torch.int64, device=fields.device)
+    rc = lib.vdm_pk(fields.data_ptr(), _ptr(fields2), f, b, c, n0, n1, n2, work.data_ptr(), nbytes, k.data_ptr(),
+                    p.data_ptr(), n.data_ptr(), _stream())
+    _C.check(rc, "vdm_pk")
+    return k, p, n
+
+
+def pk_cross3(fields1: torch.Tensor, fields2: torch.Tensor):
+    """``vdm_pk_cross3``: (k, P11, P22, P12, N) from two transforms per field pair."""
+    f, b, c, n0, n1, n2 = _pk_shape(fields1)
+    _need(fields2.shape == fields1.shape and fields2.dtype == torch.float32 and fields2.is_contiguous() and
+          fields2.is_cuda, "pk_cross3: fields2 must match fields1")
+    lib = _C.lib()
+    nbytes = lib.vdm_pk_work_bytes(f, b, c, n0, n1, n2, 1)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=fields1.device)
+    kmax = (min(n1, n2) if n0 == 1 else min(n0, n1, n2)) // 2
+    k = torch.empty((f, kmax), dtype=torch.float64, device=fields1.device)
+    p11, p22, p12 = torch.empty_like(k), torch.empty_like(k), torch.empty_like(k)
+    n = torch.empty((f, kmax), dtype=torch.int64, device=fields1.device)
+    rc = lib.vdm_pk_cross3(fields1.data_ptr(), fields2.data_ptr(), f, b, c, n0, n1, n2, work.data_ptr(), nbytes,
+                           k.data_ptr(), p11.data_ptr(), p22.data_ptr(), p12.data_ptr(), n.data_ptr(), _stream())
+    _C.check(rc, "vdm_pk_cross3")
+    return k, p11, p22, p12, n
