@@ -54,7 +54,8 @@ def test_sampler_step_injected_noise_matches_oracle_formula():
     s_t, s_s = torch.sigmoid(gt).sqrt(), torch.sigmoid(gs).sqrt()
     coef = torch.tensor([[a_s / a_t, -a_s / a_t * c * s_t, s_s * c.sqrt(), 1.0]], dtype=torch.float32, device=dev)
     got = ops.sampler_step(z.to(dev), eps.to(dev), coef, noise=noise.to(dev)).cpu()
-    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (got - want).abs().max()
+    # fp32 tolerance of the north_star (1e-5): the oracle evaluates alpha/sigma in fp32, the coefficients here are fp64
+    assert torch.allclose(got, want.detach(), rtol=1e-5, atol=1e-5), (got - want).abs().max()
 
 
 def test_sampler_step_philox_noise_steps_and_packed_output():

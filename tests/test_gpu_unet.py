@@ -1,0 +1,111 @@
+"""GPU parity of the CUNet trunk and the VDM sampler against the CPU oracle (oracle/unet_ref.py,
+oracle/vdm_ref.py: plain PyTorch fp32) on identical weights, inputs and injected noise.
+
+Tolerance: the CUDA path keeps activations in bf16 (fp32 accumulation, fp32 latent z); BASELINE.json's
+north_star allows 1e-2 relative for bf16.  It is applied to the relative L2 error of the network output
+and of one sampler step; multi-step trajectories are compared per step with the oracle re-started
+from the CUDA path's z_t (errors compound over an ancestral chain)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_RTOL = 1e-2
+
+
+def _models(shape, chs, v_dims=(6,), seed=0):
+    from oracle.unet_ref import CUNet as RefNet
+    from vdm4cdm_b200.networks import CUNet
+    torch.manual_seed(seed)
+    kw = dict(shape=shape, chs=chs, s_conditioning_channels=1, v_conditioning_dims=list(v_dims), t_conditioning=True,
+              norm_groups=8, dropout_prob=0.1)
+    ref = RefNet(**kw).eval()
+    # give biases / norm affines non-trivial values so that every epilogue term is exercised
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    net = CUNet(**kw)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    return ref, net.cuda().eval()
+
+
+def _rel_l2(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.mark.parametrize("shape,chs,batch", [((1, 32, 32, 32), (16, 32, 64, 128), 2),
+                                             ((1, 16, 32, 48), (32, 64), 1),
+                                             ((1, 24, 24, 24), (16, 32, 64), 3)])
+def test_unet_forward_matches_oracle(shape, chs, batch):
+    ref, net = _models(shape, chs)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((batch,) + shape, generator=g)
+    cond = 0.7 * x + 0.3 * torch.randn((batch,) + shape, generator=g)
+    t = torch.rand(batch, generator=g)
+    v = [torch.rand(batch, 6, generator=g)]
+    with torch.no_grad():
+        want = ref(x, t=t, s_conditioning=cond, v_conditionings=v)
+        got = net(x.cuda(), t=t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()]).cpu()
+    assert got.shape == want.shape and got.dtype == torch.float32
+    err = _rel_l2(got, want)
+    print(f"unet {shape} {chs}: relative L2 error {err:.3e}, max abs {((got - want).abs().max() / want.abs().max()).item():.3e}")
+    assert err < BF16_RTOL, err
+    # no time / parameter conditioning inputs, scalar t
+    with torch.no_grad():
+        want1 = ref(x[:1], t=torch.tensor(0.3), s_conditioning=cond[:1], v_conditionings=[v[0][:1]])
+        got1 = net(x[:1].cuda(), t=torch.tensor(0.3), s_conditioning=cond[:1].cuda(), v_conditionings=[v[0][:1].cuda()]).cpu()
+    assert _rel_l2(got1, want1) < BF16_RTOL
+
+
+def test_sampler_chain_matches_oracle_per_step_and_graph_equals_eager():
+    from oracle.vdm_ref import VDM as RefVDM
+    from vdm4cdm_b200.vdm_model import VDM
+    shape, chs, batch, n_steps = (1, 16, 16, 16), (16, 32), 2, 6
+    ref_net, net = _models(shape, chs)
+    ref_vdm, vdm = RefVDM(ref_net).eval(), VDM(net).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    noises = [torch.randn((batch,) + shape, generator=g) for _ in range(n_steps + 1)]
+    cond = torch.randn((batch,) + shape, generator=g)
+    v = [torch.rand(batch, 6, generator=g)]
+    kw_ref = dict(s_conditioning=cond, v_conditionings=v)
+    kw = dict(s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()])
+    nf = lambda d, shp: noises[d]
+    vdm.use_cuda_graph = True
+    traj = vdm.sample(batch, n_steps, "cuda:0", return_all=True, noise_fn=lambda d, s: noises[d].cuda(), **kw).cpu()
+    vdm.use_cuda_graph = False
+    traj_eager = vdm.sample(batch, n_steps, "cuda:0", return_all=True, noise_fn=lambda d, s: noises[d].cuda(), **kw).cpu()
+    assert torch.equal(traj, traj_eager), "CUDA-graph replay must reproduce the eager loop bit for bit"
+    assert traj.shape == (n_steps + 1, batch) + shape
+    steps = torch.linspace(1.0, 0.0, n_steps + 1)
+    z = noises[0]
+    worst = 0.0
+    with torch.no_grad():
+        for i in range(n_steps):
+            want = ref_vdm.sample_zs_given_zt(zt=z, t=steps[i], s=steps[i + 1], noise=noises[i + 1], **kw_ref)
+            worst = max(worst, _rel_l2(traj[i], want))
+            z = traj[i]                              # restart the oracle from the CUDA path's state
+    print(f"sampler: worst per-step relative L2 error {worst:.3e}")
+    assert worst < BF16_RTOL, worst
+    # final map x = z_0 / alpha_0 and the folded variant agree
+    x_folded = vdm.sample(batch, n_steps, "cuda:0", noise_fn=lambda d, s: noises[d].cuda(), **kw).cpu()
+    assert torch.allclose(x_folded, traj[-1], rtol=1e-5, atol=1e-5)
+    # whole-chain comparison against the oracle's own trajectory (errors compound: looser, reported)
+    with torch.no_grad():
+        full = ref_vdm.sample(batch, n_steps, "cpu", noise_fn=nf, **kw_ref)
+    print(f"sampler: end-to-end relative L2 error after {n_steps} steps {_rel_l2(x_folded, full):.3e}")
+    assert _rel_l2(x_folded, full) < 5 * BF16_RTOL
+
+
+def test_philox_sampling_is_batch_independent():
+    from vdm4cdm_b200.vdm_model import VDM
+    shape, chs = (1, 16, 16, 16), (16, 32)
+    _, net = _models(shape, chs, v_dims=())
+    vdm = VDM(net).cuda().eval()
+    cond = torch.randn((1,) + shape, generator=torch.Generator().manual_seed(5)).cuda()
+    both = vdm.sample(2, 4, "cuda:0", seed=77, realisation_ids=[4, 9], s_conditioning=cond.expand(2, -1, -1, -1, -1).contiguous())
+    one = vdm.sample(1, 4, "cuda:0", seed=77, realisation_ids=[9], s_conditioning=cond)
+    # same (seed, realisation id) -> same noise; the network sees the same sample, so results agree to bf16 noise
+    # (bit equality is not guaranteed: GroupNorm statistics are accumulated with atomics)
+    assert torch.allclose(both[1:2], one, rtol=1e-2, atol=1e-2)
+    assert not torch.allclose(both[0:1], one, rtol=1e-2, atol=1e-2)

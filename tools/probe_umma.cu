@@ -167,7 +167,7 @@ static void test_planar(int n, int ktot) {
   for (int k = 0; k < ktot; ++k)
     for (int j = 0; j < n; ++j) put(b, (size_t)(k / 8) * n * 16 + j * 16 + (k % 8) * 2, ival(k, j, 0, 2));
   const int shifts[5][2] = {{0, 0}, {1, 1}, {2, 2}, {1, 0}, {0, 1}};
-  for (int hyp = 0; hyp < 2; ++hyp) {
+  for (int hyp = 0; hyp < 1; ++hyp) {  // hyp 1 (roles swapped) faults on hardware: addresses leave shared memory
     for (auto& s : shifts) {
       ProbeParams p;
       memset(&p, 0, sizeof(p));
@@ -251,7 +251,7 @@ static void test_mn_major(int n) {
     for (int v = 0; v < vox; ++v) put(a, (size_t)(c / 8) * PA + v * 16 + (c % 8) * 2, ival(c, v, 0, 5));
   for (int c = 0; c < n; ++c)
     for (int v = 0; v < 16; ++v) put(b, (size_t)(c / 8) * PB + v * 16 + (c % 8) * 2, ival(c, v, 0, 6));
-  for (int hyp = 0; hyp < 2; ++hyp) {
+  for (int hyp = 0; hyp < 1; ++hyp) {
     for (int dw = 0; dw < 3; ++dw) {
       ProbeParams p;
       memset(&p, 0, sizeof(p));
@@ -333,16 +333,16 @@ int main() {
   cudaMalloc(&d_cyc, sizeof(long long));
   test_planar(32, 32);
   test_planar(64, 64);
-  test_swizzled(32, 128, 16);
-  test_swizzled(32, 128, 10);
-  test_swizzled(32, 64, 16);
-  test_swizzled(32, 64, 10);
-  test_mn_major(32);
-  test_mn_major(128);
   const int ns[] = {16, 32, 48, 64, 96, 128, 256};
   for (int n : ns) test_rate(n, 0);
   for (int n : ns) test_rate(n, 1);
   for (int n : ns) test_rate(n, 2);
+  test_mn_major(32);
+  test_mn_major(128);
+  test_swizzled(32, 128, 16);
+  test_swizzled(32, 128, 10);
+  test_swizzled(32, 64, 16);
+  test_swizzled(32, 64, 10);
   printf("probe done\n");
   return 0;
 }

@@ -1,0 +1,335 @@
+"""``CUNet``: the 3-D conditional UNet denoiser of vdm4cdm, B200-native.
+
+Mirrors the interface the reference imports as ``mltools.networks.networks.CUNet`` (constructor call
+sites: trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:116-127, src/utils.py:451-462;
+``forward(x, t, s_conditioning, v_conditionings)`` and the ``downs`` loop with ``no_down`` on the last
+level: networks.py:259-265 recovered in model_test.ipynb:684; ResNetDown / ResNetBlock structure:
+blocks.py:129-170, model_test.ipynb:686-692).
+
+The torch modules below only HOLD the fp32 parameters (so ``state_dict`` keys are the usual
+``conv_in.weight``, ``downs.0.resnet_blocks.0.net1.0.weight`` ...); the arithmetic of ``forward`` runs in
+the sm_100a kernels behind ``vdm4cdm_b200.ops`` on channel-planar bf16 activations:
+
+    conv_in / every Conv3d : vdm_conv3d   (tcgen05 implicit GEMM; bias + conditioning row, residual
+                                            and GroupNorm statistics fused into the epilogue)
+    GroupNorm+SiLU(+Dropout): vdm_gn_silu (one read, one write; statistics come from the producer)
+    avg_pool3d / upsample   : vdm_avgpool2 / vdm_upsample2 (concat = plane windows of one buffer)
+
+Only the tiny time / parameter embedding MLPs (B x <=256 GEMVs) stay in torch.  There is no PyTorch
+fallback for the convolutional path; autograd support lives in ``vdm4cdm_b200.autograd``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, scale: float = 1000.0) -> torch.Tensor:
+    """[sin(s t f_j), cos(s t f_j)], f_j = 1e4^(-j/half): the sinusoidal features fed to the time MLP."""
+    half = dim // 2
+    j = torch.arange(half, dtype=torch.float32, device=t.device)
+    freqs = torch.exp(-math.log(10000.0) * j / half)
+    args = (t.to(torch.float32) * scale)[:, None] * freqs[None, :]
+    return torch.cat([torch.sin(args), torch.cos(args)], dim=1)
+
+
+class ResNetBlock(nn.Module):
+    """Parameter holder of a pre-activation residual block (GroupNorm first: blocks.py:129-132)."""
+
+    def __init__(self, ch_in: int, ch_out: int, conditioning_dims: Sequence[int], dropout_prob: float,
+                 norm_groups: int, padding_mode: str = "zeros"):
+        super().__init__()
+        self.ch_in, self.ch_out = ch_in, ch_out
+        self.conditioning_dims = list(conditioning_dims)
+        self.dropout_prob = dropout_prob
+        self.norm_groups = norm_groups
+        self.net1 = nn.Sequential(nn.GroupNorm(norm_groups, ch_in), nn.SiLU(),
+                                  nn.Conv3d(ch_in, ch_out, 3, padding=1, padding_mode=padding_mode))
+        self.cond_projs = nn.ModuleList([nn.Linear(d, ch_out) for d in self.conditioning_dims])
+        self.net2 = nn.Sequential(nn.GroupNorm(norm_groups, ch_out), nn.SiLU(), nn.Dropout(dropout_prob),
+                                  nn.Conv3d(ch_out, ch_out, 3, padding=1, padding_mode=padding_mode))
+        self.skip_conv = nn.Conv3d(ch_in, ch_out, 1) if ch_in != ch_out else None
+
+    def conditioning_row(self, conditionings: Optional[List[torch.Tensor]]) -> torch.Tensor:
+        """bias of net1's conv + sum of the conditioning projections: fp32 [..., B, ch_out]."""
+        row = self.net1[2].bias
+        if conditionings is not None:
+            assert len(conditionings) == len(self.conditioning_dims)
+            for c, proj in zip(conditionings, self.cond_projs):
+                row = row + proj(c)
+        return row
+
+
+class ResNetDown(nn.Module):
+    def __init__(self, resnet_blocks: List[ResNetBlock]):
+        super().__init__()
+        self.resnet_blocks = nn.ModuleList(resnet_blocks)
+        self.attention_blocks = None
+
+
+class ResNetUp(nn.Module):
+    def __init__(self, resnet_blocks: List[ResNetBlock]):
+        super().__init__()
+        self.resnet_blocks = nn.ModuleList(resnet_blocks)
+
+
+class _Arena:
+    """Per-(batch, grid) cache of activation buffers so the steady state allocates nothing."""
+
+    def __init__(self):
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype, device, zero: bool = False) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            self.bufs[name] = t
+        return t
+
+
+class CUNet(nn.Module):
+    def __init__(self, shape=(1, 128, 128, 128), chs=(32, 64, 128, 256), s_conditioning_channels: int = 0,
+                 v_conditioning_dims: Sequence[int] = (), t_conditioning: bool = False, norm_groups: int = 8,
+                 mid_attn: bool = False, dropout_prob: float = 0.1, conv_padding_mode: str = "zeros",
+                 n_attention_heads: int = 4, t_embedding_dim: int = 64, v_embedding_dim: int = 64,
+                 out_channels: Optional[int] = None):
+        super().__init__()
+        if len(shape) != 4:
+            raise NotImplementedError("vdm4cdm_b200.CUNet covers the 3-D networks (shape=(C, D, H, W)) only")
+        if mid_attn:
+            raise NotImplementedError("mid_attn=True is used by the reference's 2-D scripts only")
+        if conv_padding_mode != "zeros":
+            raise NotImplementedError("circular padding (cropsize==256 models) is not implemented yet")
+        if shape[0] != 1 or (out_channels not in (None, 1)):
+            raise NotImplementedError("single-channel fields only (every 3-D config of the reference)")
+        if s_conditioning_channels + 1 > 8:
+            raise NotImplementedError("at most 7 spatial conditioning channels")
+        for c in chs:
+            if c % 16 != 0 or c > 256:
+                raise NotImplementedError(f"channel widths must be multiples of 16 and <= 256, got {chs}")
+        for n in shape[1:]:
+            if n % (2 ** (len(chs) - 1)) != 0:
+                raise ValueError(f"grid {shape[1:]} is not divisible by 2^{len(chs) - 1}")
+        self.shape = tuple(shape)
+        self.chs = list(chs)
+        self.s_conditioning_channels = s_conditioning_channels
+        self.v_conditioning_dims = list(v_conditioning_dims)
+        self.t_conditioning = t_conditioning
+        self.t_embedding_dim = t_embedding_dim
+        self.v_embedding_dim = v_embedding_dim
+        self.norm_groups = norm_groups
+        self.dropout_prob = dropout_prob
+        self.n_attention_heads = n_attention_heads
+        in_ch = shape[0] + s_conditioning_channels
+        pm = conv_padding_mode
+
+        cond_dims = []
+        if t_conditioning:
+            self.t_embed = nn.Sequential(nn.Linear(t_embedding_dim, 4 * t_embedding_dim), nn.SiLU(),
+                                         nn.Linear(4 * t_embedding_dim, t_embedding_dim), nn.SiLU())
+            cond_dims.append(t_embedding_dim)
+        self.v_embeds = nn.ModuleList()
+        for d in self.v_conditioning_dims:
+            self.v_embeds.append(nn.Sequential(nn.Linear(d, 4 * v_embedding_dim), nn.SiLU(),
+                                               nn.Linear(4 * v_embedding_dim, v_embedding_dim), nn.SiLU()))
+            cond_dims.append(v_embedding_dim)
+        self.conditioning_dims = cond_dims
+
+        def block(ci, co):
+            return ResNetBlock(ci, co, cond_dims, dropout_prob, norm_groups, pm)
+
+        c = self.chs
+        self.conv_in = nn.Conv3d(in_ch, c[0], 3, padding=1, padding_mode=pm)
+        self.downs = nn.ModuleList([ResNetDown([block(c[max(i - 1, 0)], c[i])]) for i in range(len(c))])
+        self.mid1 = block(c[-1], c[-1])
+        self.mid2 = block(c[-1], c[-1])
+        self.ups = nn.ModuleList([ResNetUp([block(c[i + 1] + c[i], c[i])]) for i in reversed(range(len(c) - 1))])
+        self.conv_out = nn.Sequential(nn.GroupNorm(norm_groups, c[0]), nn.SiLU(),
+                                      nn.Conv3d(c[0], 1, 3, padding=1, padding_mode=pm))
+        self._arena = _Arena()
+        self._packed_cache: Dict[str, tuple] = {}
+        self.dropout_seed = 0
+        self._dropout_calls = 0
+
+    # ---- conditioning (tiny fp32 MLPs, torch) -------------------------------------------------
+    def conditionings(self, batch: int, t, v_conditionings, device) -> Optional[List[torch.Tensor]]:
+        """List of fp32 [..., B, dim] embeddings (time first, then one per parameter vector).
+
+        ``t`` may be (B,), a scalar, or (S, B) for S pre-computed sampler steps."""
+        out = []
+        if self.t_conditioning:
+            tt = torch.as_tensor(t, dtype=torch.float32, device=device)
+            if tt.dim() == 0 or tt.numel() == 1:
+                tt = tt.reshape(1).expand(batch)
+            lead = tt.shape[:-1]
+            emb = self.t_embed(timestep_embedding(tt.reshape(-1), self.t_embedding_dim))
+            out.append(emb.reshape(*lead, batch, -1))
+        v_conditionings = [] if v_conditionings is None else v_conditionings
+        assert len(v_conditionings) == len(self.v_embeds)
+        for v, emb in zip(v_conditionings, self.v_embeds):
+            out.append(emb(v.to(torch.float32)))
+        return out if len(out) else None
+
+    # ---- packed weights (bf16, kernel layout), rebuilt when the fp32 parameter changes ------------
+    def _packed(self, name: str, conv: nn.Conv3d) -> torch.Tensor:
+        w = conv.weight
+        key = (w.data_ptr(), w._version, w.device)
+        hit = self._packed_cache.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, ops.pack_conv_weight(w.detach()))
+            self._packed_cache[name] = hit
+        return hit[1]
+
+    def _blocks(self):
+        """(name, block) in execution order."""
+        out = []
+        for i, down in enumerate(self.downs):
+            out.append((f"downs.{i}.resnet_blocks.0", down.resnet_blocks[0]))
+        out += [("mid1", self.mid1), ("mid2", self.mid2)]
+        for i, up in enumerate(self.ups):
+            out.append((f"ups.{i}.resnet_blocks.0", up.resnet_blocks[0]))
+        return out
+
+    def chan_add_rows(self, batch: int, t, v_conditionings, device) -> Dict[str, torch.Tensor]:
+        """Every per-channel row the conv epilogues add: bias (+ conditioning projections for net1).
+
+        Shapes are [B, c] or, when ``t`` is (S, B), [S, B, c] for the block convs that see the time."""
+        conds = self.conditionings(batch, t, v_conditionings, device)
+        rows = {"conv_in": self.conv_in.bias.expand(batch, -1).contiguous(),
+                "conv_out": self.conv_out[2].bias.expand(batch, -1).contiguous()}
+        for name, blk in self._blocks():
+            row = blk.conditioning_row(conds)
+            if row.dim() == 1:
+                row = row.expand(batch, -1)
+            rows[name + ".net1"] = row.contiguous().float()
+            rows[name + ".net2"] = blk.net2[3].bias.expand(batch, -1).contiguous()
+            if blk.skip_conv is not None:
+                rows[name + ".skip"] = blk.skip_conv.bias.expand(batch, -1).contiguous()
+        return rows
+
+    # ---- the convolutional trunk on channel-planar buffers --------------------------------------
+    def _run_block(self, name, blk: ResNetBlock, x, x_plane0, x_stats, rows, step_ptr, out, out_plane0, out_stats,
+                   out_stats_c0, grid, training_dropout):
+        """out[window] = block(x[window]).  x_stats: double [B, ch_in, 2] of x."""
+        b = x.shape[0]
+        dev = x.device
+        ar = self._arena
+        ci, co, g = blk.ch_in, blk.ch_out, blk.norm_groups
+        tag = f"{b}x{grid[0]}"
+        a1 = ar.get(f"a.{ci}.{tag}", (b, ci // 8) + grid + (8,), torch.bfloat16, dev)
+        ops.gn_silu(x, ci, g, x_stats, blk.net1[0].weight, blk.net1[0].bias, blk.net1[0].eps, x_plane0=x_plane0, out=a1)
+        h = ar.get(f"h.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+        h_stats = self._stats(f"{name}.h", b, co, dev)
+        ops.conv3d(a1, self._packed(name + ".net1", blk.net1[2]), co, out=h, chan_add=rows[name + ".net1"],
+                   step_ptr=step_ptr if rows[name + ".net1"].dim() == 3 else None, stats=h_stats)
+        a2 = ar.get(f"a.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+        p_drop = blk.dropout_prob if training_dropout else 0.0
+        if p_drop > 0.0:
+            self._dropout_calls += 1
+        ops.gn_silu(h, co, g, h_stats, blk.net2[0].weight, blk.net2[0].bias, blk.net2[0].eps, out=a2, dropout_p=p_drop,
+                    seed=self.dropout_seed, layer_tag=self._dropout_calls)
+        if blk.skip_conv is None:
+            res, res_plane0 = x, x_plane0
+        else:
+            res = ar.get(f"r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+            ops.conv3d(x, self._packed(name + ".skip", blk.skip_conv), co, taps=ops.TAPS_1X1X1, x_plane0=x_plane0, c_in=ci,
+                       out=res, chan_add=rows[name + ".skip"])
+            res_plane0 = 0
+        ops.conv3d(a2, self._packed(name + ".net2", blk.net2[3]), co, out=out, out_plane0=out_plane0,
+                   chan_add=rows[name + ".net2"], residual=res, residual_plane0=res_plane0, stats=out_stats,
+                   stats_c0=out_stats_c0)
+
+    def _stats(self, name: str, b: int, c: int, dev) -> torch.Tensor:
+        """A zeroed double [B, c, 2] slice of the per-forward statistics arena."""
+        off = self._stats_off
+        n = b * c * 2
+        self._stats_off += n
+        if self._stats_off > self._stats_arena.numel():
+            raise RuntimeError("statistics arena too small")  # sized generously in run_packed
+        return self._stats_arena[off:off + n].view(b, c, 2)
+
+    def run_packed(self, packed: torch.Tensor, rows: Dict[str, torch.Tensor], step_ptr: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None, training_dropout: bool = False) -> torch.Tensor:
+        """eps_hat fp32 (B, 1, D, H, W) from the packed network input (``ops.pack_input``)."""
+        b = packed.shape[0]
+        dev = packed.device
+        c = self.chs
+        nl = len(c)
+        grids = [tuple(n >> i for n in self.shape[1:]) for i in range(nl)]
+        ar = self._arena
+        self._stats_arena = ar.get(f"stats.{b}", (b * 2 * (16 * sum(c) + 64),), torch.float64, dev)
+        self._stats_arena.zero_()
+        self._stats_off = 0
+        self._dropout_calls = 0
+
+        def buf(name, ch, lvl):
+            return ar.get(f"{name}.{b}", (b, ch // 8) + grids[lvl] + (8,), torch.bfloat16, dev)
+
+        # conv_in
+        h = buf("h_in", c[0], 0)
+        h_stats = self._stats("conv_in", b, c[0], dev)
+        ops.conv3d(packed, self._packed("conv_in", self.conv_in), c[0], out=h, chan_add=rows["conv_in"], stats=h_stats)
+        x, x_plane0, x_stats = h, 0, h_stats
+        # down path: the block output of level i < last lands in the concat buffer of the matching up level
+        cats, cat_stats = {}, {}
+        for i in range(nl):
+            blk = self.downs[i].resnet_blocks[0]
+            name = f"downs.{i}.resnet_blocks.0"
+            if i < nl - 1:
+                cat = buf(f"cat{i}", c[i + 1] + c[i], i)
+                cst = self._stats(f"cat{i}", b, c[i + 1] + c[i], dev)
+                cats[i], cat_stats[i] = cat, cst
+                self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, cat, c[i + 1] // 8, cst, c[i + 1],
+                                grids[i], training_dropout)
+                pooled = buf(f"pool{i}", c[i], i + 1)
+                pst = self._stats(f"pool{i}", b, c[i], dev)
+                ops.avgpool2(cat, c[i], x_plane0=c[i + 1] // 8, out=pooled, stats=pst)
+                x, x_plane0, x_stats = pooled, 0, pst
+            else:
+                o = buf("bottom0", c[i], i)
+                ost = self._stats("bottom0", b, c[i], dev)
+                self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout)
+                x, x_plane0, x_stats = o, 0, ost
+        for j, (name, blk) in enumerate((("mid1", self.mid1), ("mid2", self.mid2))):
+            o = buf(f"bottom{1 + j}", c[-1], nl - 1)
+            ost = self._stats(name + ".out", b, c[-1], dev)
+            self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, o, 0, ost, 0, grids[-1], training_dropout)
+            x, x_plane0, x_stats = o, 0, ost
+        for k, i in enumerate(reversed(range(nl - 1))):
+            blk = self.ups[k].resnet_blocks[0]
+            name = f"ups.{k}.resnet_blocks.0"
+            cat, cst = cats[i], cat_stats[i]
+            ops.upsample2(x, c[i + 1], cat, coarse_plane0=x_plane0, out_plane0=0, stats=cst, stats_c0=0)
+            o = buf(f"up{i}", c[i], i)
+            ost = self._stats(name + ".out", b, c[i], dev)
+            self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout)
+            x, x_plane0, x_stats = o, 0, ost
+        gn = self.conv_out[0]
+        a = ar.get(f"a.{c[0]}.{b}x{grids[0][0]}", (b, c[0] // 8) + grids[0] + (8,), torch.bfloat16, dev)
+        ops.gn_silu(x, c[0], gn.num_groups, x_stats, gn.weight, gn.bias, gn.eps, out=a)
+        if out is None:
+            out = torch.empty((b, 1) + grids[0], dtype=torch.float32, device=dev)
+        ops.conv3d(a, self._packed("conv_out", self.conv_out[2]), 1, out=out, out_fp32=True, chan_add=rows["conv_out"])
+        return out
+
+    def forward(self, x, t=None, s_conditioning=None, v_conditionings=None):
+        """eps_hat / v_hat (B, 1, D, H, W) fp32.  Inference path (no autograd graph is recorded here;
+        training goes through ``vdm4cdm_b200.autograd.unet_forward``)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            from .autograd import unet_forward
+            return unet_forward(self, x, t, s_conditioning, v_conditionings)
+        with torch.no_grad():
+            b = x.shape[0]
+            rows = self.chan_add_rows(b, t, v_conditionings, x.device)
+            cond = None if s_conditioning is None else s_conditioning.contiguous().float()
+            packed = ops.pack_input(x.contiguous().float(), cond, 16,
+                                    out=self._arena.get(f"packed.{b}", (b, 2) + self.shape[1:] + (8,), torch.bfloat16,
+                                                        x.device))
+            return self.run_packed(packed, rows)

@@ -1,0 +1,310 @@
+"""``VDM`` / ``LightVDM``: variational diffusion model around the CUNet denoiser, B200-native.
+
+Mirrors what the reference imports as ``mltools.models.vdm_model`` (constructor call:
+trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:128-132; sampler lines recovered from the traceback
+in model_test.ipynb:678-682 = vdm_model.py:318-324, 370-378, 429-442, 531-557; ``return_ddnm`` /
+``sample_zt_given_zs`` contract: src/utils.py:286-299).
+
+The reverse ancestral loop is where the time goes (250-1000 denoiser calls per realisation).  Here
+  * the schedule (gamma, alpha, sigma, c for every step) and every conditioning row the conv epilogues
+    add are computed ONCE for all steps and selected on the device by a step counter,
+  * one step = the CUNet trunk (vdm4cdm_b200.networks) + ONE fused update kernel (vdm_sampler_step:
+    posterior mean, Philox noise in registers, and the packed bf16 network input of the next step),
+  * that step is captured in a CUDA graph and replayed, so the host does nothing inside the loop,
+  * realisations are independent units keyed by (seed, realisation id): shard them over ranks freely.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class LearnedLinearSchedule(nn.Module):
+    """gamma(t) = b + |w| t, initialised to [gamma_min, gamma_max]."""
+
+    def __init__(self, gamma_min: float, gamma_max: float):
+        super().__init__()
+        self.b = nn.Parameter(torch.tensor(float(gamma_min)))
+        self.w = nn.Parameter(torch.tensor(float(gamma_max - gamma_min)))
+
+    def forward(self, t):
+        return self.b + self.w.abs() * t
+
+    def slope(self):
+        return self.w.abs()
+
+
+class FixedLinearSchedule(nn.Module):
+    def __init__(self, gamma_min: float, gamma_max: float):
+        super().__init__()
+        self.register_buffer("b", torch.tensor(float(gamma_min)))
+        self.register_buffer("w", torch.tensor(float(gamma_max - gamma_min)))
+
+    def forward(self, t):
+        return self.b + self.w * t
+
+    def slope(self):
+        return self.w
+
+
+class VDM(nn.Module):
+    def __init__(self, score_model, noise_schedule: str = "learned_linear", gamma_min: float = -13.3,
+                 gamma_max: float = 13.3, antithetic_time_sampling: bool = True, data_noise: float = 1.0e-3,
+                 w_cfg=None):
+        super().__init__()
+        self.score_model = score_model
+        self.gamma_min = gamma_min
+        self.gamma_max = gamma_max
+        self.antithetic_time_sampling = antithetic_time_sampling
+        self.data_noise = data_noise
+        self.w_cfg = w_cfg
+        if noise_schedule == "learned_linear":
+            self.gamma = LearnedLinearSchedule(gamma_min, gamma_max)
+        elif noise_schedule == "fixed_linear":
+            self.gamma = FixedLinearSchedule(gamma_min, gamma_max)
+        else:
+            raise ValueError(f"Unknown noise schedule {noise_schedule}")
+        self.use_cuda_graph = True
+
+    # ---- schedule helpers -------------------------------------------------------------------------
+    @staticmethod
+    def sigma(gamma):
+        return torch.sqrt(torch.sigmoid(gamma))
+
+    @staticmethod
+    def alpha(gamma):
+        return torch.sqrt(torch.sigmoid(-gamma))
+
+    def _gamma5(self, t, ref):
+        g = self.gamma(torch.as_tensor(t, dtype=torch.float32, device=ref.device))
+        return g.reshape(-1, *([1] * (ref.dim() - 1)))
+
+    def _t_net(self, gamma):
+        return (gamma - self.gamma_min) / (self.gamma_max - self.gamma_min)
+
+    def step_coefficients(self, t: torch.Tensor, s: torch.Tensor, final_rescale: bool = False) -> torch.Tensor:
+        """fp32 [S, 4] rows (w_z, w_eps, noise_scale, out_scale) of z_s = out*(w_z z_t + w_eps eps + noise N):
+        w_z = alpha_s/alpha_t, w_eps = -alpha_s/alpha_t c sigma_t, noise = sigma_s sqrt(c), c = -expm1(g_s - g_t)
+        (vdm_model.py:370-378).  Evaluated in fp64 from the fp32 schedule parameters."""
+        gt = self.gamma(t.float()).double()
+        gs = self.gamma(s.float()).double()
+        c = -torch.expm1(gs - gt)
+        a_t, a_s = torch.sqrt(torch.sigmoid(-gt)), torch.sqrt(torch.sigmoid(-gs))
+        s_t, s_s = torch.sqrt(torch.sigmoid(gt)), torch.sqrt(torch.sigmoid(gs))
+        out = torch.ones_like(gt)
+        if final_rescale:
+            out[-1] = 1.0 / a_s[-1]          # x = z_0 / alpha_0 folded into the last update
+        return torch.stack([a_s / a_t, -a_s / a_t * c * s_t, s_s * torch.sqrt(c), out], dim=1).float().contiguous()
+
+    # ---- network call (vdm_model.py:318-327) -------------------------------------------------------
+    def get_pred_noise(self, zt, gamma_t, **kwargs):
+        t_net = self._t_net(gamma_t).reshape(-1)
+        if self.w_cfg is None or self.training:
+            return self.score_model(zt, t=t_net, **kwargs)
+        assert "v_conditionings" in kwargs, "Need v_conditionings to mask out"
+        cond = self.score_model(zt, t=t_net, **kwargs)
+        masked = dict(kwargs)
+        masked["v_conditionings"] = [torch.zeros_like(v) for v in kwargs["v_conditionings"]]
+        uncond = self.score_model(zt, t=t_net, **masked)
+        return (1.0 + self.w_cfg) * cond - self.w_cfg * uncond
+
+    # ---- forward / reverse transitions ------------------------------------------------------------------
+    def sample_zt_given_x(self, x, t, noise):
+        gamma_t = self._gamma5(t, x)
+        return self.alpha(gamma_t) * x + self.sigma(gamma_t) * noise, gamma_t
+
+    @torch.no_grad()
+    def sample_zs_given_zt(self, zt, t, s, return_ddnm=False, noise=None, seed=0, draw=1, realisation_id=None,
+                           **kwargs):
+        """One reverse step t -> s (vdm_model.py:370-378).  With ``return_ddnm`` returns
+        (w_z, w_x_0t, x_0t, scale) such that z_s = w_z z + w_x_0t x_0t + scale eps (src/utils.py:296-299)."""
+        dev = zt.device
+        tt = torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(1)
+        ss = torch.as_tensor(s, dtype=torch.float32, device=dev).reshape(1)
+        gamma_t = self._gamma5(tt, zt)
+        pred_noise = self.get_pred_noise(zt=zt, gamma_t=gamma_t.expand(zt.shape[0], *gamma_t.shape[1:]), **kwargs)
+        coef = self.step_coefficients(tt, ss)
+        if return_ddnm:
+            gt, gs = self.gamma(tt).double(), self.gamma(ss).double()
+            c = -torch.expm1(gs - gt)
+            a_t, a_s = torch.sqrt(torch.sigmoid(-gt)), torch.sqrt(torch.sigmoid(-gs))
+            s_t, s_s = torch.sqrt(torch.sigmoid(gt)), torch.sqrt(torch.sigmoid(gs))
+            x_0t = (zt - s_t.float() * pred_noise) / a_t.float()
+            return (a_s * (1.0 - c) / a_t).float(), (a_s * c).float(), x_0t, (s_s * torch.sqrt(c)).float()
+        return ops.sampler_step(zt.contiguous().float(), pred_noise.contiguous(), coef, seed=seed,
+                                realisation_id=realisation_id, draw_base=draw, noise=noise)
+
+    @torch.no_grad()
+    def sample_zt_given_zs(self, zs, t, s, noise=None, seed=0, draw=1, realisation_id=None):
+        """Forward re-noising s -> t: z_t = alpha_t/alpha_s z_s + sigma_t sqrt(c) eps (used by DDNM time travel)."""
+        dev = zs.device
+        tt = torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(1)
+        ss = torch.as_tensor(s, dtype=torch.float32, device=dev).reshape(1)
+        gt, gs = self.gamma(tt).double(), self.gamma(ss).double()
+        c = -torch.expm1(gs - gt)
+        a_t, a_s = torch.sqrt(torch.sigmoid(-gt)), torch.sqrt(torch.sigmoid(-gs))
+        s_t = torch.sqrt(torch.sigmoid(gt))
+        coef = torch.stack([a_t / a_s, torch.zeros_like(c), s_t * torch.sqrt(c), torch.ones_like(c)], dim=1).float()
+        zs = zs.contiguous().float()
+        return ops.sampler_step(zs, zs, coef.contiguous(), seed=seed, realisation_id=realisation_id, draw_base=draw,
+                                noise=noise)
+
+    # ---- ancestral sampling loop (vdm_model.py:429-442) ---------------------------------------------------
+    @torch.no_grad()
+    def sample(self, batch_size, n_sampling_steps, device, z=None, return_all=False, verbose=False, seed=0,
+               realisation_ids: Optional[Sequence[int]] = None, noise_fn=None, s_conditioning=None,
+               v_conditionings=None):
+        """x (B, 1, D, H, W) fp32 after ``n_sampling_steps`` reverse steps from z_1 ~ N(0, I).
+
+        Noise is counter based: realisation r, draw d (0 = initial latent, i+1 = step i), element e ->
+        Philox4x32-10(seed; e/4, d, r) + Box-Muller, so a realisation does not depend on the batch it
+        was sampled in.  ``noise_fn(draw, shape)`` injects noise instead (parity tests)."""
+        net = self.score_model
+        dev = torch.device(device)
+        shape = (batch_size, *net.shape)
+        if self.w_cfg is not None and not self.training:
+            return self._sample_generic(batch_size, n_sampling_steps, dev, z, return_all, seed, realisation_ids,
+                                        noise_fn, s_conditioning=s_conditioning, v_conditionings=v_conditionings)
+        rid = None
+        if realisation_ids is not None:
+            rid = torch.as_tensor(list(realisation_ids), dtype=torch.int32, device=dev)
+            assert rid.numel() == batch_size
+        if z is None:
+            z = noise_fn(0, shape).to(dev).float().contiguous() if noise_fn is not None else \
+                ops.philox_normal(shape, seed, 0, rid, device=dev)
+        else:
+            z = z.to(dev).float().contiguous().clone()
+        steps = torch.linspace(1.0, 0.0, n_sampling_steps + 1, device=dev)
+        coef = self.step_coefficients(steps[:-1], steps[1:], final_rescale=not return_all)
+        t_net = self._t_net(self.gamma(steps[:-1]).float())                         # (S,)
+        rows = net.chan_add_rows(batch_size, t_net[:, None].expand(-1, batch_size), v_conditionings, dev)
+        cond = None if s_conditioning is None else s_conditioning.to(dev).float().contiguous()
+        packed = ops.pack_input(z, cond, 16)
+        step = torch.zeros(1, dtype=torch.int32, device=dev)
+        eps = torch.empty(shape, dtype=torch.float32, device=dev)
+        noise_buf = torch.empty(shape, dtype=torch.float32, device=dev) if noise_fn is not None else None
+        zs = []
+
+        def one_step():
+            net.run_packed(packed, rows, step_ptr=step, out=eps)
+            ops.sampler_step(z, eps, coef, out=z, step_ptr=step, seed=seed, realisation_id=rid, draw_base=1,
+                             noise=noise_buf, cond=cond, packed_out=packed)
+            ops.increment(step)
+
+        graph = None
+        it = range(n_sampling_steps)
+        if verbose:
+            from tqdm import trange
+            it = trange(n_sampling_steps, desc="sampling")
+        for i in it:
+            if noise_fn is not None:
+                noise_buf.copy_(noise_fn(i + 1, shape))
+            if i == 0 or not self.use_cuda_graph:
+                one_step()                                  # also warms the buffer arena and weight caches
+            else:
+                if graph is None:
+                    torch.cuda.synchronize(dev)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        one_step()
+                else:
+                    graph.replay()
+            if return_all:
+                zs.append(z.clone())
+        if return_all:
+            x = z / self.alpha(self.gamma(steps[-1]))
+            return torch.stack(zs + [x], dim=0)
+        return z
+
+    def _sample_generic(self, batch_size, n_sampling_steps, dev, z, return_all, seed, realisation_ids, noise_fn, **kw):
+        """Step-by-step loop through ``sample_zs_given_zt`` (classifier-free guidance needs two network calls)."""
+        shape = (batch_size, *self.score_model.shape)
+        rid = None if realisation_ids is None else torch.as_tensor(list(realisation_ids), dtype=torch.int32, device=dev)
+        if z is None:
+            z = noise_fn(0, shape).to(dev).float() if noise_fn is not None else ops.philox_normal(shape, seed, 0, rid, dev)
+        steps = torch.linspace(1.0, 0.0, n_sampling_steps + 1, device=dev)
+        zs = []
+        for i in range(n_sampling_steps):
+            noise = noise_fn(i + 1, shape).to(dev).float().contiguous() if noise_fn is not None else None
+            z = self.sample_zs_given_zt(zt=z, t=steps[i], s=steps[i + 1], noise=noise, seed=seed, draw=i + 1,
+                                        realisation_id=rid, **kw)
+            if return_all:
+                zs.append(z)
+        x = z / self.alpha(self.gamma(steps[-1]))
+        return torch.stack(zs + [x], dim=0) if return_all else x
+
+    # ---- training loss (continuous-time VDM, Kingma et al. 2021) -----------------------------------------
+    def sample_times(self, batch_size, device, t0=None):
+        if self.antithetic_time_sampling:
+            if t0 is None:
+                t0 = torch.rand((), device=device)
+            return torch.remainder(t0 + torch.arange(batch_size, device=device) / batch_size, 1.0)
+        return torch.rand(batch_size, device=device)
+
+    def get_loss(self, x, noise=None, noise0=None, times=None, **kwargs):
+        """Continuous-time VDM loss in bits per dimension, plus its three terms (batch means)."""
+        bsz = x.shape[0]
+        red = tuple(range(1, x.dim()))
+        if times is None:
+            times = self.sample_times(bsz, x.device)
+        if noise is None:
+            noise = torch.randn_like(x)
+        if noise0 is None:
+            noise0 = torch.randn_like(x)
+        zt, gamma_t = self.sample_zt_given_x(x, times, noise)
+        pred = self.get_pred_noise(zt, gamma_t, **kwargs)
+        diffusion = 0.5 * self.gamma.slope() * ((noise - pred) ** 2).sum(dim=red)
+
+        gamma_1 = self._gamma5(1.0, x)
+        var_1 = torch.sigmoid(gamma_1)
+        latent = 0.5 * (var_1 + torch.sigmoid(-gamma_1) * x * x - torch.log(var_1) - 1.0).sum(dim=red)
+
+        gamma_0 = self._gamma5(0.0, x)
+        z0_rescaled = x + torch.exp(0.5 * gamma_0) * noise0
+        dn = self.data_noise
+        recons = (0.5 * ((x - z0_rescaled) / dn) ** 2 + math.log(dn) + 0.5 * math.log(2.0 * math.pi)).sum(dim=red)
+
+        bpd = 1.0 / (x[0].numel() * math.log(2.0))
+        loss = (diffusion + latent + recons).mean() * bpd
+        return loss, {"diffusion_loss": diffusion.mean() * bpd, "latent_loss": latent.mean() * bpd,
+                      "reconstruction_loss": recons.mean() * bpd}
+
+
+class LightVDM(nn.Module):
+    """Lightning-free ``LightVDM`` (ctor: trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:128-132;
+    ``draw_samples`` -> ``self.model.sample(..., device=self.device, ...)``: vdm_model.py:531-557)."""
+
+    def __init__(self, score_model, draw_figure=None, gamma_min=-13.3, gamma_max=13.3,
+                 noise_schedule="learned_linear", learning_rate=3.0e-4, **vdm_kwargs):
+        super().__init__()
+        self.model = VDM(score_model, noise_schedule=noise_schedule, gamma_min=gamma_min, gamma_max=gamma_max,
+                         **vdm_kwargs)
+        self.draw_figure = draw_figure
+        self.learning_rate = learning_rate
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def get_loss(self, batch, **kw):
+        return self.model.get_loss(batch["x"], s_conditioning=batch.get("conditioning"),
+                                   v_conditionings=batch.get("conditioning_values"), **kw)
+
+    def training_step(self, batch, batch_idx=0):
+        return self.get_loss(batch)[0]
+
+    def validation_step(self, batch, batch_idx=0):
+        with torch.no_grad():
+            return self.get_loss(batch)[0]
+
+    def configure_optimizers(self):
+        return torch.optim.AdamW(self.parameters(), lr=self.learning_rate)
+
+    def draw_samples(self, batch_size, n_sampling_steps=250, verbose=False, return_all=False, **kwargs):
+        return self.model.sample(batch_size=batch_size, n_sampling_steps=n_sampling_steps, device=self.device,
+                                 verbose=verbose, return_all=return_all, **kwargs)
