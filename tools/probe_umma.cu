@@ -98,6 +98,73 @@ probe_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_im
   }
 }
 
+// T6: tensor-pipe rate with the issue loop out of the way: the same (A, B) descriptors, 16 MMAs per trip.
+// T7: the conv kernel's issue pattern: per-MMA descriptor arithmetic (tap offsets from a table in smem).
+__global__ void __launch_bounds__(128, 1)
+rate_kernel(int n, int trips, int mode, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int tap_off[32];
+  for (int i = threadIdx.x * 16; i < 160 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 27) tap_off[threadIdx.x] = ((threadIdx.x / 9) * 180 + ((threadIdx.x / 3) % 3) * 10 + threadIdx.x % 3) * 16;
+  ptx::fence_proxy_async();
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_base_s, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_base = ptx::smem_u32(smem), b_base = a_base + 96 * 1024;
+    const uint32_t P = 6 * 18 * 10 * 16;
+    const uint64_t hi_a = ((uint64_t)((P >> 4) & 0x3FFF) << 16) | ((uint64_t)((160 >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+    const uint64_t hi_b = ((uint64_t)(((uint32_t)n * 16 >> 4) & 0x3FFF) << 16) | ((uint64_t)((128 >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+    const long long t0 = clock64();
+    if (mode == 0) {
+      const uint64_t ad = hi_a | (uint64_t)((a_base & 0x3FFFFu) >> 4), bd = hi_b | (uint64_t)((b_base & 0x3FFFFu) >> 4);
+      for (int t = 0; t < trips; ++t) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ptx::umma_bf16(tmem_base, ad, bd, idesc, 1u);
+      }
+    } else {
+      // 27 taps x 4 sub-tiles x 2 k16 = 216 MMAs per trip, descriptors rebuilt per MMA like conv3d.cu
+      for (int t = 0; t < trips; ++t) {
+        for (int tap = 0; tap < 27; ++tap) {
+          const uint32_t a_tap = a_base + (uint32_t)tap_off[tap];
+          const uint32_t b_tap = b_base + (uint32_t)(tap & 7) * (uint32_t)(4 * n * 16);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t ad = hi_a | (uint64_t)(((a_tap + (uint32_t)s * 2880u + (uint32_t)(2 * j) * P) & 0x3FFFFu) >> 4);
+              const uint64_t bd = hi_b | (uint64_t)(((b_tap + (uint32_t)(2 * j) * (uint32_t)n * 16u) & 0x3FFFFu) >> 4);
+              ptx::umma_bf16(tmem_base + (uint32_t)(s * n), ad, bd, idesc, 1u);
+            }
+          }
+        }
+      }
+    }
+    ptx::umma_commit(&bar);
+    ptx::mbar_wait(&bar, 0);
+    *cycles = clock64() - t0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------------------
 static uint64_t make_desc_hi(uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t base_off) {
   uint64_t d = 0;
@@ -337,6 +404,21 @@ int main() {
   for (int n : ns) test_rate(n, 0);
   for (int n : ns) test_rate(n, 1);
   for (int n : ns) test_rate(n, 2);
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  for (int mode = 0; mode < 2; ++mode)
+    for (int n : ns) {
+      if (mode == 1 && n > 128) continue;   // 4 accumulators of n columns
+      const int trips = mode == 0 ? 512 : 32;
+      const int per_trip = mode == 0 ? 16 : 216;
+      rate_kernel<<<1, 128, 200 * 1024>>>(n, trips, mode, d_cyc);
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("rate_kernel failed\n"); return 2; }
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost);
+      const double per = (double)cyc / (trips * per_trip);
+      printf("T%d rate N=%3d %s: %.1f cyc/MMA (M=128,K=16); 128*N/256 = %.0f; => %.0f MAC/cyc/SM\n", 6 + mode, n,
+             mode == 0 ? "same-descriptor unrolled issue" : "conv-like issue loop (27 taps x 4 tiles x 2 k16)", per,
+             128.0 * n / 256.0, 128.0 * n * 16.0 / per);
+    }
   test_mn_major(32);
   test_mn_major(128);
   test_swizzled(32, 128, 16);

@@ -183,9 +183,43 @@ class CUNet(nn.Module):
         hit = self._packed_cache.get(name)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                hit = (key, ops.pack_conv_weight(w.detach()))
+                fresh = ops.pack_conv_weight(w.detach())
+                if hit is not None and hit[1].shape == fresh.shape and hit[1].device == fresh.device:
+                    hit[1].copy_(fresh)        # keep the device pointer: captured CUDA graphs refer to it
+                    fresh = hit[1]
+                hit = (key, fresh)
             self._packed_cache[name] = hit
         return hit[1]
+
+    def _convs(self):
+        out = [("conv_in", self.conv_in), ("conv_out", self.conv_out[2])]
+        for name, blk in self._blocks():
+            out += [(name + ".net1", blk.net1[2]), (name + ".net2", blk.net2[3])]
+            if blk.skip_conv is not None:
+                out.append((name + ".skip", blk.skip_conv))
+        return out
+
+    def refresh_packed(self) -> None:
+        """Re-pack (in place) every conv filter whose fp32 parameter changed since it was packed."""
+        for name, conv in self._convs():
+            self._packed(name, conv)
+
+    def conv_flops_per_sample(self) -> float:
+        """Algorithmic conv FLOPs of one forward for one sample: sum of 2 k^3 Cin Cout D H W over the
+        Conv3d modules, with the real (un-padded) channel counts."""
+        nl = len(self.chs)
+        vox = [math.prod(n >> i for n in self.shape[1:]) for i in range(nl)]
+        level = {"conv_in": 0, "conv_out": 0, "mid1": nl - 1, "mid2": nl - 1}
+        for i in range(nl):
+            level[f"downs.{i}.resnet_blocks.0"] = i
+        for k, i in enumerate(reversed(range(nl - 1))):
+            level[f"ups.{k}.resnet_blocks.0"] = i
+        total = 0.0
+        for name, conv in self._convs():
+            base = name if name in level else name.rsplit(".", 1)[0]
+            k3 = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
+            total += 2.0 * k3 * conv.in_channels * conv.out_channels * vox[level[base]]
+        return total
 
     def _blocks(self):
         """(name, block) in execution order."""

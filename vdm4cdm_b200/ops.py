@@ -19,6 +19,29 @@ TAPS_3X3X3 = tuple((kd - 1, kh - 1, kw - 1) for kd in range(3) for kh in range(3
 TAPS_1X1X1 = ((0, 0, 0),)
 
 
+_LAUNCHES = 0
+
+
+def launch_count() -> int:
+    """Kernels of libvdm4cdm_b200.so launched through this module so far (cuFFT's own kernels not counted)."""
+    return _LAUNCHES
+
+
+def _launched(n: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+_CONV_PROFILE = None
+
+
+def set_conv_profiler(records) -> None:
+    """bench.py hook: when ``records`` is a list, every conv3d call appends (start_event, end_event, flops)
+    recorded on the launching stream; ``None`` switches it off."""
+    global _CONV_PROFILE
+    _CONV_PROFILE = records
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -140,9 +163,18 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
         epi.stats = stats.data_ptr()
         epi.stats_channels = stats.shape[1]
         epi.stats_c0 = stats_c0
+    prof = _CONV_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _C.lib().vdm_conv3d(ctypes.byref(desc), x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), ctypes.byref(epi),
                              _stream())
     _C.check(rc, "vdm_conv3d")
+    _launched(1)
+    if prof is not None:
+        e1.record()
+        # algorithmic FLOPs: real (un-padded) output channels, the channels the caller says it reads
+        prof.append((e0, e1, 2.0 * n_taps * c_in * c_out * b * d * h * w_))
     return out
 
 
@@ -158,6 +190,7 @@ def channel_stats(x: torch.Tensor, channels: int, x_plane0: int = 0, stats: Opti
     rc = _C.lib().vdm_channel_stats(ctypes.byref(v), b, voxels, channels, stats.data_ptr(), stats.shape[1], stats_c0,
                                     _stream())
     _C.check(rc, "vdm_channel_stats")
+    _launched(1)
     return stats
 
 
@@ -178,6 +211,7 @@ def gn_silu(x: torch.Tensor, channels: int, groups: int, stats: torch.Tensor, ga
     rc = _C.lib().vdm_gn_silu(ctypes.byref(vx), ctypes.byref(vy), b, voxels, channels, groups, stats.data_ptr(),
                               gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, layer_tag, _stream())
     _C.check(rc, "vdm_gn_silu")
+    _launched(1)
     return out
 
 
@@ -192,6 +226,7 @@ def avgpool2(x: torch.Tensor, channels: int, *, x_plane0: int = 0, out: Optional
     rc = _C.lib().vdm_avgpool2(ctypes.byref(vx), ctypes.byref(vy), b, d, h, w, channels, _ptr(stats),
                                0 if stats is None else stats.shape[1], stats_c0, _stream())
     _C.check(rc, "vdm_avgpool2")
+    _launched(1)
     return out
 
 
@@ -205,6 +240,7 @@ def upsample2(coarse: torch.Tensor, channels: int, out: torch.Tensor, *, coarse_
     rc = _C.lib().vdm_upsample2(ctypes.byref(vx), ctypes.byref(vy), b, d, h, w, channels, _ptr(stats),
                                 0 if stats is None else stats.shape[1], stats_c0, _stream())
     _C.check(rc, "vdm_upsample2")
+    _launched(1)
     return out
 
 
@@ -228,6 +264,7 @@ def pack_input(z: torch.Tensor, cond: Optional[torch.Tensor], c_pad: int = 16,
     vo = _view(out, 0)
     rc = _C.lib().vdm_pack_input(z.data_ptr(), _ptr(cond), ctypes.byref(vo), b, d * h * w, n_cond, c_pad, _stream())
     _C.check(rc, "vdm_pack_input")
+    _launched(1)
     return out
 
 
@@ -258,6 +295,7 @@ def sampler_step(z: torch.Tensor, eps_hat: torch.Tensor, coef: torch.Tensor, *, 
                                    _ptr(step_ptr), seed, _ptr(realisation_id), draw_base, _ptr(noise), _ptr(cond),
                                    n_cond, _ptr(packed_out), packed_planes, _stream())
     _C.check(rc, "vdm_sampler_step")
+    _launched(1)
     return out
 
 
@@ -267,11 +305,13 @@ def philox_normal(shape, seed: int, draw: int, realisation_id: Optional[torch.Te
     b = shape[0]
     rc = _C.lib().vdm_philox_normal(out.data_ptr(), b, out.numel() // b, seed, _ptr(realisation_id), draw, _stream())
     _C.check(rc, "vdm_philox_normal")
+    _launched(1)
     return out
 
 
 def increment(counter: torch.Tensor) -> None:
     _C.check(_C.lib().vdm_increment(counter.data_ptr(), _stream()), "vdm_increment")
+    _launched(1)
 
 
 # ---- P(k) --------------------------------------------------------------------------------------------
@@ -304,6 +344,7 @@ def pk_fields(fields: torch.Tensor, fields2: Optional[torch.Tensor] = None):
     rc = lib.vdm_pk(fields.data_ptr(), _ptr(fields2), f, b, c, n0, n1, n2, work.data_ptr(), nbytes, k.data_ptr(),
                     p.data_ptr(), n.data_ptr(), _stream())
     _C.check(rc, "vdm_pk")
+    _launched(3)
     return k, p, n
 
 
@@ -322,4 +363,5 @@ def pk_cross3(fields1: torch.Tensor, fields2: torch.Tensor):
     rc = lib.vdm_pk_cross3(fields1.data_ptr(), fields2.data_ptr(), f, b, c, n0, n1, n2, work.data_ptr(), nbytes,
                            k.data_ptr(), p11.data_ptr(), p22.data_ptr(), p12.data_ptr(), n.data_ptr(), _stream())
     _C.check(rc, "vdm_pk_cross3")
+    _launched(3)
     return k, p11, p22, p12, n

@@ -164,62 +164,40 @@ class VDM(nn.Module):
         Noise is counter based: realisation r, draw d (0 = initial latent, i+1 = step i), element e ->
         Philox4x32-10(seed; e/4, d, r) + Box-Muller, so a realisation does not depend on the batch it
         was sampled in.  ``noise_fn(draw, shape)`` injects noise instead (parity tests)."""
-        net = self.score_model
         dev = torch.device(device)
-        shape = (batch_size, *net.shape)
         if self.w_cfg is not None and not self.training:
             return self._sample_generic(batch_size, n_sampling_steps, dev, z, return_all, seed, realisation_ids,
                                         noise_fn, s_conditioning=s_conditioning, v_conditionings=v_conditionings)
-        rid = None
-        if realisation_ids is not None:
-            rid = torch.as_tensor(list(realisation_ids), dtype=torch.int32, device=dev)
-            assert rid.numel() == batch_size
-        if z is None:
-            z = noise_fn(0, shape).to(dev).float().contiguous() if noise_fn is not None else \
-                ops.philox_normal(shape, seed, 0, rid, device=dev)
-        else:
-            z = z.to(dev).float().contiguous().clone()
-        steps = torch.linspace(1.0, 0.0, n_sampling_steps + 1, device=dev)
-        coef = self.step_coefficients(steps[:-1], steps[1:], final_rescale=not return_all)
-        t_net = self._t_net(self.gamma(steps[:-1]).float())                         # (S,)
-        rows = net.chan_add_rows(batch_size, t_net[:, None].expand(-1, batch_size), v_conditionings, dev)
-        cond = None if s_conditioning is None else s_conditioning.to(dev).float().contiguous()
-        packed = ops.pack_input(z, cond, 16)
-        step = torch.zeros(1, dtype=torch.int32, device=dev)
-        eps = torch.empty(shape, dtype=torch.float32, device=dev)
-        noise_buf = torch.empty(shape, dtype=torch.float32, device=dev) if noise_fn is not None else None
+        sess = self.session(batch_size, n_sampling_steps, dev, z=z, seed=seed, realisation_ids=realisation_ids,
+                            noise_fn=noise_fn, s_conditioning=s_conditioning, v_conditionings=v_conditionings,
+                            fold_final_rescale=not return_all)
         zs = []
-
-        def one_step():
-            net.run_packed(packed, rows, step_ptr=step, out=eps)
-            ops.sampler_step(z, eps, coef, out=z, step_ptr=step, seed=seed, realisation_id=rid, draw_base=1,
-                             noise=noise_buf, cond=cond, packed_out=packed)
-            ops.increment(step)
-
-        graph = None
         it = range(n_sampling_steps)
         if verbose:
             from tqdm import trange
             it = trange(n_sampling_steps, desc="sampling")
-        for i in it:
-            if noise_fn is not None:
-                noise_buf.copy_(noise_fn(i + 1, shape))
-            if i == 0 or not self.use_cuda_graph:
-                one_step()                                  # also warms the buffer arena and weight caches
-            else:
-                if graph is None:
-                    torch.cuda.synchronize(dev)
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        one_step()
-                else:
-                    graph.replay()
+        for _ in it:
+            sess.step()
             if return_all:
-                zs.append(z.clone())
+                zs.append(sess.z.clone())
         if return_all:
-            x = z / self.alpha(self.gamma(steps[-1]))
+            x = sess.z / self.alpha(self.gamma(sess.steps[-1]))
             return torch.stack(zs + [x], dim=0)
-        return z
+        return sess.z.clone()
+
+    def session(self, batch_size, n_sampling_steps, device, **kw) -> "SamplerSession":
+        """A (cached) ``SamplerSession`` for this batch size / step count, reset to a new chain."""
+        key = (batch_size, n_sampling_steps, str(device), kw.get("s_conditioning") is not None,
+               0 if kw.get("v_conditionings") is None else len(kw["v_conditionings"]))
+        cache = self.__dict__.setdefault("_sessions", {})
+        sess = cache.get(key)
+        if sess is None:
+            cache.clear()                      # one resident session: its buffers are O(GB) at 128^3
+            sess = SamplerSession(self, batch_size, n_sampling_steps, device, **kw)
+            cache[key] = sess
+        else:
+            sess.reset(**kw)
+        return sess
 
     def _sample_generic(self, batch_size, n_sampling_steps, dev, z, return_all, seed, realisation_ids, noise_fn, **kw):
         """Step-by-step loop through ``sample_zs_given_zt`` (classifier-free guidance needs two network calls)."""
@@ -273,6 +251,105 @@ class VDM(nn.Module):
         loss = (diffusion + latent + recons).mean() * bpd
         return loss, {"diffusion_loss": diffusion.mean() * bpd, "latent_loss": latent.mean() * bpd,
                       "reconstruction_loss": recons.mean() * bpd}
+
+
+class SamplerSession:
+    """State of one ancestral chain for a batch of realisations: latent z (fp32), packed bf16 network
+    input, per-step coefficient and conditioning tables, the device step counter, and the CUDA graph
+    of one step.  ``step()`` advances every realisation by one reverse step; ``reset()`` starts a new
+    chain in the same buffers, so the captured graph is reused across ``draw_samples`` calls."""
+
+    def __init__(self, vdm: VDM, batch_size: int, n_sampling_steps: int, device, **kw):
+        self.vdm, self.net, self.dev = vdm, vdm.score_model, torch.device(device)
+        self.n_steps = n_sampling_steps
+        self.shape = (batch_size, *self.net.shape)
+        dev = self.dev
+        self.z = torch.empty(self.shape, dtype=torch.float32, device=dev)
+        self.eps = torch.empty(self.shape, dtype=torch.float32, device=dev)
+        self.noise_buf = torch.empty(self.shape, dtype=torch.float32, device=dev)
+        self.cond_buf = None
+        self.packed = torch.empty((batch_size, 2) + tuple(self.net.shape[1:]) + (8,), dtype=torch.bfloat16, device=dev)
+        self.step_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.rid_buf = torch.zeros(batch_size, dtype=torch.int32, device=dev)
+        self.steps = torch.linspace(1.0, 0.0, n_sampling_steps + 1, device=dev)
+        self.coef = torch.empty((n_sampling_steps, 4), dtype=torch.float32, device=dev)
+        self.rows = None
+        self.graph = None
+        self.graph_key = None
+        self.kernels_per_step = 0
+        self.reset(**kw)
+
+    @torch.no_grad()
+    def reset(self, z=None, seed: int = 0, realisation_ids: Optional[Sequence[int]] = None, noise_fn=None,
+              s_conditioning=None, v_conditionings=None, fold_final_rescale: bool = True):
+        vdm, net, dev = self.vdm, self.net, self.dev
+        batch_size = self.shape[0]
+        net.refresh_packed()
+        self.seed = seed
+        self.noise_fn = noise_fn
+        if realisation_ids is not None:
+            rid = torch.as_tensor(list(realisation_ids), dtype=torch.int32, device=dev)
+            assert rid.numel() == batch_size
+            self.rid_buf.copy_(rid)
+        else:
+            self.rid_buf.copy_(torch.arange(batch_size, dtype=torch.int32, device=dev))
+        if z is not None:
+            self.z.copy_(z.to(dev).float().reshape(self.shape))
+        elif noise_fn is not None:
+            self.z.copy_(noise_fn(0, self.shape).to(dev).float())
+        else:
+            self.z.copy_(ops.philox_normal(self.shape, seed, 0, self.rid_buf, device=dev))
+        self.coef.copy_(vdm.step_coefficients(self.steps[:-1], self.steps[1:], final_rescale=fold_final_rescale))
+        t_net = vdm._t_net(vdm.gamma(self.steps[:-1]).float())                         # (S,)
+        vc = None if v_conditionings is None else [v.to(dev) for v in v_conditionings]
+        rows = net.chan_add_rows(batch_size, t_net[:, None].expand(-1, batch_size), vc, dev)
+        if self.rows is None:
+            self.rows = rows
+        else:
+            for k, v in rows.items():
+                self.rows[k].copy_(v)
+        if s_conditioning is not None:
+            c = s_conditioning.to(dev).float()
+            if self.cond_buf is None:
+                self.cond_buf = c.contiguous().clone()
+            else:
+                self.cond_buf.copy_(c)
+        elif self.cond_buf is not None:
+            raise ValueError("a session created with spatial conditioning must be reset with one")
+        ops.pack_input(self.z, self.cond_buf, 16, out=self.packed)
+        self.step_idx.zero_()
+        self.done = 0
+        # the graph bakes in pointers and the (seed, injected-noise or Philox) choice, nothing else
+        key = (seed, noise_fn is not None)
+        if key != self.graph_key:
+            self.graph = None
+            self.graph_key = key
+
+    def _one_step(self):
+        n0 = ops.launch_count()
+        self.net.run_packed(self.packed, self.rows, step_ptr=self.step_idx, out=self.eps)
+        ops.sampler_step(self.z, self.eps, self.coef, out=self.z, step_ptr=self.step_idx, seed=self.seed,
+                         realisation_id=self.rid_buf, draw_base=1,
+                         noise=self.noise_buf if self.noise_fn is not None else None, cond=self.cond_buf,
+                         packed_out=self.packed)
+        ops.increment(self.step_idx)
+        self.kernels_per_step = ops.launch_count() - n0
+
+    @torch.no_grad()
+    def step(self):
+        assert self.done < self.n_steps, "chain already finished"
+        if self.noise_fn is not None:
+            self.noise_buf.copy_(self.noise_fn(self.done + 1, self.shape))
+        if not self.vdm.use_cuda_graph or (self.graph is None and self.done == 0):
+            self._one_step()                       # eager: also warms the buffer arena and weight caches
+        elif self.graph is None:
+            torch.cuda.synchronize(self.dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._one_step()
+        else:
+            self.graph.replay()
+        self.done += 1
 
 
 class LightVDM(nn.Module):
