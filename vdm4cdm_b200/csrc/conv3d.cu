@@ -19,7 +19,7 @@
 // (Descriptor semantics verified on hardware by tools/probe_umma.cu, profiles/r01_probe_umma.txt.)
 //
 // Pipeline per persistent CTA (7 warps):
-//   warp 0  A producer : one 5-D TMA load per (tile, channel chunk) -> halo stage (2 stages);
+//   warp 0  A producer : one 4-D TMA load per (tile, channel chunk) -> halo stage (2 stages);
 //                        out-of-range voxels are zero-filled by the TMA unit == Conv3d zero padding
 //   warp 2  B producer : weights of one (chunk, tap): KC/8 bulk copies -> ring of B stages
 //   warp 1  MMA issuer : for chunk, tap, sub-tile s < MT, k16: tcgen05.mma M=128 N=n_cta K=16 into
@@ -188,7 +188,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           const int s = it & 1;
           ptx::mbar_wait(&sh->a_empty[s], ((it >> 1) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes_per_chunk * p.plane_bytes));
-          ptx::tma_load_5d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], 0, t.w0 - p.pad,
+          ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], (t.w0 - p.pad) * 8,
                            t.h0 - p.pad, t.d0 - p.pad, t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
         }
       }
@@ -560,16 +560,19 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   VDM_CHECK_ARG(!(p.residual && d.out_fp32), "vdm_conv3d: residual is only supported for bf16 outputs");
   p.swap_lbo_sbo = g_debug_swap_lbo_sbo;
 
-  // activations: 5-D (8ch, W, H, D, B*planes), box (8, Wh, Hh, Hd, KC/8); out-of-bounds -> zeros
+  // activations: 4-D (W*8 channels-in-plane, H, D, B*planes), box (Wh*8, Hh, Hd, KC/8); out-of-bounds -> zeros.
+  // The (w, 8ch) pair is ONE tensor-map dimension on purpose: the TMA unit issues requests per
+  // innermost box row, and a 16-byte row (8 channels as their own dimension) capped the r01 kernel at
+  // one 32-byte sector per ~9 cycles per SM (profiles/r01_conv_ncu.txt).  Rows are Wh*16 = 160 bytes now.
   CUtensorMap tmx;
   {
     const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
-    cuuint64_t gdim[5] = {8, (cuuint64_t)d.width, (cuuint64_t)d.height, (cuuint64_t)d.depth,
+    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth,
                           (cuuint64_t)d.batch * x_planes};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)p.Wh, (cuuint32_t)p.Hh, (cuuint32_t)p.Hd, (cuuint32_t)(kc / 8)};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    cuuint32_t box[4] = {(cuuint32_t)p.Wh * 8, (cuuint32_t)p.Hh, (cuuint32_t)p.Hd, (cuuint32_t)(kc / 8)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

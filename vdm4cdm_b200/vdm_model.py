@@ -346,7 +346,8 @@ class SamplerSession:
             torch.cuda.synchronize(self.dev)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._one_step()
+                self._one_step()               # capture records the launches, it does not run them
+            self.graph.replay()
         else:
             self.graph.replay()
         self.done += 1
