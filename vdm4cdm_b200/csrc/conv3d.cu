@@ -51,7 +51,7 @@ struct ConvKernelParams {
   int MT, KC, k_chunks;
   int Hd, Hh, Wh;            // halo box (voxels)
   int tiles_w, tiles_h, tiles_d, n_tiles;
-  int a_stage_bytes, b_stage_bytes, nsb;
+  int a_stage_bytes, b_stage_bytes, nsb, taps_per_stage;
   int plane_bytes;           // Hd*Hh*Wh*16
   int tmem_cols;
   int x_planes, x_plane0, c_in8;
@@ -137,6 +137,10 @@ __device__ __forceinline__ uint64_t make_planar_desc(uint32_t smem_addr, uint32_
   return d;
 }
 
+// MT = d-slices (accumulators) per tile, KJ = K=16 MMAs per channel chunk (KC = 16*KJ): compile-time so
+// that the MMA issue loop is a straight line of MT*KJ*taps_per_stage tcgen05.mma with immediate offsets
+// (r01a: a generic loop cost ~240 issue cycles per MMA and was THE bottleneck, profiles/r01a_conv_ncu.txt).
+template <int MT, int KJ>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -176,7 +180,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
-  const int planes_per_chunk = p.KC >> 3;
+  constexpr int planes_per_chunk = KJ * 2;
 
   if (warp == 0) {
     // ===================== A producer: halo tiles =====================
@@ -194,64 +198,85 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
     }
   } else if (warp == 2) {
-    // ===================== B producer: weights of one (chunk, tap) =====================
+    // ===================== B producer: weights of `tps` taps of one chunk per stage =====================
     if (lane == 0) {
       uint32_t it = 0;
       const uint32_t plane_copy_bytes = (uint32_t)p.n_cta * 16u;
+      const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
+      const size_t tap_stride = (size_t)p.c_in8 * p.n_pad * 8, plane_stride = (size_t)p.n_pad * 8;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          for (int tap = 0; tap < p.n_taps; ++tap, ++it) {
-            const int s = it % p.nsb;
-            ptx::mbar_wait(&sh->b_empty[s], ((it / p.nsb) & 1) ^ 1);
-            ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk);
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++it) {
+            const int s = it % nsb;
+            ptx::mbar_wait(&sh->b_empty[s], ((it / nsb) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk * tps);
             uint8_t* dst = b_smem + (size_t)s * p.b_stage_bytes;
-            const __nv_bfloat16* src =
-                p.w + (((size_t)tap * p.c_in8 + (size_t)kc * planes_per_chunk) * p.n_pad + (size_t)t.ns * p.n_cta) * 8;
-            for (int pl = 0; pl < planes_per_chunk; ++pl)
-              ptx::bulk_load(dst + (size_t)pl * plane_copy_bytes, src + (size_t)pl * p.n_pad * 8, plane_copy_bytes,
-                             &sh->b_full[s]);
+            const __nv_bfloat16* src = p.w + (size_t)tap0 * tap_stride +
+                                       ((size_t)kc * planes_per_chunk * p.n_pad + (size_t)t.ns * p.n_cta) * 8;
+            for (int q = 0; q < tps; ++q)
+#pragma unroll
+              for (int pl = 0; pl < planes_per_chunk; ++pl)
+                ptx::bulk_load(dst + (size_t)(q * planes_per_chunk + pl) * plane_copy_bytes,
+                               src + (size_t)q * tap_stride + (size_t)pl * plane_stride, plane_copy_bytes, &sh->b_full[s]);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)p.n_cta);
-    const uint32_t a_k = (uint32_t)p.plane_bytes, a_m = (uint32_t)p.Wh * 16u;
-    const uint32_t b_k = (uint32_t)p.n_cta * 16u, b_m = 128u;
-    const uint32_t a_lbo = p.swap_lbo_sbo ? a_m : a_k, a_sbo = p.swap_lbo_sbo ? a_k : a_m;
-    const uint32_t b_lbo = p.swap_lbo_sbo ? b_m : b_k, b_sbo = p.swap_lbo_sbo ? b_k : b_m;
+    const uint32_t n_cta = (uint32_t)p.n_cta;
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n_cta);
+    // descriptor high words (LBO = plane stride = K direction, SBO = halo row pitch = 8-voxel groups)
+    const uint64_t a_hi = make_planar_desc(0, (uint32_t)p.plane_bytes, (uint32_t)p.Wh * 16u);
+    const uint64_t b_hi = make_planar_desc(0, n_cta * 16u, 128u);
+    // start addresses are handled in 16-byte units (the descriptor's address field)
+    const uint32_t a_base16 = ptx::smem_u32(a_smem) >> 4, a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t b_base16 = ptx::smem_u32(b_smem) >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+    const uint32_t slice16 = (uint32_t)(p.Hh * p.Wh);          // one d-slice of a plane
+    const uint32_t kstep_a16 = 2u * ((uint32_t)p.plane_bytes >> 4), kstep_b16 = 2u * n_cta;
+    const uint32_t btap16 = (uint32_t)planes_per_chunk * n_cta;  // one tap inside a B stage
+    // lane t keeps the halo offset (in voxels == 16-byte units) of filter tap t
+    const uint32_t my_tap16 =
+        lane < p.n_taps ? (uint32_t)(((p.tap[lane][0] + p.pad) * p.Hh + (p.tap[lane][1] + p.pad)) * p.Wh + p.tap[lane][2] + p.pad)
+                        : 0u;
+    const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
     uint32_t ita = 0, itb = 0, ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
       const uint32_t acc = ti & 1;
       ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem0 = tmem_base + acc * (uint32_t)(p.MT * p.n_cta);
-      for (int kc = 0; kc < p.k_chunks; ++kc, ++ita) {
-        const int sa = ita & 1;
+      const uint32_t d_tmem0 = tmem_base + acc * (uint32_t)MT * n_cta;
+      for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
+        const uint32_t sa = ita & 1;
         ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
-        const uint32_t a_base = ptx::smem_u32(a_smem + (size_t)sa * p.a_stage_bytes);
-        for (int tap = 0; tap < p.n_taps; ++tap, ++itb) {
-          const int sb = itb % p.nsb;
-          ptx::mbar_wait(&sh->b_full[sb], (itb / p.nsb) & 1);
+        const uint32_t a_lo0 = a_base16 + sa * a_stage16;
+        for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++itb) {
+          const uint32_t sb = itb % nsb;
+          ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
           ptx::tc_fence_after();
-          if (lane == 0) {
-            const uint32_t b_base = ptx::smem_u32(b_smem + (size_t)sb * p.b_stage_bytes);
-            const int dd = p.tap[tap][0] + p.pad, dh = p.tap[tap][1] + p.pad, dw = p.tap[tap][2] + p.pad;
-            for (int s = 0; s < p.MT; ++s) {
-              const uint32_t a_tap = a_base + (uint32_t)((((s + dd) * p.Hh + dh) * p.Wh + dw) * 16);
-              for (int j = 0; j < (p.KC >> 4); ++j) {
-                const uint64_t a_desc = make_planar_desc(a_tap + (uint32_t)(2 * j) * a_k, a_lbo, a_sbo);
-                const uint64_t b_desc = make_planar_desc(b_base + (uint32_t)(2 * j) * b_k, b_lbo, b_sbo);
-                ptx::umma_bf16(d_tmem0 + (uint32_t)(s * p.n_cta), a_desc, b_desc, idesc,
-                               (kc > 0 || tap > 0 || j > 0) ? 1u : 0u);
+          const uint32_t b_lo0 = b_base16 + sb * b_stage16;
+          for (int q = 0; q < tps; ++q) {
+            const uint32_t tap16 = __shfl_sync(0xffffffffu, my_tap16, tap0 + q);
+            if (lane == 0) {
+              const uint32_t a_lo = a_lo0 + tap16, b_lo = b_lo0 + (uint32_t)q * btap16;
+              const uint32_t first = (kc | tap0 | q) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int s = 0; s < MT; ++s) {
+#pragma unroll
+                for (int j = 0; j < KJ; ++j) {
+                  const uint64_t a_desc = a_hi | (uint64_t)((a_lo + (uint32_t)s * slice16 + (uint32_t)j * kstep_a16) & 0x3FFFu);
+                  const uint64_t b_desc = b_hi | (uint64_t)((b_lo + (uint32_t)j * kstep_b16) & 0x3FFFu);
+                  ptx::umma_bf16(d_tmem0 + (uint32_t)s * n_cta, a_desc, b_desc, idesc, j == 0 ? first : 1u);
+                }
               }
             }
+          }
+          if (lane == 0) {
             ptx::umma_commit(&sh->b_empty[sb]);
-            if (tap == p.n_taps - 1) {
+            if (tap0 + tps >= n_taps) {
               ptx::umma_commit(&sh->a_empty[sa]);
-              if (kc == p.k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
+              if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
             }
           }
           __syncwarp();
@@ -264,6 +289,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int r = q * 32 + lane;                  // tile row == TMEM lane
     const int lh = r >> 3, lw = r & 7;
     const int n_chunks = p.n_cta >> 4;
+    const int k_chunks_unused = 0; (void)k_chunks_unused;
     const long long V = (long long)p.D * p.H * p.W;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
@@ -279,11 +305,11 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const long long step = p.step_ptr ? (long long)(*p.step_ptr) : 0ll;
         cadd = p.chan_add + step * p.chan_add_step_stride + (long long)t.b * p.c_out;
       }
-      for (int s = 0; s < p.MT; ++s) {
+      for (int s = 0; s < MT; ++s) {
         const int d = t.d0 + s;
         const bool valid = hw_ok && (d < p.D);
         const long long vox = ((long long)d * p.H + h) * p.W + w;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + s) * p.n_cta);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + s) * p.n_cta);
         for (int ch = 0; ch < n_chunks; ++ch) {
           uint32_t raw[16];
           ptx::tmem_ld16(taddr + (uint32_t)(ch * 16), raw);
@@ -521,13 +547,14 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   // ---- shared memory plan: 2 halo stages + a ring of weight stages ----
   const int smem_budget = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - 256;
   int kc = 0, nsb = 0;
+  const int tps = (d.n_taps % 3 == 0) ? 3 : 1;   // one (kd, kh) row of filter taps per weight stage
   const int kc_options[3] = {64, 32, 16};
   for (int o = 0; o < 3; ++o) {
     const int c = kc_options[o];
     if (g_debug_force_kc > 0 && c != g_debug_force_kc) continue;
     if (d.c_in % c != 0) continue;
     const int a_stage = ((c / 8) * p.plane_bytes + 127) & ~127;
-    const int b_stage = c * p.n_cta * 2;
+    const int b_stage = tps * c * p.n_cta * 2;
     const int room = smem_budget - 2 * a_stage;
     if (room < 2 * b_stage) continue;
     kc = c;
@@ -537,6 +564,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     p.b_stage_bytes = b_stage;
     break;
   }
+  p.taps_per_stage = tps;
   VDM_CHECK_ARG(kc > 0, "vdm_conv3d: no channel-chunk size fits shared memory (c_in=%d, N=%d, MT=%d)", d.c_in, p.n_cta, mt);
   p.KC = kc; p.k_chunks = d.c_in / kc; p.nsb = nsb;
   VDM_CHECK_ARG(p.plane_bytes <= 0x3FFF * 16, "vdm_conv3d: halo plane too large for the descriptor stride field");
@@ -582,13 +610,28 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   }
 
   const size_t smem_bytes = 2 * (size_t)p.a_stage_bytes + (size_t)p.nsb * p.b_stage_bytes + sizeof(ConvShared) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_planar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-  conv3d_planar_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, p);
+  int rc = VDM_E_UNSUPPORTED;
+#define VDM_LAUNCH(MTv, KJv)                                                                                   \
+  if (mt == MTv && kc == 16 * KJv) {                                                                           \
+    static bool configured = false;                                                                            \
+    if (!configured) {                                                                                         \
+      VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_planar_kernel<MTv, KJv>,                                      \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));          \
+      configured = true;                                                                                       \
+    }                                                                                                          \
+    conv3d_planar_kernel<MTv, KJv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, p);                        \
+    rc = VDM_OK;                                                                                               \
+  }
+  VDM_LAUNCH(1, 1) VDM_LAUNCH(1, 2) VDM_LAUNCH(1, 4)
+  VDM_LAUNCH(2, 1) VDM_LAUNCH(2, 2) VDM_LAUNCH(2, 4)
+  VDM_LAUNCH(3, 1) VDM_LAUNCH(3, 2) VDM_LAUNCH(3, 4)
+  VDM_LAUNCH(4, 1) VDM_LAUNCH(4, 2) VDM_LAUNCH(4, 4)
+#undef VDM_LAUNCH
+  if (rc != VDM_OK) {
+    set_error("vdm_conv3d: no kernel instance for MT=%d KC=%d", mt, kc);
+    return rc;
+  }
   VDM_CHECK_LAUNCH();
   return VDM_OK;
 }
