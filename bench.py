@@ -246,7 +246,15 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     ops.set_conv_profiler(None)
     vdm.use_cuda_graph = True
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in records) / prof_steps
+    conv_ms = sum(r[0].elapsed_time(r[1]) for r in records) / prof_steps
+    per_layer = {}
+    for r in records:
+        e = per_layer.setdefault(r[3], [0.0, 0.0, 0])
+        e[0] += r[0].elapsed_time(r[1]) / prof_steps
+        e[1] += r[2] / prof_steps
+        e[2] += 1
+    for k, (ms_l, fl, n) in sorted(per_layer.items(), key=lambda kv: -kv[1][0]):
+        print(f"[conv] {k:42s} x{n // prof_steps}: {ms_l:7.3f} ms/step {fl / (ms_l * 1e-3) / 1e12:7.1f} TFLOP/s", file=sys.stderr)
     eager_step_ms = s0.elapsed_time(s1) / prof_steps
     conv_flops = net.conv_flops_per_sample() * batch
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12

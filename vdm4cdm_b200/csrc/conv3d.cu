@@ -236,17 +236,21 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const uint32_t slice16 = (uint32_t)(p.Hh * p.Wh);          // one d-slice of a plane
     const uint32_t kstep_a16 = 2u * ((uint32_t)p.plane_bytes >> 4), kstep_b16 = 2u * n_cta;
     const uint32_t btap16 = (uint32_t)planes_per_chunk * n_cta;  // one tap inside a B stage
-    // lane t keeps the halo offset (in voxels == 16-byte units) of filter tap t
-    const uint32_t my_tap16 =
-        lane < p.n_taps ? (uint32_t)(((p.tap[lane][0] + p.pad) * p.Hh + (p.tap[lane][1] + p.pad)) * p.Wh + p.tap[lane][2] + p.pad)
-                        : 0u;
+    // Everything the issue loop touches is warp-uniform (kernel parameters, the shared-memory window,
+    // tmem_base broadcast by a shuffle) and the issuing lane is chosen with elect.sync, so ptxas keeps the
+    // descriptors in uniform registers and emits back-to-back UTCHMMA.  (r01c: `if (lane == 0)` on
+    // per-thread registers compiled to an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall around every MMA,
+    // ~115 issue cycles per MMA -- profiles/r01c_conv_ncu.txt.)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const bool leader = ptx::elect_one();
     const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
+    const int Hh = p.Hh, Wh = p.Wh, pad = p.pad;
     uint32_t ita = 0, itb = 0, ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
       const uint32_t acc = ti & 1;
       ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem0 = tmem_base + acc * (uint32_t)MT * n_cta;
+      const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)MT * n_cta;
       for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
         const uint32_t sa = ita & 1;
         ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
@@ -256,9 +260,11 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
           ptx::tc_fence_after();
           const uint32_t b_lo0 = b_base16 + sb * b_stage16;
-          for (int q = 0; q < tps; ++q) {
-            const uint32_t tap16 = __shfl_sync(0xffffffffu, my_tap16, tap0 + q);
-            if (lane == 0) {
+          if (leader) {
+            for (int q = 0; q < tps; ++q) {
+              // halo offset (in voxels == 16-byte units) of filter tap tap0+q
+              const uint32_t tap16 = (uint32_t)(((p.tap[tap0 + q][0] + pad) * Hh + (p.tap[tap0 + q][1] + pad)) * Wh +
+                                                p.tap[tap0 + q][2] + pad);
               const uint32_t a_lo = a_lo0 + tap16, b_lo = b_lo0 + (uint32_t)q * btap16;
               const uint32_t first = (kc | tap0 | q) != 0 ? 1u : 0u;
 #pragma unroll
@@ -271,8 +277,6 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
               }
             }
-          }
-          if (lane == 0) {
             ptx::umma_commit(&sh->b_empty[sb]);
             if (tap0 + tps >= n_taps) {
               ptx::umma_commit(&sh->a_empty[sa]);

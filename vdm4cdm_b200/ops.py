@@ -174,7 +174,7 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
     if prof is not None:
         e1.record()
         # algorithmic FLOPs: real (un-padded) output channels, the channels the caller says it reads
-        prof.append((e0, e1, 2.0 * n_taps * c_in * c_out * b * d * h * w_))
+        prof.append((e0, e1, 2.0 * n_taps * c_in * c_out * b * d * h * w_, f"{c_in}->{c_out} taps={n_taps} grid={d}x{h}x{w_} B={b}"))
     return out
 
 
