@@ -89,6 +89,25 @@ VDM_API int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w, vo
 /* Tuning / bring-up knobs (0 = automatic): key 0 swap LBO/SBO roles, 1 force MT, 2 force KC, 3 force n_split. */
 VDM_API int vdm_debug_set(int key, int value);
 
+/* ---- conv3d weight gradient (tcgen05, both operands MN-major straight from the planar tensors) ----
+ * Stands in for the cuDNN conv3d backward-filter autograd launches for every torch.nn.Conv3d of the
+ * CUNet during LightVDM / LightSFM training_step (ctor + Trainer.fit:
+ * trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:128-160; trainSFM3D160_...:124-150).
+ *   dw[tap][ci][co] += sum_{b,d,h,w} a[b][ci][d+kd-p][h+kh-p][w+kw-p] * g[b][co][d][h][w]
+ * a: the conv's input activations, g: the gradient of its output, both channel-planar bf16 on the same
+ * grid; dw: fp32 [kernel^3][c_in][c_out], ACCUMULATED with atomics (the caller zeroes it or keeps
+ * accumulating micro-batches into a gradient bucket). */
+typedef struct VdmWgradDesc {
+  int32_t batch, depth, height, width;
+  int32_t c_in;                 /* channels of `a` read, multiple of 16 */
+  int32_t c_out;                /* real channels of g, 1..256; the g window must hold c_out rounded up to 16 */
+  int32_t kernel;               /* 3 (3x3x3, zero padding 1) or 1 */
+  int32_t a_planes, a_plane0;   /* planes per sample of the a buffer (0: c_in/8), first plane read */
+  int32_t g_planes, g_plane0;   /* same for g */
+} VdmWgradDesc;
+
+VDM_API int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const void* g, float* dw, void* stream);
+
 /* ---- fused elementwise passes (ATen group_norm / silu / dropout / avg_pool3d / interpolate /
  *      cat in the reference's ResNetBlock / ResNetDown; blocks.py:129-170) ------------------- */
 
@@ -119,6 +138,45 @@ VDM_API int vdm_avgpool2(const VdmTensor* x, const VdmTensor* y, int batch, int 
  * Accumulates channel stats of y when stats != NULL. */
 VDM_API int vdm_upsample2(const VdmTensor* coarse, const VdmTensor* y, int batch, int depth, int height, int width,
                   int channels, double* stats, int stats_channels, int stats_c0, void* stream);
+
+/* ---- backward of the fused elementwise passes (autograd's native_group_norm_backward /
+ *      silu_backward / dropout mask / avg_pool3d_backward / upsample_nearest3d_backward launches
+ *      during training_step) ----------------------------------------------------------------------
+ * For y = dropout(silu(u)), u = gamma*xhat + beta, xhat = (x - mean_g)*rstd_g:
+ *   du = dy * keep/(1-p) * silu'(u)
+ *   reduce: sums[b][c] += (sum_v du, sum_v du*xhat)            (-> dbeta, dgamma after a sum over b)
+ *   apply : dx = rstd_g*(gamma_c*du - mean_g(gamma*du) - xhat*mean_g(gamma*du*xhat)) [+ add]
+ * `stats` are the forward statistics of x (double [B][channels][2]); the dropout mask is regenerated
+ * from (seed, layer_tag).  apply also accumulates (sum, sumsq) of dx into out_stats when not NULL
+ * (the per-sample channel sums are the gradients of the conv bias / conditioning rows). */
+VDM_API int vdm_gn_silu_bwd_reduce(const VdmTensor* x, const VdmTensor* dy, int batch, int64_t voxels, int channels,
+                           int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                           float dropout_p, uint64_t seed, uint32_t layer_tag, double* sums, void* stream);
+VDM_API int vdm_gn_silu_bwd_apply(const VdmTensor* x, const VdmTensor* dy, const VdmTensor* add, const VdmTensor* dx,
+                          int batch, int64_t voxels, int channels, int groups, const double* stats,
+                          const float* gamma, const float* beta, float eps, float dropout_p, uint64_t seed,
+                          uint32_t layer_tag, const double* sums, double* out_stats, int out_stats_channels,
+                          int out_stats_c0, void* stream);
+
+/* Gradient of vdm_avgpool2: dx = (accumulate ? dx : 0) + nearest_upsample_x2(dy) / 8 on the fine grid
+ * (depth,height,width); stats (optional) accumulate (sum, sumsq) of the resulting dx. */
+VDM_API int vdm_avgpool2_bwd(const VdmTensor* dy, const VdmTensor* dx, int batch, int depth, int height, int width,
+                     int channels, int accumulate, double* stats, int stats_channels, int stats_c0, void* stream);
+
+/* Gradient of vdm_upsample2: dcoarse = sum of the 2x2x2 fine gradients; (depth,height,width) is the fine grid. */
+VDM_API int vdm_upsample2_bwd(const VdmTensor* dy, const VdmTensor* dcoarse, int batch, int depth, int height, int width,
+                      int channels, double* stats, int stats_channels, int stats_c0, void* stream);
+
+/* ---- optimizer step on a flat fp32 parameter bucket (torch.optim.AdamW + Trainer(gradient_clip_val=0.5),
+ *      trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:134-160) --------------------------------- */
+/* *out += sum_i x[i]^2 (double, atomically). */
+VDM_API int vdm_sumsq(const float* x, int64_t n, double* out, void* stream);
+/* AdamW with decoupled weight decay; the gradient is first multiplied by grad_scale (1/world for a
+ * summed all-reduce) and by min(1, max_norm / (grad_scale*sqrt(*grad_sumsq) + 1e-6)) when grad_sumsq != NULL
+ * and max_norm > 0 (torch.nn.utils.clip_grad_norm_).  `step` is the 1-based step number. */
+VDM_API int vdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq,
+                   float max_norm, float grad_scale, void* stream);
 
 /* Pack the network input: plane 0 of out = (z, cond_1..cond_n, 0...) per voxel, planes 1.. = 0.
  * z: fp32 [B][V]; cond: fp32 [B][n_cond][V] (NCDHW) or NULL; out: c_pad/8 planes; n_cond <= 7. */

@@ -37,6 +37,14 @@ class ConvEpilogue(Structure):
     ]
 
 
+class WgradDesc(Structure):
+    _fields_ = [
+        ("batch", c_int32), ("depth", c_int32), ("height", c_int32), ("width", c_int32),
+        ("c_in", c_int32), ("c_out", c_int32), ("kernel", c_int32),
+        ("a_planes", c_int32), ("a_plane0", c_int32), ("g_planes", c_int32), ("g_plane0", c_int32),
+    ]
+
+
 class Tensor(Structure):
     """VdmTensor: a window of planes inside a channel-planar buffer."""
     _fields_ = [("data", c_void_p), ("planes", c_int32), ("plane0", c_int32)]
@@ -50,6 +58,16 @@ _SIGNATURES = {
     "vdm_device_supported": (c_int, [c_int]),
     "vdm_conv3d": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(ConvEpilogue), c_void_p]),
     "vdm_debug_set": (c_int, [c_int, c_int]),
+    "vdm_conv3d_wgrad": (c_int, [POINTER(WgradDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vdm_gn_silu_bwd_reduce": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                                       c_float, c_uint64, c_uint32, c_void_p, c_void_p]),
+    "vdm_gn_silu_bwd_apply": (c_int, [_T, _T, _T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_float, c_float, c_uint64, c_uint32, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_avgpool2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_upsample2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "vdm_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                               c_float, c_int, c_void_p, c_float, c_float, c_void_p]),
     "vdm_channel_stats": (c_int, [_T, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_gn_silu": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             c_float, c_float, c_uint64, c_uint32, c_void_p]),

@@ -1,0 +1,402 @@
+// Backward of the fused elementwise passes (HBM-bound, channel-planar bf16, 16-byte accesses).
+//
+// Stand in for autograd's native_group_norm_backward / silu_backward / dropout-mask multiply /
+// avg_pool3d_backward / upsample_nearest3d_backward launches of LightVDM / LightSFM training_step
+// (trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:128-160 drives them through Lightning).
+//
+// GroupNorm + SiLU (+ dropout) backward, y = keep/(1-p) * silu(u), u = gamma*xhat + beta:
+//   du      = dy * keep/(1-p) * silu'(u)                     silu'(u) = s*(1 + u*(1 - s)), s = sigmoid(u)
+//   pass 1  : per (sample, channel) S1 = sum_v du, S2 = sum_v du*xhat   (dbeta, dgamma = sums over samples)
+//   pass 2  : dx = rstd*(gamma*du - m1 - xhat*m2) [+ add],   m1 = mean_g(gamma*du), m2 = mean_g(gamma*du*xhat)
+// The keep-mask is regenerated from (seed, layer_tag, chunk), never stored.  Algorithmic traffic:
+// pass 1 reads 4 B/element, pass 2 reads 4 (+2) and writes 2 B/element.
+#include "ew_common.cuh"
+
+namespace vdm {
+
+__device__ __forceinline__ float silu_grad(float u) {
+  const float s = 1.0f / (1.0f + __expf(-u));
+  return s * (1.0f + u * (1.0f - s));
+}
+
+struct GnBwdArgs {
+  VdmTensor x, dy, add, dx;
+  int planes;
+  int64_t voxels;
+  int groups;
+  const double* stats;
+  const float* gamma;
+  const float* beta;
+  float eps, dropout_p;
+  uint64_t seed;
+  uint32_t layer_tag;
+  double* sums;         // [B][C][2]: written by reduce, read by apply
+  double* out_stats;
+  int out_stats_channels, out_stats_c0;
+  int has_add;
+};
+
+// du for the 8 channels of one chunk; also returns xhat.
+__device__ __forceinline__ void chunk_du(const bf16x8& xv, const bf16x8& dyv, const float (&sc)[8], const float (&sh)[8],
+                                         const float (&mean)[8], const float (&rstd)[8], uint32_t keep, float keep_scale,
+                                         float (&du)[8], float (&xhat)[8]) {
+  float x[8], dy[8];
+  unpack8(xv, x);
+  unpack8(dyv, dy);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float u = x[j] * sc[j] + sh[j];
+    xhat[j] = (x[j] - mean[j]) * rstd[j];
+    const float m = ((keep >> j) & 1u) ? keep_scale : 0.f;
+    du[j] = dy[j] * m * silu_grad(u);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
+  __shared__ float s_scale[8], s_shift[8], s_mean[8], s_rstd[8];
+  const int b = blockIdx.y / a.planes, pl = blockIdx.y % a.planes;
+  const int C = a.planes * 8;
+  plane_scale_shift(a.stats + (int64_t)b * C * 2, C, a.groups, pl, (double)a.voxels, a.gamma, a.beta, a.eps, s_scale,
+                    s_shift, s_mean, s_rstd);
+  __syncthreads();
+  float sc[8], sh[8], mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_scale[j]; sh[j] = s_shift[j]; mean[j] = s_mean[j]; rstd[j] = s_rstd[j];
+  }
+  const bf16x8* xp = plane_ptr(a.x, b, pl, a.voxels);
+  const bf16x8* gp = plane_ptr(a.dy, b, pl, a.voxels);
+  const bool drop = a.dropout_p > 0.f;
+  const uint32_t thresh16 = (uint32_t)(a.dropout_p * 65536.0f + 0.5f);
+  const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+  const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += (int64_t)gridDim.x * kEwThreads) {
+    const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)i, a.layer_tag, a.seed, thresh16) : 0xffu;
+    float du[8], xhat[8];
+    chunk_du(xp[i], gp[i], sc, sh, mean, rstd, keep, keep_scale, du, xhat);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += du[j];
+      s2[j] += du[j] * xhat[j];
+    }
+  }
+  block_flush_stats(s1, s2, a.sums + ((int64_t)b * C + pl * 8) * 2);
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
+  __shared__ float s_scale[8], s_shift[8], s_mean[8], s_rstd[8], s_m1[8], s_m2[8], s_gamma[8];
+  const int b = blockIdx.y / a.planes, pl = blockIdx.y % a.planes;
+  const int C = a.planes * 8;
+  plane_scale_shift(a.stats + (int64_t)b * C * 2, C, a.groups, pl, (double)a.voxels, a.gamma, a.beta, a.eps, s_scale,
+                    s_shift, s_mean, s_rstd);
+  if (threadIdx.x < 8) {
+    const int c = pl * 8 + threadIdx.x;
+    const int cpg = C / a.groups;
+    const int g0 = (c / cpg) * cpg;
+    const double* sb = a.sums + (int64_t)b * C * 2;
+    double m1 = 0.0, m2 = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+      const double gk = (double)a.gamma[g0 + k];
+      m1 += gk * sb[2 * (g0 + k)];
+      m2 += gk * sb[2 * (g0 + k) + 1];
+    }
+    const double n = (double)a.voxels * cpg;
+    s_m1[threadIdx.x] = (float)(m1 / n);
+    s_m2[threadIdx.x] = (float)(m2 / n);
+    s_gamma[threadIdx.x] = a.gamma[c];
+  }
+  __syncthreads();
+  float sc[8], sh[8], mean[8], rstd[8], m1[8], m2[8], gam[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_scale[j]; sh[j] = s_shift[j]; mean[j] = s_mean[j]; rstd[j] = s_rstd[j];
+    m1[j] = s_m1[j]; m2[j] = s_m2[j]; gam[j] = s_gamma[j];
+  }
+  const bf16x8* xp = plane_ptr(a.x, b, pl, a.voxels);
+  const bf16x8* gp = plane_ptr(a.dy, b, pl, a.voxels);
+  const bf16x8* ap = a.has_add ? plane_ptr(a.add, b, pl, a.voxels) : nullptr;
+  bf16x8* op = plane_ptr_mut(a.dx, b, pl, a.voxels);
+  const bool drop = a.dropout_p > 0.f;
+  const uint32_t thresh16 = (uint32_t)(a.dropout_p * 65536.0f + 0.5f);
+  const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+  const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
+  float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += (int64_t)gridDim.x * kEwThreads) {
+    const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)i, a.layer_tag, a.seed, thresh16) : 0xffu;
+    float du[8], xhat[8], o[8];
+    chunk_du(xp[i], gp[i], sc, sh, mean, rstd, keep, keep_scale, du, xhat);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = rstd[j] * (gam[j] * du[j] - m1[j] - xhat[j] * m2[j]);
+    if (ap) {
+      float r[8];
+      unpack8(ap[i], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += r[j];
+    }
+    const bf16x8 packed = pack8(o);
+    op[i] = packed;
+    if (a.out_stats) {
+      float r[8];
+      unpack8(packed, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sum[j] += r[j];
+        sq[j] += r[j] * r[j];
+      }
+    }
+  }
+  if (a.out_stats)
+    block_flush_stats(sum, sq, a.out_stats + ((int64_t)b * a.out_stats_channels + a.out_stats_c0 + pl * 8) * 2);
+}
+
+// ---- avg-pool backward: fine dx = [dx +] dy(coarse)/8 -----------------------------------------------
+// One thread per coarse voxel writes its 2x2x2 fine chunks.
+__global__ void __launch_bounds__(kEwThreads)
+avgpool2_bwd_kernel(VdmTensor dy, VdmTensor dx, int planes, int D, int H, int W, int accumulate,
+                    double* __restrict__ stats, int stats_channels, int stats_c0) {
+  const int b = blockIdx.y / planes, pl = blockIdx.y % planes;
+  const int Dc = D >> 1, Hc = H >> 1, Wc = W >> 1;
+  const int64_t vc = (int64_t)Dc * Hc * Wc, vf = (int64_t)D * H * W;
+  const bf16x8* gp = plane_ptr(dy, b, pl, vc);
+  bf16x8* op = plane_ptr_mut(dx, b, pl, vf);
+  float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vc; i += (int64_t)gridDim.x * kEwThreads) {
+    int64_t v = i;
+    const int wc = (int)(v % Wc); v /= Wc;
+    const int hc = (int)(v % Hc);
+    const int dc = (int)(v / Hc);
+    float g[8];
+    unpack8(gp[i], g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= 0.125f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int d = 2 * dc + (k >> 2), h = 2 * hc + ((k >> 1) & 1), w = 2 * wc + (k & 1);
+      const int64_t idx = ((int64_t)d * H + h) * W + w;
+      float o[8];
+      if (accumulate) {
+        unpack8(op[idx], o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += g[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j];
+      }
+      const bf16x8 packed = pack8(o);
+      op[idx] = packed;
+      if (stats) {
+        float r[8];
+        unpack8(packed, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sum[j] += r[j];
+          sq[j] += r[j] * r[j];
+        }
+      }
+    }
+  }
+  if (stats) block_flush_stats(sum, sq, stats + ((int64_t)b * stats_channels + stats_c0 + pl * 8) * 2);
+}
+
+// ---- nearest-upsample backward: coarse = sum of the 8 fine gradients ----------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+upsample2_bwd_kernel(VdmTensor dy, VdmTensor dc, int planes, int D, int H, int W, double* __restrict__ stats,
+                     int stats_channels, int stats_c0) {
+  const int b = blockIdx.y / planes, pl = blockIdx.y % planes;
+  const int Do = D >> 1, Ho = H >> 1, Wo = W >> 1;
+  const int64_t vin = (int64_t)D * H * W, vout = (int64_t)Do * Ho * Wo;
+  const bf16x8* gp = plane_ptr(dy, b, pl, vin);
+  bf16x8* op = plane_ptr_mut(dc, b, pl, vout);
+  float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vout; i += (int64_t)gridDim.x * kEwThreads) {
+    int64_t v = i;
+    const int wo = (int)(v % Wo); v /= Wo;
+    const int ho = (int)(v % Ho);
+    const int dz = (int)(v / Ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int d = 2 * dz + (k >> 2), h = 2 * ho + ((k >> 1) & 1), w = 2 * wo + (k & 1);
+      float f[8];
+      unpack8(gp[((int64_t)d * H + h) * W + w], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    const bf16x8 packed = pack8(acc);
+    op[i] = packed;
+    if (stats) {
+      float r[8];
+      unpack8(packed, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sum[j] += r[j];
+        sq[j] += r[j] * r[j];
+      }
+    }
+  }
+  if (stats) block_flush_stats(sum, sq, stats + ((int64_t)b * stats_channels + stats_c0 + pl * 8) * 2);
+}
+
+// ---- optimizer -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
+  __shared__ double s_part[8];
+  double acc = 0.0;
+  const int64_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = x4[i];
+    acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = x[(n4 << 2) + threadIdx.x];
+    acc += (double)v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+             float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+             const double* __restrict__ grad_sumsq, float max_norm, float grad_scale) {
+  float gs = grad_scale;
+  if (grad_sumsq != nullptr && max_norm > 0.f) {
+    const float norm = grad_scale * (float)sqrt(*grad_sumsq);
+    const float coef = max_norm / (norm + 1e-6f);
+    if (coef < 1.0f) gs *= coef;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float gi = g[i] * gs;
+    float pi = p[i];
+    pi *= 1.0f - lr * weight_decay;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace vdm
+
+using namespace vdm;
+
+static int gn_bwd_common(const char* who, const VdmTensor* x, const VdmTensor* dy, int batch, int64_t voxels, int channels,
+                         int groups, const double* stats, const float* gamma, const float* beta, float dropout_p,
+                         const double* sums) {
+  VDM_CHECK_ARG(view_ok(x, channels) && view_ok(dy, channels) && stats && gamma && beta && sums, "%s: bad tensor argument", who);
+  VDM_CHECK_ARG(batch >= 1 && voxels >= 1, "%s: bad shape", who);
+  VDM_CHECK_ARG((int64_t)batch * (channels / 8) <= 65535, "%s: batch * planes exceeds 65535", who);
+  VDM_CHECK_ARG(groups >= 1 && channels % groups == 0, "%s: %d channels not divisible into %d groups", who, channels, groups);
+  VDM_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "%s: dropout_p %f out of [0,1)", who, dropout_p);
+  return VDM_OK;
+}
+
+extern "C" int vdm_gn_silu_bwd_reduce(const VdmTensor* x, const VdmTensor* dy, int batch, int64_t voxels, int channels,
+                                      int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                                      float dropout_p, uint64_t seed, uint32_t layer_tag, double* sums, void* stream) {
+  const int rc = gn_bwd_common("vdm_gn_silu_bwd_reduce", x, dy, batch, voxels, channels, groups, stats, gamma, beta,
+                               dropout_p, sums);
+  if (rc != VDM_OK) return rc;
+  GnBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = *x; a.dy = *dy; a.planes = channels / 8; a.voxels = voxels; a.groups = groups; a.stats = stats;
+  a.gamma = gamma; a.beta = beta; a.eps = eps; a.dropout_p = dropout_p; a.seed = seed; a.layer_tag = layer_tag;
+  a.sums = sums;
+  gn_silu_bwd_reduce_kernel<<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
+
+extern "C" int vdm_gn_silu_bwd_apply(const VdmTensor* x, const VdmTensor* dy, const VdmTensor* add, const VdmTensor* dx,
+                                     int batch, int64_t voxels, int channels, int groups, const double* stats,
+                                     const float* gamma, const float* beta, float eps, float dropout_p, uint64_t seed,
+                                     uint32_t layer_tag, const double* sums, double* out_stats, int out_stats_channels,
+                                     int out_stats_c0, void* stream) {
+  const int rc = gn_bwd_common("vdm_gn_silu_bwd_apply", x, dy, batch, voxels, channels, groups, stats, gamma, beta,
+                               dropout_p, sums);
+  if (rc != VDM_OK) return rc;
+  VDM_CHECK_ARG(view_ok(dx, channels) && (add == nullptr || view_ok(add, channels)), "vdm_gn_silu_bwd_apply: bad dx/add view");
+  GnBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = *x; a.dy = *dy; a.dx = *dx; a.planes = channels / 8; a.voxels = voxels; a.groups = groups; a.stats = stats;
+  a.gamma = gamma; a.beta = beta; a.eps = eps; a.dropout_p = dropout_p; a.seed = seed; a.layer_tag = layer_tag;
+  a.sums = const_cast<double*>(sums);
+  if (add) { a.add = *add; a.has_add = 1; }
+  a.out_stats = out_stats;
+  a.out_stats_channels = out_stats_channels > 0 ? out_stats_channels : channels;
+  a.out_stats_c0 = out_stats_c0;
+  gn_silu_bwd_apply_kernel<<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
+
+extern "C" int vdm_avgpool2_bwd(const VdmTensor* dy, const VdmTensor* dx, int batch, int depth, int height, int width,
+                                int channels, int accumulate, double* stats, int stats_channels, int stats_c0,
+                                void* stream) {
+  VDM_CHECK_ARG(view_ok(dy, channels) && view_ok(dx, channels) && batch >= 1, "vdm_avgpool2_bwd: bad argument");
+  VDM_CHECK_PLANES(batch, channels, "vdm_avgpool2_bwd");
+  VDM_CHECK_ARG(depth >= 2 && height >= 2 && width >= 2 && depth % 2 == 0 && height % 2 == 0 && width % 2 == 0,
+                "vdm_avgpool2_bwd: fine grid (%d,%d,%d) must be even", depth, height, width);
+  if (stats_channels <= 0) stats_channels = channels;
+  const int planes = channels / 8;
+  const int64_t vc = (int64_t)(depth / 2) * (height / 2) * (width / 2);
+  avgpool2_bwd_kernel<<<ew_grid(vc, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
+      *dy, *dx, planes, depth, height, width, accumulate, stats, stats_channels, stats_c0);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
+
+extern "C" int vdm_upsample2_bwd(const VdmTensor* dy, const VdmTensor* dcoarse, int batch, int depth, int height,
+                                 int width, int channels, double* stats, int stats_channels, int stats_c0, void* stream) {
+  VDM_CHECK_ARG(view_ok(dy, channels) && view_ok(dcoarse, channels) && batch >= 1, "vdm_upsample2_bwd: bad argument");
+  VDM_CHECK_PLANES(batch, channels, "vdm_upsample2_bwd");
+  VDM_CHECK_ARG(depth >= 2 && height >= 2 && width >= 2 && depth % 2 == 0 && height % 2 == 0 && width % 2 == 0,
+                "vdm_upsample2_bwd: fine grid (%d,%d,%d) must be even", depth, height, width);
+  if (stats_channels <= 0) stats_channels = channels;
+  const int planes = channels / 8;
+  const int64_t vout = (int64_t)(depth / 2) * (height / 2) * (width / 2);
+  upsample2_bwd_kernel<<<ew_grid(vout, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
+      *dy, *dcoarse, planes, depth, height, width, stats, stats_channels, stats_c0);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
+
+extern "C" int vdm_sumsq(const float* x, int64_t n, double* out, void* stream) {
+  VDM_CHECK_ARG(x && out && n >= 0, "vdm_sumsq: bad argument");
+  VDM_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "vdm_sumsq: x must be 16-byte aligned");
+  if (n == 0) return VDM_OK;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
+
+extern "C" int vdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq,
+                              float max_norm, float grad_scale, void* stream) {
+  VDM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "vdm_adamw_step: bad argument");
+  if (n == 0) return VDM_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                   eps, weight_decay, bc1, bc2_sqrt, grad_sumsq, max_norm,
+                                                                   grad_scale);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}

@@ -1,0 +1,335 @@
+// Conv3d weight gradient on the 5th-gen tensor cores:
+//     dW[tap][ci][co] += sum over (b, d, h, w) of  a[b][ci][d+kd][h+kh][w+kw] * g[b][co][d][h][w]
+// Stands in for the cuDNN conv3d backward-filter launched by autograd for every torch.nn.Conv3d of
+// mltools' CUNet during LightVDM / LightSFM training_step (trainVDM3D128_..._lowbatch.py:128-132).
+//
+// GEMM view: M = input channels, N = output channels, K = voxels.  Both operands are read from the
+// same channel-planar bf16 tensors the forward uses, as MN-major un-swizzled UMMA operands (8 channels
+// = 16 B contiguous, 8 voxels along w = one core matrix, the next 8 voxels = the next h row = LBO, the
+// next 8 channels = the next plane = SBO; verified by tools/probe_umma.cu test T4).  A filter tap is a
+// start-address offset into the halo tile of `a`, exactly as in the forward kernel.
+//
+// tcgen05 wants M = 128.  Narrow layers fold d-slices into M: with cpb = channels per block (16, 32,
+// 64 or 128, the largest that divides Cin) one operand block is S = 128 / cpb consecutive halo slices
+// x cpb channels, laid out [slice][plane][h'][w'][8] in shared memory so that the 16 groups of 8 rows
+// are equally spaced.  Against ONE slice of g, row block s of the accumulator is then filter plane
+// kd = s - 1 (+ S per further block); rows with kd > 1 are computed and dropped.  Accumulators (one per
+// (block, kh, kw) "job", N fp32 columns each) stay in TMEM over all tiles a CTA visits and are added to
+// dW with fp32 atomics once at the end, so split-K over CTAs costs one pass over dW per CTA.
+//
+// Pipeline per CTA (6 warps): warp 0 TMA producer (halo slices of a + one tile of g per stage),
+// warp 1 MMA issuer (jobs x 8 K-steps of 16 voxels per tile), warps 2-5 final TMEM -> atomics.
+// Roofline: tensor-bound, algorithmic FLOPs = 2 * taps * Cin * Cout * B*D*H*W (same as the forward).
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vdm {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgTileH = 16, kWgTileW = 8;
+constexpr int kWgMaxJobs = 27;
+constexpr int kWgMaxStages = 4;
+
+struct WgradParams {
+  int B, D, H, W;
+  int c_in, c_out;
+  int n;                 // UMMA N per CTA (c_out padded to 16, or its n-split share)
+  int n_split;
+  int cpb, S;            // channels per M block, slices folded into M
+  int n_cblocks;         // Cin / cpb
+  int n_sblocks;         // operand blocks along d: ceil(kd_count / S)
+  int kd_count, pad;     // 3 / 1 for 3x3x3, 1 / 0 for 1x1x1
+  int Hh, Wh;            // halo tile (voxels)
+  int n_jobs_total;      // n_sblocks * n_khw
+  int jobs_per_cta, n_jgroups;
+  int n_khw;             // (kh, kw) pairs: 9 or 1
+  int tiles_w, tiles_h, n_tiles;   // n_tiles = B * tiles_h * tiles_w * D
+  int n_splits;          // CTAs sharing one (cblock, jgroup, nsplit)
+  int stages, a_stage_bytes, g_stage_bytes;
+  int slice_bytes;       // (cpb/8) * Hh * Wh * 16
+  int x_planes, x_plane0, g_planes, g_plane0;
+  int tmem_cols;
+  float* dw;             // fp32 [taps][c_in][c_out]
+};
+
+struct WgradShared {
+  uint64_t full[kWgMaxStages], empty[kWgMaxStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_g,
+                    const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = p.a_stage_bytes + p.g_stage_bytes;
+  WgradShared* sh = reinterpret_cast<WgradShared*>(smem + (size_t)p.stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work unit of this CTA
+  int u = blockIdx.x;
+  const int split = u % p.n_splits; u /= p.n_splits;
+  const int ns = u % p.n_split; u /= p.n_split;
+  const int jg = u % p.n_jgroups;
+  const int cb = u / p.n_jgroups;
+  const int job0 = jg * p.jobs_per_cta;
+  const int n_jobs = min(p.jobs_per_cta, p.n_jobs_total - job0);
+  const int tile_begin = (int)((long long)p.n_tiles * split / p.n_splits);
+  const int tile_end = (int)((long long)p.n_tiles * (split + 1) / p.n_splits);
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_g);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&sh->full[s], 1);
+      ptx::mbar_init(&sh->empty[s], 1);
+    }
+    ptx::mbar_init(&sh->done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  const int n_slices = p.n_sblocks * p.S;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        int t = tile;
+        const int d = t % p.D; t /= p.D;
+        const int w0 = (t % p.tiles_w) * kWgTileW; t /= p.tiles_w;
+        const int h0 = (t % p.tiles_h) * kWgTileH;
+        const int b = t / p.tiles_h;
+        const int s = it % p.stages;
+        ptx::mbar_wait(&sh->empty[s], ((it / p.stages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(n_slices * p.slice_bytes + p.g_stage_bytes));
+        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+        for (int sl = 0; sl < n_slices; ++sl)
+          ptx::tma_load_4d(a_dst + (size_t)sl * p.slice_bytes, &tmap_a, &sh->full[s], (w0 - p.pad) * 8, h0 - p.pad,
+                           d - p.pad + sl, b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
+        ptx::tma_load_4d(a_dst + p.a_stage_bytes, &tmap_g, &sh->full[s], w0 * 8, h0, d,
+                         b * p.g_planes + p.g_plane0 + ns * (p.n >> 3));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (uniform datapath, see conv3d.cu) =====================
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const bool leader = ptx::elect_one();
+    const uint32_t n = (uint32_t)p.n;
+    // instruction descriptor: bf16 x bf16 -> f32, A and B MN-major (bits 15, 16)
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n) | (1u << 15) | (1u << 16);
+    // LBO = stride between 8-voxel groups (next h row), SBO = stride between 8-channel groups
+    const uint32_t plane16 = (uint32_t)(p.Hh * p.Wh);      // one plane of one halo slice, 16-byte units
+    const uint64_t a_hi = ((uint64_t)((uint32_t)p.Wh & 0x3FFFu) << 16) | ((uint64_t)(plane16 & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+    const uint64_t b_hi = ((uint64_t)8u << 16) | ((uint64_t)128u << 32) | ((uint64_t)1 << 46);
+    const uint32_t smem16 = ptx::smem_u32(smem) >> 4;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t block16 = 16u * plane16;                 // one 128-row operand block
+    const int Wh = p.Wh, n_khw = p.n_khw, stages = p.stages;
+    uint32_t it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const uint32_t s = it % stages;
+      ptx::mbar_wait(&sh->full[s], (it / stages) & 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        const uint32_t a0 = smem16 + s * stage16, g0 = a0 + a_stage16;
+        const uint32_t acc = it != 0 ? 1u : 0u;
+        for (int j = 0; j < n_jobs; ++j) {
+          const int job = job0 + j;
+          const int sb = job / n_khw, khw = job % n_khw;
+          const int kh = n_khw == 9 ? khw / 3 : 0, kw = n_khw == 9 ? khw % 3 : 0;
+          const uint32_t a_job = a0 + (uint32_t)sb * block16 + (uint32_t)(kh * Wh + kw);
+          const uint32_t d_tmem = tmem_u + (uint32_t)j * n;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t a_desc = a_hi | (uint64_t)((a_job + (uint32_t)(2 * k * Wh)) & 0x3FFFu);
+            const uint64_t b_desc = b_hi | (uint64_t)((g0 + (uint32_t)(16 * k)) & 0x3FFFu);
+            ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, k == 0 ? acc : 1u);
+          }
+        }
+        ptx::umma_commit(&sh->empty[s]);
+        if (tile == tile_end - 1) ptx::umma_commit(&sh->done);
+      }
+      __syncwarp();
+    }
+  } else if (tile_end > tile_begin) {
+    // ===================== final epilogue: TMEM -> fp32 atomics into dW =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;            // accumulator row
+    ptx::mbar_wait(&sh->done, 0);
+    ptx::tc_fence_after();
+    const int s_in_block = m / p.cpb, ci = cb * p.cpb + m % p.cpb;
+    for (int j = 0; j < n_jobs; ++j) {
+      const int job = job0 + j;
+      const int sb = job / p.n_khw, khw = job % p.n_khw;
+      const int kd = sb * p.S + s_in_block;               // 0..kd_count-1 are real filter planes
+      const bool row_ok = kd < p.kd_count && ci < p.c_in;
+      const int tap = kd * p.n_khw + khw;
+      for (int c0 = 0; c0 < p.n; c0 += 16) {
+        uint32_t raw[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.n + c0), raw);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          float* dst = p.dw + ((size_t)tap * p.c_in + ci) * p.c_out + ns * p.n + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (ns * p.n + c0 + i < p.c_out) atomicAdd(dst + i, __uint_as_float(raw[i]));
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 wg_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }();
+  return fn;
+}
+
+static int wg_num_sms() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return kNumSMs;
+    return v;
+  }();
+  return n;
+}
+
+}  // namespace vdm
+
+using namespace vdm;
+
+extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const void* g, float* dw, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VDM_CHECK_ARG(desc && a && g && dw, "vdm_conv3d_wgrad: NULL pointer argument");
+  const VdmWgradDesc& d = *desc;
+  VDM_CHECK_ARG(d.batch >= 1 && d.depth >= 1 && d.height >= 1 && d.width >= 1, "vdm_conv3d_wgrad: bad grid");
+  VDM_CHECK_ARG(d.c_in >= 16 && d.c_in % 16 == 0, "vdm_conv3d_wgrad: c_in=%d must be a multiple of 16", d.c_in);
+  VDM_CHECK_ARG(d.c_out >= 1 && d.c_out <= 256, "vdm_conv3d_wgrad: c_out=%d out of [1,256]", d.c_out);
+  VDM_CHECK_ARG(d.kernel == 3 || d.kernel == 1, "vdm_conv3d_wgrad: kernel size %d (3 or 1 supported)", d.kernel);
+  const int x_planes = d.a_planes > 0 ? d.a_planes : d.c_in / 8;
+  const int c_out16 = (d.c_out + 15) / 16 * 16;
+  const int g_planes = d.g_planes > 0 ? d.g_planes : c_out16 / 8;
+  VDM_CHECK_ARG(d.a_plane0 >= 0 && d.a_plane0 + d.c_in / 8 <= x_planes, "vdm_conv3d_wgrad: a plane window out of range");
+  VDM_CHECK_ARG(d.g_plane0 >= 0 && d.g_plane0 + c_out16 / 8 <= g_planes,
+                "vdm_conv3d_wgrad: g plane window out of range (g must hold c_out rounded up to 16 channels)");
+  VDM_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
+                "vdm_conv3d_wgrad: pointers must be 16-byte aligned");
+  auto encode = wg_encode_fn();
+  if (!encode) {
+    set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled is not available from the driver");
+    return VDM_E_DRIVER;
+  }
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d.batch; p.D = d.depth; p.H = d.height; p.W = d.width;
+  p.c_in = d.c_in; p.c_out = d.c_out;
+  p.kd_count = d.kernel; p.pad = d.kernel == 3 ? 1 : 0;
+  p.n_khw = d.kernel * d.kernel;
+  p.Hh = kWgTileH + 2 * p.pad; p.Wh = kWgTileW + 2 * p.pad;
+  int cpb = 128;
+  while (d.c_in % cpb != 0) cpb >>= 1;
+  p.cpb = cpb; p.S = 128 / cpb; p.n_cblocks = d.c_in / cpb;
+  p.n_sblocks = (p.kd_count + p.S - 1) / p.S;
+  p.n_jobs_total = p.n_sblocks * p.n_khw;
+  p.n_split = c_out16 > 128 ? 2 : 1;
+  VDM_CHECK_ARG(c_out16 % (16 * p.n_split) == 0, "vdm_conv3d_wgrad: c_out=%d cannot be split", d.c_out);
+  p.n = c_out16 / p.n_split;
+  p.jobs_per_cta = 512 / p.n;
+  if (p.jobs_per_cta > p.n_jobs_total) p.jobs_per_cta = p.n_jobs_total;
+  p.n_jgroups = (p.n_jobs_total + p.jobs_per_cta - 1) / p.jobs_per_cta;
+  p.jobs_per_cta = (p.n_jobs_total + p.n_jgroups - 1) / p.n_jgroups;   // balance the groups
+  int cols = 32;
+  while (cols < p.jobs_per_cta * p.n) cols <<= 1;
+  p.tmem_cols = cols;
+  p.tiles_w = ceil_div(d.width, kWgTileW);
+  p.tiles_h = ceil_div(d.height, kWgTileH);
+  const long long n_tiles = (long long)d.batch * p.tiles_h * p.tiles_w * d.depth;
+  VDM_CHECK_ARG(n_tiles < (1ll << 31), "vdm_conv3d_wgrad: too many tiles");
+  p.n_tiles = (int)n_tiles;
+  p.slice_bytes = (cpb / 8) * p.Hh * p.Wh * 16;
+  const int n_slices = p.n_sblocks * p.S;
+  p.a_stage_bytes = (n_slices * p.slice_bytes + 127) & ~127;
+  p.g_stage_bytes = p.n * kWgTileH * kWgTileW * 2;
+  const int budget = 227 * 1024 - 1024 - (int)sizeof(WgradShared) - 256;
+  int stages = budget / (p.a_stage_bytes + p.g_stage_bytes);
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  VDM_CHECK_ARG(stages >= 1, "vdm_conv3d_wgrad: one stage (%d bytes) does not fit shared memory",
+                p.a_stage_bytes + p.g_stage_bytes);
+  p.stages = stages;
+  VDM_CHECK_ARG(16 * p.Hh * p.Wh <= 0x3FFF, "vdm_conv3d_wgrad: operand block too large for the descriptor");
+  const int units = p.n_cblocks * p.n_jgroups * p.n_split;
+  int n_splits = (2 * wg_num_sms()) / units;          // about two CTAs' worth of work units per SM ...
+  if (n_splits < 1) n_splits = 1;
+  if (n_splits > p.n_tiles) n_splits = p.n_tiles;     // ... but at least one tile each
+  if (units * n_splits > wg_num_sms() && n_splits > 1) {
+    // prefer exactly one wave when that keeps >= 8 tiles per CTA
+    const int one_wave = wg_num_sms() / units;
+    if (one_wave >= 1 && p.n_tiles / one_wave >= 8) n_splits = one_wave;
+  }
+  p.n_splits = n_splits;
+  p.x_planes = x_planes; p.x_plane0 = d.a_plane0;
+  p.g_planes = g_planes; p.g_plane0 = d.g_plane0;
+  p.dw = dw;
+
+  CUtensorMap tma, tmg;
+  {
+    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
+    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * x_planes};
+    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    cuuint32_t box[4] = {(cuuint32_t)p.Wh * 8, (cuuint32_t)p.Hh, 1u, (cuuint32_t)(cpb / 8)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(a) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+    cuuint64_t gdim2[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * g_planes};
+    cuuint32_t box2[4] = {(cuuint32_t)kWgTileW * 8, (cuuint32_t)kWgTileH, 1u, (cuuint32_t)(p.n / 8)};
+    r = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g), gdim2, gstr, box2, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(g) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+  }
+  const size_t smem_bytes = (size_t)p.stages * (p.a_stage_bytes + p.g_stage_bytes) + sizeof(WgradShared) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  conv3d_wgrad_kernel<<<units * n_splits, kWgThreads, smem_bytes, stream>>>(tma, tmg, p);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}

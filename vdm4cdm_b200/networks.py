@@ -153,6 +153,7 @@ class CUNet(nn.Module):
         self.conv_out = nn.Sequential(nn.GroupNorm(norm_groups, c[0]), nn.SiLU(),
                                       nn.Conv3d(c[0], 1, 3, padding=1, padding_mode=pm))
         self._arena = _Arena()
+        self._train_arena = _Arena()
         self._packed_cache: Dict[str, tuple] = {}
         self.dropout_seed = 0
         self._dropout_calls = 0
@@ -250,29 +251,35 @@ class CUNet(nn.Module):
 
     # ---- the convolutional trunk on channel-planar buffers --------------------------------------
     def _run_block(self, name, blk: ResNetBlock, x, x_plane0, x_stats, rows, step_ptr, out, out_plane0, out_stats,
-                   out_stats_c0, grid, training_dropout):
-        """out[window] = block(x[window]).  x_stats: double [B, ch_in, 2] of x."""
+                   out_stats_c0, grid, training_dropout, tape=None):
+        """out[window] = block(x[window]).  x_stats: double [B, ch_in, 2] of x.  With a ``tape`` (training)
+        every intermediate gets its own buffer and is recorded for the backward pass."""
         b = x.shape[0]
         dev = x.device
-        ar = self._arena
+        ar = self._arena if tape is None else self._train_arena
         ci, co, g = blk.ch_in, blk.ch_out, blk.norm_groups
         tag = f"{b}x{grid[0]}"
-        a1 = ar.get(f"a.{ci}.{tag}", (b, ci // 8) + grid + (8,), torch.bfloat16, dev)
+        own = "" if tape is None else name + "."
+        a1 = ar.get(f"{own}a.{ci}.{tag}", (b, ci // 8) + grid + (8,), torch.bfloat16, dev)
         ops.gn_silu(x, ci, g, x_stats, blk.net1[0].weight, blk.net1[0].bias, blk.net1[0].eps, x_plane0=x_plane0, out=a1)
-        h = ar.get(f"h.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+        h = ar.get(f"{own}h.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
         h_stats = self._stats(f"{name}.h", b, co, dev)
         ops.conv3d(a1, self._packed(name + ".net1", blk.net1[2]), co, out=h, chan_add=rows[name + ".net1"],
                    step_ptr=step_ptr if rows[name + ".net1"].dim() == 3 else None, stats=h_stats)
-        a2 = ar.get(f"a.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+        a2 = ar.get(f"{own}a2.{co}.{tag}" if tape is not None else f"a.{co}.{tag}", (b, co // 8) + grid + (8,),
+                    torch.bfloat16, dev)
         p_drop = blk.dropout_prob if training_dropout else 0.0
         if p_drop > 0.0:
             self._dropout_calls += 1
         ops.gn_silu(h, co, g, h_stats, blk.net2[0].weight, blk.net2[0].bias, blk.net2[0].eps, out=a2, dropout_p=p_drop,
                     seed=self.dropout_seed, layer_tag=self._dropout_calls)
+        if tape is not None:
+            tape[name] = dict(x=x, x_plane0=x_plane0, x_stats=x_stats, a1=a1, h=h, h_stats=h_stats, a2=a2, grid=grid,
+                              p_drop=p_drop, drop_tag=self._dropout_calls, drop_seed=self.dropout_seed)
         if blk.skip_conv is None:
             res, res_plane0 = x, x_plane0
         else:
-            res = ar.get(f"r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+            res = ar.get(f"{own}r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
             ops.conv3d(x, self._packed(name + ".skip", blk.skip_conv), co, taps=ops.TAPS_1X1X1, x_plane0=x_plane0, c_in=ci,
                        out=res, chan_add=rows[name + ".skip"])
             res_plane0 = 0
@@ -290,14 +297,17 @@ class CUNet(nn.Module):
         return self._stats_arena[off:off + n].view(b, c, 2)
 
     def run_packed(self, packed: torch.Tensor, rows: Dict[str, torch.Tensor], step_ptr: Optional[torch.Tensor] = None,
-                   out: Optional[torch.Tensor] = None, training_dropout: bool = False) -> torch.Tensor:
-        """eps_hat fp32 (B, 1, D, H, W) from the packed network input (``ops.pack_input``)."""
+                   out: Optional[torch.Tensor] = None, training_dropout: bool = False, tape: Optional[dict] = None) -> torch.Tensor:
+        """eps_hat fp32 (B, 1, D, H, W) from the packed network input (``ops.pack_input``).
+
+        ``tape`` (a dict, training only): intermediates live in a separate arena, nothing is shared between
+        layers, and every tensor the backward pass needs is recorded in it (``vdm4cdm_b200.autograd``)."""
         b = packed.shape[0]
         dev = packed.device
         c = self.chs
         nl = len(c)
         grids = [tuple(n >> i for n in self.shape[1:]) for i in range(nl)]
-        ar = self._arena
+        ar = self._arena if tape is None else self._train_arena
         self._stats_arena = ar.get(f"stats.{b}", (b * 2 * (16 * sum(c) + 64),), torch.float64, dev)
         self._stats_arena.zero_()
         self._stats_off = 0
@@ -321,7 +331,7 @@ class CUNet(nn.Module):
                 cst = self._stats(f"cat{i}", b, c[i + 1] + c[i], dev)
                 cats[i], cat_stats[i] = cat, cst
                 self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, cat, c[i + 1] // 8, cst, c[i + 1],
-                                grids[i], training_dropout)
+                                grids[i], training_dropout, tape)
                 pooled = buf(f"pool{i}", c[i], i + 1)
                 pst = self._stats(f"pool{i}", b, c[i], dev)
                 ops.avgpool2(cat, c[i], x_plane0=c[i + 1] // 8, out=pooled, stats=pst)
@@ -329,12 +339,14 @@ class CUNet(nn.Module):
             else:
                 o = buf("bottom0", c[i], i)
                 ost = self._stats("bottom0", b, c[i], dev)
-                self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout)
+                self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout,
+                                tape)
                 x, x_plane0, x_stats = o, 0, ost
         for j, (name, blk) in enumerate((("mid1", self.mid1), ("mid2", self.mid2))):
             o = buf(f"bottom{1 + j}", c[-1], nl - 1)
             ost = self._stats(name + ".out", b, c[-1], dev)
-            self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, o, 0, ost, 0, grids[-1], training_dropout)
+            self._run_block(name, blk, x, x_plane0, x_stats, rows, step_ptr, o, 0, ost, 0, grids[-1], training_dropout,
+                            tape)
             x, x_plane0, x_stats = o, 0, ost
         for k, i in enumerate(reversed(range(nl - 1))):
             blk = self.ups[k].resnet_blocks[0]
@@ -343,11 +355,14 @@ class CUNet(nn.Module):
             ops.upsample2(x, c[i + 1], cat, coarse_plane0=x_plane0, out_plane0=0, stats=cst, stats_c0=0)
             o = buf(f"up{i}", c[i], i)
             ost = self._stats(name + ".out", b, c[i], dev)
-            self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout)
+            self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout, tape)
             x, x_plane0, x_stats = o, 0, ost
         gn = self.conv_out[0]
-        a = ar.get(f"a.{c[0]}.{b}x{grids[0][0]}", (b, c[0] // 8) + grids[0] + (8,), torch.bfloat16, dev)
+        a = ar.get(("conv_out." if tape is not None else "") + f"a.{c[0]}.{b}x{grids[0][0]}",
+                   (b, c[0] // 8) + grids[0] + (8,), torch.bfloat16, dev)
         ops.gn_silu(x, c[0], gn.num_groups, x_stats, gn.weight, gn.bias, gn.eps, out=a)
+        if tape is not None:
+            tape["trunk"] = dict(packed=packed, h_in=h, cats=cats, grids=grids, out_x=x, out_x_stats=x_stats, out_a=a)
         if out is None:
             out = torch.empty((b, 1) + grids[0], dtype=torch.float32, device=dev)
         ops.conv3d(a, self._packed("conv_out", self.conv_out[2]), 1, out=out, out_fp32=True, chan_add=rows["conv_out"])

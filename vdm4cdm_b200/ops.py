@@ -268,6 +268,144 @@ def pack_input(z: torch.Tensor, cond: Optional[torch.Tensor], c_pad: int = 16,
     return out
 
 
+# ---- backward (training) ---------------------------------------------------------------------------
+def conv3d_wgrad(a: torch.Tensor, g: torch.Tensor, c_in: int, c_out: int, kernel: int = 3, *, a_plane0: int = 0,
+                 g_plane0: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``vdm_conv3d_wgrad``: dw[tap, ci, co] += sum_v a[ci, v + tap] g[co, v]  (fp32 [k^3, c_in, c_out]).
+
+    a, g: planar buffers on the same grid; the g window must hold c_out rounded up to 16 channels.
+    ``out`` is accumulated into (allocated and zeroed when None)."""
+    _planar_ok(a, "conv3d_wgrad a")
+    _planar_ok(g, "conv3d_wgrad g")
+    b, ap, d, h, w_, _ = a.shape
+    _need(tuple(g.shape[2:5]) == (d, h, w_) and g.shape[0] == b, "conv3d_wgrad: a / g grid mismatch")
+    if out is None:
+        out = torch.zeros((kernel ** 3, c_in, c_out), dtype=torch.float32, device=a.device)
+    _need(out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and
+          tuple(out.shape) == (kernel ** 3, c_in, c_out), "conv3d_wgrad: out must be fp32 [k^3, c_in, c_out]")
+    desc = _C.WgradDesc()
+    desc.batch, desc.depth, desc.height, desc.width = b, d, h, w_
+    desc.c_in, desc.c_out, desc.kernel = c_in, c_out, kernel
+    desc.a_planes, desc.a_plane0 = ap, a_plane0
+    desc.g_planes, desc.g_plane0 = g.shape[1], g_plane0
+    prof = _CONV_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = _C.lib().vdm_conv3d_wgrad(ctypes.byref(desc), a.data_ptr(), g.data_ptr(), out.data_ptr(), _stream())
+    _C.check(rc, "vdm_conv3d_wgrad")
+    _launched(1)
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * kernel ** 3 * c_in * c_out * b * d * h * w_,
+                     f"wgrad {c_in}->{c_out} taps={kernel ** 3} grid={d}x{h}x{w_} B={b}"))
+    return out
+
+
+def wgrad_to_torch(dw: torch.Tensor, kernel: int) -> torch.Tensor:
+    """fp32 [k^3, c_in, c_out] -> torch Conv3d weight layout (c_out, c_in, k, k, k)."""
+    k3, ci, co = dw.shape
+    return dw.reshape(kernel, kernel, kernel, ci, co).permute(4, 3, 0, 1, 2).contiguous()
+
+
+def _gn_common(x, channels, stats, gamma, beta, who):
+    _planar_ok(x, f"{who} x")
+    b = x.shape[0]
+    _need(stats.dtype == torch.float64 and tuple(stats.shape) == (b, channels, 2) and stats.is_contiguous(),
+          f"{who}: stats must be double [B, channels, 2]")
+    _need(gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == channels and
+          beta.numel() == channels and gamma.is_cuda and beta.is_cuda, f"{who}: gamma/beta must be CUDA fp32 [channels]")
+    return b, x.shape[2] * x.shape[3] * x.shape[4]
+
+
+def gn_silu_bwd(x: torch.Tensor, dy: torch.Tensor, channels: int, groups: int, stats: torch.Tensor, gamma: torch.Tensor,
+                beta: torch.Tensor, eps: float = 1e-5, *, x_plane0: int = 0, dy_plane0: int = 0,
+                add: Optional[torch.Tensor] = None, add_plane0: int = 0, out: Optional[torch.Tensor] = None,
+                out_plane0: int = 0, dropout_p: float = 0.0, seed: int = 0, layer_tag: int = 0,
+                out_stats: Optional[torch.Tensor] = None, out_stats_c0: int = 0):
+    """Backward of ``gn_silu``: returns (dx, sums) with sums double [B, channels, 2] = per-sample
+    (sum du, sum du*xhat), i.e. dbeta = sums[..., 0].sum(0), dgamma = sums[..., 1].sum(0).
+    dx = GroupNorm/SiLU/dropout backward of dy [+ add]; ``out_stats`` accumulates (sum, sumsq) of dx."""
+    b, voxels = _gn_common(x, channels, stats, gamma, beta, "gn_silu_bwd")
+    _planar_ok(dy, "gn_silu_bwd dy")
+    if out is None:
+        out = torch.empty((b, channels // 8) + tuple(x.shape[2:]), dtype=torch.bfloat16, device=x.device)
+    _planar_ok(out, "gn_silu_bwd out")
+    sums = torch.zeros((b, channels, 2), dtype=torch.float64, device=x.device)
+    vx, vg, vo = _view(x, x_plane0), _view(dy, dy_plane0), _view(out, out_plane0)
+    lib = _C.lib()
+    rc = lib.vdm_gn_silu_bwd_reduce(ctypes.byref(vx), ctypes.byref(vg), b, voxels, channels, groups, stats.data_ptr(),
+                                    gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, layer_tag, sums.data_ptr(),
+                                    _stream())
+    _C.check(rc, "vdm_gn_silu_bwd_reduce")
+    va = None
+    if add is not None:
+        _planar_ok(add, "gn_silu_bwd add")
+        va = ctypes.byref(_view(add, add_plane0))
+    rc = lib.vdm_gn_silu_bwd_apply(ctypes.byref(vx), ctypes.byref(vg), va, ctypes.byref(vo), b, voxels, channels, groups,
+                                   stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, layer_tag,
+                                   sums.data_ptr(), _ptr(out_stats), 0 if out_stats is None else out_stats.shape[1],
+                                   out_stats_c0, _stream())
+    _C.check(rc, "vdm_gn_silu_bwd_apply")
+    _launched(2)
+    return out, sums
+
+
+def avgpool2_bwd(dy: torch.Tensor, channels: int, dx: torch.Tensor, *, dy_plane0: int = 0, dx_plane0: int = 0,
+                 accumulate: bool = False, stats: Optional[torch.Tensor] = None, stats_c0: int = 0) -> torch.Tensor:
+    """dx[window] = (dx[window] if accumulate else 0) + upsample(dy)/8; dx is on the fine grid."""
+    _planar_ok(dy, "avgpool2_bwd dy")
+    _planar_ok(dx, "avgpool2_bwd dx")
+    b, _, d, h, w, _ = dx.shape
+    _need(tuple(dy.shape[2:5]) == (d // 2, h // 2, w // 2), "avgpool2_bwd: dy grid must be half the dx grid")
+    vg, vx = _view(dy, dy_plane0), _view(dx, dx_plane0)
+    rc = _C.lib().vdm_avgpool2_bwd(ctypes.byref(vg), ctypes.byref(vx), b, d, h, w, channels, 1 if accumulate else 0,
+                                   _ptr(stats), 0 if stats is None else stats.shape[1], stats_c0, _stream())
+    _C.check(rc, "vdm_avgpool2_bwd")
+    _launched(1)
+    return dx
+
+
+def upsample2_bwd(dy: torch.Tensor, channels: int, *, dy_plane0: int = 0, out: Optional[torch.Tensor] = None,
+                  out_plane0: int = 0, stats: Optional[torch.Tensor] = None, stats_c0: int = 0) -> torch.Tensor:
+    """dcoarse = sum over each 2x2x2 block of the fine gradient window dy."""
+    _planar_ok(dy, "upsample2_bwd dy")
+    b, _, d, h, w, _ = dy.shape
+    if out is None:
+        out = torch.empty((b, channels // 8, d // 2, h // 2, w // 2, 8), dtype=torch.bfloat16, device=dy.device)
+    _planar_ok(out, "upsample2_bwd out")
+    vg, vo = _view(dy, dy_plane0), _view(out, out_plane0)
+    rc = _C.lib().vdm_upsample2_bwd(ctypes.byref(vg), ctypes.byref(vo), b, d, h, w, channels, _ptr(stats),
+                                    0 if stats is None else stats.shape[1], stats_c0, _stream())
+    _C.check(rc, "vdm_upsample2_bwd")
+    _launched(1)
+    return out
+
+
+def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out (double scalar tensor, accumulated) += sum(x^2) over a flat fp32 buffer."""
+    _need(x.is_cuda and x.dtype == torch.float32 and x.is_contiguous(), "sumsq: x must be contiguous CUDA fp32")
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float64, device=x.device)
+    _C.check(_C.lib().vdm_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vdm_sumsq")
+    _launched(1)
+    return out
+
+
+def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,
+               step: int, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.01,
+               grad_sumsq: Optional[torch.Tensor] = None, max_norm: float = 0.0, grad_scale: float = 1.0) -> None:
+    """``vdm_adamw_step`` on flat fp32 buckets (in place)."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        _need(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel(),
+              "adamw_step: buckets must be contiguous CUDA fp32 of equal length")
+    rc = _C.lib().vdm_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                 param.numel(), lr, beta1, beta2, eps, weight_decay, step, _ptr(grad_sumsq), max_norm,
+                                 grad_scale, _stream())
+    _C.check(rc, "vdm_adamw_step")
+    _launched(1)
+
+
 # ---- sampler ---------------------------------------------------------------------------------------
 def sampler_step(z: torch.Tensor, eps_hat: torch.Tensor, coef: torch.Tensor, *, out: Optional[torch.Tensor] = None,
                  step_ptr: Optional[torch.Tensor] = None, seed: int = 0, realisation_id: Optional[torch.Tensor] = None,
