@@ -1,0 +1,220 @@
+"""Training path of the CUNet: forward with a tape + hand-scheduled backward on the sm_100a kernels.
+
+Stands in for what autograd records and replays for ``LightVDM.training_step`` / ``LightSFM.training_step``
+(trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:128-160 and trainSFM3D160_...:124-150 drive them through
+``lightning.Trainer.fit``): cuDNN conv3d backward-data / backward-filter, native_group_norm_backward,
+silu_backward, the dropout mask multiply, avg_pool3d_backward, upsample_nearest3d_backward and the
+``cat`` split.  Here the whole trunk is ONE ``torch.autograd.Function``:
+
+  forward   ``CUNet.run_packed(..., tape=...)``: same kernels as inference, every intermediate kept
+  backward  per ResNet block (y = conv2(drop(silu(gn2(h)))) + skip(x), h = conv1(silu(gn1(x))) + row):
+              dW2 = wgrad(a2, dy)            d_a2 = dgrad(dy, W2)            (tcgen05)
+              dh  = gn_silu_bwd(h, d_a2)     dgamma2/dbeta2, d_row1 = sum_v dh
+              dW1 = wgrad(a1, dh)            d_a1 = dgrad(dh, W1)
+              dx  = gn_silu_bwd(x, d_a1) + (dy | dgrad_1x1(dy, Wskip))       dgamma1/dbeta1
+            concat split = plane windows of the gradient buffer; the skip gradient and the pooled
+            gradient meet by accumulating ``avgpool2_bwd`` in place.
+Gradients are bf16 channel-planar (fp32 accumulation inside every kernel); weight gradients are fp32.
+Only the tiny embedding MLPs, the bias/conditioning rows and the scalar loss glue run under torch autograd.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+
+def _chunks(c: int) -> List[tuple]:
+    """Split c dgrad output channels into launches of <= 256 (the UMMA N limit), multiples of 8."""
+    n = -(-c // 256)
+    while c % n != 0 or (c // n) % 8 != 0:
+        n += 1
+    step = c // n
+    return [(i * step, step) for i in range(n)]
+
+
+class _Backward:
+    """One backward pass over the tape of one forward."""
+
+    def __init__(self, net, tape: dict, names: List[str]):
+        self.net, self.tape = net, tape
+        self.ar = net._train_arena
+        self.b = tape["trunk"]["packed"].shape[0]
+        self.dev = tape["trunk"]["packed"].device
+        self.grads: Dict[str, torch.Tensor] = {}      # parameter / row name -> gradient
+        self._stats_off = 0
+        n_stats = self.b * 2 * (24 * sum(net.chs) + 256)
+        self._stats_arena = self.ar.get(f"gstats.{self.b}", (n_stats,), torch.float64, self.dev)
+        self._stats_arena.zero_()
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def stats(self, c: int) -> torch.Tensor:
+        n = self.b * c * 2
+        off = self._stats_off
+        self._stats_off += n
+        if self._stats_off > self._stats_arena.numel():
+            raise RuntimeError("gradient statistics arena too small")
+        return self._stats_arena[off:off + n].view(self.b, c, 2)
+
+    def buf(self, name: str, ch: int, grid) -> torch.Tensor:
+        return self.ar.get(f"g.{name}.{self.b}x{grid[0]}", (self.b, ch // 8) + tuple(grid) + (8,), torch.bfloat16, self.dev)
+
+    def dgrad(self, name: str, conv, g, g_plane0, g_ch, out, out_plane0=0):
+        """out[window] = conv^T(g): one launch per <=256 input channels of the conv."""
+        ci = conv.in_channels
+        taps = ops.TAPS_3X3X3 if conv.kernel_size[0] == 3 else ops.TAPS_1X1X1
+        for c0, n in _chunks(ci):
+            wp = self.net._packed_dgrad(name, conv, c0, n)
+            ops.conv3d(g, wp, n, taps=taps, x_plane0=g_plane0, c_in=g_ch, out=out, out_plane0=out_plane0 + c0 // 8)
+
+    def wgrad(self, name: str, conv, a, a_plane0, a_ch, g, g_plane0):
+        k = conv.kernel_size[0]
+        dw = ops.conv3d_wgrad(a, g, a_ch, conv.out_channels, k, a_plane0=a_plane0, g_plane0=g_plane0)
+        self.grads[name + ".weight"] = ops.wgrad_to_torch(dw, k)[:, :conv.in_channels]
+
+    def gn_grads(self, name: str, sums: torch.Tensor):
+        self.grads[name + ".weight"] = sums[..., 1].sum(0).float()
+        self.grads[name + ".bias"] = sums[..., 0].sum(0).float()
+
+    # ---- one residual block ---------------------------------------------------------------------------------
+    def block(self, name: str, blk, dy, dy_plane0, dy_stats, dy_stats_c0, dx, dx_plane0, dx_stats, dx_stats_c0):
+        """Backward of ``CUNet._run_block``: consumes dy[window] (+ its per-sample channel sums), writes
+        dx[window] (+ sums), records every parameter gradient of the block."""
+        rec = self.tape[name]
+        ci, co, groups, grid = blk.ch_in, blk.ch_out, blk.norm_groups, rec["grid"]
+        gn1, conv1, gn2, conv2 = blk.net1[0], blk.net1[2], blk.net2[0], blk.net2[3]
+        d_bias = dy_stats[:, dy_stats_c0:dy_stats_c0 + co, 0].float()
+        # net2: conv -> dropout/silu/gn
+        self.wgrad(name + ".net2", conv2, rec["a2"], 0, co, dy, dy_plane0)
+        self.grads["row." + name + ".net2"] = d_bias
+        d_a2 = self.buf(f"a.{co}", co, grid)
+        self.dgrad(name + ".net2", conv2, dy, dy_plane0, co, d_a2)
+        dh = self.buf(f"h.{co}", co, grid)
+        dh_stats = self.stats(co)
+        _, sums2 = ops.gn_silu_bwd(rec["h"], d_a2, co, groups, rec["h_stats"], gn2.weight, gn2.bias, gn2.eps, out=dh,
+                                   dropout_p=rec["p_drop"], seed=rec["drop_seed"], layer_tag=rec["drop_tag"],
+                                   out_stats=dh_stats)
+        self.gn_grads(name + ".gn2", sums2)
+        # net1: conv (+ conditioning row) -> silu/gn
+        self.wgrad(name + ".net1", conv1, rec["a1"], 0, ci, dh, 0)
+        self.grads["row." + name + ".net1"] = dh_stats[..., 0].float()
+        d_a1 = self.buf(f"a.{ci}", ci, grid)
+        self.dgrad(name + ".net1", conv1, dh, 0, co, d_a1)
+        # skip path
+        if blk.skip_conv is None:
+            add, add_plane0 = dy, dy_plane0
+        else:
+            self.wgrad(name + ".skip", blk.skip_conv, rec["x"], rec["x_plane0"], ci, dy, dy_plane0)
+            self.grads["row." + name + ".skip"] = d_bias
+            add, add_plane0 = self.buf(f"s.{ci}", ci, grid), 0
+            self.dgrad(name + ".skip", blk.skip_conv, dy, dy_plane0, co, add)
+        _, sums1 = ops.gn_silu_bwd(rec["x"], d_a1, ci, groups, rec["x_stats"], gn1.weight, gn1.bias, gn1.eps,
+                                   x_plane0=rec["x_plane0"], add=add, add_plane0=add_plane0, out=dx, out_plane0=dx_plane0,
+                                   out_stats=dx_stats, out_stats_c0=dx_stats_c0)
+        self.gn_grads(name + ".gn1", sums1)
+
+    # ---- the whole trunk ---------------------------------------------------------------------------------------
+    def run(self, d_out: torch.Tensor, need_dx: bool) -> Optional[torch.Tensor]:
+        net, tr = self.net, self.tape["trunk"]
+        c, nl, grids, b = net.chs, len(net.chs), tr["grids"], self.b
+        # conv_out: fp32 (B,1,D,H,W) gradient -> channel 0 of a 16-channel planar tensor
+        g_out = self.ar.get(f"g.out.{b}", (b, 2) + tuple(grids[0]) + (8,), torch.bfloat16, self.dev)
+        ops.pack_input(d_out.contiguous().float(), None, 16, out=g_out)
+        conv_out, gn_out = net.conv_out[2], net.conv_out[0]
+        self.wgrad("conv_out", conv_out, tr["out_a"], 0, c[0], g_out, 0)
+        self.grads["row.conv_out"] = d_out.reshape(b, -1).sum(dim=1, keepdim=True).float()
+        d_a = self.buf(f"a.{c[0]}", c[0], grids[0])
+        self.dgrad("conv_out", conv_out, g_out, 0, 16, d_a)
+        dy = self.buf(f"y.{c[0]}", c[0], grids[0])
+        dy_stats = self.stats(c[0])
+        _, sums = ops.gn_silu_bwd(tr["out_x"], d_a, c[0], gn_out.num_groups, tr["out_x_stats"], gn_out.weight, gn_out.bias,
+                                  gn_out.eps, out=dy, out_stats=dy_stats)
+        self.gn_grads("conv_out.gn", sums)
+        # up path, finest level first (reverse execution order)
+        d_cats, d_cat_stats = {}, {}
+        for k, i in reversed(list(enumerate(reversed(range(nl - 1))))):
+            name = f"ups.{k}.resnet_blocks.0"
+            cc = c[i + 1] + c[i]
+            d_cat = self.buf(f"cat{i}", cc, grids[i])
+            dcs = self.stats(cc)
+            self.block(name, net.ups[k].resnet_blocks[0], dy, 0, dy_stats, 0, d_cat, 0, dcs, 0)
+            d_cats[i], d_cat_stats[i] = d_cat, dcs
+            # gradient of the up-sampled half goes down one level
+            dy = self.buf(f"y.{c[i + 1]}", c[i + 1], grids[i + 1])
+            dy_stats = self.stats(c[i + 1])
+            ops.upsample2_bwd(d_cat, c[i + 1], dy_plane0=0, out=dy, stats=dy_stats)
+        # bottom: mid2, mid1, last down block
+        for name, blk in (("mid2", net.mid2), ("mid1", net.mid1),
+                          (f"downs.{nl - 1}.resnet_blocks.0", net.downs[nl - 1].resnet_blocks[0])):
+            ci = blk.ch_in
+            dx = self.buf(f"x.{name}", ci, grids[nl - 1])
+            dxs = self.stats(ci)
+            self.block(name, blk, dy, 0, dy_stats, 0, dx, 0, dxs, 0)
+            dy, dy_stats = dx, dxs
+        # down path: d(block output) = skip half of d_cat + avg-pool backward of the coarser gradient
+        for i in reversed(range(nl - 1)):
+            name = f"downs.{i}.resnet_blocks.0"
+            blk = net.downs[i].resnet_blocks[0]
+            d_cat, p0 = d_cats[i], c[i + 1] // 8
+            tot = self.stats(c[i])
+            ops.avgpool2_bwd(dy, c[i], d_cat, dx_plane0=p0, accumulate=True, stats=tot)
+            ci = blk.ch_in
+            dx = self.buf(f"x.{name}", ci, grids[i])
+            dxs = self.stats(ci)
+            self.block(name, blk, d_cat, p0, tot, 0, dx, 0, dxs, 0)
+            dy, dy_stats = dx, dxs
+        # conv_in
+        self.wgrad("conv_in", net.conv_in, tr["packed"], 0, 16, dy, 0)
+        self.grads["row.conv_in"] = dy_stats[..., 0].float()
+        if not need_dx:
+            return None
+        wp = net._packed_dgrad("conv_in", net.conv_in, 0, 1)
+        dz = torch.empty((b, 1) + tuple(grids[0]), dtype=torch.float32, device=self.dev)
+        ops.conv3d(dy, wp, 1, out=dz, out_fp32=True)
+        return dz
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, s_conditioning, row_names, param_names, x, *tensors):
+        b = x.shape[0]
+        rows = dict(zip(row_names, tensors[:len(row_names)]))
+        rows = {k: v.detach().contiguous() for k, v in rows.items()}
+        cond = None if s_conditioning is None else s_conditioning.detach().contiguous().float()
+        ar = net._train_arena
+        packed = ops.pack_input(x.detach().contiguous().float(), cond, 16,
+                                out=ar.get(f"packed.{b}", (b, 2) + tuple(net.shape[1:]) + (8,), torch.bfloat16, x.device))
+        tape: dict = {}
+        net.refresh_packed()
+        out = net.run_packed(packed, rows, training_dropout=net.training and net.dropout_prob > 0.0, tape=tape)
+        ctx.net, ctx.tape, ctx.row_names, ctx.param_names = net, tape, row_names, param_names
+        ctx.need_dx = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        net = ctx.net
+        bw = _Backward(net, ctx.tape, ctx.row_names)
+        dz = bw.run(d_out, ctx.need_dx)
+        g = bw.grads
+        out = [None, None, None, None, dz]
+        out += [g["row." + n] for n in ctx.row_names]
+        out += [g[n] for n in ctx.param_names]
+        ctx.tape = None
+        return tuple(out)
+
+
+def unet_forward(net, x, t=None, s_conditioning=None, v_conditionings=None):
+    """``CUNet.forward`` with gradients: eps_hat / v_hat (B, 1, D, H, W) fp32, differentiable w.r.t. every
+    parameter of ``net`` and w.r.t. ``x``."""
+    b = x.shape[0]
+    rows = net.chan_add_rows(b, t, v_conditionings, x.device)       # torch autograd: biases + embedding MLPs
+    row_names = list(rows.keys())
+    params = net.trunk_parameters()
+    param_names = [n for n, _ in params]
+    net._train_calls = getattr(net, "_train_calls", 0) + 1
+    net.dropout_seed = (int(getattr(net, "dropout_base_seed", 0)) << 32) | (net._train_calls & 0xffffffff)
+    return _UNetFn.apply(net, s_conditioning, row_names, param_names, x, *[rows[n] for n in row_names],
+                         *[p for _, p in params])

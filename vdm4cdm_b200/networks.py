@@ -178,9 +178,14 @@ class CUNet(nn.Module):
         return out if len(out) else None
 
     # ---- packed weights (bf16, kernel layout), rebuilt when the fp32 parameter changes ------------
+    def invalidate_packed(self) -> None:
+        """Tell the bf16 weight caches that the fp32 parameters changed behind torch's back (the fused
+        optimizer kernel writes through raw pointers, which does not bump ``Tensor._version``)."""
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
+
     def _packed(self, name: str, conv: nn.Conv3d) -> torch.Tensor:
         w = conv.weight
-        key = (w.data_ptr(), w._version, w.device)
+        key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
         hit = self._packed_cache.get(name)
         if hit is None or hit[0] != key:
             with torch.no_grad():
@@ -191,6 +196,37 @@ class CUNet(nn.Module):
                 hit = (key, fresh)
             self._packed_cache[name] = hit
         return hit[1]
+
+    def _packed_dgrad(self, name: str, conv: nn.Conv3d, c0: int, n: int) -> torch.Tensor:
+        """bf16 dgrad filter (roles of Cin/Cout exchanged, taps mirrored) for input channels [c0, c0+n)."""
+        w = conv.weight
+        key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
+        slot = f"{name}.dgrad.{c0}.{n}"
+        hit = self._packed_cache.get(slot)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                fresh = ops.pack_conv_weight(w.detach()[:, c0:c0 + n], transpose_flip=True)
+                if hit is not None and hit[1].shape == fresh.shape and hit[1].device == fresh.device:
+                    hit[1].copy_(fresh)
+                    fresh = hit[1]
+                hit = (key, fresh)
+            self._packed_cache[slot] = hit
+        return hit[1]
+
+    def trunk_parameters(self):
+        """(name, parameter) of everything the convolutional trunk differentiates itself: conv filters and
+        GroupNorm affines, named as ``vdm4cdm_b200.autograd`` records their gradients.  (Conv biases and the
+        embedding MLPs get theirs through the conditioning rows under torch autograd.)"""
+        gn = self.conv_out[0]
+        out = [("conv_in.weight", self.conv_in.weight), ("conv_out.weight", self.conv_out[2].weight),
+               ("conv_out.gn.weight", gn.weight), ("conv_out.gn.bias", gn.bias)]
+        for name, blk in self._blocks():
+            out += [(name + ".net1.weight", blk.net1[2].weight), (name + ".net2.weight", blk.net2[3].weight),
+                    (name + ".gn1.weight", blk.net1[0].weight), (name + ".gn1.bias", blk.net1[0].bias),
+                    (name + ".gn2.weight", blk.net2[0].weight), (name + ".gn2.bias", blk.net2[0].bias)]
+            if blk.skip_conv is not None:
+                out.append((name + ".skip.weight", blk.skip_conv.weight))
+        return out
 
     def _convs(self):
         out = [("conv_in", self.conv_in), ("conv_out", self.conv_out[2])]
@@ -369,9 +405,10 @@ class CUNet(nn.Module):
         return out
 
     def forward(self, x, t=None, s_conditioning=None, v_conditionings=None):
-        """eps_hat / v_hat (B, 1, D, H, W) fp32.  Inference path (no autograd graph is recorded here;
-        training goes through ``vdm4cdm_b200.autograd.unet_forward``)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+        """eps_hat / v_hat (B, 1, D, H, W) fp32.  Under ``torch.no_grad()`` this is the inference path; with
+        gradients enabled it goes through ``vdm4cdm_b200.autograd.unet_forward`` (dropout active iff
+        ``self.training``)."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             from .autograd import unet_forward
             return unet_forward(self, x, t, s_conditioning, v_conditionings)
         with torch.no_grad():

@@ -1,0 +1,150 @@
+"""Data-parallel training loop for ``LightVDM`` / ``LightSFM``: what ``lightning.Trainer(devices=...,
+gradient_clip_val=0.5, max_epochs=...).fit(model, datamodule)`` does for the reference
+(trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:134-160, trainSFM3D160_...:129-150), without Lightning.
+
+One process per GPU (``torch.distributed``, NCCL on GPUs / gloo on CPU for the host-logic tests):
+
+  * every parameter is a view into ONE flat fp32 bucket, every ``.grad`` a view into a second one, so
+    the gradient exchange is a single ``all_reduce(SUM)`` over NVLink and the optimizer is a single
+    kernel (``vdm_adamw_step``: grad averaging, global-norm clipping, AdamW) over the bucket;
+  * GroupNorm is per sample, so there is nothing else to synchronise;
+  * replicas start from rank 0's weights (broadcast) and stay bit-identical because every rank applies
+    the same update to the same bucket.
+
+On a CPU device (gloo tests) the update falls back to nothing: the optimizer kernel is CUDA-only and
+``Trainer`` raises, exactly like every other compute entry point of this package; the bucket/all-reduce
+logic is exercised through ``FlatBuckets`` + ``allreduce_gradients`` which are device agnostic.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class FlatBuckets:
+    """Re-homes the parameters of ``module`` into one flat fp32 buffer (and their grads into another)."""
+
+    def __init__(self, module: torch.nn.Module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        assert all(p.dtype == torch.float32 for p in params), "fp32 master parameters expected"
+        self.params = params
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]            # 16-byte aligned slots
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        n = self.offsets[-1]
+        dev = params[0].device
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                view = self.flat_param[o:o + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+
+    @property
+    def numel(self) -> int:
+        return self.flat_param.numel()
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+        for p, o in zip(self.params, self.offsets):         # re-attach views a caller may have dropped
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+
+
+def allreduce_gradients(buckets: FlatBuckets) -> None:
+    """Sum the flat gradient bucket over all ranks (no-op without an initialised process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buckets.flat_grad, op=dist.ReduceOp.SUM)
+
+
+def broadcast_parameters(buckets: FlatBuckets, src: int = 0) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(buckets.flat_param, src=src)
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> range:
+    """Item ids of this rank: i -> rank i mod world (the sampling shard rule of SURVEY.md section 8e)."""
+    return range(rank, n_items, world)
+
+
+class Trainer:
+    """``Trainer(model, ...).training_step(batch)`` = forward + backward + all-reduce + clip + AdamW.
+
+    ``model`` is a ``LightVDM`` / ``LightSFM`` (anything with ``training_step(batch) -> loss`` and
+    ``learning_rate``)."""
+
+    def __init__(self, model: torch.nn.Module, gradient_clip_val: float = 0.5, weight_decay: float = 0.01,
+                 betas=(0.9, 0.999), eps: float = 1e-8, learning_rate: Optional[float] = None):
+        self.model = model
+        self.lr = float(model.learning_rate if learning_rate is None else learning_rate)
+        self.clip, self.wd, self.betas, self.eps = float(gradient_clip_val), float(weight_decay), betas, float(eps)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.buckets = FlatBuckets(model)
+        broadcast_parameters(self.buckets)
+        self._nets_changed()
+        dev = self.buckets.flat_param.device
+        if dev.type != "cuda":
+            raise RuntimeError("vdm4cdm_b200.Trainer needs a CUDA device (there is no CPU optimizer path)")
+        self.exp_avg = torch.zeros_like(self.buckets.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.buckets.flat_param)
+        self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.step_count = 0
+
+    def _nets_changed(self):
+        for m in self.model.modules():
+            if hasattr(m, "invalidate_packed"):
+                m.invalidate_packed()
+
+    def training_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """One optimizer step on this rank's micro-batch; returns the (local) loss tensor, not synchronised."""
+        self.model.train()
+        self.buckets.zero_grad()
+        loss = self.model.training_step(batch)
+        loss.backward()
+        self.optimizer_step()
+        return loss.detach()
+
+    def optimizer_step(self) -> None:
+        allreduce_gradients(self.buckets)
+        self.step_count += 1
+        self.grad_sumsq.zero_()
+        ops.sumsq(self.buckets.flat_grad, self.grad_sumsq)
+        ops.adamw_step(self.buckets.flat_param, self.buckets.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr,
+                       step=self.step_count, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                       weight_decay=self.wd, grad_sumsq=self.grad_sumsq, max_norm=self.clip,
+                       grad_scale=1.0 / self.world)
+        self._nets_changed()
+
+    def grad_norm(self) -> float:
+        """Global gradient norm of the last step (after averaging over ranks, before clipping)."""
+        return math.sqrt(self.grad_sumsq.item()) / self.world
+
+    def fit(self, batches: Iterable[Dict[str, torch.Tensor]], max_steps: Optional[int] = None,
+            log: Optional[Callable[[int, float], None]] = None) -> None:
+        for i, batch in enumerate(batches):
+            if max_steps is not None and i >= max_steps:
+                break
+            loss = self.training_step(batch)
+            if log is not None:
+                log(i, loss.item())
+
+    def state_dict(self) -> dict:
+        return {"state_dict": self.model.state_dict(), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "step": self.step_count}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.model.load_state_dict(state["state_dict"])         # copies into the flat views in place
+        if "exp_avg" in state:
+            self.exp_avg.copy_(state["exp_avg"])
+            self.exp_avg_sq.copy_(state["exp_avg_sq"])
+            self.step_count = int(state["step"])
+        self._nets_changed()
