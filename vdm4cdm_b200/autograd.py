@@ -65,9 +65,11 @@ class _Backward:
         """out[window] = conv^T(g): one launch per <=256 input channels of the conv."""
         ci = conv.in_channels
         taps = ops.TAPS_3X3X3 if conv.kernel_size[0] == 3 else ops.TAPS_1X1X1
+        ops.set_profile_tag("dgrad ")
         for c0, n in _chunks(ci):
             wp = self.net._packed_dgrad(name, conv, c0, n)
             ops.conv3d(g, wp, n, taps=taps, x_plane0=g_plane0, c_in=g_ch, out=out, out_plane0=out_plane0 + c0 // 8)
+        ops.set_profile_tag("")
 
     def wgrad(self, name: str, conv, a, a_plane0, a_ch, g, g_plane0):
         k = conv.kernel_size[0]
@@ -172,7 +174,9 @@ class _Backward:
             return None
         wp = net._packed_dgrad("conv_in", net.conv_in, 0, 1)
         dz = torch.empty((b, 1) + tuple(grids[0]), dtype=torch.float32, device=self.dev)
+        ops.set_profile_tag("dgrad ")
         ops.conv3d(dy, wp, 1, out=dz, out_fp32=True)
+        ops.set_profile_tag("")
         return dz
 
 

@@ -36,35 +36,31 @@ struct GnBwdArgs {
   int has_add;
 };
 
-// du for the 8 channels of one chunk; also returns xhat.
-__device__ __forceinline__ void chunk_du(const bf16x8& xv, const bf16x8& dyv, const float (&sc)[8], const float (&sh)[8],
-                                         const float (&mean)[8], const float (&rstd)[8], uint32_t keep, float keep_scale,
-                                         float (&du)[8], float (&xhat)[8]) {
-  float x[8], dy[8];
+// du = dy * keep/(1-p) * silu'(x*sc + sh) for the 8 channels of one chunk; x is returned unpacked.
+__device__ __forceinline__ void chunk_du(const bf16x8& xv, const bf16x8& dyv, const float* __restrict__ sc,
+                                         const float* __restrict__ sh, uint32_t keep, float keep_scale,
+                                         float (&du)[8], float (&x)[8]) {
+  float dy[8];
   unpack8(xv, x);
   unpack8(dyv, dy);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float u = x[j] * sc[j] + sh[j];
-    xhat[j] = (x[j] - mean[j]) * rstd[j];
     const float m = ((keep >> j) & 1u) ? keep_scale : 0.f;
-    du[j] = dy[j] * m * silu_grad(u);
+    du[j] = dy[j] * m * silu_grad(x[j] * sc[j] + sh[j]);
   }
 }
 
+// Pass 1.  Per thread: sum du and sum du*x (raw); per block: xhat = (x - mean)*rstd is linear in x, so the
+// block partial of sum du*xhat is rstd*(sum du*x - mean*sum du), formed once per block before the atomics.
 __global__ void __launch_bounds__(kEwThreads)
 gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
   __shared__ float s_scale[8], s_shift[8], s_mean[8], s_rstd[8];
+  __shared__ float s_part[kEwThreads / 32][16];
   const int b = blockIdx.y / a.planes, pl = blockIdx.y % a.planes;
   const int C = a.planes * 8;
   plane_scale_shift(a.stats + (int64_t)b * C * 2, C, a.groups, pl, (double)a.voxels, a.gamma, a.beta, a.eps, s_scale,
                     s_shift, s_mean, s_rstd);
   __syncthreads();
-  float sc[8], sh[8], mean[8], rstd[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = s_scale[j]; sh[j] = s_shift[j]; mean[j] = s_mean[j]; rstd[j] = s_rstd[j];
-  }
   const bf16x8* xp = plane_ptr(a.x, b, pl, a.voxels);
   const bf16x8* gp = plane_ptr(a.dy, b, pl, a.voxels);
   const bool drop = a.dropout_p > 0.f;
@@ -72,22 +68,59 @@ gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
   const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += (int64_t)gridDim.x * kEwThreads) {
-    const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)i, a.layer_tag, a.seed, thresh16) : 0xffu;
-    float du[8], xhat[8];
-    chunk_du(xp[i], gp[i], sc, sh, mean, rstd, keep, keep_scale, du, xhat);
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += 2 * stride) {
+    const int64_t i2 = i + stride;
+    const bool two = i2 < a.voxels;
+    const bf16x8 x0 = xp[i], g0 = gp[i];          // four independent 16-byte loads in flight
+    bf16x8 x1 = x0, g1 = g0;
+    if (two) { x1 = xp[i2]; g1 = gp[i2]; }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1[j] += du[j];
-      s2[j] += du[j] * xhat[j];
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !two) break;
+      const int64_t ii = k == 0 ? i : i2;
+      const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, a.seed, thresh16) : 0xffu;
+      float du[8], x[8];
+      chunk_du(k == 0 ? x0 : x1, k == 0 ? g0 : g1, s_scale, s_shift, keep, keep_scale, du, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += du[j];
+        s2[j] += du[j] * x[j];
+      }
     }
   }
-  block_flush_stats(s1, s2, a.sums + ((int64_t)b * C + pl * 8) * 2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[j] = warp_sum(s1[j]);
+    s2[j] = warp_sum(s2[j]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_part[warp][j] = s1[j];
+      s_part[warp][8 + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kEwThreads / 32; ++w) {
+      t1 += s_part[w][threadIdx.x];
+      t2 += s_part[w][8 + threadIdx.x];
+    }
+    double* dst = a.sums + ((int64_t)b * C + pl * 8 + threadIdx.x) * 2;
+    atomicAdd(dst, (double)t1);
+    atomicAdd(dst + 1, (double)(s_rstd[threadIdx.x] * (t2 - s_mean[threadIdx.x] * t1)));
+  }
 }
 
+// Pass 2.  dx = rstd*(gamma*du - m1 - xhat*m2) [+ add]  ==  A*du + Bc + Cc*x with per-channel
+// A = rstd*gamma, Cc = -rstd^2*m2, Bc = -rstd*m1 - Cc*mean.
 __global__ void __launch_bounds__(kEwThreads)
 gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
-  __shared__ float s_scale[8], s_shift[8], s_mean[8], s_rstd[8], s_m1[8], s_m2[8], s_gamma[8];
+  __shared__ float s_scale[8], s_shift[8], s_mean[8], s_rstd[8], s_A[8], s_B[8], s_C[8];
   const int b = blockIdx.y / a.planes, pl = blockIdx.y % a.planes;
   const int C = a.planes * 8;
   plane_scale_shift(a.stats + (int64_t)b * C * 2, C, a.groups, pl, (double)a.voxels, a.gamma, a.beta, a.eps, s_scale,
@@ -104,16 +137,19 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
       m2 += gk * sb[2 * (g0 + k) + 1];
     }
     const double n = (double)a.voxels * cpg;
-    s_m1[threadIdx.x] = (float)(m1 / n);
-    s_m2[threadIdx.x] = (float)(m2 / n);
-    s_gamma[threadIdx.x] = a.gamma[c];
+    m1 /= n;
+    m2 /= n;
+    const double rstd = (double)s_rstd[threadIdx.x], mean = (double)s_mean[threadIdx.x];   // written by this thread
+    const double Cc = -rstd * rstd * m2;
+    s_A[threadIdx.x] = (float)(rstd * (double)a.gamma[c]);
+    s_C[threadIdx.x] = (float)Cc;
+    s_B[threadIdx.x] = (float)(-rstd * m1 - Cc * mean);
   }
   __syncthreads();
-  float sc[8], sh[8], mean[8], rstd[8], m1[8], m2[8], gam[8];
+  float cA[8], cB[8], cC[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc[j] = s_scale[j]; sh[j] = s_shift[j]; mean[j] = s_mean[j]; rstd[j] = s_rstd[j];
-    m1[j] = s_m1[j]; m2[j] = s_m2[j]; gam[j] = s_gamma[j];
+    cA[j] = s_A[j]; cB[j] = s_B[j]; cC[j] = s_C[j];
   }
   const bf16x8* xp = plane_ptr(a.x, b, pl, a.voxels);
   const bf16x8* gp = plane_ptr(a.dy, b, pl, a.voxels);
@@ -124,27 +160,42 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
   const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
   float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += (int64_t)gridDim.x * kEwThreads) {
-    const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)i, a.layer_tag, a.seed, thresh16) : 0xffu;
-    float du[8], xhat[8], o[8];
-    chunk_du(xp[i], gp[i], sc, sh, mean, rstd, keep, keep_scale, du, xhat);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = rstd[j] * (gam[j] * du[j] - m1[j] - xhat[j] * m2[j]);
-    if (ap) {
-      float r[8];
-      unpack8(ap[i], r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += r[j];
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += 2 * stride) {
+    const int64_t i2 = i + stride;
+    const bool two = i2 < a.voxels;
+    const bf16x8 x0 = xp[i], g0 = gp[i];
+    bf16x8 x1 = x0, g1 = g0, r0 = x0, r1 = x0;
+    if (ap) r0 = ap[i];
+    if (two) {
+      x1 = xp[i2]; g1 = gp[i2];
+      if (ap) r1 = ap[i2];
     }
-    const bf16x8 packed = pack8(o);
-    op[i] = packed;
-    if (a.out_stats) {
-      float r[8];
-      unpack8(packed, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sum[j] += r[j];
-        sq[j] += r[j] * r[j];
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !two) break;
+      const int64_t ii = k == 0 ? i : i2;
+      const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, a.seed, thresh16) : 0xffu;
+      float du[8], x[8], o[8];
+      chunk_du(k == 0 ? x0 : x1, k == 0 ? g0 : g1, s_scale, s_shift, keep, keep_scale, du, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = cA[j] * du[j] + cB[j] + cC[j] * x[j];
+      if (ap) {
+        float r[8];
+        unpack8(k == 0 ? r0 : r1, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      const bf16x8 packed = pack8(o);
+      op[ii] = packed;
+      if (a.out_stats) {
+        float r[8];
+        unpack8(packed, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sum[j] += r[j];
+          sq[j] += r[j] * r[j];
+        }
       }
     }
   }
@@ -153,48 +204,40 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
 }
 
 // ---- avg-pool backward: fine dx = [dx +] dy(coarse)/8 -----------------------------------------------
-// One thread per coarse voxel writes its 2x2x2 fine chunks.
+// One thread per FINE voxel (coalesced read-modify-write; the coarse gradient is re-read through L1/L2).
 __global__ void __launch_bounds__(kEwThreads)
 avgpool2_bwd_kernel(VdmTensor dy, VdmTensor dx, int planes, int D, int H, int W, int accumulate,
                     double* __restrict__ stats, int stats_channels, int stats_c0) {
   const int b = blockIdx.y / planes, pl = blockIdx.y % planes;
-  const int Dc = D >> 1, Hc = H >> 1, Wc = W >> 1;
-  const int64_t vc = (int64_t)Dc * Hc * Wc, vf = (int64_t)D * H * W;
+  const int Hc = H >> 1, Wc = W >> 1;
+  const int64_t vc = (int64_t)(D >> 1) * Hc * Wc, vf = (int64_t)D * H * W;
   const bf16x8* gp = plane_ptr(dy, b, pl, vc);
   bf16x8* op = plane_ptr_mut(dx, b, pl, vf);
   float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vc; i += (int64_t)gridDim.x * kEwThreads) {
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vf; i += (int64_t)gridDim.x * kEwThreads) {
     int64_t v = i;
-    const int wc = (int)(v % Wc); v /= Wc;
-    const int hc = (int)(v % Hc);
-    const int dc = (int)(v / Hc);
-    float g[8];
-    unpack8(gp[i], g);
+    const int w = (int)(v % W); v /= W;
+    const int h = (int)(v % H);
+    const int d = (int)(v / H);
+    float g[8], o[8];
+    unpack8(gp[((int64_t)(d >> 1) * Hc + (h >> 1)) * Wc + (w >> 1)], g);
+    if (accumulate) {
+      unpack8(op[i], o);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] *= 0.125f;
+      for (int j = 0; j < 8; ++j) o[j] += 0.125f * g[j];
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int d = 2 * dc + (k >> 2), h = 2 * hc + ((k >> 1) & 1), w = 2 * wc + (k & 1);
-      const int64_t idx = ((int64_t)d * H + h) * W + w;
-      float o[8];
-      if (accumulate) {
-        unpack8(op[idx], o);
+      for (int j = 0; j < 8; ++j) o[j] = 0.125f * g[j];
+    }
+    const bf16x8 packed = pack8(o);
+    op[i] = packed;
+    if (stats) {
+      float r[8];
+      unpack8(packed, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += g[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = g[j];
-      }
-      const bf16x8 packed = pack8(o);
-      op[idx] = packed;
-      if (stats) {
-        float r[8];
-        unpack8(packed, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sum[j] += r[j];
-          sq[j] += r[j] * r[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        sum[j] += r[j];
+        sq[j] += r[j] * r[j];
       }
     }
   }
@@ -351,8 +394,8 @@ extern "C" int vdm_avgpool2_bwd(const VdmTensor* dy, const VdmTensor* dx, int ba
                 "vdm_avgpool2_bwd: fine grid (%d,%d,%d) must be even", depth, height, width);
   if (stats_channels <= 0) stats_channels = channels;
   const int planes = channels / 8;
-  const int64_t vc = (int64_t)(depth / 2) * (height / 2) * (width / 2);
-  avgpool2_bwd_kernel<<<ew_grid(vc, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
+  const int64_t vf = (int64_t)depth * height * width;
+  avgpool2_bwd_kernel<<<ew_grid(vf, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
       *dy, *dx, planes, depth, height, width, accumulate, stats, stats_channels, stats_c0);
   VDM_CHECK_LAUNCH();
   return VDM_OK;

@@ -80,23 +80,36 @@ __device__ __forceinline__ float4 philox_normal4(uint32_t group, uint32_t draw, 
 // ---------------------------------------------------------------------------------------
 // bf16 <-> fp32 vector helpers (8 bf16 = one 16-byte access)
 // ---------------------------------------------------------------------------------------
+// One uint4 member so that every copy / load / store of a chunk is a single 128-bit access.  (r01h: with
+// four __nv_bfloat162 members nvcc emitted four 32-bit STG/LDG per chunk -- 4x the L2 sector requests in the
+// conv epilogue and in every elementwise kernel.)
 struct alignas(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint4 u;
 };
 
+__device__ __forceinline__ float2 bf16pair_to_float2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+  const uint32_t w[4] = {p.u.x, p.u.y, p.u.z, p.u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(p.v[i]);
+    const float2 t = bf16pair_to_float2(w[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
 
+__device__ __forceinline__ uint32_t float2_to_bf16pair(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  p.u = make_uint4(float2_to_bf16pair(f[0], f[1]), float2_to_bf16pair(f[2], f[3]), float2_to_bf16pair(f[4], f[5]),
+                   float2_to_bf16pair(f[6], f[7]));
   return p;
 }
 

@@ -42,6 +42,15 @@ def set_conv_profiler(records) -> None:
     _CONV_PROFILE = records
 
 
+_PROFILE_TAG = ""
+
+
+def set_profile_tag(tag: str) -> None:
+    """Prefix for the labels the conv profiler records (``"dgrad "`` while the backward pass issues dgrads)."""
+    global _PROFILE_TAG
+    _PROFILE_TAG = tag
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -174,7 +183,8 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
     if prof is not None:
         e1.record()
         # algorithmic FLOPs: real (un-padded) output channels, the channels the caller says it reads
-        prof.append((e0, e1, 2.0 * n_taps * c_in * c_out * b * d * h * w_, f"{c_in}->{c_out} taps={n_taps} grid={d}x{h}x{w_} B={b}"))
+        prof.append((e0, e1, 2.0 * n_taps * c_in * c_out * b * d * h * w_,
+                     f"{_PROFILE_TAG}{c_in}->{c_out} taps={n_taps} grid={d}x{h}x{w_} B={b}"))
     return out
 
 
