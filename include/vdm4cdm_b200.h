@@ -104,9 +104,23 @@ typedef struct VdmWgradDesc {
   int32_t kernel;               /* 3 (3x3x3, zero padding 1) or 1 */
   int32_t a_planes, a_plane0;   /* planes per sample of the a buffer (0: c_in/8), first plane read */
   int32_t g_planes, g_plane0;   /* same for g */
+  /* dw addressing (elements): dw[tap*stride_tap + ci*stride_ci + co*stride_co], rows ci >= c_in_real skipped.
+   * All three strides 0 selects the packed default [tap][c_in][c_out] (c_in_real = c_in).  torch's Conv3d
+   * layout (c_out, c_in_real, k, k, k) is stride_tap = 1, stride_ci = k^3, stride_co = c_in_real*k^3, which lets
+   * the kernel accumulate straight into the parameter's .grad inside a flat gradient bucket. */
+  int64_t dw_stride_tap, dw_stride_ci, dw_stride_co;
+  int32_t c_in_real;
 } VdmWgradDesc;
 
 VDM_API int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const void* g, float* dw, void* stream);
+
+/* fp32 torch Conv3d weight (c_out, c_in, k, k, k) -> bf16 kernel layout [k^3][c_in_pad/8][c_out_pad][8], zero padded
+ * (what vdm_conv3d reads).  transpose_flip != 0 packs the dgrad filter instead: the roles of c_in / c_out are
+ * exchanged and the taps mirrored; [ci0, ci0 + n_ci) then selects the slice of the conv's INPUT channels that
+ * becomes the dgrad's output channels (dgrads of convs with more than 256 input channels run as several launches).
+ * c_in_pad / c_out_pad are the padded sizes of the PACKED tensor's K and N dimensions (multiples of 16). */
+VDM_API int vdm_pack_conv_weight(const float* w, void* packed, int c_out, int c_in, int kernel, int transpose_flip,
+                         int ci0, int n_ci, int c_in_pad, int c_out_pad, void* stream);
 
 /* ---- fused elementwise passes (ATen group_norm / silu / dropout / avg_pool3d / interpolate /
  *      cat in the reference's ResNetBlock / ResNetDown; blocks.py:129-170) ------------------- */
@@ -128,6 +142,10 @@ VDM_API int vdm_channel_stats(const VdmTensor* x, int batch, int64_t voxels, int
 VDM_API int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
                 const double* stats, const float* gamma, const float* beta, float eps,
                 float dropout_p, uint64_t seed, uint32_t layer_tag, void* stream);
+/* Same with the dropout seed advanced on the device: seed_eff = seed + *seed_step (CUDA-graph replay). */
+VDM_API int vdm_gn_silu_step(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
+                     const double* stats, const float* gamma, const float* beta, float eps, float dropout_p,
+                     uint64_t seed, const int32_t* seed_step, uint32_t layer_tag, void* stream);
 
 /* 2x2x2 average pooling of a (depth,height,width) grid; accumulates channel stats of y when stats != NULL. */
 VDM_API int vdm_avgpool2(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
@@ -148,15 +166,19 @@ VDM_API int vdm_upsample2(const VdmTensor* coarse, const VdmTensor* y, int batch
  *   apply : dx = rstd_g*(gamma_c*du - mean_g(gamma*du) - xhat*mean_g(gamma*du*xhat)) [+ add]
  * `stats` are the forward statistics of x (double [B][channels][2]); the dropout mask is regenerated
  * from (seed, layer_tag).  apply also accumulates (sum, sumsq) of dx into out_stats when not NULL
- * (the per-sample channel sums are the gradients of the conv bias / conditioning rows). */
+ * (the per-sample channel sums are the gradients of the conv bias / conditioning rows).
+ * `sums` is a window of a double [B][sums_channels][2] table starting at channel sums_c0 (sums_channels = 0:
+ * a tight [B][channels][2]).  seed_step (device int32, may be NULL) is added to the dropout seed on the device,
+ * so a captured CUDA graph draws a new mask every replay. */
 VDM_API int vdm_gn_silu_bwd_reduce(const VdmTensor* x, const VdmTensor* dy, int batch, int64_t voxels, int channels,
                            int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                           float dropout_p, uint64_t seed, uint32_t layer_tag, double* sums, void* stream);
+                           float dropout_p, uint64_t seed, const int32_t* seed_step, uint32_t layer_tag, double* sums,
+                           int sums_channels, int sums_c0, void* stream);
 VDM_API int vdm_gn_silu_bwd_apply(const VdmTensor* x, const VdmTensor* dy, const VdmTensor* add, const VdmTensor* dx,
                           int batch, int64_t voxels, int channels, int groups, const double* stats,
                           const float* gamma, const float* beta, float eps, float dropout_p, uint64_t seed,
-                          uint32_t layer_tag, const double* sums, double* out_stats, int out_stats_channels,
-                          int out_stats_c0, void* stream);
+                          const int32_t* seed_step, uint32_t layer_tag, const double* sums, int sums_channels,
+                          int sums_c0, double* out_stats, int out_stats_channels, int out_stats_c0, void* stream);
 
 /* Gradient of vdm_avgpool2: dx = (accumulate ? dx : 0) + nearest_upsample_x2(dy) / 8 on the fine grid
  * (depth,height,width); stats (optional) accumulate (sum, sumsq) of the resulting dx. */
@@ -177,6 +199,10 @@ VDM_API int vdm_sumsq(const float* x, int64_t n, double* out, void* stream);
 VDM_API int vdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq,
                    float max_norm, float grad_scale, void* stream);
+/* Same with the step number read from the device: step_eff = step + *step_ptr (CUDA-graph replay). */
+VDM_API int vdm_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, const int32_t* step_ptr,
+                       const double* grad_sumsq, float max_norm, float grad_scale, void* stream);
 
 /* Pack the network input: plane 0 of out = (z, cond_1..cond_n, 0...) per voxel, planes 1.. = 0.
  * z: fp32 [B][V]; cond: fp32 [B][n_cond][V] (NCDHW) or NULL; out: c_pad/8 planes; n_cond <= 7. */

@@ -74,6 +74,39 @@ def test_wgrad_plane_windows_and_accumulation():
     assert torch.equal(ops.wgrad_to_torch(dw, 3), 2 * ref)
 
 
+def test_wgrad_accumulates_into_a_torch_layout_gradient():
+    """The Trainer's path: the kernel adds straight into weight.grad (c_out, c_in_real, k, k, k) inside a flat bucket."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(9)
+    b, ci_real, ci, co, d, h, w = 2, 2, 16, 32, 4, 16, 16             # conv_in: 2 real channels in a 16-channel tensor
+    a = _int_tensor((b, ci_real, d, h, w), -2, 2, gen, dev)
+    g = _int_tensor((b, co, d, h, w), -2, 2, gen, dev)
+    wt = torch.zeros((co, ci_real, 3, 3, 3), device=dev, dtype=torch.float64, requires_grad=True)
+    F.conv3d(a.double(), wt, padding=1).backward(g.double())
+    flat = torch.full((co * ci_real * 27 + 8,), 1.0, device=dev)
+    grad = flat[4:4 + co * ci_real * 27].view(co, ci_real, 3, 3, 3)
+    ops.conv3d_wgrad(ops.to_planar(a, 16), ops.to_planar(g, 16), ci, co, 3, grad_out=grad)
+    torch.cuda.synchronize()
+    assert torch.equal(grad, wt.grad.round().float() + 1.0)
+    assert (flat[:4] == 1).all() and (flat[-4:] == 1).all()
+
+
+@pytest.mark.parametrize("co,ci,k", [(32, 2, 3), (1, 32, 3), (64, 32, 3), (128, 384, 1), (32, 96, 3)])
+def test_pack_conv_weight_kernel_matches_host_packing(co, ci, k):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    w = torch.randn((co, ci, k, k, k), generator=torch.Generator().manual_seed(co + ci)).to(dev)
+    out = torch.empty(ops.packed_weight_shape(w.shape), dtype=torch.bfloat16, device=dev)
+    ops.pack_conv_weight_into(w, out)
+    assert torch.equal(out, ops.pack_conv_weight(w))
+    for c0, n in ((0, ci),) if ci <= 256 else ((0, ci // 2), (ci // 2, ci // 2)):
+        outd = torch.empty(ops.packed_weight_shape(w.shape, True, n), dtype=torch.bfloat16, device=dev)
+        ops.pack_conv_weight_into(w, outd, True, c0, n)
+        assert torch.equal(outd, ops.pack_conv_weight(w[:, c0:c0 + n], transpose_flip=True))
+    torch.cuda.synchronize()
+
+
 def test_dgrad_wide_input_in_two_launches():
     """dgrad of a 384 -> 128 conv: 384 output channels exceed one launch (N <= 256) -> two plane windows."""
     ops = _ops()

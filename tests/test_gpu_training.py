@@ -144,7 +144,7 @@ def test_dropout_backward_uses_the_forward_mask():
     d_out = torch.randn((1, 1, 16, 16, 16), generator=g).cuda()
 
     def run(frozen_calls):
-        net._train_calls = frozen_calls          # same (seed, layer tag) -> same masks
+        net.drop_counter.fill_(frozen_calls - 1)   # the forward increments it: same (seed + counter, layer tag) -> same masks
         return net(x, t=t, s_conditioning=cond, v_conditionings=v)
 
     out = run(7)

@@ -42,6 +42,7 @@ class WgradDesc(Structure):
         ("batch", c_int32), ("depth", c_int32), ("height", c_int32), ("width", c_int32),
         ("c_in", c_int32), ("c_out", c_int32), ("kernel", c_int32),
         ("a_planes", c_int32), ("a_plane0", c_int32), ("g_planes", c_int32), ("g_plane0", c_int32),
+        ("dw_stride_tap", c_int64), ("dw_stride_ci", c_int64), ("dw_stride_co", c_int64), ("c_in_real", c_int32),
     ]
 
 
@@ -59,10 +60,16 @@ _SIGNATURES = {
     "vdm_conv3d": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(ConvEpilogue), c_void_p]),
     "vdm_debug_set": (c_int, [c_int, c_int]),
     "vdm_conv3d_wgrad": (c_int, [POINTER(WgradDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vdm_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vdm_gn_silu_step": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_float, c_float, c_uint64, c_void_p, c_uint32, c_void_p]),
     "vdm_gn_silu_bwd_reduce": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,
-                                       c_float, c_uint64, c_uint32, c_void_p, c_void_p]),
+                                       c_float, c_uint64, c_void_p, c_uint32, c_void_p, c_int, c_int, c_void_p]),
     "vdm_gn_silu_bwd_apply": (c_int, [_T, _T, _T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                      c_float, c_float, c_uint64, c_uint32, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                      c_float, c_float, c_uint64, c_void_p, c_uint32, c_void_p, c_int, c_int, c_void_p,
+                                      c_int, c_int, c_void_p]),
+    "vdm_adamw_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                                   c_float, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "vdm_avgpool2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_upsample2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

@@ -43,20 +43,25 @@ class _Backward:
         self.ar = net._train_arena
         self.b = tape["trunk"]["packed"].shape[0]
         self.dev = tape["trunk"]["packed"].device
-        self.grads: Dict[str, torch.Tensor] = {}      # parameter / row name -> gradient
-        self._stats_off = 0
-        n_stats = self.b * 2 * (24 * sum(net.chs) + 256)
-        self._stats_arena = self.ar.get(f"gstats.{self.b}", (n_stats,), torch.float64, self.dev)
-        self._stats_arena.zero_()
+        self.grads: Dict[str, Optional[torch.Tensor]] = {}      # parameter / row name -> gradient (None: already in .grad)
+        self.params = dict(net.trunk_parameters())
+        # ONE double [B][total][2] table holds every per-channel reduction of the pass (gradient channel sums =
+        # bias / conditioning-row gradients, GroupNorm (sum du, sum du*xhat)); converted with two torch ops at the end.
+        self.tab_channels = 40 * sum(net.chs) + 512
+        self.tab = self.ar.get(f"gtab.{self.b}", (self.b, self.tab_channels, 2), torch.float64, self.dev)
+        self.tab.zero_()
+        self._c_off = 0
+        self._rows: List[tuple] = []       # (grad name, c0, channels)
+        self._gns: List[tuple] = []        # (gn name, c0, channels)
 
     # ---- helpers ------------------------------------------------------------------------------------------
-    def stats(self, c: int) -> torch.Tensor:
-        n = self.b * c * 2
-        off = self._stats_off
-        self._stats_off += n
-        if self._stats_off > self._stats_arena.numel():
-            raise RuntimeError("gradient statistics arena too small")
-        return self._stats_arena[off:off + n].view(self.b, c, 2)
+    def chan(self, c: int) -> int:
+        """Reserve c channels of the reduction table; returns the first channel."""
+        c0 = self._c_off
+        self._c_off += c
+        if self._c_off > self.tab_channels:
+            raise RuntimeError("gradient reduction table too small")
+        return c0
 
     def buf(self, name: str, ch: int, grid) -> torch.Tensor:
         return self.ar.get(f"g.{name}.{self.b}x{grid[0]}", (self.b, ch // 8) + tuple(grid) + (8,), torch.bfloat16, self.dev)
@@ -72,36 +77,57 @@ class _Backward:
         ops.set_profile_tag("")
 
     def wgrad(self, name: str, conv, a, a_plane0, a_ch, g, g_plane0):
+        """Filter gradient, accumulated by the kernel straight into ``weight.grad`` when it exists (the Trainer's
+        flat gradient bucket), else into a fresh tensor handed back to autograd."""
         k = conv.kernel_size[0]
-        dw = ops.conv3d_wgrad(a, g, a_ch, conv.out_channels, k, a_plane0=a_plane0, g_plane0=g_plane0)
-        self.grads[name + ".weight"] = ops.wgrad_to_torch(dw, k)[:, :conv.in_channels]
+        w = self.params[name + ".weight"]
+        if w.grad is not None and w.grad.is_contiguous() and w.grad.dtype == torch.float32:
+            target, ret = w.grad, None
+        else:
+            target = ret = torch.zeros_like(w, memory_format=torch.contiguous_format)
+        ops.conv3d_wgrad(a, g, a_ch, conv.out_channels, k, a_plane0=a_plane0, g_plane0=g_plane0, grad_out=target)
+        self.grads[name + ".weight"] = ret
 
-    def gn_grads(self, name: str, sums: torch.Tensor):
-        self.grads[name + ".weight"] = sums[..., 1].sum(0).float()
-        self.grads[name + ".bias"] = sums[..., 0].sum(0).float()
+    def row_grad(self, name: str, c0: int, c: int):
+        self._rows.append(("row." + name, c0, c))
+
+    def gn_bwd(self, name: str, gn, x, x_plane0, x_stats, dy, ch, **kw):
+        c0 = self.chan(ch)
+        self._gns.append((name, c0, ch))
+        ops.gn_silu_bwd(x, dy, ch, gn.num_groups, x_stats, gn.weight, gn.bias, gn.eps, x_plane0=x_plane0, sums=self.tab,
+                        sums_c0=c0, **kw)
+
+    def finish(self):
+        """Turn the reduction table into the row / GroupNorm gradients (views of two small tensors)."""
+        per_sample = self.tab[:, :self._c_off, 0].float()                 # [B, total]
+        over_batch = self.tab[:, :self._c_off].sum(dim=0).float()         # [total, 2]
+        for name, c0, c in self._rows:
+            self.grads[name] = per_sample[:, c0:c0 + c]
+        for name, c0, c in self._gns:
+            self.grads[name + ".weight"] = over_batch[c0:c0 + c, 1]
+            self.grads[name + ".bias"] = over_batch[c0:c0 + c, 0]
 
     # ---- one residual block ---------------------------------------------------------------------------------
-    def block(self, name: str, blk, dy, dy_plane0, dy_stats, dy_stats_c0, dx, dx_plane0, dx_stats, dx_stats_c0):
-        """Backward of ``CUNet._run_block``: consumes dy[window] (+ its per-sample channel sums), writes
-        dx[window] (+ sums), records every parameter gradient of the block."""
+    def block(self, name: str, blk, dy, dy_plane0, dy_c0, dx, dx_plane0, dx_c0):
+        """Backward of ``CUNet._run_block``: consumes dy[window] (its per-sample channel sums live at channel
+        ``dy_c0`` of the reduction table), writes dx[window] (sums at ``dx_c0``), records every parameter gradient."""
         rec = self.tape[name]
-        ci, co, groups, grid = blk.ch_in, blk.ch_out, blk.norm_groups, rec["grid"]
+        ci, co, grid = blk.ch_in, blk.ch_out, rec["grid"]
         gn1, conv1, gn2, conv2 = blk.net1[0], blk.net1[2], blk.net2[0], blk.net2[3]
-        d_bias = dy_stats[:, dy_stats_c0:dy_stats_c0 + co, 0].float()
+        drop = dict(dropout_p=rec["p_drop"], seed=rec["drop_seed"], layer_tag=rec["drop_tag"],
+                    seed_step=self.net.drop_counter if rec["p_drop"] > 0.0 else None)
         # net2: conv -> dropout/silu/gn
         self.wgrad(name + ".net2", conv2, rec["a2"], 0, co, dy, dy_plane0)
-        self.grads["row." + name + ".net2"] = d_bias
+        self.row_grad(name + ".net2", dy_c0, co)
         d_a2 = self.buf(f"a.{co}", co, grid)
         self.dgrad(name + ".net2", conv2, dy, dy_plane0, co, d_a2)
         dh = self.buf(f"h.{co}", co, grid)
-        dh_stats = self.stats(co)
-        _, sums2 = ops.gn_silu_bwd(rec["h"], d_a2, co, groups, rec["h_stats"], gn2.weight, gn2.bias, gn2.eps, out=dh,
-                                   dropout_p=rec["p_drop"], seed=rec["drop_seed"], layer_tag=rec["drop_tag"],
-                                   out_stats=dh_stats)
-        self.gn_grads(name + ".gn2", sums2)
+        dh_c0 = self.chan(co)
+        self.gn_bwd(name + ".gn2", gn2, rec["h"], 0, rec["h_stats"], d_a2, co, out=dh, out_stats=self.tab,
+                    out_stats_c0=dh_c0, **drop)
         # net1: conv (+ conditioning row) -> silu/gn
         self.wgrad(name + ".net1", conv1, rec["a1"], 0, ci, dh, 0)
-        self.grads["row." + name + ".net1"] = dh_stats[..., 0].float()
+        self.row_grad(name + ".net1", dh_c0, co)
         d_a1 = self.buf(f"a.{ci}", ci, grid)
         self.dgrad(name + ".net1", conv1, dh, 0, co, d_a1)
         # skip path
@@ -109,13 +135,11 @@ class _Backward:
             add, add_plane0 = dy, dy_plane0
         else:
             self.wgrad(name + ".skip", blk.skip_conv, rec["x"], rec["x_plane0"], ci, dy, dy_plane0)
-            self.grads["row." + name + ".skip"] = d_bias
+            self.row_grad(name + ".skip", dy_c0, co)
             add, add_plane0 = self.buf(f"s.{ci}", ci, grid), 0
             self.dgrad(name + ".skip", blk.skip_conv, dy, dy_plane0, co, add)
-        _, sums1 = ops.gn_silu_bwd(rec["x"], d_a1, ci, groups, rec["x_stats"], gn1.weight, gn1.bias, gn1.eps,
-                                   x_plane0=rec["x_plane0"], add=add, add_plane0=add_plane0, out=dx, out_plane0=dx_plane0,
-                                   out_stats=dx_stats, out_stats_c0=dx_stats_c0)
-        self.gn_grads(name + ".gn1", sums1)
+        self.gn_bwd(name + ".gn1", gn1, rec["x"], rec["x_plane0"], rec["x_stats"], d_a1, ci, add=add, add_plane0=add_plane0,
+                    out=dx, out_plane0=dx_plane0, out_stats=self.tab, out_stats_c0=dx_c0)
 
     # ---- the whole trunk ---------------------------------------------------------------------------------------
     def run(self, d_out: torch.Tensor, need_dx: bool) -> Optional[torch.Tensor]:
@@ -130,46 +154,45 @@ class _Backward:
         d_a = self.buf(f"a.{c[0]}", c[0], grids[0])
         self.dgrad("conv_out", conv_out, g_out, 0, 16, d_a)
         dy = self.buf(f"y.{c[0]}", c[0], grids[0])
-        dy_stats = self.stats(c[0])
-        _, sums = ops.gn_silu_bwd(tr["out_x"], d_a, c[0], gn_out.num_groups, tr["out_x_stats"], gn_out.weight, gn_out.bias,
-                                  gn_out.eps, out=dy, out_stats=dy_stats)
-        self.gn_grads("conv_out.gn", sums)
+        dy_c0 = self.chan(c[0])
+        self.gn_bwd("conv_out.gn", gn_out, tr["out_x"], 0, tr["out_x_stats"], d_a, c[0], out=dy, out_stats=self.tab,
+                    out_stats_c0=dy_c0)
         # up path, finest level first (reverse execution order)
-        d_cats, d_cat_stats = {}, {}
+        d_cats = {}
         for k, i in reversed(list(enumerate(reversed(range(nl - 1))))):
             name = f"ups.{k}.resnet_blocks.0"
             cc = c[i + 1] + c[i]
             d_cat = self.buf(f"cat{i}", cc, grids[i])
-            dcs = self.stats(cc)
-            self.block(name, net.ups[k].resnet_blocks[0], dy, 0, dy_stats, 0, d_cat, 0, dcs, 0)
-            d_cats[i], d_cat_stats[i] = d_cat, dcs
+            self.block(name, net.ups[k].resnet_blocks[0], dy, 0, dy_c0, d_cat, 0, self.chan(cc))
+            d_cats[i] = d_cat
             # gradient of the up-sampled half goes down one level
             dy = self.buf(f"y.{c[i + 1]}", c[i + 1], grids[i + 1])
-            dy_stats = self.stats(c[i + 1])
-            ops.upsample2_bwd(d_cat, c[i + 1], dy_plane0=0, out=dy, stats=dy_stats)
+            dy_c0 = self.chan(c[i + 1])
+            ops.upsample2_bwd(d_cat, c[i + 1], dy_plane0=0, out=dy, stats=self.tab, stats_c0=dy_c0)
         # bottom: mid2, mid1, last down block
         for name, blk in (("mid2", net.mid2), ("mid1", net.mid1),
                           (f"downs.{nl - 1}.resnet_blocks.0", net.downs[nl - 1].resnet_blocks[0])):
             ci = blk.ch_in
             dx = self.buf(f"x.{name}", ci, grids[nl - 1])
-            dxs = self.stats(ci)
-            self.block(name, blk, dy, 0, dy_stats, 0, dx, 0, dxs, 0)
-            dy, dy_stats = dx, dxs
+            dx_c0 = self.chan(ci)
+            self.block(name, blk, dy, 0, dy_c0, dx, 0, dx_c0)
+            dy, dy_c0 = dx, dx_c0
         # down path: d(block output) = skip half of d_cat + avg-pool backward of the coarser gradient
         for i in reversed(range(nl - 1)):
             name = f"downs.{i}.resnet_blocks.0"
             blk = net.downs[i].resnet_blocks[0]
             d_cat, p0 = d_cats[i], c[i + 1] // 8
-            tot = self.stats(c[i])
-            ops.avgpool2_bwd(dy, c[i], d_cat, dx_plane0=p0, accumulate=True, stats=tot)
+            tot_c0 = self.chan(c[i])
+            ops.avgpool2_bwd(dy, c[i], d_cat, dx_plane0=p0, accumulate=True, stats=self.tab, stats_c0=tot_c0)
             ci = blk.ch_in
             dx = self.buf(f"x.{name}", ci, grids[i])
-            dxs = self.stats(ci)
-            self.block(name, blk, d_cat, p0, tot, 0, dx, 0, dxs, 0)
-            dy, dy_stats = dx, dxs
+            dx_c0 = self.chan(ci)
+            self.block(name, blk, d_cat, p0, tot_c0, dx, 0, dx_c0)
+            dy, dy_c0 = dx, dx_c0
         # conv_in
         self.wgrad("conv_in", net.conv_in, tr["packed"], 0, 16, dy, 0)
-        self.grads["row.conv_in"] = dy_stats[..., 0].float()
+        self.row_grad("conv_in", dy_c0, c[0])
+        self.finish()
         if not need_dx:
             return None
         wp = net._packed_dgrad("conv_in", net.conv_in, 0, 1)
@@ -218,7 +241,8 @@ def unet_forward(net, x, t=None, s_conditioning=None, v_conditionings=None):
     row_names = list(rows.keys())
     params = net.trunk_parameters()
     param_names = [n for n, _ in params]
-    net._train_calls = getattr(net, "_train_calls", 0) + 1
-    net.dropout_seed = (int(getattr(net, "dropout_base_seed", 0)) << 32) | (net._train_calls & 0xffffffff)
+    if net.training and net.dropout_prob > 0.0:
+        ops.increment(net.drop_counter)          # new dropout masks every training forward (device counter: graph-safe)
+    net.dropout_seed = int(getattr(net, "dropout_base_seed", 0)) << 32
     return _UNetFn.apply(net, s_conditioning, row_names, param_names, x, *[rows[n] for n in row_names],
                          *[p for _, p in params])

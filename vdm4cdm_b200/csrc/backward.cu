@@ -29,8 +29,10 @@ struct GnBwdArgs {
   const float* beta;
   float eps, dropout_p;
   uint64_t seed;
+  const int32_t* seed_step;
   uint32_t layer_tag;
-  double* sums;         // [B][C][2]: written by reduce, read by apply
+  double* sums;         // window of [B][sums_channels][2] at sums_c0: written by reduce, read by apply
+  int sums_channels, sums_c0;
   double* out_stats;
   int out_stats_channels, out_stats_c0;
   int has_add;
@@ -67,6 +69,7 @@ gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
   const uint32_t thresh16 = (uint32_t)(a.dropout_p * 65536.0f + 0.5f);
   const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
+  const uint64_t seed = a.seed + (a.seed_step ? (uint64_t)(uint32_t)(*a.seed_step) : 0ull);
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t stride = (int64_t)gridDim.x * kEwThreads;
   for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += 2 * stride) {
@@ -79,7 +82,7 @@ gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
     for (int k = 0; k < 2; ++k) {
       if (k == 1 && !two) break;
       const int64_t ii = k == 0 ? i : i2;
-      const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, a.seed, thresh16) : 0xffu;
+      const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, seed, thresh16) : 0xffu;
       float du[8], x[8];
       chunk_du(k == 0 ? x0 : x1, k == 0 ? g0 : g1, s_scale, s_shift, keep, keep_scale, du, x);
 #pragma unroll
@@ -110,7 +113,7 @@ gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
       t1 += s_part[w][threadIdx.x];
       t2 += s_part[w][8 + threadIdx.x];
     }
-    double* dst = a.sums + ((int64_t)b * C + pl * 8 + threadIdx.x) * 2;
+    double* dst = a.sums + ((int64_t)b * a.sums_channels + a.sums_c0 + pl * 8 + threadIdx.x) * 2;
     atomicAdd(dst, (double)t1);
     atomicAdd(dst + 1, (double)(s_rstd[threadIdx.x] * (t2 - s_mean[threadIdx.x] * t1)));
   }
@@ -129,7 +132,7 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
     const int c = pl * 8 + threadIdx.x;
     const int cpg = C / a.groups;
     const int g0 = (c / cpg) * cpg;
-    const double* sb = a.sums + (int64_t)b * C * 2;
+    const double* sb = a.sums + ((int64_t)b * a.sums_channels + a.sums_c0) * 2;
     double m1 = 0.0, m2 = 0.0;
     for (int k = 0; k < cpg; ++k) {
       const double gk = (double)a.gamma[g0 + k];
@@ -159,6 +162,7 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
   const uint32_t thresh16 = (uint32_t)(a.dropout_p * 65536.0f + 0.5f);
   const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
+  const uint64_t seed = a.seed + (a.seed_step ? (uint64_t)(uint32_t)(*a.seed_step) : 0ull);
   float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t stride = (int64_t)gridDim.x * kEwThreads;
   for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += 2 * stride) {
@@ -175,7 +179,7 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
     for (int k = 0; k < 2; ++k) {
       if (k == 1 && !two) break;
       const int64_t ii = k == 0 ? i : i2;
-      const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, a.seed, thresh16) : 0xffu;
+      const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, seed, thresh16) : 0xffu;
       float du[8], x[8], o[8];
       chunk_du(k == 0 ? x0 : x1, k == 0 ? g0 : g1, s_scale, s_shift, keep, keep_scale, du, x);
 #pragma unroll
@@ -310,8 +314,11 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-             float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
-             const double* __restrict__ grad_sumsq, float max_norm, float grad_scale) {
+             float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+             const int32_t* __restrict__ step_ptr, const double* __restrict__ grad_sumsq, float max_norm, float grad_scale) {
+  const float stepf = (float)(step + (step_ptr ? *step_ptr : 0));
+  const float bc1 = 1.0f - powf(beta1, stepf);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, stepf));
   float gs = grad_scale;
   if (grad_sumsq != nullptr && max_norm > 0.f) {
     const float norm = grad_scale * (float)sqrt(*grad_sumsq);
@@ -348,7 +355,8 @@ static int gn_bwd_common(const char* who, const VdmTensor* x, const VdmTensor* d
 
 extern "C" int vdm_gn_silu_bwd_reduce(const VdmTensor* x, const VdmTensor* dy, int batch, int64_t voxels, int channels,
                                       int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                                      float dropout_p, uint64_t seed, uint32_t layer_tag, double* sums, void* stream) {
+                                      float dropout_p, uint64_t seed, const int32_t* seed_step, uint32_t layer_tag,
+                                      double* sums, int sums_channels, int sums_c0, void* stream) {
   const int rc = gn_bwd_common("vdm_gn_silu_bwd_reduce", x, dy, batch, voxels, channels, groups, stats, gamma, beta,
                                dropout_p, sums);
   if (rc != VDM_OK) return rc;
@@ -356,7 +364,10 @@ extern "C" int vdm_gn_silu_bwd_reduce(const VdmTensor* x, const VdmTensor* dy, i
   memset(&a, 0, sizeof(a));
   a.x = *x; a.dy = *dy; a.planes = channels / 8; a.voxels = voxels; a.groups = groups; a.stats = stats;
   a.gamma = gamma; a.beta = beta; a.eps = eps; a.dropout_p = dropout_p; a.seed = seed; a.layer_tag = layer_tag;
+  a.seed_step = seed_step;
   a.sums = sums;
+  a.sums_channels = sums_channels > 0 ? sums_channels : channels;
+  a.sums_c0 = sums_c0;
   gn_silu_bwd_reduce_kernel<<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
@@ -365,8 +376,9 @@ extern "C" int vdm_gn_silu_bwd_reduce(const VdmTensor* x, const VdmTensor* dy, i
 extern "C" int vdm_gn_silu_bwd_apply(const VdmTensor* x, const VdmTensor* dy, const VdmTensor* add, const VdmTensor* dx,
                                      int batch, int64_t voxels, int channels, int groups, const double* stats,
                                      const float* gamma, const float* beta, float eps, float dropout_p, uint64_t seed,
-                                     uint32_t layer_tag, const double* sums, double* out_stats, int out_stats_channels,
-                                     int out_stats_c0, void* stream) {
+                                     const int32_t* seed_step, uint32_t layer_tag, const double* sums, int sums_channels,
+                                     int sums_c0, double* out_stats, int out_stats_channels, int out_stats_c0,
+                                     void* stream) {
   const int rc = gn_bwd_common("vdm_gn_silu_bwd_apply", x, dy, batch, voxels, channels, groups, stats, gamma, beta,
                                dropout_p, sums);
   if (rc != VDM_OK) return rc;
@@ -375,7 +387,10 @@ extern "C" int vdm_gn_silu_bwd_apply(const VdmTensor* x, const VdmTensor* dy, co
   memset(&a, 0, sizeof(a));
   a.x = *x; a.dy = *dy; a.dx = *dx; a.planes = channels / 8; a.voxels = voxels; a.groups = groups; a.stats = stats;
   a.gamma = gamma; a.beta = beta; a.eps = eps; a.dropout_p = dropout_p; a.seed = seed; a.layer_tag = layer_tag;
+  a.seed_step = seed_step;
   a.sums = const_cast<double*>(sums);
+  a.sums_channels = sums_channels > 0 ? sums_channels : channels;
+  a.sums_c0 = sums_c0;
   if (add) { a.add = *add; a.has_add = 1; }
   a.out_stats = out_stats;
   a.out_stats_channels = out_stats_channels > 0 ? out_stats_channels : channels;
@@ -428,18 +443,30 @@ extern "C" int vdm_sumsq(const float* x, int64_t n, double* out, void* stream) {
   return VDM_OK;
 }
 
-extern "C" int vdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                              float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq,
-                              float max_norm, float grad_scale, void* stream) {
-  VDM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "vdm_adamw_step: bad argument");
+static int adamw_launch(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, const int32_t* step_ptr,
+                        const double* grad_sumsq, float max_norm, float grad_scale, void* stream) {
+  VDM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_ptr), "vdm_adamw_step: bad argument");
   if (n == 0) return VDM_OK;
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
   int64_t blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                   eps, weight_decay, bc1, bc2_sqrt, grad_sumsq, max_norm,
+                                                                   eps, weight_decay, step, step_ptr, grad_sumsq, max_norm,
                                                                    grad_scale);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
+}
+
+extern "C" int vdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq,
+                              float max_norm, float grad_scale, void* stream) {
+  return adamw_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, nullptr, grad_sumsq,
+                      max_norm, grad_scale, stream);
+}
+
+extern "C" int vdm_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                  float beta1, float beta2, float eps, float weight_decay, int step, const int32_t* step_ptr,
+                                  const double* grad_sumsq, float max_norm, float grad_scale, void* stream) {
+  return adamw_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_ptr, grad_sumsq,
+                      max_norm, grad_scale, stream);
 }

@@ -36,7 +36,8 @@ channel_stats_kernel(VdmTensor x, int planes, int64_t voxels, double* __restrict
 __global__ void __launch_bounds__(kEwThreads)
 gn_silu_kernel(VdmTensor x, VdmTensor y, int planes, int64_t voxels, int groups, const double* __restrict__ stats,
                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float dropout_p,
-               uint64_t seed, uint32_t layer_tag) {
+               uint64_t seed, const int32_t* __restrict__ seed_step, uint32_t layer_tag) {
+  if (seed_step) seed += (uint64_t)(uint32_t)(*seed_step);
   __shared__ float s_scale[8], s_shift[8];
   const int b = blockIdx.y / planes, pl = blockIdx.y % planes;
   const int C = planes * 8;
@@ -172,9 +173,9 @@ extern "C" int vdm_channel_stats(const VdmTensor* x, int batch, int64_t voxels, 
   return VDM_OK;
 }
 
-extern "C" int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
-                           const double* stats, const float* gamma, const float* beta, float eps, float dropout_p,
-                           uint64_t seed, uint32_t layer_tag, void* stream) {
+extern "C" int vdm_gn_silu_step(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels,
+                                int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                                float dropout_p, uint64_t seed, const int32_t* seed_step, uint32_t layer_tag, void* stream) {
   VDM_CHECK_ARG(view_ok(x, channels) && view_ok(y, channels) && stats && gamma && beta, "vdm_gn_silu: bad tensor argument");
   VDM_CHECK_ARG(batch >= 1 && voxels >= 1, "vdm_gn_silu: bad shape");
   VDM_CHECK_PLANES(batch, channels, "vdm_gn_silu");
@@ -183,9 +184,16 @@ extern "C" int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, in
   VDM_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "vdm_gn_silu: dropout_p %f out of [0,1)", dropout_p);
   const int planes = channels / 8;
   gn_silu_kernel<<<ew_grid(voxels, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
-      *x, *y, planes, voxels, groups, stats, gamma, beta, eps, dropout_p, seed, layer_tag);
+      *x, *y, planes, voxels, groups, stats, gamma, beta, eps, dropout_p, seed, seed_step, layer_tag);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
+}
+
+extern "C" int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
+                           const double* stats, const float* gamma, const float* beta, float eps, float dropout_p,
+                           uint64_t seed, uint32_t layer_tag, void* stream) {
+  return vdm_gn_silu_step(x, y, batch, voxels, channels, groups, stats, gamma, beta, eps, dropout_p, seed, nullptr,
+                          layer_tag, stream);
 }
 
 extern "C" int vdm_avgpool2(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,

@@ -51,7 +51,9 @@ struct WgradParams {
   int slice_bytes;       // (cpb/8) * Hh * Wh * 16
   int x_planes, x_plane0, g_planes, g_plane0;
   int tmem_cols;
-  float* dw;             // fp32 [taps][c_in][c_out]
+  float* dw;             // fp32, element (tap, ci, co) at tap*st_tap + ci*st_ci + co*st_co
+  long long st_tap, st_ci, st_co;
+  int c_in_real;
 };
 
 struct WgradShared {
@@ -175,17 +177,17 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int job = job0 + j;
       const int sb = job / p.n_khw, khw = job % p.n_khw;
       const int kd = sb * p.S + s_in_block;               // 0..kd_count-1 are real filter planes
-      const bool row_ok = kd < p.kd_count && ci < p.c_in;
+      const bool row_ok = kd < p.kd_count && ci < p.c_in_real;
       const int tap = kd * p.n_khw + khw;
       for (int c0 = 0; c0 < p.n; c0 += 16) {
         uint32_t raw[16];
         ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.n + c0), raw);
         ptx::tmem_ld_wait();
         if (row_ok) {
-          float* dst = p.dw + ((size_t)tap * p.c_in + ci) * p.c_out + ns * p.n + c0;
+          float* dst = p.dw + (long long)tap * p.st_tap + (long long)ci * p.st_ci + (long long)(ns * p.n + c0) * p.st_co;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (ns * p.n + c0 + i < p.c_out) atomicAdd(dst + i, __uint_as_float(raw[i]));
+            if (ns * p.n + c0 + i < p.c_out) atomicAdd(dst + (long long)i * p.st_co, __uint_as_float(raw[i]));
         }
       }
     }
@@ -298,6 +300,12 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
   p.x_planes = x_planes; p.x_plane0 = d.a_plane0;
   p.g_planes = g_planes; p.g_plane0 = d.g_plane0;
   p.dw = dw;
+  if (d.dw_stride_tap == 0 && d.dw_stride_ci == 0 && d.dw_stride_co == 0) {
+    p.st_tap = (long long)d.c_in * d.c_out; p.st_ci = d.c_out; p.st_co = 1; p.c_in_real = d.c_in;
+  } else {
+    VDM_CHECK_ARG(d.c_in_real >= 1 && d.c_in_real <= d.c_in, "vdm_conv3d_wgrad: c_in_real=%d out of [1, c_in]", d.c_in_real);
+    p.st_tap = d.dw_stride_tap; p.st_ci = d.dw_stride_ci; p.st_co = d.dw_stride_co; p.c_in_real = d.c_in_real;
+  }
 
   CUtensorMap tma, tmg;
   {

@@ -157,6 +157,8 @@ class CUNet(nn.Module):
         self._packed_cache: Dict[str, tuple] = {}
         self.dropout_seed = 0
         self._dropout_calls = 0
+        # device-side training-step counter added to the dropout seed (a captured CUDA graph draws new masks)
+        self.register_buffer("drop_counter", torch.zeros(1, dtype=torch.int32), persistent=False)
 
     # ---- conditioning (tiny fp32 MLPs, torch) -------------------------------------------------
     def conditionings(self, batch: int, t, v_conditionings, device) -> Optional[List[torch.Tensor]]:
@@ -184,32 +186,25 @@ class CUNet(nn.Module):
         self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
 
     def _packed(self, name: str, conv: nn.Conv3d) -> torch.Tensor:
-        w = conv.weight
-        key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
-        hit = self._packed_cache.get(name)
-        if hit is None or hit[0] != key:
-            with torch.no_grad():
-                fresh = ops.pack_conv_weight(w.detach())
-                if hit is not None and hit[1].shape == fresh.shape and hit[1].device == fresh.device:
-                    hit[1].copy_(fresh)        # keep the device pointer: captured CUDA graphs refer to it
-                    fresh = hit[1]
-                hit = (key, fresh)
-            self._packed_cache[name] = hit
-        return hit[1]
+        """bf16 kernel-layout copy of ``conv.weight`` (one ``vdm_pack_conv_weight`` launch when the parameter changed;
+        the buffer is allocated once, so captured CUDA graphs keep a valid pointer)."""
+        return self._packed_any(name, conv, False, 0, conv.in_channels)
 
     def _packed_dgrad(self, name: str, conv: nn.Conv3d, c0: int, n: int) -> torch.Tensor:
         """bf16 dgrad filter (roles of Cin/Cout exchanged, taps mirrored) for input channels [c0, c0+n)."""
+        return self._packed_any(f"{name}.dgrad.{c0}.{n}", conv, True, c0, n)
+
+    def _packed_any(self, slot: str, conv: nn.Conv3d, transpose_flip: bool, c0: int, n: int) -> torch.Tensor:
         w = conv.weight
         key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
-        slot = f"{name}.dgrad.{c0}.{n}"
         hit = self._packed_cache.get(slot)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                fresh = ops.pack_conv_weight(w.detach()[:, c0:c0 + n], transpose_flip=True)
-                if hit is not None and hit[1].shape == fresh.shape and hit[1].device == fresh.device:
-                    hit[1].copy_(fresh)
-                    fresh = hit[1]
-                hit = (key, fresh)
+                shape = ops.packed_weight_shape(w.shape, transpose_flip, n)
+                buf = hit[1] if hit is not None and tuple(hit[1].shape) == shape and hit[1].device == w.device else \
+                    torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+                ops.pack_conv_weight_into(w.detach().contiguous(), buf, transpose_flip, c0, n)
+                hit = (key, buf)
             self._packed_cache[slot] = hit
         return hit[1]
 
@@ -308,7 +303,8 @@ class CUNet(nn.Module):
         if p_drop > 0.0:
             self._dropout_calls += 1
         ops.gn_silu(h, co, g, h_stats, blk.net2[0].weight, blk.net2[0].bias, blk.net2[0].eps, out=a2, dropout_p=p_drop,
-                    seed=self.dropout_seed, layer_tag=self._dropout_calls)
+                    seed=self.dropout_seed, layer_tag=self._dropout_calls,
+                    seed_step=self.drop_counter if p_drop > 0.0 else None)
         if tape is not None:
             tape[name] = dict(x=x, x_plane0=x_plane0, x_stats=x_stats, a1=a1, h=h, h_stats=h_stats, a2=a2, grid=grid,
                               p_drop=p_drop, drop_tag=self._dropout_calls, drop_seed=self.dropout_seed)

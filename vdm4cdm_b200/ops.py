@@ -108,6 +108,32 @@ def pack_conv_weight(w: torch.Tensor, c_in_pad: Optional[int] = None, c_out_pad:
     return full.reshape(kd * kh * kw, cip // 8, 8, cop).permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
 
 
+def packed_weight_shape(conv_weight_shape, transpose_flip: bool = False, n_ci: Optional[int] = None):
+    """Shape of the packed bf16 filter for a torch Conv3d weight (Cout, Cin, k, k, k)."""
+    co, ci, k = conv_weight_shape[0], conv_weight_shape[1], conv_weight_shape[2]
+    if transpose_flip:
+        kdim, ndim = co, (ci if n_ci is None else n_ci)
+    else:
+        kdim, ndim = ci, co
+    return (k ** 3, -(-kdim // 16) * 16 // 8, -(-ndim // 16) * 16, 8)
+
+
+def pack_conv_weight_into(w: torch.Tensor, out: torch.Tensor, transpose_flip: bool = False, ci0: int = 0,
+                          n_ci: Optional[int] = None) -> torch.Tensor:
+    """``vdm_pack_conv_weight``: fp32 CUDA Conv3d weight -> ``out`` (bf16 [k^3, K_pad/8, N_pad, 8]) in one launch.
+    With ``transpose_flip`` the dgrad filter of input channels [ci0, ci0 + n_ci) is packed."""
+    _need(w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 5, "pack_conv_weight_into: w must be contiguous CUDA fp32 (Cout, Cin, k, k, k)")
+    co, ci, k = w.shape[0], w.shape[1], w.shape[2]
+    n_ci = ci if n_ci is None else n_ci
+    _need(out.is_cuda and out.dtype == torch.bfloat16 and out.is_contiguous() and
+          tuple(out.shape) == packed_weight_shape(w.shape, transpose_flip, n_ci), "pack_conv_weight_into: bad out tensor")
+    rc = _C.lib().vdm_pack_conv_weight(w.data_ptr(), out.data_ptr(), co, ci, k, 1 if transpose_flip else 0, ci0, n_ci,
+                                       out.shape[1] * 8, out.shape[2], _stream())
+    _C.check(rc, "vdm_pack_conv_weight")
+    _launched(1)
+    return out
+
+
 # ---- conv ------------------------------------------------------------------------------------------
 def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequence[Tuple[int, int, int]] = TAPS_3X3X3,
            x_plane0: int = 0, c_in: Optional[int] = None, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
@@ -206,7 +232,8 @@ def channel_stats(x: torch.Tensor, channels: int, x_plane0: int = 0, stats: Opti
 
 def gn_silu(x: torch.Tensor, channels: int, groups: int, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
             eps: float = 1e-5, *, x_plane0: int = 0, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
-            dropout_p: float = 0.0, seed: int = 0, layer_tag: int = 0) -> torch.Tensor:
+            dropout_p: float = 0.0, seed: int = 0, layer_tag: int = 0, seed_step: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = dropout(silu(groupnorm(x))).  ``seed_step`` (device int32) is added to ``seed`` on the device."""
     _planar_ok(x, "gn_silu x")
     b = x.shape[0]
     voxels = x.shape[2] * x.shape[3] * x.shape[4]
@@ -218,8 +245,9 @@ def gn_silu(x: torch.Tensor, channels: int, groups: int, stats: torch.Tensor, ga
         out = torch.empty((b, channels // 8) + tuple(x.shape[2:]), dtype=torch.bfloat16, device=x.device)
     _planar_ok(out, "gn_silu out")
     vx, vy = _view(x, x_plane0), _view(out, out_plane0)
-    rc = _C.lib().vdm_gn_silu(ctypes.byref(vx), ctypes.byref(vy), b, voxels, channels, groups, stats.data_ptr(),
-                              gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, layer_tag, _stream())
+    rc = _C.lib().vdm_gn_silu_step(ctypes.byref(vx), ctypes.byref(vy), b, voxels, channels, groups, stats.data_ptr(),
+                                   gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, _ptr(seed_step), layer_tag,
+                                   _stream())
     _C.check(rc, "vdm_gn_silu")
     _launched(1)
     return out
@@ -280,7 +308,7 @@ def pack_input(z: torch.Tensor, cond: Optional[torch.Tensor], c_pad: int = 16,
 
 # ---- backward (training) ---------------------------------------------------------------------------
 def conv3d_wgrad(a: torch.Tensor, g: torch.Tensor, c_in: int, c_out: int, kernel: int = 3, *, a_plane0: int = 0,
-                 g_plane0: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 g_plane0: int = 0, out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``vdm_conv3d_wgrad``: dw[tap, ci, co] += sum_v a[ci, v + tap] g[co, v]  (fp32 [k^3, c_in, c_out]).
 
     a, g: planar buffers on the same grid; the g window must hold c_out rounded up to 16 channels.
@@ -289,11 +317,20 @@ def conv3d_wgrad(a: torch.Tensor, g: torch.Tensor, c_in: int, c_out: int, kernel
     _planar_ok(g, "conv3d_wgrad g")
     b, ap, d, h, w_, _ = a.shape
     _need(tuple(g.shape[2:5]) == (d, h, w_) and g.shape[0] == b, "conv3d_wgrad: a / g grid mismatch")
-    if out is None:
-        out = torch.zeros((kernel ** 3, c_in, c_out), dtype=torch.float32, device=a.device)
-    _need(out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and
-          tuple(out.shape) == (kernel ** 3, c_in, c_out), "conv3d_wgrad: out must be fp32 [k^3, c_in, c_out]")
     desc = _C.WgradDesc()
+    if grad_out is not None:
+        # accumulate straight into a torch-layout gradient (c_out, c_in_real, k, k, k), e.g. a view of the flat bucket
+        _need(grad_out.is_cuda and grad_out.dtype == torch.float32 and grad_out.is_contiguous() and grad_out.dim() == 5 and
+              grad_out.shape[0] == c_out and grad_out.shape[1] <= c_in and tuple(grad_out.shape[2:]) == (kernel,) * 3,
+              "conv3d_wgrad: grad_out must be contiguous fp32 (c_out, c_in_real <= c_in, k, k, k)")
+        desc.dw_stride_tap, desc.dw_stride_ci, desc.dw_stride_co = 1, kernel ** 3, grad_out.shape[1] * kernel ** 3
+        desc.c_in_real = grad_out.shape[1]
+        out = grad_out
+    else:
+        if out is None:
+            out = torch.zeros((kernel ** 3, c_in, c_out), dtype=torch.float32, device=a.device)
+        _need(out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and
+              tuple(out.shape) == (kernel ** 3, c_in, c_out), "conv3d_wgrad: out must be fp32 [k^3, c_in, c_out]")
     desc.batch, desc.depth, desc.height, desc.width = b, d, h, w_
     desc.c_in, desc.c_out, desc.kernel = c_in, c_out, kernel
     desc.a_planes, desc.a_plane0 = ap, a_plane0
@@ -332,7 +369,8 @@ def gn_silu_bwd(x: torch.Tensor, dy: torch.Tensor, channels: int, groups: int, s
                 beta: torch.Tensor, eps: float = 1e-5, *, x_plane0: int = 0, dy_plane0: int = 0,
                 add: Optional[torch.Tensor] = None, add_plane0: int = 0, out: Optional[torch.Tensor] = None,
                 out_plane0: int = 0, dropout_p: float = 0.0, seed: int = 0, layer_tag: int = 0,
-                out_stats: Optional[torch.Tensor] = None, out_stats_c0: int = 0):
+                out_stats: Optional[torch.Tensor] = None, out_stats_c0: int = 0, sums: Optional[torch.Tensor] = None,
+                sums_c0: int = 0, seed_step: Optional[torch.Tensor] = None):
     """Backward of ``gn_silu``: returns (dx, sums) with sums double [B, channels, 2] = per-sample
     (sum du, sum du*xhat), i.e. dbeta = sums[..., 0].sum(0), dgamma = sums[..., 1].sum(0).
     dx = GroupNorm/SiLU/dropout backward of dy [+ add]; ``out_stats`` accumulates (sum, sumsq) of dx."""
@@ -341,21 +379,24 @@ def gn_silu_bwd(x: torch.Tensor, dy: torch.Tensor, channels: int, groups: int, s
     if out is None:
         out = torch.empty((b, channels // 8) + tuple(x.shape[2:]), dtype=torch.bfloat16, device=x.device)
     _planar_ok(out, "gn_silu_bwd out")
-    sums = torch.zeros((b, channels, 2), dtype=torch.float64, device=x.device)
+    if sums is None:
+        sums = torch.zeros((b, channels, 2), dtype=torch.float64, device=x.device)
+    _need(sums.dtype == torch.float64 and sums.is_contiguous() and sums.dim() == 3 and sums.shape[0] == b and
+          sums.shape[2] == 2 and sums_c0 + channels <= sums.shape[1], "gn_silu_bwd: sums must be a zeroed double [B, >= channels, 2]")
     vx, vg, vo = _view(x, x_plane0), _view(dy, dy_plane0), _view(out, out_plane0)
     lib = _C.lib()
     rc = lib.vdm_gn_silu_bwd_reduce(ctypes.byref(vx), ctypes.byref(vg), b, voxels, channels, groups, stats.data_ptr(),
-                                    gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, layer_tag, sums.data_ptr(),
-                                    _stream())
+                                    gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, _ptr(seed_step), layer_tag,
+                                    sums.data_ptr(), sums.shape[1], sums_c0, _stream())
     _C.check(rc, "vdm_gn_silu_bwd_reduce")
     va = None
     if add is not None:
         _planar_ok(add, "gn_silu_bwd add")
         va = ctypes.byref(_view(add, add_plane0))
     rc = lib.vdm_gn_silu_bwd_apply(ctypes.byref(vx), ctypes.byref(vg), va, ctypes.byref(vo), b, voxels, channels, groups,
-                                   stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, layer_tag,
-                                   sums.data_ptr(), _ptr(out_stats), 0 if out_stats is None else out_stats.shape[1],
-                                   out_stats_c0, _stream())
+                                   stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, _ptr(seed_step),
+                                   layer_tag, sums.data_ptr(), sums.shape[1], sums_c0, _ptr(out_stats),
+                                   0 if out_stats is None else out_stats.shape[1], out_stats_c0, _stream())
     _C.check(rc, "vdm_gn_silu_bwd_apply")
     _launched(2)
     return out, sums
@@ -404,14 +445,16 @@ def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
 
 def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,
                step: int, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.01,
-               grad_sumsq: Optional[torch.Tensor] = None, max_norm: float = 0.0, grad_scale: float = 1.0) -> None:
-    """``vdm_adamw_step`` on flat fp32 buckets (in place)."""
+               grad_sumsq: Optional[torch.Tensor] = None, max_norm: float = 0.0, grad_scale: float = 1.0,
+               step_ptr: Optional[torch.Tensor] = None) -> None:
+    """``vdm_adamw_step`` on flat fp32 buckets (in place); the step number is ``step + *step_ptr`` when a device
+    counter is given (CUDA-graph replay)."""
     for t in (param, grad, exp_avg, exp_avg_sq):
         _need(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel(),
               "adamw_step: buckets must be contiguous CUDA fp32 of equal length")
-    rc = _C.lib().vdm_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-                                 param.numel(), lr, beta1, beta2, eps, weight_decay, step, _ptr(grad_sumsq), max_norm,
-                                 grad_scale, _stream())
+    rc = _C.lib().vdm_adamw_step_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                     param.numel(), lr, beta1, beta2, eps, weight_decay, step, _ptr(step_ptr),
+                                     _ptr(grad_sumsq), max_norm, grad_scale, _stream())
     _C.check(rc, "vdm_adamw_step")
     _launched(1)
 
