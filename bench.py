@@ -337,7 +337,8 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
     losses = []
     for _ in range(n_warm):
         losses.append(trainer.training_step(resident))
-    n0 = ops.launch_count()
+    for _ in range(2):                          # the step after the warm-up captures the CUDA graph; one replay
+        losses.append(trainer.training_step(resident))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -345,7 +346,6 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
         losses.append(trainer.training_step(resident))
     e1.record()
     barrier()
-    launches = ops.launch_count() - n0
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,10 +355,19 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
     # end to end: pinned host batch -> device, step, loss scalar back, every step
     barrier()
     t0 = time.perf_counter()
+    marks = []
     for _ in range(n_steps):
-        loss = trainer.training_step(to_dev())
+        ta = time.perf_counter()
+        dev_batch = to_dev()
+        tb = time.perf_counter()
+        loss = trainer.training_step(dev_batch)
+        tc = time.perf_counter()
         loss_host = loss.item()
+        marks.append((tb - ta, tc - tb, time.perf_counter() - tc))
     e2e_s = time.perf_counter() - t0
+    if rank == 0:
+        print("[train e2e] per step (h2d issue, step issue, wait for loss) ms: " +
+              "; ".join("%.1f %.1f %.1f" % (a * 1e3, b * 1e3, c * 1e3) for a, b, c in marks), file=sys.stderr)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -368,7 +377,9 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
     # conv kernels of one training step, by kind (CUDA events around each launch)
     records = []
     ops.set_conv_profiler(records)
-    trainer.training_step(resident)
+    n0 = ops.launch_count()
+    trainer._eager_step(resident)               # same kernels as the captured step, launched one by one
+    launches = ops.launch_count() - n0
     torch.cuda.synchronize(dev)
     ops.set_conv_profiler(None)
     kinds = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
@@ -390,7 +401,7 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
             "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_step": 4,
                     "call": "Trainer.training_step(batch) with a pinned host batch in and loss.item() out"},
-            "gpu_launches_per_step": launches // n_steps, "first_loss": loss_vals[0], "last_loss": loss_host,
+            "gpu_launches_per_step": launches, "cuda_graph": trainer._graph is not None, "first_loss": loss_vals[0], "last_loss": loss_host,
             "parameters": trainer.buckets.numel,
             "conv": {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else None} for k, v in kinds.items()},
             "conv_tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "conv_frac_of_peak": conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tflops,

@@ -211,3 +211,35 @@ def test_trainer_steps_match_torch_adamw_on_the_oracle():
     cos = (d_c @ d_r / (d_c.norm() * d_r.norm())).item()
     print(f"parameter displacement after 3 steps: cosine with the oracle {cos:.4f}, |d| {d_c.norm().item():.4e} vs {d_r.norm().item():.4e}")
     assert cos > 0.9 and abs(d_c.norm().item() / d_r.norm().item() - 1.0) < 0.05
+
+
+def test_trainer_cuda_graph_replay_equals_eager_steps():
+    """The captured training step (weight re-pack, forward, backward, clip + AdamW, device step counters) must walk
+    the same parameter trajectory as eager launches when the loss sees the same times and noise."""
+    from vdm4cdm_b200.trainer import Trainer
+    from vdm4cdm_b200.vdm_model import LightVDM
+    shape, chs, batch = (1, 16, 16, 16), (16, 32), 2
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((batch,) + shape, generator=g).cuda()
+    data = {"x": x, "conditioning": (0.7 * x + 0.3 * torch.randn((batch,) + shape, generator=g).cuda()),
+            "conditioning_values": [torch.rand(batch, 6, generator=g).cuda()]}
+    noise, noise0 = torch.randn((batch,) + shape, generator=g).cuda(), torch.randn((batch,) + shape, generator=g).cuda()
+    times = torch.tensor([0.2, 0.7]).cuda()
+    results = {}
+    for mode in ("eager", "graph"):
+        _, net = _models(shape, chs, dropout=0.1)
+        mod = LightVDM(net).cuda().train()
+        mod.training_step = lambda b, m=mod: m.get_loss(b, noise=noise, noise0=noise0, times=times)[0]
+        tr = Trainer(mod, use_cuda_graph=(mode == "graph"), graph_warmup_steps=2)
+        losses = [tr.training_step(data).item() for _ in range(6)]
+        if mode == "graph":
+            assert tr._graph is not None, "the step was not captured"
+        assert tr.step_dev.item() == 6
+        results[mode] = (losses, tr.buckets.flat_param.clone())
+    print("eager", results["eager"][0])
+    print("graph", results["graph"][0])
+    for a, b in zip(results["eager"][0], results["graph"][0]):
+        assert abs(a - b) < 2e-3 * abs(a), (a, b)
+    assert results["eager"][0][-1] < results["eager"][0][0]
+    pe, pg = results["eager"][1], results["graph"][1]
+    assert ((pe - pg).norm() / pe.norm()).item() < 1e-3

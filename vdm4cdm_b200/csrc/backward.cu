@@ -15,8 +15,8 @@
 namespace vdm {
 
 __device__ __forceinline__ float silu_grad(float u) {
-  const float s = 1.0f / (1.0f + __expf(-u));
-  return s * (1.0f + u * (1.0f - s));
+  const float s = fast_sigmoid(u);
+  return s * fmaf(u, 1.0f - s, 1.0f);
 }
 
 struct GnBwdArgs {

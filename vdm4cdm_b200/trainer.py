@@ -11,9 +11,15 @@ One process per GPU (``torch.distributed``, NCCL on GPUs / gloo on CPU for the h
   * replicas start from rank 0's weights (broadcast) and stay bit-identical because every rank applies
     the same update to the same bucket.
 
-On a CPU device (gloo tests) the update falls back to nothing: the optimizer kernel is CUDA-only and
-``Trainer`` raises, exactly like every other compute entry point of this package; the bucket/all-reduce
-logic is exercised through ``FlatBuckets`` + ``allreduce_gradients`` which are device agnostic.
+  * after a few eager steps the WHOLE step (zero grads, weight re-packing, forward, backward, all-reduce,
+    gradient norm, clip + AdamW) is captured in one CUDA graph and replayed: a 128^3 step is ~1500 kernel
+    launches and torch ops, which took the host as long to issue as the GPU needs to run them (r01m).  The
+    batch is copied into static buffers; dropout masks and Adam's bias correction advance through device
+    counters, torch's own RNG is graph-safe.
+
+``Trainer`` needs a CUDA device (the optimizer kernel has no CPU path, like every compute entry point of this
+package); ``FlatBuckets`` / ``allreduce_gradients`` / ``shard_indices`` are device agnostic and are what the
+gloo tests exercise.
 """
 from __future__ import annotations
 
@@ -75,6 +81,38 @@ def shard_indices(n_items: int, rank: int, world: int) -> range:
     return range(rank, n_items, world)
 
 
+def _clone_tree(obj):
+    if torch.is_tensor(obj):
+        return obj.clone()
+    if isinstance(obj, dict):
+        return {k: _clone_tree(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_clone_tree(v) for v in obj)
+    return obj
+
+
+def _same_layout(a, b) -> bool:
+    if torch.is_tensor(a):
+        return torch.is_tensor(b) and a.shape == b.shape and a.dtype == b.dtype
+    if isinstance(a, dict):
+        return isinstance(b, dict) and a.keys() == b.keys() and all(_same_layout(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)):
+        return isinstance(b, (list, tuple)) and len(a) == len(b) and all(_same_layout(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+def _copy_tree(dst, src) -> None:
+    if torch.is_tensor(dst):
+        if dst.data_ptr() != src.data_ptr():
+            dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_tree(dst[k], src[k])
+    elif isinstance(dst, (list, tuple)):
+        for x, y in zip(dst, src):
+            _copy_tree(x, y)
+
+
 class Trainer:
     """``Trainer(model, ...).training_step(batch)`` = forward + backward + all-reduce + clip + AdamW.
 
@@ -82,8 +120,11 @@ class Trainer:
     ``learning_rate``)."""
 
     def __init__(self, model: torch.nn.Module, gradient_clip_val: float = 0.5, weight_decay: float = 0.01,
-                 betas=(0.9, 0.999), eps: float = 1e-8, learning_rate: Optional[float] = None):
+                 betas=(0.9, 0.999), eps: float = 1e-8, learning_rate: Optional[float] = None,
+                 use_cuda_graph: bool = True, graph_warmup_steps: int = 3):
         self.model = model
+        self.use_cuda_graph, self.graph_warmup_steps = use_cuda_graph, graph_warmup_steps
+        self._graph, self._static_batch, self._static_loss, self._eager_steps = None, None, None, 0
         self.lr = float(model.learning_rate if learning_rate is None else learning_rate)
         self.clip, self.wd, self.betas, self.eps = float(gradient_clip_val), float(weight_decay), betas, float(eps)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -97,7 +138,11 @@ class Trainer:
         self.exp_avg = torch.zeros_like(self.buckets.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.buckets.flat_param)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # optimizer step number, on the device
         self.step_count = 0
+        # warm-up steps and the capture run on ONE side stream, so that autograd's AccumulateGrad nodes (created by
+        # the first backward) live on the stream the graph is captured on
+        self._stream = torch.cuda.Stream(device=dev) if use_cuda_graph else None
 
     def _nets_changed(self):
         for m in self.model.modules():
@@ -107,22 +152,70 @@ class Trainer:
     def training_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """One optimizer step on this rank's micro-batch; returns the (local) loss tensor, not synchronised."""
         self.model.train()
+        if not self.use_cuda_graph:
+            return self._eager_step(batch)
+        if self._static_batch is None or not _same_layout(self._static_batch, batch):
+            self._static_batch, self._graph, self._eager_steps = _clone_tree(batch), None, 0
+        _copy_tree(self._static_batch, batch)
+        if self._graph is not None:
+            self._graph.replay()
+            self.step_count += 1
+            return self._static_loss.clone()
+        if self._eager_steps < self.graph_warmup_steps:
+            self._eager_steps += 1
+            cur = torch.cuda.current_stream()
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                loss = self._eager_step(self._static_batch)
+            cur.wait_stream(self._stream)
+            return loss
+        try:
+            self._capture()
+        except Exception as exc:                      # e.g. a collective the installed NCCL cannot capture
+            import warnings
+            warnings.warn(f"vdm4cdm_b200.Trainer: CUDA-graph capture of the training step failed ({exc}); "
+                          "continuing with eager launches")
+            self.use_cuda_graph, self._graph = False, None
+            torch.cuda.synchronize()
+            return self._eager_step(batch)
+        self._graph.replay()
+        self.step_count += 1
+        return self._static_loss.clone()
+
+    def _eager_step(self, batch) -> torch.Tensor:
         self.buckets.zero_grad()
         loss = self.model.training_step(batch)
         loss.backward()
         self.optimizer_step()
         return loss.detach()
 
-    def optimizer_step(self) -> None:
+    def _capture(self) -> None:
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        self._nets_changed()                          # the weight re-packing must be part of the graph
+        with torch.cuda.graph(graph, stream=self._stream):
+            self.buckets.zero_grad()
+            loss = self.model.training_step(self._static_batch)
+            loss.backward()
+            self._optimizer_kernels()
+            self._static_loss = loss.detach()
+        self._graph = graph
+
+    def _optimizer_kernels(self) -> None:
         allreduce_gradients(self.buckets)
-        self.step_count += 1
+        ops.increment(self.step_dev)
         self.grad_sumsq.zero_()
         ops.sumsq(self.buckets.flat_grad, self.grad_sumsq)
         ops.adamw_step(self.buckets.flat_param, self.buckets.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr,
-                       step=self.step_count, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                       step=0, step_ptr=self.step_dev, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                        weight_decay=self.wd, grad_sumsq=self.grad_sumsq, max_norm=self.clip,
                        grad_scale=1.0 / self.world)
         self._nets_changed()
+
+    def optimizer_step(self) -> None:
+        """all-reduce + gradient norm + clip + AdamW on the flat buckets (gradients must be in place)."""
+        self._optimizer_kernels()
+        self.step_count += 1
 
     def grad_norm(self) -> float:
         """Global gradient norm of the last step (after averaging over ranks, before clipping)."""
@@ -139,7 +232,7 @@ class Trainer:
 
     def state_dict(self) -> dict:
         return {"state_dict": self.model.state_dict(), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "step": self.step_count}
+                "step": int(self.step_dev.item())}
 
     def load_state_dict(self, state: dict) -> None:
         self.model.load_state_dict(state["state_dict"])         # copies into the flat views in place
@@ -147,4 +240,5 @@ class Trainer:
             self.exp_avg.copy_(state["exp_avg"])
             self.exp_avg_sq.copy_(state["exp_avg_sq"])
             self.step_count = int(state["step"])
+            self.step_dev.fill_(self.step_count)
         self._nets_changed()

@@ -81,7 +81,9 @@ class VDM(nn.Module):
         return torch.sqrt(torch.sigmoid(-gamma))
 
     def _gamma5(self, t, ref):
-        g = self.gamma(torch.as_tensor(t, dtype=torch.float32, device=ref.device))
+        if not torch.is_tensor(t):
+            t = torch.full((1,), float(t), dtype=torch.float32, device=ref.device)   # no host->device copy (graph capture)
+        g = self.gamma(t.to(device=ref.device, dtype=torch.float32))
         return g.reshape(-1, *([1] * (ref.dim() - 1)))
 
     def _t_net(self, gamma):
