@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Training entry point for the 3-D conditional models: the reference's
+``trainVDM3D{,128,160,192,224}_c_c_from_field_name_thick_lowbatch.py`` and ``trainSFM3D*_c_c_..._lowbatch.py``
+(positional CLI ``field_in field_out cropsize`` as there; hyper-parameters from those files: chs, batch_size,
+dropout 0.1, norm_groups 8, gamma_max 13.3, lr 3e-4, gradient_clip_val 0.5, seed 42) with the Lightning /
+Comet orchestration replaced by ``vdm4cdm_b200.trainer.Trainer``:
+
+    torchrun --nproc-per-node 8 scripts/train3D_c_c.py Mstar Mcdm 128 --model VDM --synthetic --max-steps 1000
+
+One process per GPU, each with its own micro-batch of ``batch_size`` samples, gradients all-reduced in one flat
+bucket over NCCL/NVLink.  ``--synthetic`` stands in for the CAMELS LH set (see scripts/_common.py).
+Checkpoints: ``{"state_dict": ...}`` files, loadable by ``vdm4cdm_b200.utils.get_model`` (src/utils.py:467).
+"""
+import argparse
+import os
+import time
+
+from _common import init_distributed, synthetic_batch
+
+import torch
+import torch.distributed as dist
+
+from mltools.models import sfm_model, vdm_model
+from mltools.networks import networks
+from vdm4cdm_b200.trainer import Trainer
+
+# per-script hyper-parameters of the reference (trainVDM3D128_...:60-72, trainVDM3D224_...:60-72, trainSFM3D160_...:60-68)
+PRESETS = {"VDM": {64: ([16, 32, 64, 128], 2), 128: ([32, 64, 128, 256], 2), 160: ([32, 64, 128, 256], 2),
+                   192: ([32, 64, 128, 256], 2), 224: ([16, 32, 64, 128], 2)},
+           "SFM": {64: ([16, 32, 64, 128], 2), 128: ([32, 64, 128, 256], 4), 160: ([32, 64, 128, 256], 4),
+                   192: ([32, 64, 128, 256], 4)}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("field_in")
+    ap.add_argument("field_out")
+    ap.add_argument("cropsize", type=int)
+    ap.add_argument("--model", choices=["VDM", "SFM"], default="VDM")
+    ap.add_argument("--synthetic", action="store_true")
+    ap.add_argument("--max-steps", type=int, default=1_000_000)
+    ap.add_argument("--batch-size", type=int, default=None, help="samples per GPU (default: the reference script's)")
+    ap.add_argument("--ckpt-dir", default="./checkpoints")
+    ap.add_argument("--ckpt-every", type=int, default=10_000)
+    ap.add_argument("--log-every", type=int, default=10)
+    args = ap.parse_args()
+    rank, world, device = init_distributed()
+    torch.manual_seed(42)                                     # seed_everything(42)
+    chs, batch_size = PRESETS[args.model].get(args.cropsize, ([32, 64, 128, 256], 2))
+    batch_size = args.batch_size or batch_size
+    n = args.cropsize
+    net = networks.CUNet(shape=(1, n, n, n), chs=chs, s_conditioning_channels=1, v_conditioning_dims=[6],
+                         t_conditioning=True, norm_groups=8, mid_attn=False, dropout_prob=0.1,
+                         conv_padding_mode="circular" if n == 256 else "zeros", n_attention_heads=4)
+    if args.model == "VDM":
+        model = vdm_model.LightVDM(score_model=net, draw_figure=None, gamma_max=13.3, learning_rate=3.0e-4)
+    else:
+        model = sfm_model.LightSFM(velocity_model=net, draw_figure=None, learning_rate=3.0e-4)
+    model = model.to(device)
+    trainer = Trainer(model, gradient_clip_val=0.5)
+    if not args.synthetic:
+        raise NotImplementedError("the CAMELS AstroDataModule is not part of this package yet (SURVEY.md section 8f); "
+                                  "run with --synthetic")
+    t0 = time.perf_counter()
+    for step in range(args.max_steps):
+        raw = synthetic_batch(batch_size, n, 42 + step * world + rank, device=device)
+        if args.model == "VDM":
+            batch = raw
+        else:                                                  # trainSFM3D160_...:71-72
+            batch = {"x0": raw["conditioning"], "x1": raw["x"], "conditioning_values": raw["conditioning_values"]}
+        loss = trainer.training_step(batch)
+        if rank == 0 and (step + 1) % args.log_every == 0:
+            dt = time.perf_counter() - t0
+            print(f"step {step + 1}: loss {loss.item():.5f}  {(step + 1) * batch_size * world / dt:.1f} samples/s")
+        if rank == 0 and (step + 1) % args.ckpt_every == 0:
+            os.makedirs(args.ckpt_dir, exist_ok=True)
+            name = f"{args.model}_{args.field_in}_{args.field_out}_c_c_{n}_step={step + 1}.ckpt"
+            torch.save({"state_dict": model.state_dict()}, os.path.join(args.ckpt_dir, name))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+"""CPU tests of the host-side logic: the ``mltools`` compat namespace, the model factory and registry, state_dict
+compatibility with the oracle, the sampler's schedule algebra, and the data-parallel plumbing (flat buckets,
+gradient all-reduce, realisation sharding) over a world_size-2 ``gloo`` group."""
+import math
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mltools_namespace_resolves_to_this_package():
+    import mltools.ml_utils as ml_utils
+    import mltools.models.sfm_model as sfm_model
+    import mltools.models.vdm_model as vdm_model
+    import mltools.networks.networks as networks
+    from mltools.utils import cuda_tools
+    import vdm4cdm_b200.networks
+    import vdm4cdm_b200.sfm_model
+    import vdm4cdm_b200.vdm_model
+    assert networks.CUNet is vdm4cdm_b200.networks.CUNet
+    assert vdm_model.LightVDM is vdm4cdm_b200.vdm_model.LightVDM
+    assert sfm_model.LightSFM is vdm4cdm_b200.sfm_model.LightSFM
+    assert ml_utils.to_np(torch.arange(3.0, requires_grad=True)).tolist() == [0.0, 1.0, 2.0]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            cuda_tools.get_freer_device()
+
+
+def test_registry_and_model_factory():
+    from vdm4cdm_b200 import utils
+    from vdm4cdm_b200.vdm_model import LightVDM
+    configs = yaml.safe_load(open(os.path.join(ROOT, "configs.yaml")))
+    ref_names = ["VDM_Go7_Mcdm_c_c_128", "VDM_Mstar_Mcdm_c_c_128", "VDM_Mstar_Mcdm_c_c_160", "VDM_Mstar_Mcdm_c_c_192",
+                 "VDM_Mstar_Mcdm_c_c_224", "VDM_Mstar_Mcdm_c_c_256", "SFM_Mstar_Mcdm_c_c_128"]
+    for n in ref_names:
+        assert n in configs, n
+    m = utils.get_model(configs["VDM_Mstar_Mcdm_c_c_224"])
+    assert isinstance(m, LightVDM) and m.model.score_model.shape == (1, 224, 224, 224)
+    assert m.model.score_model.chs == [16, 32, 64, 128] and m.learning_rate == 3.0e-4 and m.model.gamma_max == 13.3
+    assert utils.get_model(configs["SFM_Mstar_Mcdm_c_c_128"]) is None          # src/utils.py:472-473 does `pass`
+    with pytest.raises(ValueError):
+        utils.get_model({"type": "GAN"})
+    with pytest.raises(NotImplementedError, match="circular"):                  # cropsize 256 models: next row, section 8f
+        utils.get_model(configs["VDM_Mstar_Mcdm_c_c_256"])
+
+
+def test_state_dict_is_interchangeable_with_the_oracle():
+    from oracle.unet_ref import CUNet as RefNet
+    from oracle.vdm_ref import LightVDM as RefLight
+    from vdm4cdm_b200.networks import CUNet
+    from vdm4cdm_b200.vdm_model import LightVDM
+    kw = dict(shape=(1, 16, 16, 16), chs=(16, 32, 64), s_conditioning_channels=1, v_conditioning_dims=[6],
+              t_conditioning=True)
+    ref, mine = RefLight(RefNet(**kw)), LightVDM(CUNet(**kw))
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    ref.load_state_dict(mine.state_dict(), strict=True)
+    for (ka, a), (kb, b) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert ka == kb and torch.equal(a, b)
+
+
+def test_step_coefficients_follow_the_reference_algebra():
+    """z_s = alpha_s/alpha_t (z_t - c sigma_t eps) + sigma_s sqrt(c) noise (vdm_model.py:370-378) and its DDNM
+    decomposition (src/utils.py:296-299)."""
+    from vdm4cdm_b200.networks import CUNet
+    from vdm4cdm_b200.vdm_model import VDM
+    vdm = VDM(CUNet(shape=(1, 8, 8, 8), chs=(16, 32)))
+    steps = torch.linspace(1.0, 0.0, 11)
+    coef = vdm.step_coefficients(steps[:-1], steps[1:], final_rescale=True).double()
+    g = vdm.gamma(steps).double()
+    for i in range(10):
+        gt, gs = g[i], g[i + 1]
+        c = -math.expm1((gs - gt).item())
+        a_t, a_s = math.sqrt(torch.sigmoid(-gt).item()), math.sqrt(torch.sigmoid(-gs).item())
+        s_t, s_s = math.sqrt(torch.sigmoid(gt).item()), math.sqrt(torch.sigmoid(gs).item())
+        assert coef[i, 0].item() == pytest.approx(a_s / a_t, rel=1e-6)
+        assert coef[i, 1].item() == pytest.approx(-a_s / a_t * c * s_t, rel=1e-6)
+        assert coef[i, 2].item() == pytest.approx(s_s * math.sqrt(c), rel=1e-6)
+        assert coef[i, 3].item() == pytest.approx(1.0 / a_s if i == 9 else 1.0, rel=1e-6)
+        # DDNM form: w_z z + w_x x0_hat + scale eps with x0_hat = (z - sigma_t eps)/alpha_t
+        w_z, w_x = a_s * (1 - c) / a_t, a_s * c
+        assert w_z + w_x / a_t == pytest.approx(a_s / a_t, rel=1e-9)
+        assert -w_x * s_t / a_t == pytest.approx(-a_s / a_t * c * s_t, rel=1e-9)
+
+
+def test_realisation_sharding_and_dgrad_chunks():
+    from vdm4cdm_b200.autograd import _chunks
+    from vdm4cdm_b200.trainer import shard_indices
+    for world in (1, 2, 3, 8):
+        got = sorted(i for r in range(world) for i in shard_indices(64, r, world))
+        assert got == list(range(64))
+    assert _chunks(32) == [(0, 32)] and _chunks(256) == [(0, 256)]
+    assert _chunks(384) == [(0, 192), (192, 192)]
+    for c in (16, 48, 96, 192, 320, 384, 512):
+        parts = _chunks(c)
+        assert sum(n for _, n in parts) == c and all(n <= 256 and n % 8 == 0 for _, n in parts)
+
+
+def test_trainer_needs_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-GPU failure mode")
+    from vdm4cdm_b200.trainer import Trainer
+    m = torch.nn.Linear(4, 4)
+    m.learning_rate = 1e-3
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Trainer(m)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from vdm4cdm_b200.trainer import FlatBuckets, allreduce_gradients, broadcast_parameters, shard_indices
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                               # replicas start DIFFERENT on purpose
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.SiLU(), torch.nn.Linear(5, 3))
+    buckets = FlatBuckets(model)
+    assert all(p.data_ptr() >= buckets.flat_param.data_ptr() for p in model.parameters())
+    broadcast_parameters(buckets, src=0)
+    # rank-dependent micro-batch -> rank-dependent gradients, written by autograd INTO the flat bucket
+    buckets.zero_grad()
+    x = torch.full((4, 7), float(rank + 1))
+    model(x).sum().backward()
+    local = buckets.flat_grad.clone()
+    assert local.abs().sum() > 0, "autograd did not accumulate into the flat gradient views"
+    allreduce_gradients(buckets)
+    torch.save({"param": buckets.flat_param.clone(), "local": local, "summed": buckets.flat_grad.clone(),
+                "mine": list(shard_indices(10, rank, world))}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_over_gloo(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_ddp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"rank{i}.pt")) for i in range(world)]
+    assert torch.equal(r[0]["param"], r[1]["param"]), "broadcast did not equalise the replicas"
+    assert torch.allclose(r[0]["summed"], r[0]["local"] + r[1]["local"])
+    assert torch.equal(r[0]["summed"], r[1]["summed"])
+    assert sorted(r[0]["mine"] + r[1]["mine"]) == list(range(10))
