@@ -147,7 +147,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": label},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -301,7 +301,7 @@ def run_b200(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu
     if train is not None:
         line["train"] = train
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def train_leg(args, model, net, dev, rank, world, peak_tflops):
@@ -372,16 +372,17 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item() * 1e3 / n_steps
-    if rank != 0:
-        return None
-    # conv kernels of one training step, by kind (CUDA events around each launch)
+    # conv kernels of one training step, by kind (CUDA events around each launch).  Every rank runs the step (it
+    # contains the gradient all-reduce); only rank 0 keeps the records.
     records = []
-    ops.set_conv_profiler(records)
+    ops.set_conv_profiler(records if rank == 0 else None)
     n0 = ops.launch_count()
     trainer._eager_step(resident)               # same kernels as the captured step, launched one by one
     launches = ops.launch_count() - n0
     torch.cuda.synchronize(dev)
     ops.set_conv_profiler(None)
+    if rank != 0:
+        return None
     kinds = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
     per_layer = {}
     for r in records:
@@ -408,7 +409,26 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
             "conv_share_of_step": conv_ms / ms}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: everything libraries print there (NCCL prints its version banner on
+    stdout) is routed to stderr at the file-descriptor level; ``emit`` writes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -432,7 +452,9 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))   # a desynchronised collective must fail fast
     try:
         run_b200(args, rank, world, local_rank)
     finally:
