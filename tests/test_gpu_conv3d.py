@@ -47,6 +47,9 @@ CASES = [
     (1, 384, 128, 2, 16, 8, 3),
     (1, 96, 32, 4, 16, 16, 1),      # 1x1x1 skip conv
     (3, 16, 32, 3, 8, 8, 3),        # H < tile height
+    (1, 48, 16, 5, 16, 8, 3),       # kd-folded schedule over 3 channel chunks (the 224^3 network's level-0 up block)
+    (2, 64, 32, 7, 20, 12, 3),      # folded, 2 or 4 chunks, ragged grid
+    (1, 128, 32, 4, 16, 8, 3),      # folded only if the resident weights fit; else the generic path
 ]
 
 

@@ -157,10 +157,12 @@ __device__ __forceinline__ uint64_t make_planar_desc(uint32_t smem_addr, uint32_
 // A fetches: N = 96 runs at 56 cycles for 3x the math (86% of peak), the two edge slices of a tile at N = 64 / 32.
 // The accumulator of slice s = i is first touched at (kh, kw, k16) = (0, 0, 0) of input slice i, as the LAST block
 // of that MMA's span, so that one MMA is split in two (fresh block / accumulating blocks).
+// Layers with more input channels than one halo stage holds run the schedule once per channel chunk (FIRST = false
+// accumulates everywhere); all chunks' weights stay resident.
 // Everything is compile-time: the schedule is a straight line of (MT+2)*9*KJ (+MT) MMAs with immediate
 // descriptor offsets, because the per-tap bookkeeping of the generic loop, not the MMAs, bounded these
 // layers (r01i: identical time with the epilogue and the halo loads switched off).
-template <int MT, int KJ, int NF>
+template <int MT, int KJ, int NF, bool FIRST>
 __device__ __forceinline__ void issue_fold_tile(uint32_t a_lo0, uint32_t b_base16, uint64_t a_hi, uint64_t b_hi,
                                                 uint32_t d_tmem0) {
   constexpr int Hh = kTileH + 2, Wh = kTileW + 2, Hd = MT + 2;
@@ -172,7 +174,8 @@ __device__ __forceinline__ void issue_fold_tile(uint32_t a_lo0, uint32_t b_base1
     const int kd_hi = i < 2 ? i : 2;
     const int s_lo = i - kd_hi;
     const int nblk = kd_hi - kd_lo + 1;
-    const bool starts = i < MT;          // accumulator s = i receives its first contribution (kd = 0, the last block)
+    // accumulator s = i receives its first contribution (kd = 0, the last block) in the first channel chunk
+    const bool starts = FIRST && i < MT;
 #pragma unroll
     for (int khw = 0; khw < 9; ++khw) {
 #pragma unroll
@@ -266,15 +269,17 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
       const size_t tap_stride = (size_t)p.c_in8 * p.n_pad * 8, plane_stride = (size_t)p.n_pad * 8;
       if constexpr (kFold) {
-        // resident, kd-folded order: [khw][plane][2 - kd][co] (see issue_fold_tile); n_split == 1, one chunk
-        ptx::mbar_arrive_expect_tx(&sh->b_full[0], plane_copy_bytes * planes_per_chunk * (uint32_t)n_taps);
-        for (int tap = 0; tap < n_taps; ++tap) {
-          const int kd = p.tap_kd[tap], khw = p.tap_khw[tap];
+        // resident, kd-folded order: [chunk][khw][plane][2 - kd][co] (see issue_fold_tile); n_split == 1
+        ptx::mbar_arrive_expect_tx(&sh->b_full[0], plane_copy_bytes * planes_per_chunk * (uint32_t)(n_taps * k_chunks));
+        for (int kc = 0; kc < k_chunks; ++kc)
+          for (int tap = 0; tap < n_taps; ++tap) {
+            const int kd = p.tap_kd[tap], khw = p.tap_khw[tap];
 #pragma unroll
-          for (int pl = 0; pl < planes_per_chunk; ++pl)
-            ptx::bulk_load(b_smem + (size_t)((khw * planes_per_chunk + pl) * 3 + (2 - kd)) * plane_copy_bytes,
-                           p.w + (size_t)tap * tap_stride + (size_t)pl * plane_stride, plane_copy_bytes, &sh->b_full[0]);
-        }
+            for (int pl = 0; pl < planes_per_chunk; ++pl)
+              ptx::bulk_load(b_smem + (size_t)(((kc * 9 + khw) * planes_per_chunk + pl) * 3 + (2 - kd)) * plane_copy_bytes,
+                             p.w + (size_t)tap * tap_stride + (size_t)(kc * planes_per_chunk + pl) * plane_stride,
+                             plane_copy_bytes, &sh->b_full[0]);
+          }
       } else if (p.b_resident) {
         // Weights fit next to the halo stages: load every (chunk, tap) once.  Per-tile weight streaming was a
         // fixed cost per tile (r01h: 0.454 -> 0.410 ms on the 32->32 layer); n_split == 1 on this path.
@@ -326,20 +331,29 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const uint64_t a_hi = make_planar_desc(0, (uint32_t)p.plane_bytes, (uint32_t)p.Wh * 16u);
     if constexpr (kFold) {
       const uint64_t b_hi = make_planar_desc(0, 3u * (uint32_t)NF * 16u, 128u);
-      uint32_t ti = 0;
+      constexpr uint32_t chunk_b16 = 9u * 2u * KJ * 3u * NF;       // one channel chunk of the folded weights, 16-byte units
+      const int k_chunks = p.k_chunks;
+      uint32_t ti = 0, ita = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t acc = ti & 1, sa = ti & 1;
+        const uint32_t acc = ti & 1;
         ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
         if (ti == 0) ptx::mbar_wait(&sh->b_full[0], 0);
-        ptx::mbar_wait(&sh->a_full[sa], (ti >> 1) & 1);
-        ptx::tc_fence_after();
-        if (leader) {
-          issue_fold_tile<MT, KJ, NF>(a_base16 + sa * a_stage16, b_base16, a_hi, b_hi,
-                                                      tmem_u + acc * (uint32_t)(MT * NF));
-          ptx::umma_commit(&sh->a_empty[sa]);
-          ptx::umma_commit(&sh->tmem_full[acc]);
+        const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
+        for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
+          const uint32_t sa = ita & 1;
+          ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
+          ptx::tc_fence_after();
+          if (leader) {
+            if (kc == 0)
+              issue_fold_tile<MT, KJ, NF, true>(a_base16 + sa * a_stage16, b_base16, a_hi, b_hi, d_tmem0);
+            else
+              issue_fold_tile<MT, KJ, NF, false>(a_base16 + sa * a_stage16, b_base16 + (uint32_t)kc * chunk_b16, a_hi, b_hi,
+                                                 d_tmem0);
+            ptx::umma_commit(&sh->a_empty[sa]);
+            if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     } else {
       const uint32_t idesc = ptx::make_idesc_bf16(128, n_cta);
@@ -677,8 +691,21 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     }
   p.pad = pad;
   // kd-folded schedule (issue_fold_tile): the full 3x3x3 stencil on a narrow layer
-  bool fold = d.n_taps == 27 && pad == 1 && (d.c_in == 16 || d.c_in == 32) && (d.c_out_pad == 16 || d.c_out_pad == 32) &&
+  bool fold = d.n_taps == 27 && pad == 1 && d.c_in % 16 == 0 && (d.c_out_pad == 16 || d.c_out_pad == 32) &&
               d.depth >= 3 && g_debug_no_fold == 0 && g_debug_force_mt == 0 && g_debug_force_nsplit == 0;
+  int fold_mt = 0, fold_kc = 0;
+  if (fold) {
+    // all weights resident + two halo stages must fit; prefer tall tiles (halo efficiency), then wide chunks
+    const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - 2 * 8 * d.c_out_pad * 4 - 256;
+    const int w_bytes = 27 * d.c_in * d.c_out_pad * 2;
+    for (int m = 4; m >= 2 && !fold_mt; --m)
+      for (int c = 32; c >= 16 && !fold_mt; c -= 16) {
+        if (d.c_in % c != 0) continue;
+        const int a_stage = (((c / 8) * (m + 2) * (kTileH + 2) * (kTileW + 2) * 16) + 127) & ~127;
+        if (2 * a_stage + w_bytes <= budget) { fold_mt = m; fold_kc = c; }
+      }
+    fold = fold_mt != 0;
+  }
   if (fold) {
     unsigned seen = 0;
     for (int t = 0; t < 27; ++t) {
@@ -731,7 +758,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   }
   if (fold) {
     n_split = 1;
-    mt = 4;
+    mt = fold_mt;
   }
   if (g_debug_force_nsplit > 0) n_split = g_debug_force_nsplit;
   VDM_CHECK_ARG(d.c_out_pad % (n_split * 16) == 0, "vdm_conv3d: n_split=%d does not divide c_out_pad=%d", n_split,
@@ -757,9 +784,9 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   const int tps = (d.n_taps % 3 == 0) ? 3 : 1;   // one (kd, kh) row of filter taps per weight stage
   const int kc_options[3] = {64, 32, 16};
   if (fold) {
-    kc = d.c_in;
+    kc = fold_kc;
     p.a_stage_bytes = ((kc / 8) * p.plane_bytes + 127) & ~127;
-    p.b_stage_bytes = d.n_taps * kc * p.n_cta * 2;
+    p.b_stage_bytes = d.n_taps * d.c_in * p.n_cta * 2;
     nsb = 1;
     p.b_resident = 1;
     VDM_CHECK_ARG(2 * p.a_stage_bytes + p.b_stage_bytes <= smem_budget, "vdm_conv3d: folded layer does not fit shared memory");
@@ -846,6 +873,8 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   VDM_LAUNCH(3, 1, 0) VDM_LAUNCH(3, 2, 0) VDM_LAUNCH(3, 4, 0)
   VDM_LAUNCH(4, 1, 0) VDM_LAUNCH(4, 2, 0) VDM_LAUNCH(4, 4, 0)
   VDM_LAUNCH(4, 1, 16) VDM_LAUNCH(4, 1, 32) VDM_LAUNCH(4, 2, 16) VDM_LAUNCH(4, 2, 32)
+  VDM_LAUNCH(3, 1, 16) VDM_LAUNCH(3, 1, 32) VDM_LAUNCH(3, 2, 16) VDM_LAUNCH(3, 2, 32)
+  VDM_LAUNCH(2, 1, 16) VDM_LAUNCH(2, 1, 32) VDM_LAUNCH(2, 2, 16) VDM_LAUNCH(2, 2, 32)
 #undef VDM_LAUNCH
   if (rc != VDM_OK) {
     set_error("vdm_conv3d: no kernel instance for MT=%d KC=%d", mt, kc);

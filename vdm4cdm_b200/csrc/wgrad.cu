@@ -201,6 +201,207 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// ---- narrow layers (c_out <= 32, 3x3x3): kw folded into N, halo slices streamed along d -----------------------
+// With N = c_out = 32 the MMAs of the kernel above run at the shared-memory operand rate (41 cycles for 16 cycles of
+// math), every tile re-loads S halo slices of `a` for ONE slice of g, and 9 (kh, kw) jobs share nothing.  Here
+//   dW[kd,kh,kw][ci][co] = sum_u a[u + (kd-1, kh-1, 0)][ci] * g[u - (0, 0, kw-1)][co]
+// so for a fixed kh the three kw taps are ONE MMA against three w-shifted copies of the g tile stacked along N
+// (3*n rows; the copies are three TMA loads of the same tile at shifted coordinates, zero-filled at the borders):
+// 3 jobs x 8 K-steps of N = 96 per output slice instead of 9 x 8 of N = 32.  A CTA marches along d: segments of LEN
+// output slices at a fixed (b, h0, w0); halo slice k of a segment lives in slot k of a window of LEN + S - 1 slots,
+// output j reads slots j..j+S-1 (rows of filter planes > 2 are garbage and dropped), and slot k is handed back to
+// the producer as soon as output k's MMAs completed, so the next segment's loads overlap this segment's MMAs and
+// every halo slice is loaded (LEN+2)/LEN times instead of S times.
+constexpr int kWnLen = 8;          // output slices per segment
+constexpr int kWnMaxSlots = kWnLen + 8;
+constexpr int kWnGStages = 3;
+constexpr int kWnThreads = 224;    // halo producer, MMA issuer, g producer, 4 epilogue warps (one per TMEM lane quarter)
+
+struct WgradNarrowParams {
+  int B, D, H, W;
+  int c_in, c_out, c_in_real;
+  int n;                 // c_out rounded up to 16 (16 or 32): UMMA N = 3*n
+  int cpb, S, n_cblocks;
+  int n_slots;           // kWnLen + S - 1
+  int tiles_w, tiles_h, segs_d, n_segs;
+  int n_splits;          // CTAs per channel block
+  int slice_bytes, g_tile_bytes, g_stage_bytes;
+  int x_planes, x_plane0, g_planes, g_plane0;
+  float* dw;
+  long long st_tap, st_ci, st_co;
+};
+
+struct WgradNarrowShared {
+  uint64_t slot_full[kWnMaxSlots], slot_empty[kWnMaxSlots];
+  uint64_t g_full[kWnGStages], g_empty[kWnGStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWnThreads, 1)
+conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_g,
+                           const __grid_constant__ WgradNarrowParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_smem = smem;                                              // n_slots halo slices
+  uint8_t* g_smem = smem + (size_t)p.n_slots * p.slice_bytes;          // kWnGStages x 3 shifted g tiles
+  WgradNarrowShared* sh = reinterpret_cast<WgradNarrowShared*>(g_smem + (size_t)kWnGStages * p.g_stage_bytes);
+  constexpr int Hh = kWgTileH + 2, Wh = kWgTileW + 2;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x % p.n_splits;
+  const int cb = blockIdx.x / p.n_splits;
+  const int n_my = (p.n_segs - split + p.n_splits - 1) / p.n_splits;   // segments split, split + n_splits, ...
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_g);
+    for (int s = 0; s < p.n_slots; ++s) {
+      ptx::mbar_init(&sh->slot_full[s], 1);
+      ptx::mbar_init(&sh->slot_empty[s], 1);
+    }
+    for (int s = 0; s < kWnGStages; ++s) {
+      ptx::mbar_init(&sh->g_full[s], 1);
+      ptx::mbar_init(&sh->g_empty[s], 1);
+    }
+    ptx::mbar_init(&sh->done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&sh->tmem_base, 512u);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  auto seg_coord = [&](int i, int& b, int& d0, int& h0, int& w0) {
+    int t = split + i * p.n_splits;
+    d0 = (t % p.segs_d) * kWnLen; t /= p.segs_d;
+    w0 = (t % p.tiles_w) * kWgTileW; t /= p.tiles_w;
+    h0 = (t % p.tiles_h) * kWgTileH;
+    b = t / p.tiles_h;
+  };
+
+  if (warp == 0) {
+    // ===================== halo-slice producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < n_my; ++i) {
+        int b, d0, h0, w0;
+        seg_coord(i, b, d0, h0, w0);
+        for (int k = 0; k < kWnLen + 2; ++k) {
+          ptx::mbar_wait(&sh->slot_empty[k], (i & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&sh->slot_full[k], (uint32_t)p.slice_bytes);
+          ptx::tma_load_4d(a_smem + (size_t)k * p.slice_bytes, &tmap_a, &sh->slot_full[k], (w0 - 1) * 8, h0 - 1, d0 - 1 + k,
+                           b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== g producer: three w-shifted copies of one tile per stage =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int i = 0; i < n_my; ++i) {
+        int b, d0, h0, w0;
+        seg_coord(i, b, d0, h0, w0);
+        for (int j = 0; j < kWnLen; ++j, ++it) {
+          const int s = it % kWnGStages;
+          ptx::mbar_wait(&sh->g_empty[s], ((it / kWnGStages) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&sh->g_full[s], (uint32_t)p.g_stage_bytes);
+          uint8_t* dst = g_smem + (size_t)s * p.g_stage_bytes;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)      // copy kw holds g(u - (kw - 1)) along w
+            ptx::tma_load_4d(dst + (size_t)kw * p.g_tile_bytes, &tmap_g, &sh->g_full[s], (w0 + 1 - kw) * 8, h0, d0 + j,
+                             b * p.g_planes + p.g_plane0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const bool leader = ptx::elect_one();
+    const uint32_t n3 = 3u * (uint32_t)p.n;
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n3) | (1u << 15) | (1u << 16);     // A and B MN-major
+    const uint32_t plane16 = (uint32_t)(Hh * Wh);
+    // A: LBO = next 8 voxels (next h row), SBO = next 8 channels (next plane; slices are contiguous planes)
+    const uint64_t a_hi = ((uint64_t)(uint32_t)Wh << 16) | ((uint64_t)plane16 << 32) | ((uint64_t)1 << 46);
+    // B: LBO = next h row of the dense 16x8 tile, SBO = next 8 output channels (planes, then the next shifted copy)
+    const uint64_t b_hi = ((uint64_t)8u << 16) | ((uint64_t)128u << 32) | ((uint64_t)1 << 46);
+    const uint32_t a_base16 = ptx::smem_u32(a_smem) >> 4, g_base16 = ptx::smem_u32(g_smem) >> 4;
+    const uint32_t slice16 = (uint32_t)p.slice_bytes >> 4, gstage16 = (uint32_t)p.g_stage_bytes >> 4;
+    uint32_t it = 0;
+    for (int i = 0; i < n_my; ++i) {
+      int b, d0, h0, w0;
+      seg_coord(i, b, d0, h0, w0);
+      const int len_eff = min(kWnLen, p.D - d0);
+      ptx::mbar_wait(&sh->slot_full[0], i & 1);
+      ptx::mbar_wait(&sh->slot_full[1], i & 1);
+      for (int j = 0; j < kWnLen; ++j, ++it) {
+        const uint32_t gs = it % kWnGStages;
+        ptx::mbar_wait(&sh->slot_full[j + 2], i & 1);
+        ptx::mbar_wait(&sh->g_full[gs], (it / kWnGStages) & 1);
+        ptx::tc_fence_after();
+        if (leader) {
+          if (j < len_eff) {
+            const uint32_t a0 = a_base16 + (uint32_t)j * slice16 + 1u;       // + 1: centre column of the halo
+            const uint32_t g0 = g_base16 + gs * gstage16;
+            const uint32_t acc = it != 0 ? 1u : 0u;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t a_desc = a_hi | (uint64_t)(a0 + (uint32_t)((kh + 2 * k) * Wh));
+                const uint64_t b_desc = b_hi | (uint64_t)(g0 + (uint32_t)(16 * k));
+                ptx::umma_bf16(tmem_u + (uint32_t)kh * n3, a_desc, b_desc, idesc, k == 0 ? acc : 1u);
+              }
+            }
+          }
+          ptx::umma_commit(&sh->slot_empty[j]);
+          ptx::umma_commit(&sh->g_empty[gs]);
+          if (j == kWnLen - 1) {
+            ptx::umma_commit(&sh->slot_empty[kWnLen]);
+            ptx::umma_commit(&sh->slot_empty[kWnLen + 1]);
+            if (i == n_my - 1) ptx::umma_commit(&sh->done);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (n_my > 0) {
+    // ===================== final epilogue: TMEM -> fp32 atomics into dW =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;            // accumulator row = (slice block, channel)
+    ptx::mbar_wait(&sh->done, 0);
+    ptx::tc_fence_after();
+    const int kd = m / p.cpb, ci = cb * p.cpb + m % p.cpb;
+    const bool row_ok = kd < 3 && ci < p.c_in_real;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tap = (kd * 3 + kh) * 3 + kw;
+        for (int c0 = 0; c0 < p.n; c0 += 16) {
+          uint32_t raw[16];
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kh * 3 + kw) * p.n + c0), raw);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            float* dst = p.dw + (long long)tap * p.st_tap + (long long)ci * p.st_ci + (long long)c0 * p.st_co;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < p.c_out) atomicAdd(dst + (long long)i * p.st_co, __uint_as_float(raw[i]));
+          }
+        }
+      }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 wg_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
     void* ptr = nullptr;
@@ -223,9 +424,86 @@ static int wg_num_sms() {
   return n;
 }
 
+static int g_wgrad_no_narrow = 0;
+
+static int launch_wgrad_narrow(const VdmWgradDesc& d, const void* a, const void* g, float* dw, int x_planes, int g_planes,
+                               int c_out16, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t stream) {
+  WgradNarrowParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d.batch; p.D = d.depth; p.H = d.height; p.W = d.width;
+  p.c_in = d.c_in; p.c_out = d.c_out; p.n = c_out16;
+  int cpb = 32;
+  while (d.c_in % cpb != 0) cpb >>= 1;          // 32 or 16 (c_in is a multiple of 16)
+  p.cpb = cpb; p.S = 128 / cpb; p.n_cblocks = d.c_in / cpb;
+  p.n_slots = kWnLen + p.S - 1;
+  p.tiles_w = ceil_div(d.width, kWgTileW);
+  p.tiles_h = ceil_div(d.height, kWgTileH);
+  p.segs_d = ceil_div(d.depth, kWnLen);
+  const long long n_segs = (long long)d.batch * p.tiles_h * p.tiles_w * p.segs_d;
+  VDM_CHECK_ARG(n_segs < (1ll << 31), "vdm_conv3d_wgrad: too many segments");
+  p.n_segs = (int)n_segs;
+  int n_splits = wg_num_sms() / p.n_cblocks;
+  if (n_splits < 1) n_splits = 1;
+  if (n_splits > p.n_segs) n_splits = p.n_segs;
+  p.n_splits = n_splits;
+  p.slice_bytes = (cpb / 8) * (kWgTileH + 2) * (kWgTileW + 2) * 16;
+  p.g_tile_bytes = p.n * kWgTileH * kWgTileW * 2;
+  p.g_stage_bytes = 3 * p.g_tile_bytes;
+  p.x_planes = x_planes; p.x_plane0 = d.a_plane0;
+  p.g_planes = g_planes; p.g_plane0 = d.g_plane0;
+  p.dw = dw;
+  if (d.dw_stride_tap == 0 && d.dw_stride_ci == 0 && d.dw_stride_co == 0) {
+    p.st_tap = (long long)d.c_in * d.c_out; p.st_ci = d.c_out; p.st_co = 1; p.c_in_real = d.c_in;
+  } else {
+    VDM_CHECK_ARG(d.c_in_real >= 1 && d.c_in_real <= d.c_in, "vdm_conv3d_wgrad: c_in_real=%d out of [1, c_in]", d.c_in_real);
+    p.st_tap = d.dw_stride_tap; p.st_ci = d.dw_stride_ci; p.st_co = d.dw_stride_co; p.c_in_real = d.c_in_real;
+  }
+  const size_t smem_bytes = (size_t)p.n_slots * p.slice_bytes + (size_t)kWnGStages * p.g_stage_bytes +
+                            sizeof(WgradNarrowShared) + 1024;
+  VDM_CHECK_ARG(smem_bytes <= 227 * 1024, "vdm_conv3d_wgrad: narrow-layer plan needs %zu bytes of shared memory", smem_bytes);
+  CUtensorMap tma, tmg;
+  {
+    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
+    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * x_planes};
+    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(kWgTileW + 2) * 8, (cuuint32_t)(kWgTileH + 2), 1u, (cuuint32_t)(cpb / 8)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(a) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+    cuuint64_t gdim2[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * g_planes};
+    cuuint32_t box2[4] = {(cuuint32_t)kWgTileW * 8, (cuuint32_t)kWgTileH, 1u, (cuuint32_t)(p.n / 8)};
+    r = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g), gdim2, gstr, box2, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(g) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+  }
+  static bool configured = false;
+  if (!configured) {
+    VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  conv3d_wgrad_narrow_kernel<<<p.n_cblocks * p.n_splits, kWnThreads, smem_bytes, stream>>>(tma, tmg, p);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
+
 }  // namespace vdm
 
 using namespace vdm;
+
+extern "C" int vdm_wgrad_debug_set(int key, int value) {
+  if (key == 0) { g_wgrad_no_narrow = value; return VDM_OK; }
+  set_error("vdm_wgrad_debug_set: unknown key %d", key);
+  return VDM_E_BADARG;
+}
 
 extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const void* g, float* dw, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -248,6 +526,9 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
     set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled is not available from the driver");
     return VDM_E_DRIVER;
   }
+
+  if (d.kernel == 3 && c_out16 <= 32 && d.depth >= 2 && g_wgrad_no_narrow == 0)
+    return launch_wgrad_narrow(d, a, g, dw, x_planes, g_planes, c_out16, encode, stream);
 
   WgradParams p;
   memset(&p, 0, sizeof(p));
