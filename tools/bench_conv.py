@@ -58,6 +58,11 @@ def main():
     zero = torch.zeros_like(x)
     ms = timeit(lambda: ops.conv3d(zero, w, co, taps=taps, out=out))
     print(f"  all-zero input, no epilogue extras: {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s")
+    for flags, what in ((1, "epilogue does nothing"), (2, "no halo loads after the fill"), (3, "neither")):
+        lib.vdm_debug_set(5, flags)
+        ms = timeit(lambda: ops.conv3d(x, w, co, taps=taps, out=out))
+        print(f"  EXPERIMENT (automatic schedule) {what}: {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s")
+    lib.vdm_debug_set(5, 0)
     for mt in (1, 2, 3, 4):
         lib.vdm_debug_set(1, mt)
         try:

@@ -168,7 +168,11 @@ __device__ __forceinline__ void issue_fold_tile(uint32_t a_lo0, uint32_t b_base1
   constexpr int Hh = kTileH + 2, Wh = kTileW + 2, Hd = MT + 2;
   constexpr uint32_t plane16 = (uint32_t)(Hd * Hh * Wh);
   constexpr uint32_t kstep_a16 = 2u * plane16;
-#pragma unroll
+  const uint32_t a_hi32 = (uint32_t)(a_hi >> 32), b_hi32 = (uint32_t)(b_hi >> 32);
+  // One loop trip per input slice (NOT unrolled: a fully unrolled schedule made ptxas software-pipeline the
+  // descriptor arithmetic over dozens of MMAs and spill uniform registers, ~65 issue cycles per MMA); inside a
+  // trip the 9*KJ MMAs differ only by immediate offsets from per-slice bases.
+#pragma unroll 1
   for (int i = 0; i < MT + 2; ++i) {
     const int kd_lo = (i - MT + 1) > 0 ? (i - MT + 1) : 0;
     const int kd_hi = i < 2 ? i : 2;
@@ -176,22 +180,29 @@ __device__ __forceinline__ void issue_fold_tile(uint32_t a_lo0, uint32_t b_base1
     const int nblk = kd_hi - kd_lo + 1;
     // accumulator s = i receives its first contribution (kd = 0, the last block) in the first channel chunk
     const bool starts = FIRST && i < MT;
+    // low descriptor words: start address (16-byte units) | LBO << 16 (the low word of a_hi / b_hi)
+    const uint32_t a_i = a_lo0 + (uint32_t)(i * Hh * Wh) + (uint32_t)a_hi;
+    const uint32_t b_i = b_base16 + (uint32_t)((2 - kd_hi) * NF) + (uint32_t)b_hi;
+    const uint32_t d_i = d_tmem0 + (uint32_t)(s_lo * NF);
+    const uint32_t idesc_i = ptx::make_idesc_bf16(128, (uint32_t)(nblk * NF));
 #pragma unroll
     for (int khw = 0; khw < 9; ++khw) {
 #pragma unroll
       for (int j = 0; j < KJ; ++j) {
-        const uint32_t a_off = (uint32_t)((i * Hh + khw / 3) * Wh + khw % 3) + (uint32_t)j * kstep_a16;
-        const uint32_t b_off = (uint32_t)(((khw * 2 * KJ + 2 * j) * 3 + (2 - kd_hi)) * NF);
-        const uint64_t a_desc = a_hi | (uint64_t)(a_lo0 + a_off);
-        if (starts && khw == 0 && j == 0) {
-          if (nblk > 1)
-            ptx::umma_bf16(d_tmem0 + (uint32_t)(s_lo * NF), a_desc, b_hi | (uint64_t)(b_base16 + b_off),
-                           ptx::make_idesc_bf16(128, (uint32_t)((nblk - 1) * NF)), 1u);
-          ptx::umma_bf16(d_tmem0 + (uint32_t)(i * NF), a_desc, b_hi | (uint64_t)(b_base16 + b_off + (uint32_t)((nblk - 1) * NF)),
-                         ptx::make_idesc_bf16(128, (uint32_t)NF), 0u);
+        const uint32_t a_off = (uint32_t)((khw / 3) * Wh + khw % 3) + (uint32_t)j * kstep_a16;
+        const uint32_t b_off = (uint32_t)((khw * 2 * KJ + 2 * j) * 3 * NF);
+        if (khw == 0 && j == 0) {
+          if (starts) {
+            if (nblk > 1)
+              ptx::umma_bf16_off(d_i, 0u, a_i, a_off, a_hi32, b_i, b_off, b_hi32,
+                                 ptx::make_idesc_bf16(128, (uint32_t)((nblk - 1) * NF)), 1u);
+            ptx::umma_bf16_off(d_tmem0, (uint32_t)(i * NF), a_i, a_off, a_hi32, b_i, b_off + (uint32_t)((nblk - 1) * NF), b_hi32,
+                               ptx::make_idesc_bf16(128, (uint32_t)NF), 0u);
+          } else {
+            ptx::umma_bf16_off(d_i, 0u, a_i, a_off, a_hi32, b_i, b_off, b_hi32, idesc_i, 1u);
+          }
         } else {
-          ptx::umma_bf16(d_tmem0 + (uint32_t)(s_lo * NF), a_desc, b_hi | (uint64_t)(b_base16 + b_off),
-                         ptx::make_idesc_bf16(128, (uint32_t)(nblk * NF)), 1u);
+          ptx::umma_bf16_off(d_i, 0u, a_i, a_off, a_hi32, b_i, b_off, b_hi32, idesc_i, 1u);
         }
       }
     }
@@ -427,6 +438,19 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int n_units = ns_w * nch_w;                            // unit k = (chunk k / ns_w, slice k % ns_w) of this warp
     const long long V = (long long)p.D * p.H * p.W;
     const uint4* res_base = reinterpret_cast<const uint4*>(p.residual);
+    // Bias + conditioning rows: when the [B][n_pad] table fits the 512-float buffer it is loaded ONCE per CTA
+    // (r01r: a per-tile global load + barrier in front of every tile cost ~1 us on the epilogue-bound layers).
+    const bool cadd_table = p.chan_add != nullptr && p.B * p.n_pad <= 512;
+    if (cadd_table) {
+      const long long step = p.step_ptr ? (long long)(*p.step_ptr) : 0ll;
+      const float* cadd = p.chan_add + step * p.chan_add_step_stride;
+      float* tab = &sh->cadd[0][0];
+      for (int i = et; i < p.B * p.n_pad; i += kEpiThreads) {
+        const int bb = i / p.n_pad, c = i - bb * p.n_pad;
+        tab[i] = c < p.c_out ? __ldg(cadd + (long long)bb * p.c_out + c) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
       const TileCoord t = decode_tile(p, tile);
@@ -435,7 +459,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const int cbase = t.ns * p.n_cta;
       const uint32_t acc = ti & 1;
       const int buf = ti & 1;
-      if (p.chan_add) {
+      if (p.chan_add && !cadd_table) {
         // bias + conditioning row of this sample -> shared memory (16 scalar global loads per unit cost ~10% of
         // the epilogue's stall samples in r01h)
         const long long step = p.step_ptr ? (long long)(*p.step_ptr) : 0ll;
@@ -466,7 +490,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
         for (int i = 0; i < kResDepth; ++i) res_issue(i, rq[i]);
       }
-      if (p.chan_add) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (p.chan_add && !cadd_table) asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* cadd_row = cadd_table ? &sh->cadd[0][0] + t.b * p.n_pad + cbase : &sh->cadd[buf][0];
       ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
       ptx::tc_fence_after();
       if (!(p.debug_flags & 1)) {
@@ -477,13 +502,10 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           float s1[16], s2[16];            // per-lane statistics of this chunk over the warp's slices
 #pragma unroll
           for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
-          for (int s = s0; s < MT; s += s_step, ++unit) {
+          auto process = [&](int s, const uint32_t (&raw)[16]) __attribute__((always_inline)) {
             const int d = t.d0 + s;
             const bool valid = hw_ok && (d < p.D);
             const long long vox = ((long long)d * p.H + h) * p.W + w;
-            uint32_t raw[16];
-            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + s) * p.n_cta + ch * 16), raw);
-            ptx::tmem_ld_wait();
             // rotate the residual ring: rq[0] is this unit's data, refill the tail
             uint4 rcur[2];
             if (p.residual) {
@@ -492,12 +514,13 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
               for (int i = 0; i + 1 < kResDepth; ++i) { rq[i][0] = rq[i + 1][0]; rq[i][1] = rq[i + 1][1]; }
               res_issue(unit + kResDepth, rq[kResDepth - 1]);
             }
-            if (c0 >= p.c_out) continue;  // padded output channels (warp-uniform)
+            ++unit;
+            if (c0 >= p.c_out) return;  // padded output channels (warp-uniform)
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(raw[j]);
             if (p.chan_add) {
-              const float4* cs = reinterpret_cast<const float4*>(&sh->cadd[buf][ch * 16]);
+              const float4* cs = reinterpret_cast<const float4*>(cadd_row + ch * 16);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 cv = cs[j4];
@@ -511,7 +534,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 for (int j = 0; j < 16; ++j)
                   if (full16 || c0 + j < p.c_out) yp[(long long)j * V] = f[j];
               }
-              continue;
+              return;
             }
             // bf16 planar output: two planes of 8 channels (c_out % 8 == 0 is checked on the host)
 #pragma unroll
@@ -539,6 +562,13 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
               }
             }
+          };
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.n_cta + ch * 16);
+          for (int s = s0; s < MT; s += s_step) {
+            uint32_t raw0[16];
+            ptx::tmem_ld16(trow + (uint32_t)(s * p.n_cta), raw0);
+            ptx::tmem_ld_wait();
+            process(s, raw0);
           }
           if (p.stats && c0 < p.c_out) {
             // one transpose-reduction per chunk and tile (r01j: per (slice, chunk) it cost 0.22 -> 0.30 ms on 32->32)

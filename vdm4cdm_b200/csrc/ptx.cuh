@@ -132,6 +132,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors assembled INSIDE the asm block from warp-uniform bases plus per-MMA offsets:
+//   a_desc = {a_lo + a_off, a_hi32}, b_desc = {b_lo + b_off, b_hi32}, d = d_tmem + d_off.
+// Keeping the adds next to the (volatile) MMA stops ptxas from pre-computing hundreds of descriptors into vector
+// registers and moving them back with R2UR (r01s: ~65 issue cycles per MMA in the unrolled schedule).
+__device__ __forceinline__ void umma_bf16_off(uint32_t d_tmem, uint32_t d_off, uint32_t a_lo, uint32_t a_off, uint32_t a_hi32,
+                                              uint32_t b_lo, uint32_t b_off, uint32_t b_hi32, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 alo, blo, dd;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "add.u32 alo, %1, %2;\n\t"
+      "add.u32 blo, %4, %5;\n\t"
+      "add.u32 dd, %0, %9;\n\t"
+      "mov.b64 da, {alo, %3};\n\t"
+      "mov.b64 db, {blo, %6};\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [dd], da, db, %7, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_off), "r"(a_hi32), "r"(b_lo), "r"(b_off), "r"(b_hi32), "r"(idesc), "r"(accumulate), "r"(d_off)
+      : "memory");
+}
 // Arrive on `bar` when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
