@@ -58,6 +58,8 @@ struct ConvKernelParams {
   int MT, KC, k_chunks;
   int Hd, Hh, Wh;            // halo box (voxels)
   int tiles_w, tiles_h, tiles_d, n_tiles;
+  int fast_div_ok;           // n_tiles < 2^22: tile decoding by float reciprocals
+  float inv_n_split, inv_tiles_w, inv_tiles_h, inv_tiles_d;
   int a_stage_bytes, b_stage_bytes, nsb, taps_per_stage;
   int b_resident;            // all weights of this CTA's channel slice stay in shared memory (loaded once)
   int plane_bytes;           // Hd*Hh*Wh*16
@@ -125,13 +127,29 @@ __device__ __forceinline__ void warp_column_sums16(float (&v)[16]) {
 struct TileCoord {
   int b, d0, h0, w0, ns;
 };
+// x / d for 0 <= x < 2^22 with inv = 1.0f / d: (x + 0.5) * inv is at least 0.5/d away from an integer, far more than
+// the fp32 rounding error, so truncation is exact.  (Every epilogue thread decodes every tile; four integer divisions
+// by run-time values were 9% of the epilogue's instructions in r01t.)
+__device__ __forceinline__ int fast_div(int x, int d, float inv) {
+  (void)d;
+  return __float2int_rz(((float)x + 0.5f) * inv);
+}
 __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int tile) {
   TileCoord t;
-  t.ns = tile % p.n_split; tile /= p.n_split;
-  t.w0 = (tile % p.tiles_w) * kTileW; tile /= p.tiles_w;
-  t.h0 = (tile % p.tiles_h) * kTileH; tile /= p.tiles_h;
-  t.d0 = (tile % p.tiles_d) * p.MT;
-  t.b = tile / p.tiles_d;
+  int q;
+  if (p.fast_div_ok) {
+    q = fast_div(tile, p.n_split, p.inv_n_split); t.ns = tile - q * p.n_split; tile = q;
+    q = fast_div(tile, p.tiles_w, p.inv_tiles_w); t.w0 = (tile - q * p.tiles_w) * kTileW; tile = q;
+    q = fast_div(tile, p.tiles_h, p.inv_tiles_h); t.h0 = (tile - q * p.tiles_h) * kTileH; tile = q;
+    q = fast_div(tile, p.tiles_d, p.inv_tiles_d); t.d0 = (tile - q * p.tiles_d) * p.MT;
+    t.b = q;
+  } else {
+    t.ns = tile % p.n_split; tile /= p.n_split;
+    t.w0 = (tile % p.tiles_w) * kTileW; tile /= p.tiles_w;
+    t.h0 = (tile % p.tiles_h) * kTileH; tile /= p.tiles_h;
+    t.d0 = (tile % p.tiles_d) * p.MT;
+    t.b = tile / p.tiles_d;
+  }
   return t;
 }
 
@@ -451,6 +469,46 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    // Residual prefetch ring.  The residual does not depend on the accumulator, and a dependent 16-byte global load
+    // per (unit, half) cost ~700 cycles each (r01f: 0.44 -> 0.76 ms on the 32->32 level-0 conv).  This warp consumes its
+    // units in a fixed order; kResDepth of them are always in flight, and the prefetch stream runs AHEAD ACROSS TILE
+    // BOUNDARIES (its own tile cursor), so a tile's first residuals were requested about one tile time earlier -- on the
+    // epilogue-bound layers nothing else can hide their latency (r01u: +1.4 us per tile).
+    constexpr int kResDepth = 4;
+    uint4 rq[kResDepth][2];
+    const long long HW = (long long)p.H * p.W;
+    int r_tile = blockIdx.x - (int)gridDim.x;        // tile the prefetch cursor is in (advanced before first use)
+    int ru_s = 0, ru_ch = n_chunks;                  // (slice, chunk) of the next unit to prefetch; "tile exhausted"
+    const uint4* r_ptr = nullptr;
+    int r_d0 = 0, r_cbase = 0;
+    bool r_hw_ok = false;
+    auto res_issue = [&](uint4 (&dst)[2]) {
+      if (ru_ch >= n_chunks) {                       // move the cursor to this CTA's next tile
+        r_tile += (int)gridDim.x;
+        if (r_tile >= p.n_tiles) return;
+        const TileCoord tr = decode_tile(p, r_tile);
+        const int hr = tr.h0 + lh, wr = tr.w0 + lw;
+        r_hw_ok = (hr < p.H) && (wr < p.W);
+        r_d0 = tr.d0;
+        r_cbase = tr.ns * p.n_cta;
+        r_ptr = res_base + ((long long)tr.b * p.r_planes + p.r_plane0 + (r_cbase >> 3)) * V +
+                ((long long)tr.d0 * p.H + hr) * p.W + wr;
+        ru_s = s0; ru_ch = ch0;
+        if (ru_ch >= n_chunks) return;
+      }
+      const int su = ru_s, chu = ru_ch;
+      ru_s += s_step;
+      if (ru_s >= MT) { ru_s = s0; ru_ch += ch_step; }
+      if (!(r_hw_ok && r_d0 + su < p.D)) return;
+      const uint4* src = r_ptr + (long long)(chu * 2) * V + (long long)su * HW;
+      const int cu = r_cbase + chu * 16;
+      if (cu < p.c_out) dst[0] = __ldg(src);
+      if (cu + 8 < p.c_out) dst[1] = __ldg(src + V);
+    };
+    if (p.residual) {
+#pragma unroll
+      for (int i = 0; i < kResDepth; ++i) res_issue(rq[i]);
+    }
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
       const TileCoord t = decode_tile(p, tile);
@@ -466,30 +524,9 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const float* cadd = p.chan_add + step * p.chan_add_step_stride + (long long)t.b * p.c_out;
         if (et < p.n_cta) sh->cadd[buf][et] = (cbase + et < p.c_out) ? __ldg(cadd + cbase + et) : 0.f;
       }
-      // Residual prefetch ring: the residual does not depend on the accumulator, and a dependent 16-byte global
-      // load per (unit, half) cost ~700 cycles each (r01f: 0.44 -> 0.76 ms on the 32->32 level-0 conv).  This
-      // warp consumes units half, half+2, ...; kResDepth of them are in flight, the first ones issued BEFORE
-      // waiting for the accumulator.
-      constexpr int kResDepth = 4;
-      uint4 rq[kResDepth][2];
-      auto res_issue = [&](int u, uint4 (&dst)[2]) {
-        if (u >= n_units) return;
-        const int ku = u / ns_w;
-        const int su = s0 + (u - ku * ns_w) * s_step, chu = ch0 + ku * ch_step;
-        const int du = t.d0 + su;
-        const int cu = cbase + chu * 16;
-        if (!(hw_ok && du < p.D)) return;
-        const long long voxu = ((long long)du * p.H + h) * p.W + w;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int c = cu + hf * 8;
-          if (c < p.c_out) dst[hf] = __ldg(res_base + ((long long)t.b * p.r_planes + p.r_plane0 + (c >> 3)) * V + voxu);
-        }
-      };
-      if (p.residual) {
-#pragma unroll
-        for (int i = 0; i < kResDepth; ++i) res_issue(i, rq[i]);
-      }
+      // per-tile bases (64-bit once per tile; per unit only adds): voxel of slice 0, plane 0 of this thread
+      const long long vox0 = ((long long)t.d0 * p.H + h) * p.W + w;
+      bf16x8* y_tile = reinterpret_cast<bf16x8*>(p.y) + ((long long)t.b * p.y_planes + p.y_plane0 + (cbase >> 3)) * V + vox0;
       if (p.chan_add && !cadd_table) asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* cadd_row = cadd_table ? &sh->cadd[0][0] + t.b * p.n_pad + cbase : &sh->cadd[buf][0];
       ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
@@ -505,14 +542,14 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           auto process = [&](int s, const uint32_t (&raw)[16]) __attribute__((always_inline)) {
             const int d = t.d0 + s;
             const bool valid = hw_ok && (d < p.D);
-            const long long vox = ((long long)d * p.H + h) * p.W + w;
+            const long long vox = vox0 + (long long)s * HW;
             // rotate the residual ring: rq[0] is this unit's data, refill the tail
             uint4 rcur[2];
             if (p.residual) {
               rcur[0] = rq[0][0]; rcur[1] = rq[0][1];
 #pragma unroll
               for (int i = 0; i + 1 < kResDepth; ++i) { rq[i][0] = rq[i + 1][0]; rq[i][1] = rq[i + 1][1]; }
-              res_issue(unit + kResDepth, rq[kResDepth - 1]);
+              res_issue(rq[kResDepth - 1]);
             }
             ++unit;
             if (c0 >= p.c_out) return;  // padded output channels (warp-uniform)
@@ -552,8 +589,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
               }
               const bf16x8 packed = pack8(g);
               if (valid) {
-                bf16x8* yp = reinterpret_cast<bf16x8*>(p.y) + ((long long)t.b * p.y_planes + p.y_plane0 + (c >> 3)) * V + vox;
-                *yp = packed;
+                y_tile[(long long)(ch * 2 + hf) * V + (long long)s * HW] = packed;
                 unpack8(packed, g);  // statistics describe the stored (rounded) tensor
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -802,6 +838,9 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   const long long n_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * d.batch * n_split;
   VDM_CHECK_ARG(n_tiles < (1ll << 31), "vdm_conv3d: too many tiles");
   p.n_tiles = (int)n_tiles;
+  p.fast_div_ok = n_tiles < (1ll << 22) ? 1 : 0;
+  p.inv_n_split = 1.0f / (float)n_split; p.inv_tiles_w = 1.0f / (float)p.tiles_w;
+  p.inv_tiles_h = 1.0f / (float)p.tiles_h; p.inv_tiles_d = 1.0f / (float)p.tiles_d;
   p.Hd = mt + 2 * pad; p.Hh = kTileH + 2 * pad; p.Wh = kTileW + 2 * pad;
   p.plane_bytes = p.Hd * p.Hh * p.Wh * 16;
   for (int t = 0; t < d.n_taps; ++t)
