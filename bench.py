@@ -285,6 +285,9 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_train:
         train = train_leg(args, model, net, dev, rank, world, peak)
 
+    # ---- P(k) / r(k) of generated fields (SURVEY.md section 8d metric iii) ----
+    pk = pk_leg(grid, dev, peaks)
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -309,7 +312,43 @@ def run_b200(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu
     if train is not None:
         line["train"] = train
+    line["pk"] = pk
     emit(line)
+
+
+def pk_leg(grid, dev, peaks):
+    """fields/s of utils.pk (cuFFT R2C + k-shell binning) and utils.get_ccs on 16 mass-like 128^3 fields; the binning
+    pass is HBM-bound: algorithmic bytes = 4 N^3 (field read by the FFT) + 16 N^2 (N/2+1) (spectrum written and read)."""
+    from vdm4cdm_b200 import utils
+    n_fields = 16
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn((n_fields, 1, grid, grid, grid), generator=g, device=dev)
+    mass = 10.0 ** (x * 0.552 + 10.019) - 1.0                         # calc_SS.py:67-70 input definition
+    mass = mass / mass.sum((2, 3, 4), keepdim=True)
+    other = 0.7 * mass + 0.3 * mass.flip(2)
+
+    def timed(fn, iters=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    ms_pk = timed(lambda: utils.pk(mass))
+    ms_cc = timed(lambda: utils.get_ccs(mass, other))
+    bytes_field = 4.0 * grid ** 3 + 16.0 * grid * grid * (grid // 2 + 1)
+    hbm = float(peaks.get("hbm_gbs", 6550.0))
+    gbs = n_fields * bytes_field / (ms_pk * 1e-3) / 1e9
+    return {"metric": f"P(k) fields/s at {grid}^3 (cuFFT R2C + binning, {n_fields} fields per call)",
+            "value": n_fields / (ms_pk * 1e-3), "unit": "fields/s", "ms_per_call": ms_pk,
+            "get_ccs_pairs_per_s": n_fields / (ms_cc * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                         "algorithmic_bytes_per_field": bytes_field}}
 
 
 def train_leg(args, model, net, dev, rank, world, peak_tflops):

@@ -1,0 +1,110 @@
+"""Full-size (128^3, the BASELINE.json grid) checks through size-independent properties: the CPU oracle needs
+seconds to minutes per 128^3 call, so at this size the CUDA path is tested against identities that hold for the
+exact operator (SURVEY.md section 4 / prompt section 3): linearity and translation equivariance of the convolution
+on integer-valued inputs (bit-exact), Parseval and the delta-function / single-mode spectra for P(k), and
+reproducibility + batch independence of the sampler."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+N = 128
+
+
+def _ops():
+    from vdm4cdm_b200 import ops
+    return ops
+
+
+def _ints(shape, lo, hi, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(lo, hi + 1, shape, generator=g, device="cuda").float()
+
+
+@pytest.mark.parametrize("ci,co", [(32, 32), (96, 32), (64, 64)])
+def test_conv3d_linearity_and_shift_equivariance_128(ci, co):
+    ops = _ops()
+    n = N if ci * co <= 96 * 32 else N // 2
+    x1, x2 = _ints((1, ci, n, n, n), -1, 1, 1), _ints((1, ci, n, n, n), -1, 1, 2)
+    # sparse +-1 filter (density 1/6) keeps every partial and final sum far below 256
+    w = ops.pack_conv_weight(_ints((co, ci, 3, 3, 3), -1, 1, 3) * (_ints((co, ci, 3, 3, 3), 0, 3, 4) == 0).float())
+    y1 = ops.from_planar(ops.conv3d(ops.to_planar(x1), w, co))
+    y2 = ops.from_planar(ops.conv3d(ops.to_planar(x2), w, co))
+    y12 = ops.from_planar(ops.conv3d(ops.to_planar(x1 - x2), w, co))
+    # |sums| stay below 256: every value is an integer that bf16 represents exactly -> exact linearity
+    assert y1.abs().max() < 256 and y12.abs().max() < 256
+    assert torch.equal(y12, y1 - y2)
+    # translation by (1, 2, 3) voxels: interior outputs move with the input
+    xs = torch.roll(x1, shifts=(1, 2, 3), dims=(2, 3, 4))
+    ys = ops.from_planar(ops.conv3d(ops.to_planar(xs), w, co))
+    assert torch.equal(ys[:, :, 3:-3, 4:-4, 5:-5], torch.roll(y1, shifts=(1, 2, 3), dims=(2, 3, 4))[:, :, 3:-3, 4:-4, 5:-5])
+
+
+def test_wgrad_is_bilinear_128():
+    ops = _ops()
+    ci = co = 32
+    a1, a2 = _ints((1, ci, N, N, N), -1, 1, 4), _ints((1, ci, N, N, N), -1, 1, 5)
+    g = _ints((1, co, N, N, N), -1, 1, 6)
+    gp = ops.to_planar(g)
+    d1 = ops.conv3d_wgrad(ops.to_planar(a1), gp, ci, co, 3)
+    d2 = ops.conv3d_wgrad(ops.to_planar(a2), gp, ci, co, 3)
+    d12 = ops.conv3d_wgrad(ops.to_planar(a1 + a2), gp, ci, co, 3)
+    # 2^21 products of magnitude <= 2 per entry: exact in fp32 (|sum| < 2^24)
+    assert torch.equal(d12, d1 + d2)
+    # centre tap of the filter gradient = plain correlation sum_v a[ci, v] g[co, v]
+    ref = torch.einsum("cv,ov->co", a1.reshape(ci, -1).double(), g.reshape(co, -1).double()).float()
+    assert torch.equal(d1[13], ref)
+
+
+def test_pk_identities_128():
+    from vdm4cdm_b200 import utils
+    # delta function: flat spectrum P = 1, mode counts = number of integer wave vectors per shell
+    x = torch.zeros((1, 1, N, N, N), device="cuda")
+    x[0, 0, 3, 5, 7] = 1.0
+    k, p, n = utils.power(x)
+    assert torch.allclose(p, torch.ones_like(p), rtol=1e-5)
+    kk = torch.fft.fftfreq(N, 1.0 / N)
+    kmag = torch.sqrt(kk[:, None, None] ** 2 + kk[None, :, None] ** 2 + kk[None, None, :] ** 2)
+    shells = torch.ceil(kmag).long()
+    want = torch.bincount(shells.flatten(), minlength=N // 2 + 1)[1:N // 2 + 1]
+    assert torch.equal(n.cpu().long(), want)
+    # Parseval over the binned shells of a random field: sum_k N(k) P(k) = sum over those modes of |X|^2
+    g = torch.Generator(device="cuda").manual_seed(9)
+    f = torch.randn((1, 1, N, N, N), generator=g, device="cuda")
+    k, p, n = utils.power(f)
+    X = torch.fft.fftn(f[0, 0].double())
+    mask = (shells >= 1) & (shells <= N // 2)
+    total = (X.abs() ** 2)[mask.cuda()].sum().item()
+    assert abs((p.double() * n.double()).sum().item() - total) < 1e-5 * total
+    # r(k) of a field with itself is 1, with its negative -1
+    _, cc = utils.get_ccs(f, f)
+    assert torch.allclose(cc, torch.ones_like(cc), atol=2e-5)
+    _, cc = utils.get_ccs(f, -f)
+    assert torch.allclose(cc, -torch.ones_like(cc), atol=2e-5)
+
+
+def test_sampler_reproducible_and_batch_independent_128():
+    from vdm4cdm_b200.networks import CUNet
+    from vdm4cdm_b200.vdm_model import LightVDM
+    torch.manual_seed(0)
+    net = CUNet(shape=(1, N, N, N), chs=[32, 64, 128, 256], s_conditioning_channels=1, v_conditioning_dims=[6],
+                t_conditioning=True)
+    model = LightVDM(net).cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    cond = torch.randn((1, 1, N, N, N), generator=g, device="cuda")
+    vals = torch.rand((1, 6), generator=g, device="cuda")
+
+    def draw(ids):
+        b = len(ids)
+        return model.draw_samples(batch_size=b, n_sampling_steps=4, s_conditioning=cond.expand(b, -1, -1, -1, -1).contiguous(),
+                                  v_conditionings=[vals.expand(b, -1).contiguous()], seed=5, realisation_ids=ids)
+
+    a = draw([3, 8])
+    b = draw([3, 8])
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b), "same seed and realisation ids must reproduce the samples bit for bit"
+    c = draw([8])
+    rel = ((a[1:] - c).norm() / c.norm()).item()
+    assert rel < 1e-2, rel            # same realisation in another batch: equal up to bf16 rounding noise
+    assert ((a[:1] - c).norm() / c.norm()).item() > 0.3

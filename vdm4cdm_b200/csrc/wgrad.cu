@@ -540,6 +540,17 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
   int cpb = 128;
   while (d.c_in % cpb != 0) cpb >>= 1;
   p.cpb = cpb; p.S = 128 / cpb; p.n_cblocks = d.c_in / cpb;
+  int over_read = 0;
+  if (d.kernel == 1) {
+    // 1x1x1: there is no filter plane to fold into M, and the layer is HBM-bound: load each `a` slice ONCE.  One block
+    // = the widest multiple of 16 channels <= 128 dividing c_in; accumulator rows beyond it are garbage (the operand
+    // descriptor walks 16 plane-strides into whatever follows in shared memory) and are dropped in the epilogue.
+    // (r01r: 0.38 ms for the 96->32 skip conv with S = 4 slices loaded per tile, 4x its HBM floor.)
+    cpb = 128;
+    while (d.c_in % cpb != 0) cpb -= 16;
+    p.cpb = cpb; p.S = 1; p.n_cblocks = d.c_in / cpb;
+    over_read = 16 * kWgTileH * kWgTileW * 16;
+  }
   p.n_sblocks = (p.kd_count + p.S - 1) / p.S;
   p.n_jobs_total = p.n_sblocks * p.n_khw;
   p.n_split = c_out16 > 128 ? 2 : 1;
@@ -561,7 +572,7 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
   const int n_slices = p.n_sblocks * p.S;
   p.a_stage_bytes = (n_slices * p.slice_bytes + 127) & ~127;
   p.g_stage_bytes = p.n * kWgTileH * kWgTileW * 2;
-  const int budget = 227 * 1024 - 1024 - (int)sizeof(WgradShared) - 256;
+  const int budget = 227 * 1024 - 1024 - (int)sizeof(WgradShared) - 256 - over_read;
   int stages = budget / (p.a_stage_bytes + p.g_stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   VDM_CHECK_ARG(stages >= 1, "vdm_conv3d_wgrad: one stage (%d bytes) does not fit shared memory",
@@ -612,7 +623,7 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
       return VDM_E_DRIVER;
     }
   }
-  const size_t smem_bytes = (size_t)p.stages * (p.a_stage_bytes + p.g_stage_bytes) + sizeof(WgradShared) + 1024;
+  const size_t smem_bytes = (size_t)p.stages * (p.a_stage_bytes + p.g_stage_bytes) + sizeof(WgradShared) + 1024 + over_read;
   static bool configured = false;
   if (!configured) {
     VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
