@@ -273,7 +273,7 @@ def run_b200(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("conv3d_planar_kernel_dram_bytes_per_launch")
+            traffic = json.load(f).get("conv_dram_bytes_per_step")   # DRAM read + write of one step's conv launches (ncu)
     roofline = {"kernel": "conv3d_planar_kernel (all conv launches of one step)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": traffic,
