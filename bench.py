@@ -481,7 +481,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=2, help="realisations per GPU")
+    ap.add_argument("--batch", type=int, default=8,
+                    help="realisations sampled together per GPU (BASELINE.json configs[4]: 64 realisations over 8 GPUs)")
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--chs", type=int, nargs="+", default=[32, 64, 128, 256])
     ap.add_argument("--no-cpu-baseline", action="store_true")

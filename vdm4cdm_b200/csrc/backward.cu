@@ -54,7 +54,8 @@ __device__ __forceinline__ void chunk_du(const bf16x8& xv, const bf16x8& dyv, co
 
 // Pass 1.  Per thread: sum du and sum du*x (raw); per block: xhat = (x - mean)*rstd is linear in x, so the
 // block partial of sum du*xhat is rstd*(sum du*x - mean*sum du), formed once per block before the atomics.
-__global__ void __launch_bounds__(kEwThreads)
+template <bool DROP>
+__global__ void __launch_bounds__(kEwThreads, DROP ? 2 : 4)
 gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
   __shared__ float s_scale[8], s_shift[8], s_mean[8], s_rstd[8];
   __shared__ float s_part[kEwThreads / 32][16];
@@ -65,7 +66,7 @@ gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
   __syncthreads();
   const bf16x8* xp = plane_ptr(a.x, b, pl, a.voxels);
   const bf16x8* gp = plane_ptr(a.dy, b, pl, a.voxels);
-  const bool drop = a.dropout_p > 0.f;
+  constexpr bool drop = DROP;
   const uint32_t thresh16 = (uint32_t)(a.dropout_p * 65536.0f + 0.5f);
   const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
@@ -121,7 +122,8 @@ gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
 
 // Pass 2.  dx = rstd*(gamma*du - m1 - xhat*m2) [+ add]  ==  A*du + Bc + Cc*x with per-channel
 // A = rstd*gamma, Cc = -rstd^2*m2, Bc = -rstd*m1 - Cc*mean.
-__global__ void __launch_bounds__(kEwThreads)
+template <bool DROP>
+__global__ void __launch_bounds__(kEwThreads, DROP ? 2 : 3)
 gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
   __shared__ float s_scale[8], s_shift[8], s_mean[8], s_rstd[8], s_A[8], s_B[8], s_C[8];
   const int b = blockIdx.y / a.planes, pl = blockIdx.y % a.planes;
@@ -158,7 +160,7 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
   const bf16x8* gp = plane_ptr(a.dy, b, pl, a.voxels);
   const bf16x8* ap = a.has_add ? plane_ptr(a.add, b, pl, a.voxels) : nullptr;
   bf16x8* op = plane_ptr_mut(a.dx, b, pl, a.voxels);
-  const bool drop = a.dropout_p > 0.f;
+  constexpr bool drop = DROP;
   const uint32_t thresh16 = (uint32_t)(a.dropout_p * 65536.0f + 0.5f);
   const float keep_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   const uint64_t chunk0 = ((uint64_t)b * a.planes + pl) * (uint64_t)a.voxels;
@@ -368,7 +370,10 @@ extern "C" int vdm_gn_silu_bwd_reduce(const VdmTensor* x, const VdmTensor* dy, i
   a.sums = sums;
   a.sums_channels = sums_channels > 0 ? sums_channels : channels;
   a.sums_c0 = sums_c0;
-  gn_silu_bwd_reduce_kernel<<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  if (dropout_p > 0.f)
+    gn_silu_bwd_reduce_kernel<true><<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  else
+    gn_silu_bwd_reduce_kernel<false><<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
 }
@@ -395,7 +400,10 @@ extern "C" int vdm_gn_silu_bwd_apply(const VdmTensor* x, const VdmTensor* dy, co
   a.out_stats = out_stats;
   a.out_stats_channels = out_stats_channels > 0 ? out_stats_channels : channels;
   a.out_stats_c0 = out_stats_c0;
-  gn_silu_bwd_apply_kernel<<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  if (dropout_p > 0.f)
+    gn_silu_bwd_apply_kernel<true><<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  else
+    gn_silu_bwd_apply_kernel<false><<<ew_grid(voxels, batch * a.planes), kEwThreads, 0, (cudaStream_t)stream>>>(a);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
 }
