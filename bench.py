@@ -380,6 +380,14 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
         torch.cuda.synchronize(dev)
 
     resident = to_dev()
+    staging = to_dev()                           # device staging buffers of the end-to-end loop (allocated once)
+
+    def h2d():
+        staging["x"].copy_(host["x"], non_blocking=True)
+        staging["conditioning"].copy_(host["conditioning"], non_blocking=True)
+        staging["conditioning_values"][0].copy_(host["conditioning_values"], non_blocking=True)
+        return staging
+
     n_steps, n_warm = args.train_steps, 3
     losses = []
     for _ in range(n_warm):
@@ -405,7 +413,7 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
     marks = []
     for _ in range(n_steps):
         ta = time.perf_counter()
-        dev_batch = to_dev()
+        dev_batch = h2d()
         tb = time.perf_counter()
         loss = trainer.training_step(dev_batch)
         tc = time.perf_counter()
