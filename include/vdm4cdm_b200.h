@@ -189,6 +189,17 @@ VDM_API int vdm_avgpool2_bwd(const VdmTensor* dy, const VdmTensor* dx, int batch
 VDM_API int vdm_upsample2_bwd(const VdmTensor* dy, const VdmTensor* dcoarse, int batch, int depth, int height, int width,
                       int channels, double* stats, int stats_channels, int stats_c0, void* stream);
 
+/* ---- training-batch preparation: periodic crop + log-normalise + flip + permute in one gather -----------------
+ * AstroDataset.__getitem__ (src/dataset/CAMELS_3D_dataset.py:53-74) with Crop / LogTransform / Normalize / Flip /
+ * Permutate (src/dataset/augmentation.py:8-127).  in: fp32 [S0][S1][S2] raw box; out: fp32 [n0][n1][n2] with
+ * n[d] = crop_size[perm[d]]:
+ *   out[o] = do_log ? (log10(in[src] + alpha) - mean) / std : in[src],
+ *   cropped index c with c[perm[d]] = o[d];  c'[a] = flip[a] ? crop_size[a]-1-c[a] : c[a];  src[a] = (anchor[a] + c'[a]) mod S[a].
+ * All five index arrays are HOST int32[3]. */
+VDM_API int vdm_augment_crop(const float* in, float* out, const int32_t* full_size, const int32_t* crop_size,
+                     const int32_t* anchor, const int32_t* flip, const int32_t* perm, float alpha, float mean, float std,
+                     int do_log, void* stream);
+
 /* ---- optimizer step on a flat fp32 parameter bucket (torch.optim.AdamW + Trainer(gradient_clip_val=0.5),
  *      trainVDM3D128_c_c_from_field_name_thick_lowbatch.py:134-160) --------------------------------- */
 /* *out += sum_i x[i]^2 (double, atomically). */
@@ -246,6 +257,13 @@ VDM_API int vdm_pk(const float* fields, const float* fields2, int n_fields, int 
 VDM_API int vdm_pk_cross3(const float* fields1, const float* fields2, int n_fields, int batch, int chan,
                   int n0, int n1, int n2, void* work, size_t work_bytes, double* k_mean,
                   double* p11, double* p22, double* p12, int64_t* n_modes, void* stream);
+
+/* ---- log-PDF histograms (calc_SS.py:51-65 get_logpdf_3d / get_logpdf_2d) -----------------------------------------
+ * counts[f][b] += #{voxels v of field f : log10(fields[f][v] + add) in bin b} for nbins equal bins on [lo, hi]
+ * (numpy.histogram semantics: left-closed bins, the last one closed on the right, values outside ignored).
+ * fields: fp32 [n_fields][voxels]; counts: int64 [n_fields][nbins], accumulated (the caller zeroes it). */
+VDM_API int vdm_log_histogram(const float* fields, int n_fields, int64_t voxels, float add, double lo, double hi, int nbins,
+                      int64_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

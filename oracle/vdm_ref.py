@@ -212,3 +212,38 @@ class LightVDM(nn.Module):
     def draw_samples(self, batch_size, n_sampling_steps=250, verbose=False, return_all=False, **kwargs):
         return self.model.sample(batch_size=batch_size, n_sampling_steps=n_sampling_steps,
                                  device=self.device, verbose=verbose, return_all=return_all, **kwargs)
+
+
+def get_ddnm_result(vdm, y, A, AT, n_sampling_steps=250, l=10, return_all=False, noise_fn=None, **kwargs):
+    """Oracle restatement of src/utils.py:277-304 (DDNM with time travel) with injectable noise:
+    ``noise_fn(draw, shape)`` is called once for the initial latent and once per re-noise / reverse update, in loop
+    order.  ``vdm`` is an oracle ``LightVDM``."""
+    import numpy as np
+    if isinstance(l, int):
+        l = np.full(n_sampling_steps, l)
+    l = np.asarray(l)
+    model = vdm.model
+    steps = torch.linspace(1.0, 0.0, n_sampling_steps + 1)
+    shape = (y.shape[0], *model.score_model.shape)
+    draw = [0]
+
+    def noise():
+        d = draw[0]
+        draw[0] += 1
+        return noise_fn(d, shape) if noise_fn is not None else torch.randn(shape)
+
+    z = noise()
+    ATy = AT(y)
+    xs = []
+    with torch.no_grad():
+        for i in range(n_sampling_steps):
+            L = int(min(l[i], i))
+            z = model.sample_zt_given_zs(zs=z, t=steps[i - L], s=steps[i], noise=noise())
+            for j in range(L, -1, -1):
+                w_z, w_x_0t, x_0t, scale = model.sample_zs_given_zt(zt=z, t=steps[i - j], s=steps[i + 1 - j],
+                                                                    return_ddnm=True, **kwargs)
+                x_0t_r = ATy + x_0t - AT(A(x_0t))
+                z = w_z * z + w_x_0t * x_0t_r + scale * noise()
+            if return_all:
+                xs.append(x_0t_r)
+    return torch.stack(xs, dim=0) if return_all else x_0t_r

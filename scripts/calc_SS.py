@@ -8,8 +8,9 @@ reads every ``gen_*.npy`` (rep, 1, N, N, N) written by scripts/generate_3D.py, u
 (``10**(x*std+mean)-1``), and writes ``SAVE_PATH/summary.npz`` with, per file: the 3-D P(k) of every
 realisation, the projected 2-D P(k) of the half / quarter slabs, posterior mean/std maps of the half slab and,
 when a truth field is given, the cross-correlation coefficient r(k) of every realisation with it.
-Files are independent units: file i goes to rank i mod world_size.  (The wavelet-scattering and log-PDF
-statistics of the reference are "next" rows of SURVEY.md section 8f.)
+Also the log-PDF histograms (get_logpdf_3d / get_logpdf_2d: calc_SS.py:51-65) on the histogram kernel.
+Files are independent units: file i goes to rank i mod world_size.  (The wavelet-scattering statistics
+(``mltools.archive.LWT``) are out of scope: SURVEY.md section 8f.)
 """
 import argparse
 import glob
@@ -52,7 +53,8 @@ def main():
         data = np.load(files[i])
         n = data.shape[-1]
         half, quarter = n // 2, n // 4
-        out = {"pk3d": [], "pk2d_half": [], "pk2d_quarter": [], "cc": []}
+        out = {"pk3d": [], "pk2d_half": [], "pk2d_quarter": [], "cc": [], "logpdf3d": [], "logpdf2d_half": [],
+               "logpdf2d_quarter": []}
         mean_acc = torch.zeros((1, 1, n, n), dtype=torch.float64, device=device)
         sq_acc = torch.zeros_like(mean_acc)
         for j0 in range(0, data.shape[0], args.chunk):
@@ -62,6 +64,9 @@ def main():
             k2, p2h = get_pk_2d(slab_h)
             _, p2q = get_pk_2d(slab_q)
             out["pk3d"].append(p3); out["pk2d_half"].append(p2h); out["pk2d_quarter"].append(p2q)
+            out["logpdf3d"].append(utils.get_logpdf_3d(x).cpu().numpy())               # calc_SS.py:51-57
+            out["logpdf2d_half"].append(utils.get_logpdf_2d(slab_h).cpu().numpy())     # calc_SS.py:59-65
+            out["logpdf2d_quarter"].append(utils.get_logpdf_2d(slab_q).cpu().numpy())
             mean_acc += slab_h.double().sum(0, keepdim=True)
             sq_acc += (slab_h.double() ** 2).sum(0, keepdim=True)
             if truth is not None:

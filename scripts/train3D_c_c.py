@@ -38,6 +38,8 @@ def main():
     ap.add_argument("cropsize", type=int)
     ap.add_argument("--model", choices=["VDM", "SFM"], default="VDM")
     ap.add_argument("--synthetic", action="store_true")
+    ap.add_argument("--synthetic-boxes", action="store_true",
+                    help="with --synthetic: synthetic RAW simulation boxes through the device-resident dataset pipeline")
     ap.add_argument("--max-steps", type=int, default=1_000_000)
     ap.add_argument("--batch-size", type=int, default=None, help="samples per GPU (default: the reference script's)")
     ap.add_argument("--ckpt-dir", default="./checkpoints")
@@ -59,10 +61,32 @@ def main():
     model = model.to(device)
     trainer = Trainer(model, gradient_clip_val=0.5)
     if not args.synthetic:
-        raise NotImplementedError("the CAMELS AstroDataModule is not part of this package yet (SURVEY.md section 8f); "
-                                  "run with --synthetic")
+        raise NotImplementedError("reading the CAMELS .npy boxes is site specific (CAMELS_3D_dataset.py:105-128 hard-codes "
+                                  "the author's paths): load them into CUDA tensors and hand them to "
+                                  "vdm4cdm_b200.dataset.DeviceAstroDataset, or run with --synthetic")
+    stream = None
+    if args.synthetic_boxes:
+        # the full data path: raw boxes resident in HBM -> vdm_augment_crop (periodic crop, log-normalise, flip, permute)
+        from vdm4cdm_b200.dataset import DeviceAstroDataset
+        S, n_sims = max(2 * n, 256) if n < 256 else n, 4
+        g = torch.Generator().manual_seed(7)
+        base = torch.randn((n_sims, S, S, S), generator=g)
+        raw_x = (10.0 ** (base * 0.552 + 10.019)).to(device)
+        raw_c = (10.0 ** ((0.7 * base + 0.3 * torch.randn((n_sims, S, S, S), generator=g)) * 0.6 + 8.0)).to(device)
+        params = torch.rand((n_sims, 6), generator=g)
+        key_c, key_x = ("conditioning", "x") if args.model == "VDM" else ("x0", "x1")
+        ds = DeviceAstroDataset([raw_c, raw_x], params, lambda fields, params: {key_c: fields[0], key_x: fields[1],
+                                                                               "conditioning_values": [params]},
+                                alphas=[1.0, 1.0], means=[8.0, 10.019], stds=[0.6, 0.552], crop=n, seed=42 + rank)
+        stream = ds.batches(batch_size, rank=rank, world=world)
     t0 = time.perf_counter()
     for step in range(args.max_steps):
+        if stream is not None:
+            loss = trainer.training_step(next(stream))
+            if rank == 0 and (step + 1) % args.log_every == 0:
+                dt = time.perf_counter() - t0
+                print(f"step {step + 1}: loss {loss.item():.5f}  {(step + 1) * batch_size * world / dt:.1f} samples/s")
+            continue
         raw = synthetic_batch(batch_size, n, 42 + step * world + rank, device=device)
         if args.model == "VDM":
             batch = raw

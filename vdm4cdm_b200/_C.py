@@ -72,6 +72,9 @@ _SIGNATURES = {
                                    c_float, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "vdm_avgpool2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_upsample2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_augment_crop": (c_int, [c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
+                                 POINTER(c_int32), c_float, c_float, c_float, c_int, c_void_p]),
+    "vdm_log_histogram": (c_int, [c_void_p, c_int, c_int64, c_float, c_double, c_double, c_int, c_void_p, c_void_p]),
     "vdm_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "vdm_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                c_float, c_int, c_void_p, c_float, c_float, c_void_p]),

@@ -433,6 +433,38 @@ def upsample2_bwd(dy: torch.Tensor, channels: int, *, dy_plane0: int = 0, out: O
     return out
 
 
+def augment_crop(raw: torch.Tensor, crop, anchor, flip, perm, *, alpha: float = 0.0, mean: float = 0.0, std: float = 1.0,
+                 do_log: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``vdm_augment_crop``: periodic crop (start ``anchor``, extent ``crop``) of a raw fp32 box (S0, S1, S2), optional
+    ``(log10(x + alpha) - mean) / std``, flip of the cropped axes in ``flip`` and ``permute`` by ``perm`` in one pass."""
+    _need(raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous() and raw.dim() == 3, "augment_crop: raw must be contiguous CUDA fp32 (S0, S1, S2)")
+    crop, anchor, flip, perm = [int(v) for v in crop], [int(v) for v in anchor], [int(bool(v)) for v in flip], [int(v) for v in perm]
+    n = tuple(crop[perm[d]] for d in range(3))
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=raw.device)
+    _need(out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape[-3:]) == n and out.numel() == n[0] * n[1] * n[2],
+          "augment_crop: out must be contiguous CUDA fp32 with the permuted crop shape")
+    arr = lambda v: (ctypes.c_int32 * 3)(*v)
+    rc = _C.lib().vdm_augment_crop(raw.data_ptr(), out.data_ptr(), arr(raw.shape), arr(crop), arr(anchor), arr(flip), arr(perm),
+                                   alpha, mean, std, 1 if do_log else 0, _stream())
+    _C.check(rc, "vdm_augment_crop")
+    _launched(1)
+    return out
+
+
+def log_histogram(fields: torch.Tensor, lo: float, hi: float, nbins: int, add: float = 1.0) -> torch.Tensor:
+    """``vdm_log_histogram``: per-field histogram of log10(field + add) on ``nbins`` equal bins of [lo, hi]
+    (numpy.histogram semantics).  fields: CUDA fp32 (F, ...) -> int64 (F, nbins)."""
+    _need(fields.is_cuda and fields.dtype == torch.float32 and fields.is_contiguous() and fields.dim() >= 2,
+          "log_histogram: fields must be contiguous CUDA fp32 (F, ...)")
+    f = fields.shape[0]
+    counts = torch.zeros((f, nbins), dtype=torch.int64, device=fields.device)
+    rc = _C.lib().vdm_log_histogram(fields.data_ptr(), f, fields.numel() // f, add, lo, hi, nbins, counts.data_ptr(), _stream())
+    _C.check(rc, "vdm_log_histogram")
+    _launched(1)
+    return counts
+
+
 def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out (double scalar tensor, accumulated) += sum(x^2) over a flat fp32 buffer."""
     _need(x.is_cuda and x.dtype == torch.float32 and x.is_contiguous(), "sumsq: x must be contiguous CUDA fp32")

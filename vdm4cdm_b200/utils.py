@@ -68,6 +68,84 @@ def get_ccs(fields1: torch.Tensor, fields2: torch.Tensor, full: bool = False):
     return k.float(), (p12 / torch.sqrt(p11[:, None] * p22[None, :])).float()
 
 
+def get_logpdf(fields: torch.Tensor, lo: float, hi: float, nbins: int = 99) -> torch.Tensor:
+    """Histogram of log10(field + 1) per sample, ``np.histogram(..., bins=np.linspace(lo, hi, nbins + 1))`` as in
+    calc_SS.py:51-65 (3-D: lo, hi = 8.5, 15; 2-D slabs: 10.5, 15.5; 99 bins).  fields: CUDA fp32 (B, C, ...) -> int64 (B, nbins)."""
+    f = _as_fields(fields)
+    return ops.log_histogram(f.reshape(f.shape[0], -1), float(lo), float(hi), int(nbins), 1.0)
+
+
+def get_logpdf_3d(fields: torch.Tensor) -> torch.Tensor:
+    return get_logpdf(fields, 8.5, 15.0, 99)
+
+
+def get_logpdf_2d(fields: torch.Tensor) -> torch.Tensor:
+    return get_logpdf(fields, 10.5, 15.5, 99)
+
+
+def get_ddnm_result(vdm, y, A, AT, n_sampling_steps=250, l=10, return_all=False, verbose=0, noise_fn=None, seed=0,
+                    **kwargs):
+    """DDNM inpainting / linear-inverse sampler with time travel (src/utils.py:277-304), same signature and loop:
+
+        z ~ N(0, I);  for i in range(n):  L = min(l[i], i)
+            z = sample_zt_given_zs(z, t=steps[i-L], s=steps[i])                      # re-noise L steps back
+            for j in L..0:  (w_z, w_x, x0_hat, scale) = sample_zs_given_zt(z, t=steps[i-j], s=steps[i+1-j], return_ddnm=True)
+                            x0_r = A^T y + x0_hat - A^T A x0_hat                      # range-null space correction
+                            z = w_z z + w_x x0_r + scale N(0, I)
+
+    The denoiser call and the three-term update run on the CUDA kernels (``vdm_conv3d`` trunk, ``vdm_sampler_step``
+    with coefficients (w_z, w_x, scale)); ``A`` / ``AT`` are the caller's torch callables.  Noise comes from the
+    counter-based Philox stream (draw index = position in the loop) or from ``noise_fn(draw, shape)``.
+    """
+    import numpy as np
+    if not isinstance(l, np.ndarray):
+        if isinstance(l, int):
+            l = np.full(n_sampling_steps, l)
+        elif isinstance(l, list):
+            l = np.array(l)
+    assert np.all(l >= 0), "l must be non-negative"
+    assert np.issubdtype(l.dtype, np.integer), "l must be integer"
+    assert isinstance(l, np.ndarray) and l.ndim == 1 and len(l) == n_sampling_steps, \
+        "l must be 1d array of length n_sampling_steps or a single integer>0 or a list of integers>0"
+    model = vdm.model
+    dev = vdm.device
+    steps = torch.linspace(1.0, 0.0, n_sampling_steps + 1, device=dev)
+    shape = (y.shape[0], *model.score_model.shape)
+    draw = [0]
+
+    def noise(shape_):
+        d = draw[0]
+        draw[0] += 1
+        if noise_fn is not None:
+            return noise_fn(d, shape_).to(dev).float().contiguous()
+        return ops.philox_normal(shape_, seed, d, None, dev)
+
+    z = noise(shape)
+    ATy = AT(y)
+    xs = []
+    it = range(n_sampling_steps)
+    if verbose >= 1:
+        from tqdm import trange
+        it = trange(n_sampling_steps, desc="sampling")
+    x_0t_r = None
+    with torch.no_grad():
+        for i in it:
+            L = int(min(l[i], i))
+            z = model.sample_zt_given_zs(zs=z, t=steps[i - L], s=steps[i], noise=noise(shape))
+            for j in range(L, -1, -1):
+                w_z, w_x_0t, x_0t, scale = model.sample_zs_given_zt(zt=z, t=steps[i - j], s=steps[i + 1 - j],
+                                                                    return_ddnm=True, **kwargs)
+                x_0t_r = ATy + x_0t - AT(A(x_0t))
+                coef = torch.stack([w_z.reshape(()), w_x_0t.reshape(()), scale.reshape(()),
+                                    torch.ones((), device=dev)]).float().reshape(1, 4).contiguous()
+                z = ops.sampler_step(z.contiguous().float(), x_0t_r.contiguous().float(), coef, noise=noise(shape))
+            if return_all:
+                xs.append(x_0t_r)
+    if return_all:
+        return torch.stack(xs, dim=0)
+    return x_0t_r
+
+
 def get_model(config: dict, device=None):
     """``CUNet`` + ``LightVDM`` from a ``configs.yaml`` entry (src/utils.py:434-471): ``chs`` default
     [32, 64, 128, 256], ``norm_groups=8``, ``dropout_prob=0.1``, ``gamma_max=13.3``, circular padding iff
