@@ -193,7 +193,8 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
         for (int j = 0; j < 8; ++j) o[j] += r[j];
       }
       const bf16x8 packed = pack8(o);
-      op[ii] = packed;
+      if (a.voxels * a.planes > ((int64_t)4 << 20)) st_stream(op + ii, packed);
+      else op[ii] = packed;
       if (a.out_stats) {
         float r[8];
         unpack8(packed, r);
@@ -221,10 +222,10 @@ avgpool2_bwd_kernel(VdmTensor dy, VdmTensor dx, int planes, int D, int H, int W,
   bf16x8* op = plane_ptr_mut(dx, b, pl, vf);
   float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vf; i += (int64_t)gridDim.x * kEwThreads) {
-    int64_t v = i;
-    const int w = (int)(v % W); v /= W;
-    const int h = (int)(v % H);
-    const int d = (int)(v / H);
+    unsigned v = (unsigned)i;                       // a plane has < 2^31 voxels (checked on the host): 32-bit divisions
+    const int w = (int)(v % (unsigned)W); v /= (unsigned)W;
+    const int h = (int)(v % (unsigned)H);
+    const int d = (int)(v / (unsigned)H);
     float g[8], o[8];
     unpack8(gp[((int64_t)(d >> 1) * Hc + (h >> 1)) * Wc + (w >> 1)], g);
     if (accumulate) {
@@ -261,10 +262,10 @@ upsample2_bwd_kernel(VdmTensor dy, VdmTensor dc, int planes, int D, int H, int W
   bf16x8* op = plane_ptr_mut(dc, b, pl, vout);
   float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vout; i += (int64_t)gridDim.x * kEwThreads) {
-    int64_t v = i;
-    const int wo = (int)(v % Wo); v /= Wo;
-    const int ho = (int)(v % Ho);
-    const int dz = (int)(v / Ho);
+    unsigned v = (unsigned)i;
+    const int wo = (int)(v % (unsigned)Wo); v /= (unsigned)Wo;
+    const int ho = (int)(v % (unsigned)Ho);
+    const int dz = (int)(v / (unsigned)Ho);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -413,6 +414,7 @@ extern "C" int vdm_avgpool2_bwd(const VdmTensor* dy, const VdmTensor* dx, int ba
                                 void* stream) {
   VDM_CHECK_ARG(view_ok(dy, channels) && view_ok(dx, channels) && batch >= 1, "vdm_avgpool2_bwd: bad argument");
   VDM_CHECK_PLANES(batch, channels, "vdm_avgpool2_bwd");
+  VDM_CHECK_ARG((int64_t)depth * height * width < ((int64_t)1 << 31), "vdm_avgpool2_bwd: grid too large for 32-bit voxel indices");
   VDM_CHECK_ARG(depth >= 2 && height >= 2 && width >= 2 && depth % 2 == 0 && height % 2 == 0 && width % 2 == 0,
                 "vdm_avgpool2_bwd: fine grid (%d,%d,%d) must be even", depth, height, width);
   if (stats_channels <= 0) stats_channels = channels;
@@ -428,6 +430,7 @@ extern "C" int vdm_upsample2_bwd(const VdmTensor* dy, const VdmTensor* dcoarse, 
                                  int width, int channels, double* stats, int stats_channels, int stats_c0, void* stream) {
   VDM_CHECK_ARG(view_ok(dy, channels) && view_ok(dcoarse, channels) && batch >= 1, "vdm_upsample2_bwd: bad argument");
   VDM_CHECK_PLANES(batch, channels, "vdm_upsample2_bwd");
+  VDM_CHECK_ARG((int64_t)depth * height * width < ((int64_t)1 << 31), "vdm_upsample2_bwd: grid too large for 32-bit voxel indices");
   VDM_CHECK_ARG(depth >= 2 && height >= 2 && width >= 2 && depth % 2 == 0 && height % 2 == 0 && width % 2 == 0,
                 "vdm_upsample2_bwd: fine grid (%d,%d,%d) must be even", depth, height, width);
   if (stats_channels <= 0) stats_channels = channels;

@@ -87,6 +87,14 @@ struct alignas(16) bf16x8 {
   uint4 u;
 };
 
+// streaming (evict-first) 128-bit accesses for tensors that are read or written exactly once per kernel
+__device__ __forceinline__ bf16x8 ld_stream(const bf16x8* p) {
+  bf16x8 r;
+  r.u = __ldcs(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(bf16x8* p, const bf16x8& v) { __stcs(reinterpret_cast<uint4*>(p), v.u); }
+
 __device__ __forceinline__ float2 bf16pair_to_float2(uint32_t w) {
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
