@@ -202,7 +202,9 @@ def run_b200(args, rank, world, local_rank):
     assert torch.isfinite(sess.z).all(), "sampler state went non-finite"
 
     # ---- end to end through the public API: host conditioning in, host sample out ----
-    n_e2e = args.steps
+    # one public-API call = one whole chain: the reference's default length (LightVDM.draw_samples(n_sampling_steps=250),
+    # model_test.ipynb:667); conditioning goes in and the samples come out once per chain
+    n_e2e = max(args.steps, args.e2e_chain)
     cond_h, params_h = cond.pin_memory(), params.pin_memory()
     out_h = torch.empty((batch, 1, grid, grid, grid), dtype=torch.float32).pin_memory()
 
@@ -494,6 +496,7 @@ def main():
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--chs", type=int, nargs="+", default=[32, 64, 128, 256])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chain", type=int, default=250, help="reverse steps of the end-to-end draw_samples call")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--train-batch", type=int, default=2, help="training samples per GPU (reference: batch_size = 2)")
     ap.add_argument("--train-steps", type=int, default=5)

@@ -55,6 +55,8 @@ struct ConvKernelParams {
   uint16_t tap16[VDM_MAX_TAPS];  // halo offset of every tap in voxels (== 16-byte units)
   int8_t tap_kd[VDM_MAX_TAPS];   // fold path: which filter plane (0..2) a tap belongs to, and its (kh, kw) index
   int8_t tap_khw[VDM_MAX_TAPS];
+  int8_t tap_of[3][9];           // fold path: tap index of (kd, khw)
+  int fold_streamed;             // fold path with the weights streamed per (chunk, kh, kw) stage instead of resident
   int MT, KC, k_chunks;
   int Hd, Hh, Wh;            // halo box (voxels)
   int tiles_w, tiles_h, tiles_d, n_tiles;
@@ -227,6 +229,40 @@ __device__ __forceinline__ void issue_fold_tile(uint32_t a_lo0, uint32_t b_base1
   }
 }
 
+// Same schedule for layers whose weights do not fit shared memory (Cout_pad = 64): the weights of ONE (chunk, kh, kw)
+// for the three kd stacked along N are a ring stage [plane][2 - kd][co]; the stage's MMAs run over all input slices.
+// N = 192 is tensor-bound (96 cycles of math for 80 cycles of operand fetch) where N = 64 is fetch-bound (48 for 32).
+template <int MT, int KJ, int NF>
+__device__ __forceinline__ void issue_fold_stage(uint32_t a_lo, uint32_t b_lo, uint32_t a_hi32, uint32_t b_hi32,
+                                                 uint32_t d_tmem0, bool first) {
+  constexpr int Hh = kTileH + 2, Wh = kTileW + 2, Hd = MT + 2;
+  constexpr uint32_t plane16 = (uint32_t)(Hd * Hh * Wh);
+  constexpr uint32_t kstep_a16 = 2u * plane16;
+#pragma unroll
+  for (int i = 0; i < MT + 2; ++i) {
+    const int kd_lo = (i - MT + 1) > 0 ? (i - MT + 1) : 0;
+    const int kd_hi = i < 2 ? i : 2;
+    const int s_lo = i - kd_hi;
+    const int nblk = kd_hi - kd_lo + 1;
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+      const uint32_t a_off = (uint32_t)(i * Hh * Wh) + (uint32_t)j * kstep_a16;
+      const uint32_t b_off = (uint32_t)((2 * j * 3 + (2 - kd_hi)) * NF);
+      if (j == 0 && i < MT && first) {
+        // accumulator s = i receives its first contribution here (kd = 0, the last block of the span)
+        if (nblk > 1)
+          ptx::umma_bf16_off(d_tmem0, (uint32_t)(s_lo * NF), a_lo, a_off, a_hi32, b_lo, b_off, b_hi32,
+                             ptx::make_idesc_bf16(128, (uint32_t)((nblk - 1) * NF)), 1u);
+        ptx::umma_bf16_off(d_tmem0, (uint32_t)(i * NF), a_lo, a_off, a_hi32, b_lo, b_off + (uint32_t)((nblk - 1) * NF), b_hi32,
+                           ptx::make_idesc_bf16(128, (uint32_t)NF), 0u);
+      } else {
+        ptx::umma_bf16_off(d_tmem0, (uint32_t)(s_lo * NF), a_lo, a_off, a_hi32, b_lo, b_off, b_hi32,
+                           ptx::make_idesc_bf16(128, (uint32_t)(nblk * NF)), 1u);
+      }
+    }
+  }
+}
+
 // MT = d-slices (accumulators) per tile, KJ = K=16 MMAs per channel chunk (KC = 16*KJ), NF = 0 for the generic
 // path or Cout_pad for the kd-folded path: compile-time so that the MMA issue loops are straight lines of
 // tcgen05.mma with immediate offsets (r01a: a generic loop cost ~240 issue cycles per MMA).
@@ -298,6 +334,26 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
       const size_t tap_stride = (size_t)p.c_in8 * p.n_pad * 8, plane_stride = (size_t)p.n_pad * 8;
       if constexpr (kFold) {
+       if (p.fold_streamed) {
+        // one ring stage per (tile, chunk, kh, kw): [plane][2 - kd][co] (see issue_fold_stage); n_split == 1
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+          for (int kc = 0; kc < k_chunks; ++kc)
+            for (int khw = 0; khw < 9; ++khw, ++it) {
+              const int s = it % nsb;
+              ptx::mbar_wait(&sh->b_empty[s], ((it / nsb) & 1) ^ 1);
+              ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk * 3u);
+              uint8_t* dst = b_smem + (size_t)s * p.b_stage_bytes;
+#pragma unroll
+              for (int kd = 0; kd < 3; ++kd) {
+                const __nv_bfloat16* src = p.w + (size_t)p.tap_of[kd][khw] * tap_stride + (size_t)kc * planes_per_chunk * plane_stride;
+#pragma unroll
+                for (int pl = 0; pl < planes_per_chunk; ++pl)
+                  ptx::bulk_load(dst + (size_t)(pl * 3 + (2 - kd)) * plane_copy_bytes, src + (size_t)pl * plane_stride,
+                                 plane_copy_bytes, &sh->b_full[s]);
+              }
+            }
+       } else {
         // resident, kd-folded order: [chunk][khw][plane][2 - kd][co] (see issue_fold_tile); n_split == 1
         ptx::mbar_arrive_expect_tx(&sh->b_full[0], plane_copy_bytes * planes_per_chunk * (uint32_t)(n_taps * k_chunks));
         for (int kc = 0; kc < k_chunks; ++kc)
@@ -309,6 +365,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                              p.w + (size_t)tap * tap_stride + (size_t)(kc * planes_per_chunk + pl) * plane_stride,
                              plane_copy_bytes, &sh->b_full[0]);
           }
+       }
       } else if (p.b_resident) {
         // Weights fit next to the halo stages: load every (chunk, tap) once.  Per-tile weight streaming was a
         // fixed cost per tile (r01h: 0.454 -> 0.410 ms on the 32->32 layer); n_split == 1 on this path.
@@ -363,6 +420,39 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       constexpr uint32_t chunk_b16 = 9u * 2u * KJ * 3u * NF;       // one channel chunk of the folded weights, 16-byte units
       const int k_chunks = p.k_chunks;
       uint32_t ti = 0, ita = 0;
+      if (p.fold_streamed) {
+        const uint32_t a_hi32 = (uint32_t)(a_hi >> 32), b_hi32 = (uint32_t)(b_hi >> 32);
+        const uint32_t a_lbo = (uint32_t)a_hi, b_lbo = (uint32_t)b_hi;       // LBO << 16: low descriptor words
+        const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+        const int nsb = p.nsb;
+        uint32_t itb = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+          const uint32_t acc = ti & 1;
+          ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
+          const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
+          for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
+            const uint32_t sa = ita & 1;
+            ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
+            const uint32_t a_st = a_base16 + sa * a_stage16 + a_lbo;
+            for (int khw = 0; khw < 9; ++khw, ++itb) {
+              const uint32_t sb = itb % nsb;
+              ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
+              ptx::tc_fence_after();
+              if (leader) {
+                const uint32_t kh = (uint32_t)khw / 3u, kw = (uint32_t)khw - 3u * kh;
+                issue_fold_stage<MT, KJ, NF>(a_st + kh * (uint32_t)(kTileW + 2) + kw, b_base16 + sb * b_stage16 + b_lbo, a_hi32,
+                                             b_hi32, d_tmem0, kc == 0 && khw == 0);
+                ptx::umma_commit(&sh->b_empty[sb]);
+                if (khw == 8) {
+                  ptx::umma_commit(&sh->a_empty[sa]);
+                  if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1;
         ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
@@ -757,10 +847,14 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     }
   p.pad = pad;
   // kd-folded schedule (issue_fold_tile): the full 3x3x3 stencil on a narrow layer
-  bool fold = d.n_taps == 27 && pad == 1 && d.c_in % 16 == 0 && (d.c_out_pad == 16 || d.c_out_pad == 32) &&
+  bool fold = d.n_taps == 27 && pad == 1 && d.c_in % 16 == 0 && (d.c_out_pad == 16 || d.c_out_pad == 32 || d.c_out_pad == 64) &&
               d.depth >= 3 && g_debug_no_fold == 0 && g_debug_force_mt == 0 && g_debug_force_nsplit == 0;
-  int fold_mt = 0, fold_kc = 0;
-  if (fold) {
+  int fold_mt = 0, fold_kc = 0, fold_streamed = 0;
+  if (fold && d.c_out_pad == 64) {
+    // N = 3*64: weights streamed per (chunk, kh, kw); MT = 4 (2 x 4 x 64 = all 512 TMEM columns), 32-channel chunks
+    fold = d.c_in % 32 == 0 && d.depth >= 4 && g_debug_no_fold < 2;
+    fold_mt = 4; fold_kc = 32; fold_streamed = 1;
+  } else if (fold) {
     // all weights resident + two halo stages must fit; prefer tall tiles (halo efficiency), then wide chunks
     const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - 2 * 8 * d.c_out_pad * 4 - 256;
     const int w_bytes = 27 * d.c_in * d.c_out_pad * 2;
@@ -781,6 +875,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
       seen |= 1u << (kd * 9 + khw);
     }
     fold = seen == (1u << 27) - 1u;
+    for (int t = 0; t < 27; ++t) p.tap_of[p.tap_kd[t]][p.tap_khw[t]] = (int8_t)t;
   }
   p.c_in8 = d.c_in / 8;
   p.x_planes = x_planes; p.x_plane0 = d.x_plane0;
@@ -852,7 +947,16 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   int kc = 0, nsb = 0;
   const int tps = (d.n_taps % 3 == 0) ? 3 : 1;   // one (kd, kh) row of filter taps per weight stage
   const int kc_options[3] = {64, 32, 16};
-  if (fold) {
+  if (fold && fold_streamed) {
+    kc = fold_kc;
+    p.a_stage_bytes = ((kc / 8) * p.plane_bytes + 127) & ~127;
+    p.b_stage_bytes = 3 * kc * p.n_cta * 2;
+    nsb = (smem_budget - 2 * p.a_stage_bytes) / p.b_stage_bytes;
+    if (nsb > kMaxBStages) nsb = kMaxBStages;
+    VDM_CHECK_ARG(nsb >= 2, "vdm_conv3d: folded streamed layer does not fit shared memory");
+    p.b_resident = 0;
+    p.fold_streamed = 1;
+  } else if (fold) {
     kc = fold_kc;
     p.a_stage_bytes = ((kc / 8) * p.plane_bytes + 127) & ~127;
     p.b_stage_bytes = d.n_taps * d.c_in * p.n_cta * 2;
@@ -941,7 +1045,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   VDM_LAUNCH(2, 1, 0) VDM_LAUNCH(2, 2, 0) VDM_LAUNCH(2, 4, 0)
   VDM_LAUNCH(3, 1, 0) VDM_LAUNCH(3, 2, 0) VDM_LAUNCH(3, 4, 0)
   VDM_LAUNCH(4, 1, 0) VDM_LAUNCH(4, 2, 0) VDM_LAUNCH(4, 4, 0)
-  VDM_LAUNCH(4, 1, 16) VDM_LAUNCH(4, 1, 32) VDM_LAUNCH(4, 2, 16) VDM_LAUNCH(4, 2, 32)
+  VDM_LAUNCH(4, 1, 16) VDM_LAUNCH(4, 1, 32) VDM_LAUNCH(4, 2, 16) VDM_LAUNCH(4, 2, 32) VDM_LAUNCH(4, 2, 64)
   VDM_LAUNCH(3, 1, 16) VDM_LAUNCH(3, 1, 32) VDM_LAUNCH(3, 2, 16) VDM_LAUNCH(3, 2, 32)
   VDM_LAUNCH(2, 1, 16) VDM_LAUNCH(2, 1, 32) VDM_LAUNCH(2, 2, 16) VDM_LAUNCH(2, 2, 32)
 #undef VDM_LAUNCH
