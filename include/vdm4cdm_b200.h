@@ -64,7 +64,9 @@ typedef struct VdmConvDesc {
   int32_t c_out_pad;                     /* rows per (tap, plane) in the weight tensor, multiple of 16, <= 256 */
   int32_t n_taps;                        /* 1..27 */
   int8_t tap_offset[VDM_MAX_TAPS][3];    /* (dd, dh, dw) read offset of each tap, each in [-1, 1] */
-  int32_t circular;                      /* 0: zero padding (TMA out-of-bounds fill). 1: unsupported yet */
+  int32_t circular;                      /* 0: zero padding (TMA out-of-bounds fill).  1: periodic (Conv3d padding_mode="circular",
+                                          *    the cropsize == 256 models, src/utils.py:460): x is a buffer with a one-voxel periodic
+                                          *    halo, [B][planes][D+2][H+2][W+2][8], as written by vdm_pad_circular */
   int32_t out_fp32;                      /* 0: y is bf16 channel-planar; 1: y is fp32 [B][c_out][D][H][W] */
   int32_t x_planes, x_plane0;            /* planes per sample of the x buffer (0: c_in/8), first plane read */
   int32_t y_planes, y_plane0;            /* same for y (bf16 output only) */
@@ -110,6 +112,9 @@ typedef struct VdmWgradDesc {
    * the kernel accumulate straight into the parameter's .grad inside a flat gradient bucket. */
   int64_t dw_stride_tap, dw_stride_ci, dw_stride_co;
   int32_t c_in_real;
+  int32_t a_padded;             /* 1: `a` carries a one-voxel periodic halo ([D+2][H+2][W+2], circular convs) */
+  int32_t g_padded;             /* 1: so does g (required with a_padded for 3x3x3 filters: the kw taps of the narrow-layer
+                                 *    kernel read w-shifted g tiles, which must wrap periodically too) */
 } VdmWgradDesc;
 
 VDM_API int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const void* g, float* dw, void* stream);
@@ -214,6 +219,11 @@ VDM_API int vdm_adamw_step(float* param, const float* grad, float* exp_avg, floa
 VDM_API int vdm_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int step, const int32_t* step_ptr,
                        const double* grad_sumsq, float max_norm, float grad_scale, void* stream);
+
+/* Periodic one-voxel halo: y[b][p][dp][hp][wp] = x[b][p][(dp-1) mod D][(hp-1) mod H][(wp-1) mod W] for
+ * dp in [0, D+2) etc.  x: [B][planes][D][H][W][8] view, y: [B][planes][D+2][H+2][W+2][8] view. */
+VDM_API int vdm_pad_circular(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
+                     int channels, void* stream);
 
 /* Pack the network input: plane 0 of out = (z, cond_1..cond_n, 0...) per voxel, planes 1.. = 0.
  * z: fp32 [B][V]; cond: fp32 [B][n_cond][V] (NCDHW) or NULL; out: c_pad/8 planes; n_cond <= 7. */

@@ -156,3 +156,32 @@ def test_conv3d_rejects_bad_arguments():
     w = torch.zeros((27, 1, 16, 8), dtype=torch.bfloat16, device=dev)
     with pytest.raises(RuntimeError, match="multiple of 16"):
         ops.conv3d(x, w, 16)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 8, 16, 16), (1, 96, 32, 5, 20, 12), (1, 64, 64, 6, 16, 8), (1, 16, 128, 4, 16, 8)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv3d_circular_padding_exact_integers(case):
+    """Conv3d(padding_mode="circular") of the cropsize == 256 models: vdm_pad_circular + vdm_conv3d(circular=1)."""
+    ops = _ops()
+    b, ci, co, d, h, w = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(77 + ci + co)
+    x = _int_tensor((b, ci, d, h, w), -2, 2, g, dev)
+    wt = _int_tensor((co, ci, 3, 3, 3), -1, 1, g, dev)
+    xp = F.pad(x.double(), (1, 1, 1, 1, 1, 1), mode="circular")
+    ref = F.conv3d(xp, wt.double()).round().float().to(torch.bfloat16).float()
+    xpad = ops.pad_circular(ops.to_planar(x), ci)
+    assert torch.equal(ops.from_planar(xpad), xp.float())
+    y = ops.conv3d(xpad, ops.pack_conv_weight(wt), co, circular=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ops.from_planar(y, co), ref)
+    # dgrad and wgrad of the circular conv
+    xg = x.double().clone().requires_grad_(True)
+    wg = wt.double().clone().requires_grad_(True)
+    dy = _int_tensor((b, co, d, h, w), -1, 1, g, dev)
+    F.conv3d(F.pad(xg, (1, 1, 1, 1, 1, 1), mode="circular"), wg).backward(dy.double())
+    dyp = ops.pad_circular(ops.to_planar(dy), co)
+    dx = ops.conv3d(dyp, ops.pack_conv_weight(wt, transpose_flip=True), ci, circular=True)
+    assert torch.equal(ops.from_planar(dx, ci), xg.grad.round().float().to(torch.bfloat16).float())
+    dw = ops.conv3d_wgrad(xpad, ops.pad_circular(ops.to_planar(dy, 16), -(-co // 16) * 16), ci, co, 3, a_padded=True, g_padded=True)
+    assert torch.equal(ops.wgrad_to_torch(dw, 3), wg.grad.round().float())

@@ -12,12 +12,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _models(shape, chs, v_dims=(6,), seed=0, dropout=0.0):
+def _models(shape, chs, v_dims=(6,), seed=0, dropout=0.0, padding="zeros"):
     from oracle.unet_ref import CUNet as RefNet
     from vdm4cdm_b200.networks import CUNet
     torch.manual_seed(seed)
     kw = dict(shape=shape, chs=chs, s_conditioning_channels=1, v_conditioning_dims=list(v_dims), t_conditioning=True,
-              norm_groups=8, dropout_prob=dropout)
+              norm_groups=8, dropout_prob=dropout, conv_padding_mode=padding)
     ref = RefNet(**kw)
     with torch.no_grad():
         for n, p in ref.named_parameters():
@@ -82,6 +82,23 @@ def test_unet_backward_matches_oracle_autograd(shape, chs, batch):
     e = _rel(xc.grad.cpu(), xr.grad)
     print(f"input gradient relative L2 {e:.3e}")
     assert e < 3e-2, e
+
+
+def test_unet_backward_circular_padding_matches_oracle_autograd():
+    shape, chs, batch = (1, 16, 16, 32), (16, 32, 64), 2
+    ref, net = _models(shape, chs, padding="circular")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((batch,) + shape, generator=g)
+    cond = 0.7 * x + 0.3 * torch.randn((batch,) + shape, generator=g)
+    t, v = torch.rand(batch, generator=g), [torch.rand(batch, 6, generator=g)]
+    d_out = torch.randn((batch,) + shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref(xr, t=t, s_conditioning=cond, v_conditionings=v).backward(d_out)
+    xc = x.cuda().requires_grad_(True)
+    net(xc, t=t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()]).backward(d_out.cuda())
+    torch.cuda.synchronize()
+    _compare_grads(ref, net)
+    assert _rel(xc.grad.cpu(), xr.grad) < 3e-2
 
 
 def test_vdm_loss_and_gradients_match_oracle():

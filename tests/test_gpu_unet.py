@@ -13,12 +13,12 @@ pytestmark = pytest.mark.gpu
 BF16_RTOL = 1e-2
 
 
-def _models(shape, chs, v_dims=(6,), seed=0):
+def _models(shape, chs, v_dims=(6,), seed=0, padding="zeros"):
     from oracle.unet_ref import CUNet as RefNet
     from vdm4cdm_b200.networks import CUNet
     torch.manual_seed(seed)
     kw = dict(shape=shape, chs=chs, s_conditioning_channels=1, v_conditioning_dims=list(v_dims), t_conditioning=True,
-              norm_groups=8, dropout_prob=0.1)
+              norm_groups=8, dropout_prob=0.1, conv_padding_mode=padding)
     ref = RefNet(**kw).eval()
     # give biases / norm affines non-trivial values so that every epilogue term is exercised
     with torch.no_grad():
@@ -56,6 +56,41 @@ def test_unet_forward_matches_oracle(shape, chs, batch):
         want1 = ref(x[:1], t=torch.tensor(0.3), s_conditioning=cond[:1], v_conditionings=[v[0][:1]])
         got1 = net(x[:1].cuda(), t=torch.tensor(0.3), s_conditioning=cond[:1].cuda(), v_conditionings=[v[0][:1].cuda()]).cpu()
     assert _rel_l2(got1, want1) < BF16_RTOL
+
+
+def test_unet_forward_circular_padding_matches_oracle():
+    """conv_padding_mode="circular" (the cropsize == 256 registry entries, src/utils.py:460)."""
+    shape, chs, batch = (1, 16, 32, 16), (16, 32, 64), 2
+    ref, net = _models(shape, chs, padding="circular")
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((batch,) + shape, generator=g)
+    cond = 0.7 * x + 0.3 * torch.randn((batch,) + shape, generator=g)
+    t, v = torch.rand(batch, generator=g), [torch.rand(batch, 6, generator=g)]
+    with torch.no_grad():
+        want = ref(x, t=t, s_conditioning=cond, v_conditionings=v)
+        got = net(x.cuda(), t=t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()]).cpu()
+        zero_pad = _models(shape, chs, padding="zeros")[0](x, t=t, s_conditioning=cond, v_conditionings=v)
+    err = _rel_l2(got, want)
+    # Tolerance for a whole random-init network: the error torch's own bf16 autocast of the ORACLE makes on this
+    # input (measured 1.6e-2 here; circular padding is ~30% noisier than zero padding for torch too, 1.3e-2), and
+    # never looser than 2e-2.  A wrong halo anywhere shows up at the 1e-1 level (zero padding: 0.89).
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        autocast_err = _rel_l2(ref(x, t=t, s_conditioning=cond, v_conditionings=v).float(), want)
+    print(f"circular unet: relative L2 error {err:.3e} (torch bf16 autocast of the oracle: {autocast_err:.3e}; "
+          f"zero-padded network differs by {_rel_l2(zero_pad, want):.3e})")
+    assert err < min(max(BF16_RTOL, autocast_err), 2e-2), (err, autocast_err)
+    # periodic boundaries make the network equivariant under shifts by a multiple of the coarsest cell (4 voxels)
+    shift = dict(shifts=(4, 8, 4), dims=(2, 3, 4))
+    with torch.no_grad():
+        rolled = net(torch.roll(x, **shift).cuda(), t=t.cuda(), s_conditioning=torch.roll(cond, **shift).cuda(),
+                     v_conditionings=[v[0].cuda()]).cpu()
+    eq = _rel_l2(rolled, torch.roll(got, **shift))
+    print(f"circular unet: shift equivariance defect {eq:.3e}")
+    assert eq < 1e-4, eq          # measured 1.1e-7: same kernels, same per-voxel summation order
+    # the sampler works on top of it (packed input is re-padded every step)
+    from vdm4cdm_b200.vdm_model import VDM
+    xs = VDM(net).cuda().eval().sample(batch, 3, "cuda:0", seed=1, s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()])
+    assert torch.isfinite(xs).all()
 
 
 def test_sampler_chain_matches_oracle_per_step_and_graph_equals_eager():

@@ -47,8 +47,9 @@ def test_registry_and_model_factory():
     assert utils.get_model(configs["SFM_Mstar_Mcdm_c_c_128"]) is None          # src/utils.py:472-473 does `pass`
     with pytest.raises(ValueError):
         utils.get_model({"type": "GAN"})
-    with pytest.raises(NotImplementedError, match="circular"):                  # cropsize 256 models: next row, section 8f
-        utils.get_model(configs["VDM_Mstar_Mcdm_c_c_256"])
+    m256 = utils.get_model(configs["VDM_Mstar_Mcdm_c_c_256"])                   # cropsize 256 -> circular padding (src/utils.py:460)
+    assert m256.model.score_model.circular and m256.model.score_model.conv_in.padding_mode == "circular"
+    assert not m.model.score_model.circular
 
 
 def test_state_dict_is_interchangeable_with_the_oracle():

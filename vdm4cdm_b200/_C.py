@@ -43,6 +43,7 @@ class WgradDesc(Structure):
         ("c_in", c_int32), ("c_out", c_int32), ("kernel", c_int32),
         ("a_planes", c_int32), ("a_plane0", c_int32), ("g_planes", c_int32), ("g_plane0", c_int32),
         ("dw_stride_tap", c_int64), ("dw_stride_ci", c_int64), ("dw_stride_co", c_int64), ("c_in_real", c_int32),
+        ("a_padded", c_int32), ("g_padded", c_int32),
     ]
 
 
@@ -83,6 +84,7 @@ _SIGNATURES = {
                             c_float, c_float, c_uint64, c_uint32, c_void_p]),
     "vdm_avgpool2": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_upsample2": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vdm_pad_circular": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vdm_pack_input": (c_int, [c_void_p, c_void_p, _T, c_int, c_int64, c_int, c_int, c_void_p]),
     "vdm_sampler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_uint64,
                                  c_void_p, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),

@@ -41,8 +41,8 @@ class _Backward:
     def __init__(self, net, tape: dict, names: List[str]):
         self.net, self.tape = net, tape
         self.ar = net._train_arena
-        self.b = tape["trunk"]["packed"].shape[0]
-        self.dev = tape["trunk"]["packed"].device
+        self.b = tape["trunk"]["h_in"].shape[0]
+        self.dev = tape["trunk"]["h_in"].device
         self.grads: Dict[str, Optional[torch.Tensor]] = {}      # parameter / row name -> gradient (None: already in .grad)
         self.params = dict(net.trunk_parameters())
         # ONE double [B][total][2] table holds every per-channel reduction of the pass (gradient channel sums =
@@ -66,20 +66,31 @@ class _Backward:
     def buf(self, name: str, ch: int, grid) -> torch.Tensor:
         return self.ar.get(f"g.{name}.{self.b}x{grid[0]}", (self.b, ch // 8) + tuple(grid) + (8,), torch.bfloat16, self.dev)
 
-    def dgrad(self, name: str, conv, g, g_plane0, g_ch, out, out_plane0=0):
+    def pad(self, g, g_plane0, g_ch):
+        """Periodic one-voxel halo around a gradient window (circular convs only): the dgrad of a circular conv is a
+        circular conv of the padded gradient, and the narrow-layer wgrad reads w-shifted gradient tiles."""
+        d, h, w = g.shape[2:5]
+        gp = self.ar.get(f"g.pad.{g_ch}.{self.b}x{d}", (self.b, g_ch // 8, d + 2, h + 2, w + 2, 8), torch.bfloat16, self.dev)
+        return ops.pad_circular(g, g_ch, x_plane0=g_plane0, out=gp)
+
+    def dgrad(self, name: str, conv, g, g_plane0, g_ch, out, out_plane0=0, g_pad=None):
         """out[window] = conv^T(g): one launch per <=256 input channels of the conv."""
         ci = conv.in_channels
         taps = ops.TAPS_3X3X3 if conv.kernel_size[0] == 3 else ops.TAPS_1X1X1
+        circ = self.net.circular and conv.kernel_size[0] == 3
+        if circ:
+            g, g_plane0 = (g_pad if g_pad is not None else self.pad(g, g_plane0, g_ch)), 0
         ops.set_profile_tag("dgrad ")
         # a 3x3x3 dgrad with <= 32 gradient channels runs on the kd-folded schedule when its N is <= 32: three
         # 32-wide launches beat one N = 96 launch on the generic schedule (r01r: 0.94 ms vs 3 x 0.21 ms)
         limit = 32 if (conv.kernel_size[0] == 3 and g_ch in (16, 32) and ci > 32 and ci % 32 == 0) else 256
         for c0, n in _chunks(ci, limit):
             wp = self.net._packed_dgrad(name, conv, c0, n)
-            ops.conv3d(g, wp, n, taps=taps, x_plane0=g_plane0, c_in=g_ch, out=out, out_plane0=out_plane0 + c0 // 8)
+            ops.conv3d(g, wp, n, taps=taps, x_plane0=g_plane0, c_in=g_ch, out=out, out_plane0=out_plane0 + c0 // 8,
+                       circular=circ)
         ops.set_profile_tag("")
 
-    def wgrad(self, name: str, conv, a, a_plane0, a_ch, g, g_plane0):
+    def wgrad(self, name: str, conv, a, a_plane0, a_ch, g, g_plane0, g_pad=None):
         """Filter gradient, accumulated by the kernel straight into ``weight.grad`` when it exists (the Trainer's
         flat gradient bucket), else into a fresh tensor handed back to autograd."""
         k = conv.kernel_size[0]
@@ -88,7 +99,11 @@ class _Backward:
             target, ret = w.grad, None
         else:
             target = ret = torch.zeros_like(w, memory_format=torch.contiguous_format)
-        ops.conv3d_wgrad(a, g, a_ch, conv.out_channels, k, a_plane0=a_plane0, g_plane0=g_plane0, grad_out=target)
+        circ = self.net.circular and k == 3
+        if circ:
+            g, g_plane0 = (g_pad if g_pad is not None else self.pad(g, g_plane0, -(-conv.out_channels // 16) * 16)), 0
+        ops.conv3d_wgrad(a, g, a_ch, conv.out_channels, k, a_plane0=a_plane0, g_plane0=g_plane0, grad_out=target,
+                         a_padded=circ, g_padded=circ)
         self.grads[name + ".weight"] = ret
 
     def row_grad(self, name: str, c0: int, c: int):
@@ -120,19 +135,21 @@ class _Backward:
         drop = dict(dropout_p=rec["p_drop"], seed=rec["drop_seed"], layer_tag=rec["drop_tag"],
                     seed_step=self.net.drop_counter if rec["p_drop"] > 0.0 else None)
         # net2: conv -> dropout/silu/gn
-        self.wgrad(name + ".net2", conv2, rec["a2"], 0, co, dy, dy_plane0)
+        dy_pad = self.pad(dy, dy_plane0, co) if self.net.circular else None
+        self.wgrad(name + ".net2", conv2, rec["a2"], 0, co, dy, dy_plane0, g_pad=dy_pad)
         self.row_grad(name + ".net2", dy_c0, co)
         d_a2 = self.buf(f"a.{co}", co, grid)
-        self.dgrad(name + ".net2", conv2, dy, dy_plane0, co, d_a2)
+        self.dgrad(name + ".net2", conv2, dy, dy_plane0, co, d_a2, g_pad=dy_pad)
         dh = self.buf(f"h.{co}", co, grid)
         dh_c0 = self.chan(co)
         self.gn_bwd(name + ".gn2", gn2, rec["h"], 0, rec["h_stats"], d_a2, co, out=dh, out_stats=self.tab,
                     out_stats_c0=dh_c0, **drop)
         # net1: conv (+ conditioning row) -> silu/gn
-        self.wgrad(name + ".net1", conv1, rec["a1"], 0, ci, dh, 0)
+        dh_pad = self.pad(dh, 0, co) if self.net.circular else None
+        self.wgrad(name + ".net1", conv1, rec["a1"], 0, ci, dh, 0, g_pad=dh_pad)
         self.row_grad(name + ".net1", dh_c0, co)
         d_a1 = self.buf(f"a.{ci}", ci, grid)
-        self.dgrad(name + ".net1", conv1, dh, 0, co, d_a1)
+        self.dgrad(name + ".net1", conv1, dh, 0, co, d_a1, g_pad=dh_pad)
         # skip path
         if blk.skip_conv is None:
             add, add_plane0 = dy, dy_plane0
@@ -152,10 +169,11 @@ class _Backward:
         g_out = self.ar.get(f"g.out.{b}", (b, 2) + tuple(grids[0]) + (8,), torch.bfloat16, self.dev)
         ops.pack_input(d_out.contiguous().float(), None, 16, out=g_out)
         conv_out, gn_out = net.conv_out[2], net.conv_out[0]
-        self.wgrad("conv_out", conv_out, tr["out_a"], 0, c[0], g_out, 0)
+        g_out_pad = self.pad(g_out, 0, 16) if net.circular else None
+        self.wgrad("conv_out", conv_out, tr["out_a"], 0, c[0], g_out, 0, g_pad=g_out_pad)
         self.grads["row.conv_out"] = d_out.reshape(b, -1).sum(dim=1, keepdim=True).float()
         d_a = self.buf(f"a.{c[0]}", c[0], grids[0])
-        self.dgrad("conv_out", conv_out, g_out, 0, 16, d_a)
+        self.dgrad("conv_out", conv_out, g_out, 0, 16, d_a, g_pad=g_out_pad)
         dy = self.buf(f"y.{c[0]}", c[0], grids[0])
         dy_c0 = self.chan(c[0])
         self.gn_bwd("conv_out.gn", gn_out, tr["out_x"], 0, tr["out_x_stats"], d_a, c[0], out=dy, out_stats=self.tab,
@@ -193,15 +211,18 @@ class _Backward:
             self.block(name, blk, d_cat, p0, tot_c0, dx, 0, dx_c0)
             dy, dy_c0 = dx, dx_c0
         # conv_in
-        self.wgrad("conv_in", net.conv_in, tr["packed"], 0, 16, dy, 0)
+        dy_pad = self.pad(dy, 0, c[0]) if net.circular else None
+        self.wgrad("conv_in", net.conv_in, tr["packed"], 0, 16, dy, 0, g_pad=dy_pad)
         self.row_grad("conv_in", dy_c0, c[0])
         self.finish()
         if not need_dx:
             return None
         wp = net._packed_dgrad("conv_in", net.conv_in, 0, 1)
         dz = torch.empty((b, 1) + tuple(grids[0]), dtype=torch.float32, device=self.dev)
+        if net.circular:
+            dy = dy_pad
         ops.set_profile_tag("dgrad ")
-        ops.conv3d(dy, wp, 1, out=dz, out_fp32=True)
+        ops.conv3d(dy, wp, 1, out=dz, out_fp32=True, circular=net.circular)
         ops.set_profile_tag("")
         return dz
 

@@ -67,6 +67,7 @@ struct ConvKernelParams {
   int plane_bytes;           // Hd*Hh*Wh*16
   int tmem_cols;
   int x_planes, x_plane0, c_in8;
+  int x_shift;               // 1 when x carries a one-voxel periodic halo (circular padding)
   const __nv_bfloat16* w;
   // epilogue
   void* y;
@@ -322,8 +323,9 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             continue;
           }
           ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes_per_chunk * p.plane_bytes));
-          ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], (t.w0 - p.pad) * 8,
-                           t.h0 - p.pad, t.d0 - p.pad, t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
+          ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], (t.w0 - p.pad + p.x_shift) * 8,
+                           t.h0 - p.pad + p.x_shift, t.d0 - p.pad + p.x_shift,
+                           t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
         }
       }
     }
@@ -816,10 +818,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   VDM_CHECK_ARG(d.c_out >= 1 && d.c_out <= d.c_out_pad, "vdm_conv3d: c_out=%d vs c_out_pad=%d", d.c_out, d.c_out_pad);
   VDM_CHECK_ARG(d.out_fp32 || d.c_out % 8 == 0, "vdm_conv3d: bf16 planar output needs c_out %% 8 == 0 (got %d)", d.c_out);
   VDM_CHECK_ARG(d.n_taps >= 1 && d.n_taps <= VDM_MAX_TAPS, "vdm_conv3d: n_taps=%d", d.n_taps);
-  if (d.circular) {
-    set_error("vdm_conv3d: circular padding is not implemented");
-    return VDM_E_UNSUPPORTED;
-  }
+  const int halo = d.circular ? 1 : 0;      // x carries a one-voxel periodic halo: padded dims, coordinates shifted by one
   const int x_planes = d.x_planes > 0 ? d.x_planes : d.c_in / 8;
   const int y_planes = d.y_planes > 0 ? d.y_planes : (d.c_out + 7) / 8;
   VDM_CHECK_ARG(d.x_plane0 >= 0 && d.x_plane0 + d.c_in / 8 <= x_planes, "vdm_conv3d: x plane window out of range");
@@ -879,6 +878,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   }
   p.c_in8 = d.c_in / 8;
   p.x_planes = x_planes; p.x_plane0 = d.x_plane0;
+  p.x_shift = halo;
 
   // ---- tiling ----
   p.tiles_w = ceil_div(d.width, kTileW);
@@ -1012,10 +1012,10 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   // one 32-byte sector per ~9 cycles per SM (profiles/r01_conv_ncu.txt).  Rows are Wh*16 = 160 bytes now.
   CUtensorMap tmx;
   {
-    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
-    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth,
-                          (cuuint64_t)d.batch * x_planes};
-    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    const cuuint64_t Dx = d.depth + 2 * halo, Hx = d.height + 2 * halo, Wx = d.width + 2 * halo;
+    const cuuint64_t V = Dx * Hx * Wx;
+    cuuint64_t gdim[4] = {Wx * 8, Hx, Dx, (cuuint64_t)d.batch * x_planes};
+    cuuint64_t gstr[3] = {Wx * 16, Hx * Wx * 16, V * 16};
     cuuint32_t box[4] = {(cuuint32_t)p.Wh * 8, (cuuint32_t)p.Hh, (cuuint32_t)p.Hd, (cuuint32_t)(kc / 8)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,

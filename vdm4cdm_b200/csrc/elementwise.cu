@@ -166,9 +166,43 @@ upsample2_kernel(VdmTensor coarse, VdmTensor y, int planes, int D, int H, int W,
   if (stats) block_flush_stats(sum, sq, stats + ((int64_t)b * stats_channels + stats_c0 + pl * 8) * 2);
 }
 
+// ---- periodic one-voxel halo (circular convolutions) ---------------------------------------------------
+// One thread per PADDED voxel: coalesced 16-byte stores, reads coalesced except at the wrapped faces.
+__global__ void __launch_bounds__(kEwThreads)
+pad_circular_kernel(VdmTensor x, VdmTensor y, int planes, int D, int H, int W) {
+  const int b = blockIdx.y / planes, pl = blockIdx.y % planes;
+  const int Dp = D + 2, Hp = H + 2, Wp = W + 2;
+  const int64_t vin = (int64_t)D * H * W, vout = (int64_t)Dp * Hp * Wp;
+  const bf16x8* xp = plane_ptr(x, b, pl, vin);
+  bf16x8* yp = plane_ptr_mut(y, b, pl, vout);
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vout; i += (int64_t)gridDim.x * kEwThreads) {
+    unsigned v = (unsigned)i;
+    const int wp = (int)(v % (unsigned)Wp); v /= (unsigned)Wp;
+    const int hp = (int)(v % (unsigned)Hp);
+    const int dp = (int)(v / (unsigned)Hp);
+    const int d = dp == 0 ? D - 1 : (dp == Dp - 1 ? 0 : dp - 1);
+    const int h = hp == 0 ? H - 1 : (hp == Hp - 1 ? 0 : hp - 1);
+    const int w = wp == 0 ? W - 1 : (wp == Wp - 1 ? 0 : wp - 1);
+    yp[i] = xp[((int64_t)d * H + h) * W + w];
+  }
+}
+
 }  // namespace vdm
 
 using namespace vdm;
+
+extern "C" int vdm_pad_circular(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
+                                int channels, void* stream) {
+  VDM_CHECK_ARG(view_ok(x, channels) && view_ok(y, channels) && batch >= 1, "vdm_pad_circular: bad argument");
+  VDM_CHECK_PLANES(batch, channels, "vdm_pad_circular");
+  VDM_CHECK_ARG(depth >= 1 && height >= 1 && width >= 1 && (int64_t)(depth + 2) * (height + 2) * (width + 2) < ((int64_t)1 << 31),
+                "vdm_pad_circular: bad grid (%d,%d,%d)", depth, height, width);
+  const int planes = channels / 8;
+  const int64_t vout = (int64_t)(depth + 2) * (height + 2) * (width + 2);
+  pad_circular_kernel<<<ew_grid(vout, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(*x, *y, planes, depth, height, width);
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
 
 extern "C" int vdm_channel_stats(const VdmTensor* x, int batch, int64_t voxels, int channels, double* stats,
                                  int stats_channels, int stats_c0, void* stream) {

@@ -50,6 +50,8 @@ struct WgradParams {
   int stages, a_stage_bytes, g_stage_bytes;
   int slice_bytes;       // (cpb/8) * Hh * Wh * 16
   int x_planes, x_plane0, g_planes, g_plane0;
+  int a_shift;           // 1 when `a` carries a one-voxel periodic halo
+  int g_shift;           // same for g
   int tmem_cols;
   float* dw;             // fp32, element (tap, ci, co) at tap*st_tap + ci*st_ci + co*st_co
   long long st_tap, st_ci, st_co;
@@ -119,8 +121,8 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         ptx::mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(n_slices * p.slice_bytes + p.g_stage_bytes));
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         for (int sl = 0; sl < n_slices; ++sl)
-          ptx::tma_load_4d(a_dst + (size_t)sl * p.slice_bytes, &tmap_a, &sh->full[s], (w0 - p.pad) * 8, h0 - p.pad,
-                           d - p.pad + sl, b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
+          ptx::tma_load_4d(a_dst + (size_t)sl * p.slice_bytes, &tmap_a, &sh->full[s], (w0 - p.pad + p.a_shift) * 8,
+                           h0 - p.pad + p.a_shift, d - p.pad + sl + p.a_shift, b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
         ptx::tma_load_4d(a_dst + p.a_stage_bytes, &tmap_g, &sh->full[s], w0 * 8, h0, d,
                          b * p.g_planes + p.g_plane0 + ns * (p.n >> 3));
       }
@@ -227,6 +229,7 @@ struct WgradNarrowParams {
   int n_splits;          // CTAs per channel block
   int slice_bytes, g_tile_bytes, g_stage_bytes;
   int x_planes, x_plane0, g_planes, g_plane0;
+  int a_shift, g_shift;
   float* dw;
   long long st_tap, st_ci, st_co;
 };
@@ -239,7 +242,8 @@ struct WgradNarrowShared {
 };
 
 __global__ void __launch_bounds__(kWnThreads, 1)
-conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_g,
+conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_g0,
+                           const __grid_constant__ CUtensorMap tmap_g1, const __grid_constant__ CUtensorMap tmap_g2,
                            const __grid_constant__ WgradNarrowParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -256,7 +260,9 @@ conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap_a);
-    ptx::prefetch_tensormap(&tmap_g);
+    ptx::prefetch_tensormap(&tmap_g0);
+    ptx::prefetch_tensormap(&tmap_g1);
+    ptx::prefetch_tensormap(&tmap_g2);
     for (int s = 0; s < p.n_slots; ++s) {
       ptx::mbar_init(&sh->slot_full[s], 1);
       ptx::mbar_init(&sh->slot_empty[s], 1);
@@ -294,7 +300,8 @@ conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         for (int k = 0; k < kWnLen + 2; ++k) {
           ptx::mbar_wait(&sh->slot_empty[k], (i & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&sh->slot_full[k], (uint32_t)p.slice_bytes);
-          ptx::tma_load_4d(a_smem + (size_t)k * p.slice_bytes, &tmap_a, &sh->slot_full[k], (w0 - 1) * 8, h0 - 1, d0 - 1 + k,
+          ptx::tma_load_4d(a_smem + (size_t)k * p.slice_bytes, &tmap_a, &sh->slot_full[k], (w0 - 1 + p.a_shift) * 8,
+                           h0 - 1 + p.a_shift, d0 - 1 + k + p.a_shift,
                            b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
         }
       }
@@ -311,10 +318,15 @@ conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           ptx::mbar_wait(&sh->g_empty[s], ((it / kWnGStages) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&sh->g_full[s], (uint32_t)p.g_stage_bytes);
           uint8_t* dst = g_smem + (size_t)s * p.g_stage_bytes;
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw)      // copy kw holds g(u - (kw - 1)) along w
-            ptx::tma_load_4d(dst + (size_t)kw * p.g_tile_bytes, &tmap_g, &sh->g_full[s], (w0 + 1 - kw) * 8, h0, d0 + j,
-                             b * p.g_planes + p.g_plane0);
+          // copy kw holds g(u - (kw - 1)) along w.  Zero padding: one map, shifted coordinates, out-of-range zero-filled.
+          // Circular padding (g with a periodic halo): map kw is a (W, H, D) window of the padded tensor that starts
+          // (2 - kw) voxels into a row, so the shift wraps periodically while positions u >= W still read zeros.
+          const int sh_w = p.g_shift ? 0 : 1;
+          ptx::tma_load_4d(dst, &tmap_g0, &sh->g_full[s], (w0 + sh_w) * 8, h0, d0 + j, b * p.g_planes + p.g_plane0);
+          ptx::tma_load_4d(dst + (size_t)p.g_tile_bytes, &tmap_g1, &sh->g_full[s], w0 * 8, h0, d0 + j,
+                           b * p.g_planes + p.g_plane0);
+          ptx::tma_load_4d(dst + (size_t)2 * p.g_tile_bytes, &tmap_g2, &sh->g_full[s], (w0 - sh_w) * 8, h0, d0 + j,
+                           b * p.g_planes + p.g_plane0);
         }
       }
     }
@@ -450,6 +462,8 @@ static int launch_wgrad_narrow(const VdmWgradDesc& d, const void* a, const void*
   p.g_tile_bytes = p.n * kWgTileH * kWgTileW * 2;
   p.g_stage_bytes = 3 * p.g_tile_bytes;
   p.x_planes = x_planes; p.x_plane0 = d.a_plane0;
+  p.a_shift = d.a_padded ? 1 : 0;
+  p.g_shift = d.g_padded ? 1 : 0;
   p.g_planes = g_planes; p.g_plane0 = d.g_plane0;
   p.dw = dw;
   if (d.dw_stride_tap == 0 && d.dw_stride_ci == 0 && d.dw_stride_co == 0) {
@@ -461,28 +475,37 @@ static int launch_wgrad_narrow(const VdmWgradDesc& d, const void* a, const void*
   const size_t smem_bytes = (size_t)p.n_slots * p.slice_bytes + (size_t)kWnGStages * p.g_stage_bytes +
                             sizeof(WgradNarrowShared) + 1024;
   VDM_CHECK_ARG(smem_bytes <= 227 * 1024, "vdm_conv3d_wgrad: narrow-layer plan needs %zu bytes of shared memory", smem_bytes);
-  CUtensorMap tma, tmg;
+  CUtensorMap tma, tmg[3];
   {
-    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
-    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * x_planes};
-    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    const cuuint64_t ah = d.a_padded ? 1 : 0;         // `a` with a one-voxel periodic halo: padded dims
+    const cuuint64_t Da = d.depth + 2 * ah, Ha = d.height + 2 * ah, Wa = d.width + 2 * ah;
+    cuuint64_t gdim[4] = {Wa * 8, Ha, Da, (cuuint64_t)d.batch * x_planes};
+    cuuint64_t gstr_a[3] = {Wa * 16, Ha * Wa * 16, Da * Ha * Wa * 16};
     cuuint32_t box[4] = {(cuuint32_t)(kWgTileW + 2) * 8, (cuuint32_t)(kWgTileH + 2), 1u, (cuuint32_t)(cpb / 8)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), gdim, gstr, box, estr,
+    CUresult r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), gdim, gstr_a, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(a) failed with %d", (int)r);
       return VDM_E_DRIVER;
     }
+    // g: logical dims (W, H, D) always (positions beyond the grid read zeros); with a periodic halo the window
+    // of copy kw starts (2 - kw) voxels into the padded row (see the kernel), else all three maps are the same.
+    const cuuint64_t gh = d.g_padded ? 1 : 0;
+    const cuuint64_t Dg = d.depth + 2 * gh, Hg = d.height + 2 * gh, Wg = d.width + 2 * gh;
     cuuint64_t gdim2[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * g_planes};
+    cuuint64_t gstr_g[3] = {Wg * 16, Hg * Wg * 16, Dg * Hg * Wg * 16};
     cuuint32_t box2[4] = {(cuuint32_t)kWgTileW * 8, (cuuint32_t)kWgTileH, 1u, (cuuint32_t)(p.n / 8)};
-    r = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g), gdim2, gstr, box2, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(g) failed with %d", (int)r);
-      return VDM_E_DRIVER;
+    for (int kw = 0; kw < 3; ++kw) {
+      const char* base = static_cast<const char*>(g) + (gh ? ((Hg + 1) * Wg + (cuuint64_t)(2 - kw)) * 16 : 0);
+      r = encode(&tmg[kw], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), gdim2, gstr_g, box2, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(g) failed with %d", (int)r);
+        return VDM_E_DRIVER;
+      }
     }
   }
   static bool configured = false;
@@ -490,7 +513,7 @@ static int launch_wgrad_narrow(const VdmWgradDesc& d, const void* a, const void*
     VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  conv3d_wgrad_narrow_kernel<<<p.n_cblocks * p.n_splits, kWnThreads, smem_bytes, stream>>>(tma, tmg, p);
+  conv3d_wgrad_narrow_kernel<<<p.n_cblocks * p.n_splits, kWnThreads, smem_bytes, stream>>>(tma, tmg[0], tmg[1], tmg[2], p);
   VDM_CHECK_LAUNCH();
   return VDM_OK;
 }
@@ -513,6 +536,7 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
   VDM_CHECK_ARG(d.c_in >= 16 && d.c_in % 16 == 0, "vdm_conv3d_wgrad: c_in=%d must be a multiple of 16", d.c_in);
   VDM_CHECK_ARG(d.c_out >= 1 && d.c_out <= 256, "vdm_conv3d_wgrad: c_out=%d out of [1,256]", d.c_out);
   VDM_CHECK_ARG(d.kernel == 3 || d.kernel == 1, "vdm_conv3d_wgrad: kernel size %d (3 or 1 supported)", d.kernel);
+  VDM_CHECK_ARG(!(d.kernel == 3 && d.a_padded && !d.g_padded), "vdm_conv3d_wgrad: a periodic `a` needs a periodic g (g_padded)");
   const int x_planes = d.a_planes > 0 ? d.a_planes : d.c_in / 8;
   const int c_out16 = (d.c_out + 15) / 16 * 16;
   const int g_planes = d.g_planes > 0 ? d.g_planes : c_out16 / 8;
@@ -590,6 +614,8 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
   }
   p.n_splits = n_splits;
   p.x_planes = x_planes; p.x_plane0 = d.a_plane0;
+  p.a_shift = d.a_padded ? 1 : 0;
+  p.g_shift = d.g_padded ? 1 : 0;
   p.g_planes = g_planes; p.g_plane0 = d.g_plane0;
   p.dw = dw;
   if (d.dw_stride_tap == 0 && d.dw_stride_ci == 0 && d.dw_stride_co == 0) {
@@ -601,21 +627,34 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
 
   CUtensorMap tma, tmg;
   {
+    const cuuint64_t ah = d.a_padded ? 1 : 0;         // `a` with a one-voxel periodic halo: padded dims
+    const cuuint64_t Da = d.depth + 2 * ah, Ha = d.height + 2 * ah, Wa = d.width + 2 * ah;
+    cuuint64_t gdim[4] = {Wa * 8, Ha, Da, (cuuint64_t)d.batch * x_planes};
+    cuuint64_t gstr_a[3] = {Wa * 16, Ha * Wa * 16, Da * Ha * Wa * 16};
     const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
-    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * x_planes};
     cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
     cuuint32_t box[4] = {(cuuint32_t)p.Wh * 8, (cuuint32_t)p.Hh, 1u, (cuuint32_t)(cpb / 8)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), gdim, gstr, box, estr,
+    CUresult r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), gdim, gstr_a, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("vdm_conv3d_wgrad: cuTensorMapEncodeTiled(a) failed with %d", (int)r);
       return VDM_E_DRIVER;
     }
+    // g: logical dims (W, H, D) always (positions beyond the grid read zeros); with a periodic halo the window
+    // of copy kw starts (2 - kw) voxels into the padded row (see the kernel), else all three maps are the same.
+    // g: logical dims (W, H, D) (positions beyond the grid read zeros); with a periodic halo the window starts at
+    // the interior of the padded tensor
+    // g: logical dims (W, H, D) (positions beyond the grid read zeros); with a periodic halo the window starts at
+    // the interior of the padded tensor
+    const cuuint64_t gh = d.g_padded ? 1 : 0;
+    const cuuint64_t Dg = d.depth + 2 * gh, Hg = d.height + 2 * gh, Wg = d.width + 2 * gh;
     cuuint64_t gdim2[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * g_planes};
+    cuuint64_t gstr_g[3] = {Wg * 16, Hg * Wg * 16, Dg * Hg * Wg * 16};
     cuuint32_t box2[4] = {(cuuint32_t)kWgTileW * 8, (cuuint32_t)kWgTileH, 1u, (cuuint32_t)(p.n / 8)};
-    r = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g), gdim2, gstr, box2, estr,
+    const char* gbase = static_cast<const char*>(g) + (gh ? ((Hg + 1) * Wg + 1) * 16 : 0);
+    r = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(gbase), gdim2, gstr_g, box2, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

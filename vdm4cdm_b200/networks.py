@@ -104,8 +104,8 @@ class CUNet(nn.Module):
             raise NotImplementedError("vdm4cdm_b200.CUNet covers the 3-D networks (shape=(C, D, H, W)) only")
         if mid_attn:
             raise NotImplementedError("mid_attn=True is used by the reference's 2-D scripts only")
-        if conv_padding_mode != "zeros":
-            raise NotImplementedError("circular padding (cropsize==256 models) is not implemented yet")
+        if conv_padding_mode not in ("zeros", "circular"):
+            raise NotImplementedError(f"conv_padding_mode={conv_padding_mode!r}: 'zeros' and 'circular' are supported")
         if shape[0] != 1 or (out_channels not in (None, 1)):
             raise NotImplementedError("single-channel fields only (every 3-D config of the reference)")
         if s_conditioning_channels + 1 > 8:
@@ -117,6 +117,7 @@ class CUNet(nn.Module):
             if n % (2 ** (len(chs) - 1)) != 0:
                 raise ValueError(f"grid {shape[1:]} is not divisible by 2^{len(chs) - 1}")
         self.shape = tuple(shape)
+        self.circular = conv_padding_mode == "circular"     # the cropsize == 256 models (src/utils.py:460)
         self.chs = list(chs)
         self.s_conditioning_channels = s_conditioning_channels
         self.v_conditioning_dims = list(v_conditioning_dims)
@@ -295,8 +296,9 @@ class CUNet(nn.Module):
         ops.gn_silu(x, ci, g, x_stats, blk.net1[0].weight, blk.net1[0].bias, blk.net1[0].eps, x_plane0=x_plane0, out=a1)
         h = ar.get(f"{own}h.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
         h_stats = self._stats(f"{name}.h", b, co, dev)
-        ops.conv3d(a1, self._packed(name + ".net1", blk.net1[2]), co, out=h, chan_add=rows[name + ".net1"],
-                   step_ptr=step_ptr if rows[name + ".net1"].dim() == 3 else None, stats=h_stats)
+        a1c, _ = self._conv_input(a1, ci, 0, name + ".a1p", tape)
+        ops.conv3d(a1c, self._packed(name + ".net1", blk.net1[2]), co, out=h, chan_add=rows[name + ".net1"],
+                   step_ptr=step_ptr if rows[name + ".net1"].dim() == 3 else None, stats=h_stats, circular=self.circular)
         a2 = ar.get(f"{own}a2.{co}.{tag}" if tape is not None else f"a.{co}.{tag}", (b, co // 8) + grid + (8,),
                     torch.bfloat16, dev)
         p_drop = blk.dropout_prob if training_dropout else 0.0
@@ -305,8 +307,9 @@ class CUNet(nn.Module):
         ops.gn_silu(h, co, g, h_stats, blk.net2[0].weight, blk.net2[0].bias, blk.net2[0].eps, out=a2, dropout_p=p_drop,
                     seed=self.dropout_seed, layer_tag=self._dropout_calls,
                     seed_step=self.drop_counter if p_drop > 0.0 else None)
+        a2c, _ = self._conv_input(a2, co, 0, name + ".a2p", tape)
         if tape is not None:
-            tape[name] = dict(x=x, x_plane0=x_plane0, x_stats=x_stats, a1=a1, h=h, h_stats=h_stats, a2=a2, grid=grid,
+            tape[name] = dict(x=x, x_plane0=x_plane0, x_stats=x_stats, a1=a1c, h=h, h_stats=h_stats, a2=a2c, grid=grid,
                               p_drop=p_drop, drop_tag=self._dropout_calls, drop_seed=self.dropout_seed)
         if blk.skip_conv is None:
             res, res_plane0 = x, x_plane0
@@ -315,9 +318,22 @@ class CUNet(nn.Module):
             ops.conv3d(x, self._packed(name + ".skip", blk.skip_conv), co, taps=ops.TAPS_1X1X1, x_plane0=x_plane0, c_in=ci,
                        out=res, chan_add=rows[name + ".skip"])
             res_plane0 = 0
-        ops.conv3d(a2, self._packed(name + ".net2", blk.net2[3]), co, out=out, out_plane0=out_plane0,
+        ops.conv3d(a2c, self._packed(name + ".net2", blk.net2[3]), co, out=out, out_plane0=out_plane0,
                    chan_add=rows[name + ".net2"], residual=res, residual_plane0=res_plane0, stats=out_stats,
-                   stats_c0=out_stats_c0)
+                   stats_c0=out_stats_c0, circular=self.circular)
+
+    def _conv_input(self, x, ch, x_plane0, slot, tape):
+        """The tensor a 3x3x3 conv reads: ``x`` itself (zero padding is the TMA unit's out-of-bounds fill) or, for
+        circular padding, a copy with a one-voxel periodic halo (``vdm_pad_circular``)."""
+        if not self.circular:
+            return x, x_plane0
+        b = x.shape[0]
+        d, h, w = x.shape[2:5]
+        ar = self._arena if tape is None else self._train_arena
+        name = (slot if tape is not None else "pad") + f".{ch}.{b}x{d}"
+        buf = ar.get(name, (b, ch // 8, d + 2, h + 2, w + 2, 8), torch.bfloat16, x.device)
+        ops.pad_circular(x, ch, x_plane0=x_plane0, out=buf)
+        return buf, 0
 
     def _stats(self, name: str, b: int, c: int, dev) -> torch.Tensor:
         """A zeroed double [B, c, 2] slice of the per-forward statistics arena."""
@@ -351,7 +367,9 @@ class CUNet(nn.Module):
         # conv_in
         h = buf("h_in", c[0], 0)
         h_stats = self._stats("conv_in", b, c[0], dev)
-        ops.conv3d(packed, self._packed("conv_in", self.conv_in), c[0], out=h, chan_add=rows["conv_in"], stats=h_stats)
+        packed_c, _ = self._conv_input(packed, 16, 0, "conv_in.xp", tape)
+        ops.conv3d(packed_c, self._packed("conv_in", self.conv_in), c[0], out=h, chan_add=rows["conv_in"], stats=h_stats,
+                   circular=self.circular)
         x, x_plane0, x_stats = h, 0, h_stats
         # down path: the block output of level i < last lands in the concat buffer of the matching up level
         cats, cat_stats = {}, {}
@@ -393,11 +411,13 @@ class CUNet(nn.Module):
         a = ar.get(("conv_out." if tape is not None else "") + f"a.{c[0]}.{b}x{grids[0][0]}",
                    (b, c[0] // 8) + grids[0] + (8,), torch.bfloat16, dev)
         ops.gn_silu(x, c[0], gn.num_groups, x_stats, gn.weight, gn.bias, gn.eps, out=a)
+        a_c, _ = self._conv_input(a, c[0], 0, "conv_out.ap", tape)
         if tape is not None:
-            tape["trunk"] = dict(packed=packed, h_in=h, cats=cats, grids=grids, out_x=x, out_x_stats=x_stats, out_a=a)
+            tape["trunk"] = dict(packed=packed_c, h_in=h, cats=cats, grids=grids, out_x=x, out_x_stats=x_stats, out_a=a_c)
         if out is None:
             out = torch.empty((b, 1) + grids[0], dtype=torch.float32, device=dev)
-        ops.conv3d(a, self._packed("conv_out", self.conv_out[2]), 1, out=out, out_fp32=True, chan_add=rows["conv_out"])
+        ops.conv3d(a_c, self._packed("conv_out", self.conv_out[2]), 1, out=out, out_fp32=True, chan_add=rows["conv_out"],
+                   circular=self.circular)
         return out
 
     def forward(self, x, t=None, s_conditioning=None, v_conditionings=None):

@@ -139,7 +139,7 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
            x_plane0: int = 0, c_in: Optional[int] = None, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
            out_fp32: bool = False, chan_add: Optional[torch.Tensor] = None, step_ptr: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, residual_plane0: int = 0, stats: Optional[torch.Tensor] = None,
-           stats_c0: int = 0) -> torch.Tensor:
+           stats_c0: int = 0, circular: bool = False) -> torch.Tensor:
     """``vdm_conv3d``: y = conv(x, w) [+ chan_add[b, co]] [+ residual], optional GroupNorm statistics.
 
     x: planar buffer; the conv reads ``c_in`` channels starting at plane ``x_plane0``.
@@ -151,6 +151,8 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
     """
     _planar_ok(x, "conv3d x")
     b, xp, d, h, w_, _ = x.shape
+    if circular:                       # x carries a one-voxel periodic halo (``pad_circular``)
+        d, h, w_ = d - 2, h - 2, w_ - 2
     n_taps, cin8, c_out_pad, eight = w_packed.shape
     _need(w_packed.is_cuda and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous() and eight == 8,
           "conv3d: w_packed must be a contiguous CUDA bf16 [taps, Cin/8, Cout_pad, 8] tensor")
@@ -163,7 +165,7 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
     for i, t in enumerate(taps):
         for k in range(3):
             desc.tap_offset[i][k] = t[k]
-    desc.circular = 0
+    desc.circular = 1 if circular else 0
     desc.out_fp32 = 1 if out_fp32 else 0
     desc.x_planes, desc.x_plane0 = xp, x_plane0
     if out is None:
@@ -282,6 +284,21 @@ def upsample2(coarse: torch.Tensor, channels: int, out: torch.Tensor, *, coarse_
     return out
 
 
+def pad_circular(x: torch.Tensor, channels: int, *, x_plane0: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``vdm_pad_circular``: planar [B, P, D, H, W, 8] -> [B, channels/8, D+2, H+2, W+2, 8] with a periodic one-voxel halo."""
+    _planar_ok(x, "pad_circular x")
+    b, _, d, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty((b, channels // 8, d + 2, h + 2, w + 2, 8), dtype=torch.bfloat16, device=x.device)
+    _planar_ok(out, "pad_circular out")
+    _need(tuple(out.shape[2:5]) == (d + 2, h + 2, w + 2) and out.shape[0] == b, "pad_circular: out must have the padded grid")
+    vx, vy = _view(x, x_plane0), _view(out, 0)
+    rc = _C.lib().vdm_pad_circular(ctypes.byref(vx), ctypes.byref(vy), b, d, h, w, channels, _stream())
+    _C.check(rc, "vdm_pad_circular")
+    _launched(1)
+    return out
+
+
 def pack_input(z: torch.Tensor, cond: Optional[torch.Tensor], c_pad: int = 16,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """z: fp32 (B, 1, D, H, W) or (B, D, H, W); cond: fp32 (B, n_cond, D, H, W) -> planar [B, c_pad/8, D, H, W, 8]."""
@@ -308,7 +325,8 @@ def pack_input(z: torch.Tensor, cond: Optional[torch.Tensor], c_pad: int = 16,
 
 # ---- backward (training) ---------------------------------------------------------------------------
 def conv3d_wgrad(a: torch.Tensor, g: torch.Tensor, c_in: int, c_out: int, kernel: int = 3, *, a_plane0: int = 0,
-                 g_plane0: int = 0, out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 g_plane0: int = 0, out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None,
+                 a_padded: bool = False, g_padded: bool = False) -> torch.Tensor:
     """``vdm_conv3d_wgrad``: dw[tap, ci, co] += sum_v a[ci, v + tap] g[co, v]  (fp32 [k^3, c_in, c_out]).
 
     a, g: planar buffers on the same grid; the g window must hold c_out rounded up to 16 channels.
@@ -316,7 +334,10 @@ def conv3d_wgrad(a: torch.Tensor, g: torch.Tensor, c_in: int, c_out: int, kernel
     _planar_ok(a, "conv3d_wgrad a")
     _planar_ok(g, "conv3d_wgrad g")
     b, ap, d, h, w_, _ = a.shape
-    _need(tuple(g.shape[2:5]) == (d, h, w_) and g.shape[0] == b, "conv3d_wgrad: a / g grid mismatch")
+    if a_padded:                       # a carries a one-voxel periodic halo (circular convs)
+        d, h, w_ = d - 2, h - 2, w_ - 2
+    gd = tuple(int(v) - (2 if g_padded else 0) for v in g.shape[2:5])
+    _need(gd == (d, h, w_) and g.shape[0] == b, "conv3d_wgrad: a / g grid mismatch")
     desc = _C.WgradDesc()
     if grad_out is not None:
         # accumulate straight into a torch-layout gradient (c_out, c_in_real, k, k, k), e.g. a view of the flat bucket
@@ -335,6 +356,8 @@ def conv3d_wgrad(a: torch.Tensor, g: torch.Tensor, c_in: int, c_out: int, kernel
     desc.c_in, desc.c_out, desc.kernel = c_in, c_out, kernel
     desc.a_planes, desc.a_plane0 = ap, a_plane0
     desc.g_planes, desc.g_plane0 = g.shape[1], g_plane0
+    desc.a_padded = 1 if a_padded else 0
+    desc.g_padded = 1 if g_padded else 0
     prof = _CONV_PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
