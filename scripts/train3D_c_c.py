@@ -38,10 +38,16 @@ def main():
     ap.add_argument("cropsize", type=int)
     ap.add_argument("--model", choices=["VDM", "SFM"], default="VDM")
     ap.add_argument("--synthetic", action="store_true")
+    ap.add_argument("--data-root", default=os.environ.get("VDM4CDM_DATA_ROOT"),
+                    help="directory with the CAMELS grids (Grids_{field}_{suite}_LH_{res}_z=0.0.npy) and params_LH_{suite}.txt")
+    ap.add_argument("--suite-name", default="Astrid")
+    ap.add_argument("--host-boxes", action="store_true", help="keep the boxes memory-mapped on the host (mmap=True)")
+    ap.add_argument("--max-epochs", type=int, default=1000)
     ap.add_argument("--synthetic-boxes", action="store_true",
                     help="with --synthetic: synthetic RAW simulation boxes through the device-resident dataset pipeline")
     ap.add_argument("--max-steps", type=int, default=1_000_000)
     ap.add_argument("--batch-size", type=int, default=None, help="samples per GPU (default: the reference script's)")
+    ap.add_argument("--chs", type=int, nargs="+", default=None, help="override the channel widths per level")
     ap.add_argument("--ckpt-dir", default="./checkpoints")
     ap.add_argument("--ckpt-every", type=int, default=10_000)
     ap.add_argument("--log-every", type=int, default=10)
@@ -50,6 +56,7 @@ def main():
     torch.manual_seed(42)                                     # seed_everything(42)
     chs, batch_size = PRESETS[args.model].get(args.cropsize, ([32, 64, 128, 256], 2))
     batch_size = args.batch_size or batch_size
+    chs = args.chs or chs
     n = args.cropsize
     net = networks.CUNet(shape=(1, n, n, n), chs=chs, s_conditioning_channels=1, v_conditioning_dims=[6],
                          t_conditioning=True, norm_groups=8, mid_attn=False, dropout_prob=0.1,
@@ -60,11 +67,21 @@ def main():
         model = sfm_model.LightSFM(velocity_model=net, draw_figure=None, learning_rate=3.0e-4)
     model = model.to(device)
     trainer = Trainer(model, gradient_clip_val=0.5)
-    if not args.synthetic:
-        raise NotImplementedError("reading the CAMELS .npy boxes is site specific (CAMELS_3D_dataset.py:105-128 hard-codes "
-                                  "the author's paths): load them into CUDA tensors and hand them to "
-                                  "vdm4cdm_b200.dataset.DeviceAstroDataset, or run with --synthetic")
     stream = None
+    if not args.synthetic:
+        # trainVDM3D128_...:75-89: LH set of the re-gridded boxes, stage "fit", mmap=False (boxes resident in HBM)
+        from vdm4cdm_b200.dataset import get_dataset
+        key_c, key_x = ("conditioning", "x") if args.model == "VDM" else ("x0", "x1")
+        dm = get_dataset(dataset_name="CMD" if n == 256 else f"CMD_{n}", suite_name=args.suite_name,
+                         return_func=lambda fields, params: {key_c: fields[0], key_x: fields[1], "conditioning_values": [params]},
+                         set_name="LH", z_name="z_0.0", channel_names=[args.field_in, args.field_out], stage="fit",
+                         batch_size=batch_size, cropsize=n, mmap=args.host_boxes, data_root=args.data_root, device=device,
+                         seed=42, rank=rank, world=world)
+
+        def epochs():
+            for _ in range(args.max_epochs):
+                yield from dm.train_dataloader()
+        stream = epochs()
     if args.synthetic_boxes:
         # the full data path: raw boxes resident in HBM -> vdm_augment_crop (periodic crop, log-normalise, flip, permute)
         from vdm4cdm_b200.dataset import DeviceAstroDataset
@@ -82,7 +99,10 @@ def main():
     t0 = time.perf_counter()
     for step in range(args.max_steps):
         if stream is not None:
-            loss = trainer.training_step(next(stream))
+            batch = next(stream, None)
+            if batch is None:
+                break
+            loss = trainer.training_step(batch)
             if rank == 0 and (step + 1) % args.log_every == 0:
                 dt = time.perf_counter() - t0
                 print(f"step {step + 1}: loss {loss.item():.5f}  {(step + 1) * batch_size * world / dt:.1f} samples/s")

@@ -69,3 +69,47 @@ def test_device_dataset_batch_schema_and_statistics():
         assert torch.equal(batch["conditioning_values"][0][j].cpu(), params[bidx])
     x = batch["x"]
     assert torch.allclose(norm_func(unnorm_func(x, 1.0, 11.0, 0.6), 1.0, 11.0, 0.6), x, atol=1e-4)
+
+
+def test_datamodule_batches_from_files_match_oracle(tmp_path):
+    """utils.get_datamodule (src/utils.py:401-432) over a miniature CAMELS-like directory: test-stage batches are the
+    log-normalised boxes themselves (HBM-resident and host-staged boxes give the same batch); fit-stage batches
+    replay through the oracle's crop/flip/permutate."""
+    from oracle import augment_ref
+    from vdm4cdm_b200 import dataset, utils
+    rng = np.random.default_rng(1)
+    n_sims, S = 6, 16
+    raws = {}
+    for c in ("Mstar", "Mcdm"):
+        raws[c] = (rng.random((n_sims, S, S, S)) * 1e10).astype(np.float32)
+        np.save(tmp_path / f"Grids_{c}_Astrid_1P_16_z=0.0.npy", raws[c])
+    par = rng.random((n_sims, 6))
+    np.savetxt(tmp_path / "params_1P_Astrid.txt", par)
+    config = {"cropsize": 16, "in_field_name": "Mstar", "out_field_name": "Mcdm",
+              "data_params": {"dataset_name": "CMD_16", "set_name": "1P", "batch_size": 2}}
+    dm = utils.get_datamodule(config, data_root=str(tmp_path))
+    batches = list(dm.test_dataloader())
+    assert len(batches) == 3 and batches[0]["x"].is_cuda and batches[0]["x"].shape == (2, 1, S, S, S)
+    m, s = dataset.NORMALIZATIONS_3D["Mcdm"]
+    want = (np.log10(raws["Mcdm"].astype(np.float64) + 1.0) - m) / s
+    got = torch.cat([b["x"] for b in batches])[:, 0].cpu().numpy()
+    assert np.allclose(got, want, rtol=2e-6, atol=2e-6)
+    assert np.allclose(torch.cat([b["conditioning_values"][0] for b in batches]).cpu().numpy(), par, atol=1e-6)
+    assert torch.allclose(dm.unnorm_func(batches[0]["x"], 1)[:, 0].cpu(), torch.from_numpy(raws["Mcdm"][:2]), rtol=2e-4)
+    # boxes left on the host (mmap=True) give bit-identical batches
+    rf = lambda fields, params: {"conditioning": fields[0], "x": fields[1], "conditioning_values": [params]}
+    dmh = dataset.get_dataset(dataset_name="CMD_16", set_name="1P", channel_names=["Mstar", "Mcdm"], return_func=rf,
+                              stage="test", batch_size=2, cropsize=16, data_root=str(tmp_path), mmap=True)
+    assert torch.equal(next(iter(dmh.test_dataloader()))["conditioning"], batches[0]["conditioning"])
+    # fit stage: random crops + flips + permutations, replayed through the oracle from the same seed
+    kw = dict(dataset_name="CMD_16", set_name="1P", channel_names=["Mstar", "Mcdm"], return_func=rf, stage="fit",
+              batch_size=4, cropsize=8, data_root=str(tmp_path), mmap=False, seed=9)
+    dmf, dmr = dataset.get_dataset(**kw), dataset.get_dataset(**kw)
+    loader = dmf.train_dataloader()
+    assert len(dmf.train_ids) == int(n_sims * 8 * 0.95)
+    batch = next(iter(loader))
+    order = [dmr.train_ids[i] for i in torch.randperm(len(dmr.train_ids), generator=dmr.data.gen).tolist()][:4]
+    for j, idx in enumerate(order):
+        bidx, anchor, flip, perm = dmr.data.draw(idx)
+        want = augment_ref.prepare(raws["Mcdm"][bidx][None], anchor, (8, 8, 8), flip, perm, 1.0, m, s)
+        assert np.allclose(batch["x"][j].cpu().numpy(), want, rtol=2e-6, atol=2e-6)

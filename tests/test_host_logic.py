@@ -151,3 +151,51 @@ def test_flat_bucket_allreduce_over_gloo(tmp_path):
     assert torch.allclose(r[0]["summed"], r[0]["local"] + r[1]["local"])
     assert torch.equal(r[0]["summed"], r[1]["summed"])
     assert sorted(r[0]["mine"] + r[1]["mine"]) == list(range(10))
+
+
+def _write_camels_like(tmp_path, n_sims=20, size=16, set_name="CV", channels=("Mstar", "Mcdm"), res=16):
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for c in channels:
+        np.save(tmp_path / f"Grids_{c}_Astrid_{set_name}_{res}_z=0.0.npy",
+                (rng.random((n_sims, size, size, size)) * 1e10).astype(np.float32))
+    np.savetxt(tmp_path / f"params_{set_name}_Astrid.txt", rng.random((n_sims, 6)))
+
+
+def test_datamodule_file_lookup_cv_exclusion_and_split(tmp_path):
+    """Host logic of AstroDataModule (CAMELS_3D_dataset.py:76-144) on a miniature CAMELS-like directory; boxes stay
+    memory-mapped on the host (mmap=True), so no device is touched."""
+    import numpy as np
+    from vdm4cdm_b200 import dataset
+    _write_camels_like(tmp_path)
+    rf = lambda fields, params: {"conditioning": fields[0], "x": fields[1], "conditioning_values": [params]}
+    sel = {"dataset_name": "CMD_16", "suite_name": "Astrid", "set_name": "CV", "z_name": "z_0.0"}
+    assert dataset.grid_file_name("Mcdm", sel) == "Grids_Mcdm_Astrid_CV_16_z=0.0.npy"
+    assert dataset.grid_file_name("Mcdm", dict(sel, dataset_name="CMD")) == "Grids_Mcdm_Astrid_CV_256_z=0.0.npy"
+    dm = dataset.AstroDataModule(sel, ["Mstar", "Mcdm"], rf, stage="fit", batch_size=2, do_crop=True, cropsize=8,
+                                 data_root=str(tmp_path), mmap=True)
+    assert dm.data.n_sims == 17 and dm.data.ncrops == 8            # boxes 2, 8, 17 of the CV set are dropped
+    raw = np.load(tmp_path / "Grids_Mcdm_Astrid_CV_16_z=0.0.npy")
+    assert np.array_equal(dm.data.fields[1][2], raw[3]) and np.array_equal(dm.data.fields[1][15], raw[18])
+    par = np.loadtxt(tmp_path / "params_CV_Astrid.txt")
+    assert np.allclose(dm.data.params[7].numpy(), par[9], atol=1e-7)
+    assert len(dm.train_ids) == int(17 * 8 * 0.95) and len(dm.train_ids) + len(dm.valid_ids) == 17 * 8
+    assert not set(dm.train_ids) & set(dm.valid_ids)
+    assert len(dm.train_dataloader()) == -(-len(dm.train_ids) // 2)
+    assert dm.means[1] == pytest.approx(10.019186475678042) and dm.alphas == [1.0, 1.0]
+    # two ranks see disjoint halves of an epoch
+    a = dataset._Loader(dm.data, dm.train_ids, 2, shuffle=False, rank=0, world=2)
+    b = dataset._Loader(dm.data, dm.train_ids, 2, shuffle=False, rank=1, world=2)
+    assert not set(a.ids[0::2]) & set(b.ids[1::2])
+    # test stage: no exclusion for non-CV sets, deterministic ids, missing files are reported by name
+    _write_camels_like(tmp_path, n_sims=5, set_name="1P")
+    dmt = dataset.get_dataset(dataset_name="CMD_16", set_name="1P", channel_names=["Mstar", "Mcdm"], return_func=rf,
+                              stage="test", cropsize=16, data_root=str(tmp_path), mmap=True)
+    assert dmt.data.n_sims == 5 and dmt.do_crop and dmt.data.ncrops == 1 and dmt.test_ids == list(range(5))
+    assert dmt.data.draw(3)[1].tolist() == [0, 0, 0] and not dmt.data.augment
+    with pytest.raises(FileNotFoundError, match="Grids_Go7_Astrid_1P_16"):
+        dataset.get_dataset(dataset_name="CMD_16", set_name="1P", channel_names=["Go7"], stage="test",
+                            data_root=str(tmp_path))
+    with pytest.raises(FileNotFoundError, match="VDM4CDM_DATA_ROOT"):
+        os.environ.pop("VDM4CDM_DATA_ROOT", None)
+        dataset.get_dataset(dataset_name="CMD_16", set_name="1P", stage="test")

@@ -146,6 +146,27 @@ def get_ddnm_result(vdm, y, A, AT, n_sampling_steps=250, l=10, return_all=False,
     return x_0t_r
 
 
+def get_datamodule(config: dict, **kw):
+    """``AstroDataModule`` of a ``configs.yaml`` entry (src/utils.py:401-432): channels ``[in_field_name,
+    out_field_name]``, batch schema {"conditioning", "x", "conditioning_values": [params]}, defaults suite Astrid /
+    set CV / z_0.0 / stage test / batch 1, boxes resident in HBM (the reference passes ``mmap=False``).
+    ``kw`` (data_root, device, seed, rank, world) goes to ``vdm4cdm_b200.dataset.get_dataset``."""
+    from . import dataset
+    if "data_params" not in config:
+        assert False, "data_params not in config"
+    data_params = config["data_params"]
+
+    def return_func(fields, params):
+        return {"conditioning": fields[0], "x": fields[1], "conditioning_values": [params]}
+
+    return dataset.get_dataset(dataset_name=data_params["dataset_name"], suite_name=data_params.get("suite_name", "Astrid"),
+                               return_func=return_func, set_name=data_params.get("set_name", "CV"),
+                               z_name=data_params.get("z_name", "z_0.0"),
+                               channel_names=[config["in_field_name"], config["out_field_name"]],
+                               stage=data_params.get("stage", "test"), batch_size=data_params.get("batch_size", 1),
+                               cropsize=config["cropsize"], num_workers=8, mmap=False, **kw)
+
+
 def get_model(config: dict, device=None):
     """``CUNet`` + ``LightVDM`` from a ``configs.yaml`` entry (src/utils.py:434-471): ``chs`` default
     [32, 64, 128, 256], ``norm_groups=8``, ``dropout_prob=0.1``, ``gamma_max=13.3``, circular padding iff
