@@ -49,6 +49,25 @@ def test_generate_scripts_on_a_camels_like_directory(tmp_path):
     assert not np.array_equal(gen[0], gen[1])                     # realisations differ (Philox key = (seed, r))
     _run("generate_3D_1P.py", "VDM_Mstar_Mcdm_c_c_16", out, "1P_24", *common, "--fields", 2)
     assert sorted(os.listdir(out)) == ["Om_m2_3.npy", "fid_3.npy", "gen_0.npy"]
+    # calc_SS.py over ensembles of both naming schemes; P(k) and posterior statistics against the oracle / numpy
+    # (an untrained network's samples are far outside the data range, so the ensemble here is synthetic)
+    ss = tmp_path / "ss"
+    os.makedirs(ss)
+    np.save(ss / "fid_3.npy", np.random.default_rng(3).standard_normal((3, 1, 16, 16, 16)).astype(np.float32))
+    np.save(ss / "gen_0.npy", np.random.default_rng(4).standard_normal((2, 1, 16, 16, 16)).astype(np.float32))
+    _run("calc_SS.py", ss, "--chunk", 2)
+    assert os.path.exists(ss / "gen_0_summary.npz")
+    summ = np.load(ss / "fid_3_summary.npz")
+    fid = 10.0 ** (np.load(ss / "fid_3.npy").astype(np.float64) * 0.552 + 10.019) - 1.0
+    assert summ["pk3d"].shape == (3, 8) and summ["pk2d_half"].shape == (3, 8) and summ["logpdf3d"].shape == (3, 99)
+    assert np.allclose(summ["post_means"], fid.mean(0, keepdims=True), rtol=1e-3)
+    assert np.allclose(summ["post_stds"], fid.std(0, ddof=1, keepdims=True), rtol=1e-3, atol=1e-3 * fid.std())
+    assert np.allclose(summ["mean3d"], fid.reshape(3, -1).mean(1), rtol=1e-3)
+    from oracle import power_ref
+    field = np.load(ss / "fid_3.npy")[:1].astype(np.float32)
+    un = (10.0 ** (field * np.float32(0.552) + np.float32(10.019)) - 1.0).astype(np.float32)
+    k_ref, p_ref, _ = power_ref.power(un / un.sum())
+    assert np.allclose(summ["pk3d"][0], p_ref, rtol=2e-3), (summ["pk3d"][0], p_ref)
     # same ensemble whatever the batch size
     out1 = tmp_path / "out1"
     _run("generate_3D.py", "VDM_Mstar_Mcdm_c_c_16", out1, "CV_1_128", *common[:-1], 1)
