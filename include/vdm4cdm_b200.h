@@ -81,6 +81,10 @@ typedef struct VdmConvEpilogue {
   double* stats;                /* double [B][stats_channels][2], atomically accumulated (sum, sumsq), or NULL */
   int32_t stats_channels;       /* channels per sample of the stats buffer (0: c_out) */
   int32_t stats_c0;             /* first stats channel this conv's output maps to */
+  int32_t residual_upsample;    /* != 0: the residual lives on the HALF-resolution grid (D/2, H/2, W/2) and is read through a
+                                 *       nearest x2 up-sampling (a 1x1x1 conv commutes with it: the up blocks' skip conv over
+                                 *       cat([interpolate(h), skip]) = conv(skip) + interpolate(conv(h))) */
+  int32_t reserved;
 } VdmConvEpilogue;
 
 /* y = conv(x, w) [+ chan_add[b][co]] [+ residual]; also the dgrad when w holds the flipped,
@@ -147,6 +151,16 @@ VDM_API int vdm_channel_stats(const VdmTensor* x, int batch, int64_t voxels, int
 VDM_API int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
                 const double* stats, const float* gamma, const float* beta, float eps,
                 float dropout_p, uint64_t seed, uint32_t layer_tag, void* stream);
+
+/* silu(groupnorm(.)) restricted to channels [c_off, c_off + channels) of a channels_total-channel norm whose
+ * statistics are stats (double [B][channels_total][2], of the tensor at the resolution of y); gamma / beta are the
+ * norm's full vectors.  (depth, height, width) is the grid of y.  upsample != 0: x is at HALF that resolution and
+ * y = silu(gn(nearest_upsample2(x))) -- the up blocks' torch.cat([interpolate(h), skip]) -> GroupNorm -> SiLU
+ * (blocks.py ResNetUp / ResNetBlock.net1) without ever writing the up-sampled tensor (its per-channel sums are 8x
+ * the coarse tensor's).  No dropout: net1 has none. */
+VDM_API int vdm_gn_silu_view(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
+                     int channels, int c_off, int channels_total, int groups, const double* stats,
+                     const float* gamma, const float* beta, float eps, int upsample, void* stream);
 /* Same with the dropout seed advanced on the device: seed_eff = seed + *seed_step (CUDA-graph replay). */
 VDM_API int vdm_gn_silu_step(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
                      const double* stats, const float* gamma, const float* beta, float eps, float dropout_p,

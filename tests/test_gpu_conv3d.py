@@ -185,3 +185,27 @@ def test_conv3d_circular_padding_exact_integers(case):
     assert torch.equal(ops.from_planar(dx, ci), xg.grad.round().float().to(torch.bfloat16).float())
     dw = ops.conv3d_wgrad(xpad, ops.pad_circular(ops.to_planar(dy, 16), -(-co // 16) * 16), ci, co, 3, a_padded=True, g_padded=True)
     assert torch.equal(ops.wgrad_to_torch(dw, 3), wg.grad.round().float())
+
+
+def test_conv3d_residual_read_through_upsampling():
+    """residual_upsample: y = conv1x1(x) + bias + interpolate(r_coarse) -- the split skip conv of the up blocks."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    for (b, ci, co, d, h, w, k) in [(2, 32, 32, 6, 20, 12, 1), (1, 64, 64, 4, 16, 8, 3), (1, 16, 128, 2, 6, 10, 1)]:
+        x = _int_tensor((b, ci, d, h, w), -2, 2, g, dev)
+        wt = _int_tensor((co, ci, k, k, k), -1, 1, g, dev)
+        cadd = _int_tensor((b, co), -3, 3, g, dev)
+        rc = _int_tensor((b, co, d // 2, h // 2, w // 2), -4, 4, g, dev)
+        ref = _reference(x, wt, cadd, F.interpolate(rc, scale_factor=2, mode="nearest")).to(torch.bfloat16).float()
+        rbuf = torch.zeros((b, co // 8 + 3, d // 2, h // 2, w // 2, 8), dtype=torch.bfloat16, device=dev)
+        rbuf[:, 2:2 + co // 8] = ops.to_planar(rc)
+        taps = ops.TAPS_3X3X3 if k == 3 else ops.TAPS_1X1X1
+        y = ops.conv3d(ops.to_planar(x), ops.pack_conv_weight(wt), co, taps=taps, chan_add=cadd, residual=rbuf,
+                       residual_plane0=2, residual_upsample=True)
+        torch.cuda.synchronize()
+        assert torch.equal(ops.from_planar(y, co), ref), (b, ci, co, d, h, w, k)
+    with pytest.raises(RuntimeError, match="even grid"):
+        ops.conv3d(ops.to_planar(torch.zeros((1, 16, 3, 8, 8), device=dev)), ops.pack_conv_weight(torch.zeros((16, 16, 1, 1, 1), device=dev)),
+                   16, taps=ops.TAPS_1X1X1, residual=torch.zeros((1, 2, 1, 4, 4, 8), dtype=torch.bfloat16, device=dev),
+                   residual_upsample=True)

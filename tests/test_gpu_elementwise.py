@@ -107,3 +107,38 @@ def test_pack_input_layout():
     assert torch.equal(dense[:, 0:1], z.to(torch.bfloat16).float())
     assert torch.equal(dense[:, 1:2], cond.to(torch.bfloat16).float())
     assert dense[:, 2:].abs().sum().item() == 0
+
+
+def test_gn_silu_view_channel_window_and_fused_upsampling():
+    """vdm_gn_silu_view: GroupNorm+SiLU over cat([interpolate(coarse), skip]) without the up-sampled tensor; groups
+    straddle the boundary between the two parts (96 channels, 8 groups of 12, boundary at 64)."""
+    from vdm4cdm_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    b, c_up, c_skip, grid = 2, 64, 32, (8, 12, 16)
+    cg = tuple(n // 2 for n in grid)
+    coarse = (torch.randn((b, c_up) + cg, generator=g) * 1.5 + 0.3).to(torch.bfloat16).float()
+    skip = (torch.randn((b, c_skip) + grid, generator=g) * 0.7 - 0.2).to(torch.bfloat16).float()
+    cat = torch.cat([F.interpolate(coarse, scale_factor=2, mode="nearest"), skip], dim=1)
+    gamma, beta = torch.randn(96, generator=g), torch.randn(96, generator=g)
+    want = F.silu(F.group_norm(cat, 8, gamma, beta, 1e-5))
+    # statistics of the fine-resolution concat: 8x the coarse sums for the up-sampled channels
+    stats = torch.zeros((b, 96, 2), dtype=torch.float64)
+    stats[:, :c_up, 0] = 8 * coarse.double().sum(dim=(2, 3, 4))
+    stats[:, :c_up, 1] = 8 * (coarse.double() ** 2).sum(dim=(2, 3, 4))
+    stats[:, c_up:, 0] = skip.double().sum(dim=(2, 3, 4))
+    stats[:, c_up:, 1] = (skip.double() ** 2).sum(dim=(2, 3, 4))
+    stats = stats.cuda()
+    # coarse tensor in a window of a wider buffer; skip in the concat buffer at its usual planes
+    cbuf = torch.zeros((b, c_up // 8 + 2) + cg + (8,), dtype=torch.bfloat16, device="cuda")
+    cbuf[:, 1:1 + c_up // 8] = ops.to_planar(coarse.cuda())
+    catbuf = torch.full((b, 12) + grid + (8,), 7.0, dtype=torch.bfloat16, device="cuda")
+    catbuf[:, c_up // 8:] = ops.to_planar(skip.cuda())
+    out = torch.zeros((b, 12) + grid + (8,), dtype=torch.bfloat16, device="cuda")
+    ops.gn_silu_view(cbuf, c_up, 0, 96, 8, stats, gamma.cuda(), beta.cuda(), 1e-5, out, x_plane0=1, out_plane0=0, upsample=True)
+    ops.gn_silu_view(catbuf, c_skip, c_up, 96, 8, stats, gamma.cuda(), beta.cuda(), 1e-5, out, x_plane0=c_up // 8,
+                     out_plane0=c_up // 8)
+    got = ops.from_planar(out, 96).cpu()
+    assert torch.allclose(got, want, rtol=1e-2, atol=1e-2), (got - want).abs().max()
+    assert ((got - want).norm() / want.norm()).item() < 3e-3
+    with pytest.raises(RuntimeError, match="outside the 96-channel norm"):
+        ops.gn_silu_view(catbuf, 64, 64, 96, 8, stats, gamma.cuda(), beta.cuda(), 1e-5, out)

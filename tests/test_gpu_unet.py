@@ -58,6 +58,28 @@ def test_unet_forward_matches_oracle(shape, chs, batch):
     assert _rel_l2(got1, want1) < BF16_RTOL
 
 
+def test_unet_fused_upsampling_equals_the_materialised_concat():
+    """Inference reads the coarse tensor in the up blocks (CUNet.fuse_upsample); the result must agree with the path
+    that writes interpolate(h) into the concat buffer (the one training uses) to bf16 rounding."""
+    shape, chs, batch = (1, 16, 32, 16), (16, 32, 64), 2
+    ref, net = _models(shape, chs)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((batch,) + shape, generator=g)
+    cond = 0.7 * x + 0.3 * torch.randn((batch,) + shape, generator=g)
+    t, v = torch.rand(batch, generator=g), [torch.rand(batch, 6, generator=g)]
+    kw = dict(t=t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()])
+    with torch.no_grad():
+        want = ref(x, t=t, s_conditioning=cond, v_conditionings=v)
+        assert net.fuse_upsample
+        fused = net(x.cuda(), **kw).cpu()
+        net.fuse_upsample = False
+        plain = net(x.cuda(), **kw).cpu()
+    print(f"fused vs materialised: {_rel_l2(fused, plain):.3e}; vs oracle: fused {_rel_l2(fused, want):.3e}, "
+          f"materialised {_rel_l2(plain, want):.3e}")
+    assert _rel_l2(fused, plain) < BF16_RTOL
+    assert _rel_l2(fused, want) < 1.2e-2 and _rel_l2(plain, want) < 1.2e-2
+
+
 def test_unet_forward_circular_padding_matches_oracle():
     """conv_padding_mode="circular" (the cropsize == 256 registry entries, src/utils.py:460)."""
     shape, chs, batch = (1, 16, 32, 16), (16, 32, 64), 2

@@ -34,6 +34,7 @@ class ConvEpilogue(Structure):
     _fields_ = [
         ("chan_add", c_void_p), ("step_ptr", c_void_p), ("chan_add_step_stride", c_int64),
         ("residual", c_void_p), ("stats", c_void_p), ("stats_channels", c_int32), ("stats_c0", c_int32),
+        ("residual_upsample", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -82,6 +83,8 @@ _SIGNATURES = {
     "vdm_channel_stats": (c_int, [_T, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_gn_silu": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             c_float, c_float, c_uint64, c_uint32, c_void_p]),
+    "vdm_gn_silu_view": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_float, c_int, c_void_p]),
     "vdm_avgpool2": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_upsample2": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_pad_circular": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -43,6 +43,7 @@ namespace vdm {
 constexpr int kConvThreads = 352;       // 11 warps
 constexpr int kEpiThreads = 256;        // warps 3..10
 constexpr int kEpiFirst = 96;
+constexpr int kResSlotBytes = 2 * 16 * kEpiThreads;   // one unit (two 8-channel planes) of residual for every epilogue thread
 constexpr int kMaxBStages = 16;
 constexpr int kTileH = 16, kTileW = 8;
 
@@ -77,6 +78,9 @@ struct ConvKernelParams {
   long long chan_add_step_stride;
   const __nv_bfloat16* residual;
   int r_planes, r_plane0;
+  int r_up;                  // residual on the half-resolution grid, read through a nearest x2 up-sampling
+  int res_depth;             // units of residual in flight per epilogue thread (cp.async ring), 1..4
+  int res_ring_off;          // byte offset of that ring in dynamic shared memory
   double* stats;
   int stats_channels, stats_c0;
   int debug_flags;           // bring-up experiments: 1 = epilogue does no work, 2 = halo loaded for the first two tiles only
@@ -542,10 +546,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // Work split between the two warps of a lane quarter: by 16-channel chunk when there are at least two (each
     // warp then owns whole channels and reduces their statistics over all MT slices in registers), else by slice.
     const int ch0 = n_chunks >= 2 ? half : 0, ch_step = n_chunks >= 2 ? 2 : 1;
-    const int s0 = n_chunks >= 2 ? 0 : half, s_step = n_chunks >= 2 ? 1 : 2;
-    const int ns_w = (MT - s0 + s_step - 1) / s_step;            // slices per chunk for this warp
-    const int nch_w = (n_chunks - ch0 + ch_step - 1) / ch_step;  // chunks of this warp
-    const int n_units = ns_w * nch_w;                            // unit k = (chunk k / ns_w, slice k % ns_w) of this warp
+    const int s_step = n_chunks >= 2 ? 1 : 2;
     const long long V = (long long)p.D * p.H * p.W;
     const uint4* res_base = reinterpret_cast<const uint4*>(p.residual);
     // Bias + conditioning rows: when the [B][n_pad] table fits the 512-float buffer it is loaded ONCE per CTA
@@ -561,45 +562,62 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    // Residual prefetch ring.  The residual does not depend on the accumulator, and a dependent 16-byte global load
-    // per (unit, half) cost ~700 cycles each (r01f: 0.44 -> 0.76 ms on the 32->32 level-0 conv).  This warp consumes its
-    // units in a fixed order; kResDepth of them are always in flight, and the prefetch stream runs AHEAD ACROSS TILE
-    // BOUNDARIES (its own tile cursor), so a tile's first residuals were requested about one tile time earlier -- on the
-    // epilogue-bound layers nothing else can hide their latency (r01u: +1.4 us per tile).
-    constexpr int kResDepth = 4;
-    uint4 rq[kResDepth][2];
+    // Residual prefetch ring in SHARED memory.  The residual does not depend on the accumulator, and a dependent
+    // 16-byte global load per (unit, half) cost ~700 cycles each (r01f: 0.44 -> 0.76 ms on the 32->32 level-0 conv).
+    // This warp consumes its units in a fixed order; p.res_depth of them are always in flight as cp.async copies
+    // (one commit group per unit) into per-thread slots, and the prefetch cursor runs AHEAD ACROSS TILE BOUNDARIES.
+    // The earlier REGISTER ring rotated its entries with moves, and a move out of a register that a load is still
+    // writing waits for that load: every unit waited for the load issued one unit before it (r02g: 18% of the 1x1x1
+    // skip conv's stall samples, +0.3 ms per GB of residual).  cp.async has no destination register; the only wait
+    // is cp.async.wait_group on the oldest group.
+    constexpr int kResPrefetchTiles = 3;
+    const int r_depth = p.res_depth;
+    uint4* r_ring = reinterpret_cast<uint4*>(smem + p.res_ring_off) + et;   // slot i, plane hf: r_ring[(2*i + hf) * kEpiThreads]
+    int r_slot = 0;                                  // oldest slot == the one refilled next (the ring is always full)
     const long long HW = (long long)p.H * p.W;
+    // residual grid: the output grid, or (r_up) its half-resolution parent (coordinates shifted right by one)
+    const int r_sh = p.r_up;
+    const int r_H = p.H >> r_sh, r_W = p.W >> r_sh;
+    const long long r_HW = (long long)r_H * r_W, r_V = (long long)(p.D >> r_sh) * r_HW;
     int r_tile = blockIdx.x - (int)gridDim.x;        // tile the prefetch cursor is in (advanced before first use)
     int ru_s = 0, ru_ch = n_chunks;                  // (slice, chunk) of the next unit to prefetch; "tile exhausted"
     const uint4* r_ptr = nullptr;
     int r_d0 = 0, r_cbase = 0;
     bool r_hw_ok = false;
-    auto res_issue = [&](uint4 (&dst)[2]) {
+    const int s0 = n_chunks >= 2 ? 0 : half;
+    auto res_issue = [&](int slot) {
+      bool live = true;
       if (ru_ch >= n_chunks) {                       // move the cursor to this CTA's next tile
         r_tile += (int)gridDim.x;
-        if (r_tile >= p.n_tiles) return;
-        const TileCoord tr = decode_tile(p, r_tile);
-        const int hr = tr.h0 + lh, wr = tr.w0 + lw;
-        r_hw_ok = (hr < p.H) && (wr < p.W);
-        r_d0 = tr.d0;
-        r_cbase = tr.ns * p.n_cta;
-        r_ptr = res_base + ((long long)tr.b * p.r_planes + p.r_plane0 + (r_cbase >> 3)) * V +
-                ((long long)tr.d0 * p.H + hr) * p.W + wr;
-        ru_s = s0; ru_ch = ch0;
-        if (ru_ch >= n_chunks) return;
+        if (r_tile < p.n_tiles) {
+          const TileCoord tr = decode_tile(p, r_tile);
+          const int hr = tr.h0 + lh, wr = tr.w0 + lw;
+          r_hw_ok = (hr < p.H) && (wr < p.W);
+          r_d0 = tr.d0;
+          r_cbase = tr.ns * p.n_cta;
+          r_ptr = res_base + ((long long)tr.b * p.r_planes + p.r_plane0 + (r_cbase >> 3)) * r_V +
+                  (long long)(hr >> r_sh) * r_W + (wr >> r_sh);
+          ru_s = s0; ru_ch = ch0;
+        } else {
+          live = false;
+        }
       }
-      const int su = ru_s, chu = ru_ch;
-      ru_s += s_step;
-      if (ru_s >= MT) { ru_s = s0; ru_ch += ch_step; }
-      if (!(r_hw_ok && r_d0 + su < p.D)) return;
-      const uint4* src = r_ptr + (long long)(chu * 2) * V + (long long)su * HW;
-      const int cu = r_cbase + chu * 16;
-      if (cu < p.c_out) dst[0] = __ldg(src);
-      if (cu + 8 < p.c_out) dst[1] = __ldg(src + V);
+      if (live) {
+        const int su = ru_s, chu = ru_ch;
+        ru_s += s_step;
+        if (ru_s >= MT) { ru_s = s0; ru_ch += ch_step; }
+        if (r_hw_ok && r_d0 + su < p.D) {
+          const uint4* src = r_ptr + (long long)(chu * 2) * r_V + (long long)((r_d0 + su) >> r_sh) * r_HW;
+          const int cu = r_cbase + chu * 16;
+          uint4* dst = r_ring + (2 * slot) * kEpiThreads;
+          if (cu < p.c_out) ptx::cp_async16(dst, src);
+          if (cu + 8 < p.c_out) ptx::cp_async16(dst + kEpiThreads, src + r_V);
+        }
+      }
+      ptx::cp_async_commit();                        // one group per unit, also when nothing was copied
     };
     if (p.residual) {
-#pragma unroll
-      for (int i = 0; i < kResDepth; ++i) res_issue(rq[i]);
+      for (int i = 0; i < r_depth; ++i) res_issue(i);
     }
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
@@ -608,6 +626,26 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const bool hw_ok = (h < p.H) && (w < p.W);
       const int cbase = t.ns * p.n_cta;
       const uint32_t acc = ti & 1;
+      if (p.residual) {
+        // The register ring above runs about one tile ahead, which covers an L2 hit but not an HBM miss (r02g: 18% of
+        // the 1x1x1 skip conv's stall samples were the ring's first use).  Pull the residual rows of the tile this CTA
+        // processes kResPrefetchTiles from now into L2: one 128-byte row (8 voxels of one plane) per thread.
+        const int pt = tile + kResPrefetchTiles * (int)gridDim.x;
+        if (pt < p.n_tiles) {
+          const TileCoord tp = decode_tile(p, pt);
+          const int pc0 = tp.ns * p.n_cta;
+          const int n_rows = (p.n_cta >> 3) * MT * 16;
+          const uint4* pbase = res_base + ((long long)tp.b * p.r_planes + p.r_plane0 + (pc0 >> 3)) * r_V + (tp.w0 >> r_sh);
+          for (int idx = et; idx < n_rows; idx += kEpiThreads) {
+            const int hh = tp.h0 + (idx & 15);
+            const int sp = idx >> 4;
+            const int pp = sp / MT;
+            const int dd = tp.d0 + (sp - pp * MT);
+            if (hh < p.H && dd < p.D && pc0 + pp * 8 < p.c_out && !(r_sh && ((hh | dd) & 1)))
+              ptx::prefetch_l2(pbase + (long long)pp * r_V + ((long long)(dd >> r_sh) * r_H + (hh >> r_sh)) * r_W);
+          }
+        }
+      }
       const int buf = ti & 1;
       if (p.chan_add && !cadd_table) {
         // bias + conditioning row of this sample -> shared memory (16 scalar global loads per unit cost ~10% of
@@ -624,7 +662,6 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
       ptx::tc_fence_after();
       if (!(p.debug_flags & 1)) {
-        int unit = 0;
         for (int ch = ch0; ch < n_chunks; ch += ch_step) {
           const int c0 = cbase + ch * 16;
           const bool full16 = (c0 + 16 <= p.c_out);
@@ -635,15 +672,15 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const int d = t.d0 + s;
             const bool valid = hw_ok && (d < p.D);
             const long long vox = vox0 + (long long)s * HW;
-            // rotate the residual ring: rq[0] is this unit's data, refill the tail
+            // the oldest slot is this unit's residual; refill it for the unit r_depth ahead
             uint4 rcur[2];
             if (p.residual) {
-              rcur[0] = rq[0][0]; rcur[1] = rq[0][1];
-#pragma unroll
-              for (int i = 0; i + 1 < kResDepth; ++i) { rq[i][0] = rq[i + 1][0]; rq[i][1] = rq[i + 1][1]; }
-              res_issue(rq[kResDepth - 1]);
+              ptx::cp_async_wait(r_depth - 1);
+              const uint4* slot = r_ring + (2 * r_slot) * kEpiThreads;
+              rcur[0] = slot[0]; rcur[1] = slot[kEpiThreads];
+              res_issue(r_slot);
+              r_slot = (r_slot + 1 == r_depth) ? 0 : r_slot + 1;
             }
-            ++unit;
             if (c0 >= p.c_out) return;  // padded output channels (warp-uniform)
             float f[16];
 #pragma unroll
@@ -845,6 +882,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
       if (d.tap_offset[t][k] != 0) pad = 1;
     }
   p.pad = pad;
+  const bool has_residual = epi && epi->residual;
   // kd-folded schedule (issue_fold_tile): the full 3x3x3 stencil on a narrow layer
   bool fold = d.n_taps == 27 && pad == 1 && d.c_in % 16 == 0 && (d.c_out_pad == 16 || d.c_out_pad == 32 || d.c_out_pad == 64) &&
               d.depth >= 3 && g_debug_no_fold == 0 && g_debug_force_mt == 0 && g_debug_force_nsplit == 0;
@@ -855,7 +893,8 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     fold_mt = 4; fold_kc = 32; fold_streamed = 1;
   } else if (fold) {
     // all weights resident + two halo stages must fit; prefer tall tiles (halo efficiency), then wide chunks
-    const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - 2 * 8 * d.c_out_pad * 4 - 256;
+    const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - 2 * 8 * d.c_out_pad * 4 - 256 -
+                       (has_residual ? 2 * kResSlotBytes : 0);      // room for at least two residual slots
     const int w_bytes = 27 * d.c_in * d.c_out_pad * 2;
     for (int m = 4; m >= 2 && !fold_mt; --m)
       for (int c = 32; c >= 16 && !fold_mt; c -= 16) {
@@ -943,7 +982,10 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
 
   // ---- shared memory plan: 2 halo stages + a ring of weight stages ----
   const int stat_part_bytes = 2 * 8 * p.n_cta * 4;
-  const int smem_budget = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - stat_part_bytes - 256;
+  const int smem_total = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - stat_part_bytes - 256;
+  // layers with a residual keep a cp.async ring of it in shared memory: 4 units deep where the weights are streamed
+  // anyway, at least 2 where they are resident (the fold search above left room)
+  const int smem_budget = smem_total - (has_residual ? (fold && !fold_streamed ? 2 : 4) * kResSlotBytes : 0);
   int kc = 0, nsb = 0;
   const int tps = (d.n_taps % 3 == 0) ? 3 : 1;   // one (kd, kh) row of filter taps per weight stage
   const int kc_options[3] = {64, 32, 16};
@@ -998,12 +1040,15 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     p.residual = static_cast<const __nv_bfloat16*>(epi->residual);
     p.r_planes = d.r_planes > 0 ? d.r_planes : d.c_out / 8;
     p.r_plane0 = d.r_plane0;
+    p.r_up = (epi->residual && epi->residual_upsample) ? 1 : 0;
     p.stats = epi->stats;
     p.stats_channels = epi->stats_channels > 0 ? epi->stats_channels : d.c_out;
     p.stats_c0 = epi->stats_c0;
   }
   VDM_CHECK_ARG(!(p.stats && d.out_fp32), "vdm_conv3d: stats are only produced for bf16 outputs");
   VDM_CHECK_ARG(!(p.residual && d.out_fp32), "vdm_conv3d: residual is only supported for bf16 outputs");
+  VDM_CHECK_ARG(!p.r_up || (d.depth % 2 == 0 && d.height % 2 == 0 && d.width % 2 == 0),
+                "vdm_conv3d: an up-sampled residual needs an even grid, got (%d,%d,%d)", d.depth, d.height, d.width);
   p.debug_flags = g_debug_flags;
 
   // activations: 4-D (W*8 channels-in-plane, H, D, B*planes), box (Wh*8, Hh, Hd, KC/8); out-of-bounds -> zeros.
@@ -1027,7 +1072,15 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     }
   }
 
-  const size_t smem_bytes = 2 * (size_t)p.a_stage_bytes + (size_t)p.nsb * p.b_stage_bytes + sizeof(ConvShared) + stat_part_bytes + 1024;
+  const int used = 2 * p.a_stage_bytes + p.nsb * p.b_stage_bytes;
+  if (has_residual) {
+    int depth = (smem_total - used) / kResSlotBytes;
+    p.res_depth = depth > 4 ? 4 : depth;
+    VDM_CHECK_ARG(p.res_depth >= 1, "vdm_conv3d: no shared memory left for the residual ring");
+    p.res_ring_off = used + (int)sizeof(ConvShared) + stat_part_bytes;
+    p.res_ring_off = (p.res_ring_off + 15) & ~15;
+  }
+  const size_t smem_bytes = (size_t)used + sizeof(ConvShared) + stat_part_bytes + 16 + (size_t)p.res_depth * kResSlotBytes + 1024;
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   int rc = VDM_E_UNSUPPORTED;
 #define VDM_LAUNCH(MTv, KJv, NFv)                                                                              \

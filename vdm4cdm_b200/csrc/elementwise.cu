@@ -87,6 +87,74 @@ gn_silu_kernel(VdmTensor x, VdmTensor y, int planes, int64_t voxels, int groups,
   }
 }
 
+// ---- GroupNorm + SiLU of a channel window of a wider norm, optionally through a nearest x2 up-sampling ------------
+// The up blocks normalise cat([upsample(h_coarse), skip]).  Nearest-neighbour up-sampling commutes with every
+// pointwise operation and leaves per-channel means and variances unchanged, so the up-sampled tensor is never
+// written: this kernel reads the COARSE channels [c_off, c_off + 8*planes) of the C_total-channel norm and writes
+// silu(gn(.)) at the fine resolution (UP), or handles the skip channels of the same norm in place (!UP).
+// stats: double [B][C_total][2] of the FINE-resolution concat (for up-sampled channels: 8x the coarse sums).
+// (D, H, W) is the grid of y.
+template <bool UP>
+__global__ void __launch_bounds__(kEwThreads)
+gn_silu_view_kernel(VdmTensor x, VdmTensor y, int planes, int c_off, int C_total, int groups, int D, int H, int W,
+                    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float eps) {
+  __shared__ float s_scale[8], s_shift[8];
+  const int b = blockIdx.y / planes, pl = blockIdx.y % planes;
+  const int64_t vf = (int64_t)D * H * W;
+  plane_scale_shift(stats + (int64_t)b * C_total * 2, C_total, groups, (c_off >> 3) + pl, (double)vf, gamma, beta, eps,
+                    s_scale, s_shift, nullptr, nullptr);
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_scale[j];
+    sh[j] = s_shift[j];
+  }
+  bf16x8* yp = plane_ptr_mut(y, b, pl, vf);
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  if (UP) {
+    const int Hc = H >> 1, Wc = W >> 1;
+    const bf16x8* cp = plane_ptr(x, b, pl, vf >> 3);
+    // one thread per (fine d, fine h, COARSE w): one 16-byte read (repeats hit L1/L2), two adjacent 16-byte stores
+    const int64_t vh = vf >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vh; i += stride) {
+      unsigned v = (unsigned)i;
+      const int wc = (int)(v % (unsigned)Wc); v /= (unsigned)Wc;
+      const int h = (int)(v % (unsigned)H);
+      const int d = (int)(v / (unsigned)H);
+      float f[8];
+      unpack8(cp[((int64_t)(d >> 1) * Hc + (h >> 1)) * Wc + wc], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu(f[j] * sc[j] + sh[j]);
+      const bf16x8 val = pack8(f);
+      bf16x8* dst = yp + ((int64_t)d * H + h) * W + 2 * wc;
+      st_stream(dst, val);
+      st_stream(dst + 1, val);
+    }
+  } else {
+    const bf16x8* xp = plane_ptr(x, b, pl, vf);
+    for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vf; i += 2 * stride) {
+      const int64_t i2 = i + stride;
+      const bool two = i2 < vf;
+      const bf16x8 v0 = ld_stream(xp + i);
+      bf16x8 v1 = v0;
+      if (two) v1 = ld_stream(xp + i2);
+      float f[8];
+      unpack8(v0, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu(f[j] * sc[j] + sh[j]);
+      st_stream(yp + i, pack8(f));
+      if (two) {
+        unpack8(v1, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu(f[j] * sc[j] + sh[j]);
+        st_stream(yp + i2, pack8(f));
+      }
+    }
+  }
+}
+
 // ---- 2x2x2 average pooling (+ stats of the output) ---------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
 avgpool2_kernel(VdmTensor x, VdmTensor y, int planes, int D, int H, int W, double* __restrict__ stats,
@@ -241,6 +309,33 @@ extern "C" int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, in
                            uint64_t seed, uint32_t layer_tag, void* stream) {
   return vdm_gn_silu_step(x, y, batch, voxels, channels, groups, stats, gamma, beta, eps, dropout_p, seed, nullptr,
                           layer_tag, stream);
+}
+
+extern "C" int vdm_gn_silu_view(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
+                                int channels, int c_off, int channels_total, int groups, const double* stats,
+                                const float* gamma, const float* beta, float eps, int upsample, void* stream) {
+  VDM_CHECK_ARG(view_ok(x, channels) && view_ok(y, channels) && stats && gamma && beta, "vdm_gn_silu_view: bad tensor argument");
+  VDM_CHECK_ARG(batch >= 1 && depth >= 1 && height >= 1 && width >= 1, "vdm_gn_silu_view: bad shape");
+  VDM_CHECK_PLANES(batch, channels, "vdm_gn_silu_view");
+  VDM_CHECK_ARG(c_off >= 0 && c_off % 8 == 0 && c_off + channels <= channels_total,
+                "vdm_gn_silu_view: channel window [%d, %d) outside the %d-channel norm (c_off must be a multiple of 8)", c_off,
+                c_off + channels, channels_total);
+  VDM_CHECK_ARG(groups >= 1 && channels_total % groups == 0, "vdm_gn_silu_view: %d channels not divisible into %d groups",
+                channels_total, groups);
+  const int64_t vf = (int64_t)depth * height * width;
+  VDM_CHECK_ARG(vf < ((int64_t)1 << 31), "vdm_gn_silu_view: grid too large for 32-bit voxel indices");
+  const int planes = channels / 8;
+  if (upsample) {
+    VDM_CHECK_ARG(depth % 2 == 0 && height % 2 == 0 && width % 2 == 0, "vdm_gn_silu_view: fine grid (%d,%d,%d) must be even",
+                  depth, height, width);
+    gn_silu_view_kernel<true><<<ew_grid(vf / 2, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
+        *x, *y, planes, c_off, channels_total, groups, depth, height, width, stats, gamma, beta, eps);
+  } else {
+    gn_silu_view_kernel<false><<<ew_grid(vf, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
+        *x, *y, planes, c_off, channels_total, groups, depth, height, width, stats, gamma, beta, eps);
+  }
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
 }
 
 extern "C" int vdm_avgpool2(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,

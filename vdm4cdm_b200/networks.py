@@ -118,6 +118,7 @@ class CUNet(nn.Module):
                 raise ValueError(f"grid {shape[1:]} is not divisible by 2^{len(chs) - 1}")
         self.shape = tuple(shape)
         self.circular = conv_padding_mode == "circular"     # the cropsize == 256 models (src/utils.py:460)
+        self.fuse_upsample = True       # inference: up blocks read the coarse tensor instead of its up-sampled copy
         self.chs = list(chs)
         self.s_conditioning_channels = s_conditioning_channels
         self.v_conditioning_dims = list(v_conditioning_dims)
@@ -209,6 +210,23 @@ class CUNet(nn.Module):
             self._packed_cache[slot] = hit
         return hit[1]
 
+    def _packed_in_slice(self, slot: str, conv: nn.Conv3d, c0: int, n: int) -> torch.Tensor:
+        """bf16 filter of the conv restricted to INPUT channels [c0, c0 + n) (the two halves of an up block's 1x1x1
+        skip conv over the concatenation, see ``_run_block``)."""
+        w = conv.weight
+        key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
+        hit = self._packed_cache.get(slot)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                part = w.detach()[:, c0:c0 + n].contiguous()
+                shape = ops.packed_weight_shape(part.shape)
+                buf = hit[1] if hit is not None and tuple(hit[1].shape) == shape and hit[1].device == w.device else \
+                    torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+                ops.pack_conv_weight_into(part, buf)
+                hit = (key, buf)
+            self._packed_cache[slot] = hit
+        return hit[1]
+
     def trunk_parameters(self):
         """(name, parameter) of everything the convolutional trunk differentiates itself: conv filters and
         GroupNorm affines, named as ``vdm4cdm_b200.autograd`` records their gradients.  (Conv biases and the
@@ -283,9 +301,16 @@ class CUNet(nn.Module):
 
     # ---- the convolutional trunk on channel-planar buffers --------------------------------------
     def _run_block(self, name, blk: ResNetBlock, x, x_plane0, x_stats, rows, step_ptr, out, out_plane0, out_stats,
-                   out_stats_c0, grid, training_dropout, tape=None):
+                   out_stats_c0, grid, training_dropout, tape=None, up_from=None):
         """out[window] = block(x[window]).  x_stats: double [B, ch_in, 2] of x.  With a ``tape`` (training)
-        every intermediate gets its own buffer and is recorded for the backward pass."""
+        every intermediate gets its own buffer and is recorded for the backward pass.
+
+        ``up_from = (coarse, plane0, c_up)`` (inference, up blocks): the first ``c_up`` channels of the block input are
+        ``interpolate(coarse)`` and have NOT been written to ``x``.  Nearest up-sampling commutes with pointwise
+        operations and with 1x1x1 convs and keeps per-channel means / variances, so the block reads the coarse tensor
+        instead: net1's GroupNorm+SiLU up-samples while it normalises, and the skip conv becomes
+        ``conv(x[c_up:]) + interpolate(conv(coarse))`` -- the concatenated up-sampled tensor (2/3 of the block input)
+        is never materialised, which removes one write and two reads of it per up block (r02f)."""
         b = x.shape[0]
         dev = x.device
         ar = self._arena if tape is None else self._train_arena
@@ -293,7 +318,15 @@ class CUNet(nn.Module):
         tag = f"{b}x{grid[0]}"
         own = "" if tape is None else name + "."
         a1 = ar.get(f"{own}a.{ci}.{tag}", (b, ci // 8) + grid + (8,), torch.bfloat16, dev)
-        ops.gn_silu(x, ci, g, x_stats, blk.net1[0].weight, blk.net1[0].bias, blk.net1[0].eps, x_plane0=x_plane0, out=a1)
+        n1 = blk.net1[0]
+        if up_from is None:
+            ops.gn_silu(x, ci, g, x_stats, n1.weight, n1.bias, n1.eps, x_plane0=x_plane0, out=a1)
+        else:
+            xc, xc_plane0, c_up = up_from
+            ops.gn_silu_view(xc, c_up, 0, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a1, x_plane0=xc_plane0,
+                             out_plane0=0, upsample=True)
+            ops.gn_silu_view(x, ci - c_up, c_up, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a1,
+                             x_plane0=x_plane0 + c_up // 8, out_plane0=c_up // 8)
         h = ar.get(f"{own}h.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
         h_stats = self._stats(f"{name}.h", b, co, dev)
         a1c, _ = self._conv_input(a1, ci, 0, name + ".a1p", tape)
@@ -313,6 +346,16 @@ class CUNet(nn.Module):
                               p_drop=p_drop, drop_tag=self._dropout_calls, drop_seed=self.dropout_seed)
         if blk.skip_conv is None:
             res, res_plane0 = x, x_plane0
+        elif up_from is not None:
+            xc, xc_plane0, c_up = up_from
+            res = ar.get(f"{own}r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+            rc = ar.get(f"rc.{co}.{b}x{grid[0] // 2}", (b, co // 8) + tuple(n // 2 for n in grid) + (8,), torch.bfloat16, dev)
+            ops.conv3d(xc, self._packed_in_slice(name + ".skip.up", blk.skip_conv, 0, c_up), co, taps=ops.TAPS_1X1X1,
+                       x_plane0=xc_plane0, c_in=c_up, out=rc)
+            ops.conv3d(x, self._packed_in_slice(name + ".skip.skip", blk.skip_conv, c_up, ci - c_up), co,
+                       taps=ops.TAPS_1X1X1, x_plane0=x_plane0 + c_up // 8, c_in=ci - c_up, out=res,
+                       chan_add=rows[name + ".skip"], residual=rc, residual_upsample=True)
+            res_plane0 = 0
         else:
             res = ar.get(f"{own}r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
             ops.conv3d(x, self._packed(name + ".skip", blk.skip_conv), co, taps=ops.TAPS_1X1X1, x_plane0=x_plane0, c_in=ci,
@@ -402,10 +445,16 @@ class CUNet(nn.Module):
             blk = self.ups[k].resnet_blocks[0]
             name = f"ups.{k}.resnet_blocks.0"
             cat, cst = cats[i], cat_stats[i]
-            ops.upsample2(x, c[i + 1], cat, coarse_plane0=x_plane0, out_plane0=0, stats=cst, stats_c0=0)
             o = buf(f"up{i}", c[i], i)
             ost = self._stats(name + ".out", b, c[i], dev)
-            self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout, tape)
+            if self.fuse_upsample and tape is None and not self.circular and blk.skip_conv is not None:
+                # the up-sampled channels are never written (see _run_block); their sums are 8x the coarse tensor's
+                torch.mul(x_stats, 8.0, out=cst[:, :c[i + 1]])
+                self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout, tape,
+                                up_from=(x, x_plane0, c[i + 1]))
+            else:
+                ops.upsample2(x, c[i + 1], cat, coarse_plane0=x_plane0, out_plane0=0, stats=cst, stats_c0=0)
+                self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout, tape)
             x, x_plane0, x_stats = o, 0, ost
         gn = self.conv_out[0]
         a = ar.get(("conv_out." if tape is not None else "") + f"a.{c[0]}.{b}x{grids[0][0]}",

@@ -139,8 +139,9 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
            x_plane0: int = 0, c_in: Optional[int] = None, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
            out_fp32: bool = False, chan_add: Optional[torch.Tensor] = None, step_ptr: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, residual_plane0: int = 0, stats: Optional[torch.Tensor] = None,
-           stats_c0: int = 0, circular: bool = False) -> torch.Tensor:
+           stats_c0: int = 0, circular: bool = False, residual_upsample: bool = False) -> torch.Tensor:
     """``vdm_conv3d``: y = conv(x, w) [+ chan_add[b, co]] [+ residual], optional GroupNorm statistics.
+    ``residual_upsample``: the residual lives on the half-resolution grid and is added through a nearest x2 up-sampling.
 
     x: planar buffer; the conv reads ``c_in`` channels starting at plane ``x_plane0``.
     w_packed: ``pack_conv_weight`` output, shape [taps, c_in/8, c_out_pad, 8].
@@ -191,8 +192,10 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
             epi.step_ptr = step_ptr.data_ptr()
     if residual is not None:
         _planar_ok(residual, "conv3d residual")
-        _need(tuple(residual.shape[2:5]) == (d, h, w_) and residual.shape[0] == b, "conv3d: residual grid mismatch")
+        r_grid = (d // 2, h // 2, w_ // 2) if residual_upsample else (d, h, w_)
+        _need(tuple(residual.shape[2:5]) == r_grid and residual.shape[0] == b, "conv3d: residual grid mismatch")
         epi.residual = residual.data_ptr()
+        epi.residual_upsample = 1 if residual_upsample else 0
         desc.r_planes, desc.r_plane0 = residual.shape[1], residual_plane0
     if stats is not None:
         _need(stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous() and stats.dim() == 3 and
@@ -251,6 +254,29 @@ def gn_silu(x: torch.Tensor, channels: int, groups: int, stats: torch.Tensor, ga
                                    gamma.data_ptr(), beta.data_ptr(), eps, dropout_p, seed, _ptr(seed_step), layer_tag,
                                    _stream())
     _C.check(rc, "vdm_gn_silu")
+    _launched(1)
+    return out
+
+
+def gn_silu_view(x: torch.Tensor, channels: int, c_off: int, channels_total: int, groups: int, stats: torch.Tensor,
+                 gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: torch.Tensor, *, x_plane0: int = 0,
+                 out_plane0: int = 0, upsample: bool = False) -> torch.Tensor:
+    """silu(groupnorm(.)) of channels [c_off, c_off + channels) of a ``channels_total``-channel norm, written to a plane
+    window of ``out``; with ``upsample`` x is at half the resolution of ``out`` (``vdm_gn_silu_view``)."""
+    _planar_ok(x, "gn_silu_view x")
+    _planar_ok(out, "gn_silu_view out")
+    b, _, d, h, w, _ = out.shape
+    _need(tuple(x.shape[2:5]) == ((d // 2, h // 2, w // 2) if upsample else (d, h, w)) and x.shape[0] == b,
+          "gn_silu_view: x grid does not match out")
+    _need(stats.dtype == torch.float64 and tuple(stats.shape) == (b, channels_total, 2) and stats.is_contiguous(),
+          "gn_silu_view: stats must be double [B, channels_total, 2]")
+    _need(gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == channels_total and
+          beta.numel() == channels_total and gamma.is_cuda and beta.is_cuda,
+          "gn_silu_view: gamma/beta must be CUDA fp32 [channels_total]")
+    vx, vy = _view(x, x_plane0), _view(out, out_plane0)
+    rc = _C.lib().vdm_gn_silu_view(ctypes.byref(vx), ctypes.byref(vy), b, d, h, w, channels, c_off, channels_total, groups,
+                                   stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, 1 if upsample else 0, _stream())
+    _C.check(rc, "vdm_gn_silu_view")
     _launched(1)
     return out
 
