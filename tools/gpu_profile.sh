@@ -10,9 +10,9 @@ $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 150 -c 330 --csv \
     --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
-# full capture of the conv kernels of one sampler step (first eager step of the session: 26 launches)
+# full capture of the conv kernels of one sampler step (first eager step of the session: 29 launches)
 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:conv3d_planar -s 0 -c 26 -o gpurun_out/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv3d_planar -s 0 -c 29 -o gpurun_out/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
 echo "ncu full rc=$?"
 # training step: launch list of one eager step (profile_step.py drives sampler + trainer; skip to the trainer part)
 ls -la gpurun_out | tail -8
