@@ -275,7 +275,10 @@ def run_b200(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("conv_dram_bytes_per_step")   # DRAM read + write of one step's conv launches (ncu)
+            tj = json.load(f)
+        # DRAM read + write of one step's conv launches (ncu --set full), valid for the workload it was captured on
+        if tj.get("grid", 128) == args.grid and tj.get("realisations_per_gpu") == args.batch:
+            traffic = tj.get("conv_dram_bytes_per_step")
     roofline = {"kernel": "conv3d_planar_kernel (all conv launches of one step)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": traffic,

@@ -12,7 +12,11 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 echo "ncu launches rc=$?"
 # full capture of the conv kernels of one sampler step (first eager step of the session: 29 launches)
 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:conv3d_planar -s 0 -c 29 -o gpurun_out/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv3d_planar -s 0 -c 29 -f -o /tmp/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
 echo "ncu full rc=$?"
+# the report of 29 launches with source counters is ~75 MB (gpurun_out/ carries 64 MB back): summarise it here
+python tools/ncu_summary.py /tmp/${tag}_conv.ncu-rep > gpurun_out/${tag}_conv_ncu.txt 2> gpurun_out/${tag}_summary.err
+python tools/ncu_stalls.py /tmp/${tag}_conv.ncu-rep 14 > gpurun_out/${tag}_conv_stalls.txt 2>> gpurun_out/${tag}_summary.err
+python tools/launch_share.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launch_share.txt 2>> gpurun_out/${tag}_summary.err
 # training step: launch list of one eager step (profile_step.py drives sampler + trainer; skip to the trainer part)
 ls -la gpurun_out | tail -8

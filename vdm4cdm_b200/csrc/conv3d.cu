@@ -302,10 +302,10 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     ptx::tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
-  float* stat_part = reinterpret_cast<float*>(sh + 1);     // [sum | sumsq][epilogue warp][channel of this CTA]
+  float* stat_part = reinterpret_cast<float*>(sh + 1);     // [tile parity][sum | sumsq][epilogue warp][channel of this CTA]
   if (warp >= 3) {
     for (int i = threadIdx.x - kEpiFirst; i < 2 * 256; i += kEpiThreads) (&sh->stat_acc[0][0])[i] = 0.0;
-    for (int i = threadIdx.x - kEpiFirst; i < 2 * 8 * p.n_cta; i += kEpiThreads) stat_part[i] = 0.f;
+    for (int i = threadIdx.x - kEpiFirst; i < 2 * 2 * 8 * p.n_cta; i += kEpiThreads) stat_part[i] = 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -658,7 +658,10 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const long long vox0 = ((long long)t.d0 * p.H + h) * p.W + w;
       bf16x8* y_tile = reinterpret_cast<bf16x8*>(p.y) + ((long long)t.b * p.y_planes + p.y_plane0 + (cbase >> 3)) * V + vox0;
       if (p.chan_add && !cadd_table) asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float* cadd_row = cadd_table ? &sh->cadd[0][0] + t.b * p.n_pad + cbase : &sh->cadd[buf][0];
+      // (an index into the shared array, not a pointer selected at run time: the latter compiled to generic loads,
+      // 6% of the stall samples in r02i)
+      const int cadd_off = cadd_table ? t.b * p.n_pad + cbase : buf * 256;
+      float* sp = stat_part + (ti & 1) * (16 * p.n_cta);   // this tile's partials (double-buffered by tile parity)
       ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
       ptx::tc_fence_after();
       if (!(p.debug_flags & 1)) {
@@ -686,7 +689,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(raw[j]);
             if (p.chan_add) {
-              const float4* cs = reinterpret_cast<const float4*>(cadd_row + ch * 16);
+              const float4* cs = reinterpret_cast<const float4*>(&sh->cadd[0][0] + cadd_off + ch * 16);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 cv = cs[j4];
@@ -742,8 +745,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             if ((lane & 1) == 0) {
               // one slot per (warp, channel), summed in a fixed order below: statistics do not depend on timing
               const int c = ch * 16 + (lane >> 1);
-              stat_part[(warp - 3) * p.n_cta + c] = s1[0];
-              stat_part[(8 + warp - 3) * p.n_cta + c] = s2[0];
+              sp[(warp - 3) * p.n_cta + c] = s1[0];
+              sp[(8 + warp - 3) * p.n_cta + c] = s2[0];
             }
           }
         }
@@ -755,21 +758,24 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         // Fold this tile's per-warp fp32 partials into the CTA's fp64 running sums (fixed order: the result is
         // reproducible run to run up to the order of the final fp64 atomics); global atomics happen only when
         // this CTA moves on to another (sample, channel slice) or finishes.
+        // ONE barrier per tile: the partials are double-buffered by tile parity, and the fold of tile i is ordered
+        // before the writes of tile i+2 by the barrier of tile i+1 (r02i: 14% of the samples sat in two barriers).
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        const int next_tile = tile + (int)gridDim.x;
-        bool flush = next_tile >= p.n_tiles;
-        if (!flush) {
-          const TileCoord tn = decode_tile(p, next_tile);
-          flush = (tn.b != t.b) || (tn.ns != t.ns);
-        }
-        for (int c = et; c < p.n_cta; c += kEpiThreads) {
+        if (et < p.n_cta) {
+          const int next_tile = tile + (int)gridDim.x;
+          bool flush = next_tile >= p.n_tiles;
+          if (!flush) {
+            const TileCoord tn = decode_tile(p, next_tile);
+            flush = (tn.b != t.b) || (tn.ns != t.ns);
+          }
+          const int c = et;
           float t1 = 0.f, t2 = 0.f;
 #pragma unroll
           for (int wv = 0; wv < 8; ++wv) {
-            t1 += stat_part[wv * p.n_cta + c];
-            t2 += stat_part[(8 + wv) * p.n_cta + c];
-            stat_part[wv * p.n_cta + c] = 0.f;
-            stat_part[(8 + wv) * p.n_cta + c] = 0.f;
+            t1 += sp[wv * p.n_cta + c];
+            t2 += sp[(8 + wv) * p.n_cta + c];
+            sp[wv * p.n_cta + c] = 0.f;
+            sp[(8 + wv) * p.n_cta + c] = 0.f;
           }
           const double a1 = sh->stat_acc[0][c] + (double)t1;
           const double a2 = sh->stat_acc[1][c] + (double)t2;
@@ -786,7 +792,6 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             sh->stat_acc[1][c] = a2;
           }
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
     }
   }
@@ -893,7 +898,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     fold_mt = 4; fold_kc = 32; fold_streamed = 1;
   } else if (fold) {
     // all weights resident + two halo stages must fit; prefer tall tiles (halo efficiency), then wide chunks
-    const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - 2 * 8 * d.c_out_pad * 4 - 256 -
+    const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - 2 * 2 * 8 * d.c_out_pad * 4 - 256 -
                        (has_residual ? 2 * kResSlotBytes : 0);      // room for at least two residual slots
     const int w_bytes = 27 * d.c_in * d.c_out_pad * 2;
     for (int m = 4; m >= 2 && !fold_mt; --m)
@@ -902,6 +907,8 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
         const int a_stage = (((c / 8) * (m + 2) * (kTileH + 2) * (kTileW + 2) * 16) + 127) & ~127;
         if (2 * a_stage + w_bytes <= budget) { fold_mt = m; fold_kc = c; }
       }
+    // (r02j: re-streaming the weights per tile so that a 96 -> 32 layer could use MT = 4 tiles instead of MT = 2 was
+    // slower, 4.42 vs 3.05 ms at 128^3 x 8: the 6 KB (chunk, kh, kw) stages are dominated by their hand-off cost.)
     fold = fold_mt != 0;
   }
   if (fold) {
@@ -981,7 +988,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     p.tap16[t] = (uint16_t)(((d.tap_offset[t][0] + pad) * p.Hh + (d.tap_offset[t][1] + pad)) * p.Wh + d.tap_offset[t][2] + pad);
 
   // ---- shared memory plan: 2 halo stages + a ring of weight stages ----
-  const int stat_part_bytes = 2 * 8 * p.n_cta * 4;
+  const int stat_part_bytes = 2 * 2 * 8 * p.n_cta * 4;
   const int smem_total = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - stat_part_bytes - 256;
   // layers with a residual keep a cp.async ring of it in shared memory: 4 units deep where the weights are streamed
   // anyway, at least 2 where they are resident (the fold search above left room)
