@@ -69,54 +69,80 @@ template <int NSPEC>
 __global__ void __launch_bounds__(256)
 pk_bin_kernel(const float2* __restrict__ X, const float2* __restrict__ X2, PkGeom g, int n_transforms,
               double* __restrict__ acc) {
-  extern __shared__ double s_acc[];  // [NSPEC][kmax+1]
+  extern __shared__ double s_acc[];  // [warp][NSPEC][kmax+1]: private bins per warp
   const int nb = g.kmax + 1;
-  for (int i = threadIdx.x; i < NSPEC * nb; i += blockDim.x) s_acc[i] = 0.0;
+  const int n_warps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < n_warps * NSPEC * nb; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
+  double* my = s_acc + (threadIdx.x >> 5) * NSPEC * nb;
 
+  // One warp per (i0, i1) row of the half spectrum: the row's n2h modes are contiguous, (f0, f1) are computed once
+  // per row instead of two 64-bit divisions per mode, and |k| grows along the row, so equal-bin runs are long.
+  // Four 32-mode trips are loaded before any is reduced (four 8-byte loads in flight per lane).
+  // (r02l: the one-mode-per-thread version ran at 0.9 TB/s, instruction-bound.)
   const int field = blockIdx.y;
   const float2* x = X + (int64_t)field * n_transforms * g.modes;
   const float2* x2 = X2 + (int64_t)field * n_transforms * g.modes;
-  const int64_t span = (int64_t)gridDim.x * blockDim.x;
-  // all lanes of a warp run the same number of iterations (shuffles inside)
-  const int64_t iters = (g.modes + span - 1) / span;
-  for (int64_t it = 0; it < iters; ++it) {
-    const int64_t m = it * span + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int bin = -1, w = 0;
-    float kmag;
-    float v[NSPEC];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int rows = g.n0 * g.n1;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const int i1 = row % g.n1, i0 = row / g.n1;
+    const int f0 = i0 > g.n0 / 2 ? i0 - g.n0 : i0;
+    const int f1 = i1 > g.n1 / 2 ? i1 - g.n1 : i1;
+    const int k01 = f0 * f0 + f1 * f1;
+    const float2* xr = x + (int64_t)row * g.n2h;
+    const float2* xr2 = x2 + (int64_t)row * g.n2h;
+    for (int base = 0; base < g.n2h; base += 128) {
+      int bins[4];
+      float v[4][NSPEC];
 #pragma unroll
-    for (int i = 0; i < NSPEC; ++i) v[i] = 0.f;
-    if (m < g.modes) {
-      mode_bin(g, m, bin, w, kmag);
-      if (bin >= 1 && bin <= g.kmax) {
-        for (int t = 0; t < n_transforms; ++t) {
-          const float2 a = __ldg(x + (int64_t)t * g.modes + m);
-          const float2 b = __ldg(x2 + (int64_t)t * g.modes + m);
-          if constexpr (NSPEC == 1) {
-            v[0] += a.x * b.x + a.y * b.y;
-          } else {
-            v[0] += a.x * a.x + a.y * a.y;
-            v[NSPEC - 2] += b.x * b.x + b.y * b.y;
-            v[NSPEC - 1] += a.x * b.x + a.y * b.y;
+      for (int u = 0; u < 4; ++u) {
+        const int i2 = base + u * 32 + lane;
+        bins[u] = -1;
+#pragma unroll
+        for (int i = 0; i < NSPEC; ++i) v[u][i] = 0.f;
+        if (i2 < g.n2h) {
+          const int b = (int)ceilf(sqrtf((float)(k01 + i2 * i2)));
+          if (b >= 1 && b <= g.kmax) {
+            bins[u] = b;
+            for (int t = 0; t < n_transforms; ++t) {
+              const float2 a = __ldg(xr + (int64_t)t * g.modes + i2);
+              const float2 c = __ldg(xr2 + (int64_t)t * g.modes + i2);
+              if constexpr (NSPEC == 1) {
+                v[u][0] += a.x * c.x + a.y * c.y;
+              } else {
+                v[u][0] += a.x * a.x + a.y * a.y;
+                v[u][NSPEC - 2] += c.x * c.x + c.y * c.y;
+                v[u][NSPEC - 1] += a.x * c.x + a.y * c.y;
+              }
+            }
+            const float w = (i2 == 0 || (g.last_even && i2 == g.n2h - 1)) ? 1.f : 2.f;
+#pragma unroll
+            for (int i = 0; i < NSPEC; ++i) v[u][i] *= w;
           }
         }
-#pragma unroll
-        for (int i = 0; i < NSPEC; ++i) v[i] *= (float)w;
-      } else {
-        bin = -1;
       }
-    }
-    const bool tail = warp_run_sum<NSPEC>(bin, v);
-    if (tail && bin >= 1) {
 #pragma unroll
-      for (int i = 0; i < NSPEC; ++i) atomicAdd(&s_acc[i * nb + bin], (double)v[i]);
+      for (int u = 0; u < 4; ++u) {
+        if (base + u * 32 >= g.n2h) break;           // warp-uniform
+        // |k| grows along a row, so after the run merge every bin has at most ONE tail lane in this trip: the
+        // warp's private bins take plain read-modify-writes (fp64 shared-memory atomics are compare-and-swap loops;
+        // with eight warps of neighbouring rows hitting the same few bins they were the cost of this kernel, r02m)
+        const bool tail = warp_run_sum<NSPEC>(bins[u], v[u]);
+        if (tail && bins[u] >= 1) {
+#pragma unroll
+          for (int i = 0; i < NSPEC; ++i) my[i * nb + bins[u]] += (double)v[u][i];
+        }
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
   double* out = acc + (int64_t)field * NSPEC * nb;
   for (int i = threadIdx.x; i < NSPEC * nb; i += blockDim.x) {
-    const double s = s_acc[i];
+    double s = 0.0;
+    for (int wv = 0; wv < n_warps; ++wv) s += s_acc[wv * NSPEC * nb + i];
     if (s != 0.0) atomicAdd(out + i, s);
   }
 }
@@ -284,10 +310,16 @@ static int pk_run(const float* f1, const float* f2, int n_fields, int batch, int
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, n_fields);
   const int ntr = batch * chan;
+  const size_t bin_smem = (size_t)(threads / 32) * nspec * nb * sizeof(double);     // private bins per warp
+  VDM_CHECK_ARG(bin_smem <= 200 * 1024, "vdm_pk: grid too large for the shared-memory bins (kmax = %d)", L.g.kmax);
   if (nspec == 1) {
-    pk_bin_kernel<1><<<grid, threads, nb * sizeof(double), stream>>>(X, X2, L.g, ntr, acc);
+    if (bin_smem > 48 * 1024)
+      VDM_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
+    pk_bin_kernel<1><<<grid, threads, bin_smem, stream>>>(X, X2, L.g, ntr, acc);
   } else {
-    pk_bin_kernel<3><<<grid, threads, 3 * nb * sizeof(double), stream>>>(X, X2, L.g, ntr, acc);
+    if (bin_smem > 48 * 1024)
+      VDM_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
+    pk_bin_kernel<3><<<grid, threads, bin_smem, stream>>>(X, X2, L.g, ntr, acc);
   }
   VDM_CHECK_LAUNCH();
   int gx = (int)((L.g.modes + threads * 8 - 1) / (threads * 8));
