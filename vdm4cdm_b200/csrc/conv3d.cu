@@ -83,7 +83,9 @@ struct ConvKernelParams {
   int res_ring_off;          // byte offset of that ring in dynamic shared memory
   double* stats;
   int stats_channels, stats_c0;
-  int debug_flags;           // bring-up experiments: 1 = epilogue does no work, 2 = halo loaded for the first two tiles only
+  int debug_flags;           // bring-up experiments (results are wrong): 1 = epilogue does no work, 2 = halo loaded for the
+                             // first two tiles only, 4 = no TMEM reads, 8 = no output stores, 16 = no statistics
+                             // transpose-reduction, 32 = no statistics barrier + fold
 };
 
 struct ConvShared {
@@ -721,7 +723,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
               }
               const bf16x8 packed = pack8(g);
               if (valid) {
-                y_tile[(long long)(ch * 2 + hf) * V + (long long)s * HW] = packed;
+                if (!(p.debug_flags & 8)) y_tile[(long long)(ch * 2 + hf) * V + (long long)s * HW] = packed;
                 unpack8(packed, g);  // statistics describe the stored (rounded) tensor
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -734,11 +736,16 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.n_cta + ch * 16);
           for (int s = s0; s < MT; s += s_step) {
             uint32_t raw0[16];
-            ptx::tmem_ld16(trow + (uint32_t)(s * p.n_cta), raw0);
-            ptx::tmem_ld_wait();
+            if (p.debug_flags & 4) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) raw0[j] = (uint32_t)(lane + j);     // experiment: no TMEM reads
+            } else {
+              ptx::tmem_ld16(trow + (uint32_t)(s * p.n_cta), raw0);
+              ptx::tmem_ld_wait();
+            }
             process(s, raw0);
           }
-          if (p.stats && c0 < p.c_out) {
+          if (p.stats && c0 < p.c_out && !(p.debug_flags & 16)) {
             // one transpose-reduction per chunk and tile (r01j: per (slice, chunk) it cost 0.22 -> 0.30 ms on 32->32)
             warp_column_sums16(s1);
             warp_column_sums16(s2);
@@ -754,7 +761,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       // all TMEM reads of this accumulator set are complete (wait::ld above): hand it back
       ptx::tc_fence_before();
       ptx::mbar_arrive(&sh->tmem_empty[acc]);
-      if (p.stats) {
+      if (p.stats && !(p.debug_flags & 32)) {
         // Fold this tile's per-warp fp32 partials into the CTA's fp64 running sums (fixed order: the result is
         // reproducible run to run up to the order of the final fp64 atomics); global atomics happen only when
         // this CTA moves on to another (sample, channel slice) or finishes.
