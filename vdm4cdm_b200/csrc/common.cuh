@@ -136,4 +136,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2: two fp32 lanes per instruction, same rounding as the scalar ops).
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+// (c0, c1) += (a0 * a0, a1 * a1)
+__device__ __forceinline__ void fma2_sq(float& c0, float& c1, float a0, float a1) {
+  uint64_t a, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(c) : "l"(a));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+}
+
 }  // namespace vdm

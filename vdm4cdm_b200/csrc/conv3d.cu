@@ -695,7 +695,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 cv = cs[j4];
-                f[4 * j4] += cv.x; f[4 * j4 + 1] += cv.y; f[4 * j4 + 2] += cv.z; f[4 * j4 + 3] += cv.w;
+                add2(f[4 * j4], f[4 * j4 + 1], cv.x, cv.y);
+                add2(f[4 * j4 + 2], f[4 * j4 + 3], cv.z, cv.w);
               }
             }
             if (p.out_fp32) {
@@ -719,16 +720,16 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 float rr[8];
                 unpack8(*reinterpret_cast<const bf16x8*>(&rcur[hf]), rr);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] += rr[j];
+                for (int j = 0; j < 8; j += 2) add2(g[j], g[j + 1], rr[j], rr[j + 1]);
               }
               const bf16x8 packed = pack8(g);
               if (valid) {
                 if (!(p.debug_flags & 8)) y_tile[(long long)(ch * 2 + hf) * V + (long long)s * HW] = packed;
                 unpack8(packed, g);  // statistics describe the stored (rounded) tensor
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  s1[hf * 8 + j] += g[j];
-                  s2[hf * 8 + j] += g[j] * g[j];
+                for (int j = 0; j < 8; j += 2) {       // FADD2 / FFMA2: the epilogue is bound by its own arithmetic (r02n)
+                  add2(s1[hf * 8 + j], s1[hf * 8 + j + 1], g[j], g[j + 1]);
+                  fma2_sq(s2[hf * 8 + j], s2[hf * 8 + j + 1], g[j], g[j + 1]);
                 }
               }
             }
