@@ -93,8 +93,10 @@ struct ConvShared {
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
-  // (per-tile, per-warp statistics partials follow this struct in shared memory: float [2][8][n_cta])
-  double stat_acc[2][256];   // per-CTA running (sum, sumsq) of the current sample, flushed when the sample changes
+  // (statistics scratch follows this struct in shared memory, sized by the CTA's channel count: per-tile, per-warp
+  //  partials float [2 parities][2][8][n_cta], then the per-CTA running (sum, sumsq) of the current sample,
+  //  double [2][n_cta], flushed when the sample changes -- 3.5 KB less than fixed 256-channel arrays, which is what
+  //  lets the 96 -> 32 layer keep its weights resident next to MT = 3 halo stages)
   alignas(16) float cadd[2][256];  // bias + conditioning row of this tile's sample, double-buffered by tile parity
 };
 
@@ -305,8 +307,9 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     ptx::tmem_relinquish();
   }
   float* stat_part = reinterpret_cast<float*>(sh + 1);     // [tile parity][sum | sumsq][epilogue warp][channel of this CTA]
+  double* stat_acc = reinterpret_cast<double*>(stat_part + 2 * 2 * 8 * p.n_cta);   // [sum | sumsq][channel of this CTA]
   if (warp >= 3) {
-    for (int i = threadIdx.x - kEpiFirst; i < 2 * 256; i += kEpiThreads) (&sh->stat_acc[0][0])[i] = 0.0;
+    for (int i = threadIdx.x - kEpiFirst; i < 2 * p.n_cta; i += kEpiThreads) stat_acc[i] = 0.0;
     for (int i = threadIdx.x - kEpiFirst; i < 2 * 2 * 8 * p.n_cta; i += kEpiThreads) stat_part[i] = 0.f;
   }
   ptx::tc_fence_before();
@@ -785,19 +788,19 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             sp[wv * p.n_cta + c] = 0.f;
             sp[(8 + wv) * p.n_cta + c] = 0.f;
           }
-          const double a1 = sh->stat_acc[0][c] + (double)t1;
-          const double a2 = sh->stat_acc[1][c] + (double)t2;
+          const double a1 = stat_acc[c] + (double)t1;
+          const double a2 = stat_acc[p.n_cta + c] + (double)t2;
           if (flush) {
             if (cbase + c < p.c_out) {
               double* dst = p.stats + ((long long)t.b * p.stats_channels + p.stats_c0 + cbase + c) * 2;
               atomicAdd(dst, a1);
               atomicAdd(dst + 1, a2);
             }
-            sh->stat_acc[0][c] = 0.0;
-            sh->stat_acc[1][c] = 0.0;
+            stat_acc[c] = 0.0;
+            stat_acc[p.n_cta + c] = 0.0;
           } else {
-            sh->stat_acc[0][c] = a1;
-            sh->stat_acc[1][c] = a2;
+            stat_acc[c] = a1;
+            stat_acc[p.n_cta + c] = a2;
           }
         }
       }
@@ -906,7 +909,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     fold_mt = 4; fold_kc = 32; fold_streamed = 1;
   } else if (fold) {
     // all weights resident + two halo stages must fit; prefer tall tiles (halo efficiency), then wide chunks
-    const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - 2 * 2 * 8 * d.c_out_pad * 4 - 256 -
+    const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - (2 * 2 * 8 * d.c_out_pad * 4 + 2 * d.c_out_pad * 8) - 256 -
                        (has_residual ? 2 * kResSlotBytes : 0);      // room for at least two residual slots
     const int w_bytes = 27 * d.c_in * d.c_out_pad * 2;
     for (int m = 4; m >= 2 && !fold_mt; --m)
@@ -996,7 +999,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     p.tap16[t] = (uint16_t)(((d.tap_offset[t][0] + pad) * p.Hh + (d.tap_offset[t][1] + pad)) * p.Wh + d.tap_offset[t][2] + pad);
 
   // ---- shared memory plan: 2 halo stages + a ring of weight stages ----
-  const int stat_part_bytes = 2 * 2 * 8 * p.n_cta * 4;
+  const int stat_part_bytes = 2 * 2 * 8 * p.n_cta * 4 + 2 * p.n_cta * 8;    // partials + running sums
   const int smem_total = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - stat_part_bytes - 256;
   // layers with a residual keep a cp.async ring of it in shared memory: 4 units deep where the weights are streamed
   // anyway, at least 2 where they are resident (the fold search above left room)
