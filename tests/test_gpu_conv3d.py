@@ -209,3 +209,47 @@ def test_conv3d_residual_read_through_upsampling():
         ops.conv3d(ops.to_planar(torch.zeros((1, 16, 3, 8, 8), device=dev)), ops.pack_conv_weight(torch.zeros((16, 16, 1, 1, 1), device=dev)),
                    16, taps=ops.TAPS_1X1X1, residual=torch.zeros((1, 2, 1, 4, 4, 8), dtype=torch.bfloat16, device=dev),
                    residual_upsample=True)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 32, 6, 20, 12), (1, 16, 16, 16, 5, 16, 8), (1, 32, 32, 64, 4, 16, 16),
+                                  (1, 64, 32, 32, 8, 16, 8), (1, 16, 32, 48, 3, 9, 7)], ids=lambda c: "x".join(map(str, c)))
+def test_conv3d_fused_skip_conv_exact_integers(case):
+    """skip_x / skip_w: y = conv3x3x3(x) + conv1x1x1(x_skip) + bias + interpolate(r_coarse) in ONE launch (the up
+    blocks' net2 conv + skip conv), with the GroupNorm statistics of the sum."""
+    ops = _ops()
+    b, ci, co, cs, d, h, w = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(300 + ci + cs)
+    x = _int_tensor((b, ci, d, h, w), -2, 2, g, dev)
+    xs = _int_tensor((b, cs, d, h, w), -2, 2, g, dev)
+    wt = _int_tensor((co, ci, 3, 3, 3), -1, 1, g, dev)
+    ws = _int_tensor((co, cs, 1, 1, 1), -1, 1, g, dev)
+    cadd = _int_tensor((b, co), -3, 3, g, dev)
+    even = d % 2 == 0 and h % 2 == 0 and w % 2 == 0
+    ref = _reference(x, wt, cadd) + F.conv3d(xs.double(), ws.double()).round().float()
+    rbuf = None
+    if even:
+        rc = _int_tensor((b, co, d // 2, h // 2, w // 2), -4, 4, g, dev)
+        ref = ref + F.interpolate(rc, scale_factor=2, mode="nearest")
+        rbuf = ops.to_planar(rc)
+    ref = ref.to(torch.bfloat16).float()
+    # the skip tensor sits at planes 3.. of a wider buffer (the concat buffer of the up block)
+    sbuf = torch.zeros((b, cs // 8 + 4, d, h, w, 8), dtype=torch.bfloat16, device=dev)
+    sbuf[:, 3:3 + cs // 8] = ops.to_planar(xs)
+    stats = torch.zeros((b, co, 2), dtype=torch.float64, device=dev)
+    y = ops.conv3d(ops.to_planar(x), ops.pack_conv_weight(wt), co, chan_add=cadd, residual=rbuf, residual_upsample=even,
+                   stats=stats, skip_x=sbuf, skip_w=ops.pack_conv_weight(ws), skip_plane0=3)
+    torch.cuda.synchronize()
+    got = ops.from_planar(y, co)
+    assert torch.equal(got, ref), f"{(got != ref).sum().item()} differ, max |diff| {(got - ref).abs().max().item()}"
+    assert torch.allclose(stats[..., 0], ref.double().sum(dim=(2, 3, 4)), rtol=1e-6, atol=1e-3)
+
+
+def test_conv3d_fused_skip_conv_declined_for_wide_layers():
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    x = torch.zeros((1, 8, 4, 16, 8, 8), dtype=torch.bfloat16, device=dev)
+    w = ops.pack_conv_weight(torch.zeros((64, 64, 3, 3, 3), device=dev))
+    ws = ops.pack_conv_weight(torch.zeros((64, 32, 1, 1, 1), device=dev))
+    with pytest.raises(ops.UnsupportedFusion):
+        ops.conv3d(x, w, 64, skip_x=torch.zeros((1, 4, 4, 16, 8, 8), dtype=torch.bfloat16, device=dev), skip_w=ws)

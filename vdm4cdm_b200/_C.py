@@ -35,6 +35,8 @@ class ConvEpilogue(Structure):
         ("chan_add", c_void_p), ("step_ptr", c_void_p), ("chan_add_step_stride", c_int64),
         ("residual", c_void_p), ("stats", c_void_p), ("stats_channels", c_int32), ("stats_c0", c_int32),
         ("residual_upsample", c_int32), ("reserved", c_int32),
+        ("skip_x", c_void_p), ("skip_w", c_void_p), ("skip_c_in", c_int32), ("skip_planes", c_int32),
+        ("skip_plane0", c_int32), ("reserved2", c_int32),
     ]
 
 
@@ -123,6 +125,14 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = argtypes
         _lib = handle
     return _lib
+
+
+E_UNSUPPORTED = -2          # VDM_E_UNSUPPORTED
+
+
+class UnsupportedFusion(RuntimeError):
+    """An optional fused form was requested for a layer that cannot take it (VDM_E_UNSUPPORTED); the caller runs the
+    unfused launches instead."""
 
 
 def check(rc: int, what: str) -> None:

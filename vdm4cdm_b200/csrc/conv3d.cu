@@ -69,6 +69,11 @@ struct ConvKernelParams {
   int tmem_cols;
   int x_planes, x_plane0, c_in8;
   int x_shift;               // 1 when x carries a one-voxel periodic halo (circular padding)
+  // fused 1x1x1 skip-path conv (kd-folded resident layers): extra channel chunks read from a second tensor, centre tap only
+  int skip_chunks;           // number of KC-channel chunks of the second tensor (0: none)
+  int x2_planes, x2_plane0;
+  int skip_w_bytes;          // bytes of its weights in shared memory, right after the main weights
+  const __nv_bfloat16* w2;   // packed [1][skip_c_in/8][n_pad][8]
   const __nv_bfloat16* w;
   // epilogue
   void* y;
@@ -238,6 +243,28 @@ __device__ __forceinline__ void issue_fold_tile(uint32_t a_lo0, uint32_t b_base1
   }
 }
 
+// Fused 1x1x1 skip-path conv of a ResNet block (h_out = conv3x3x3(a2) + conv1x1x1(x_skip) + ...): one more channel
+// chunk whose halo box comes from the skip tensor and of which only the centre tap (kd = kh = kw = 1) is multiplied,
+// MT*KJ MMAs of N = NF on top of the (MT+2)*9*KJ of a main chunk.  Weights: [plane][co] (LBO = NF*16 bytes).
+template <int MT, int KJ, int NF>
+__device__ __forceinline__ void issue_skip_chunk(uint32_t a_lo0, uint32_t b_lo16, uint64_t a_hi, uint32_t d_tmem0) {
+  constexpr int Hh = kTileH + 2, Wh = kTileW + 2, Hd = MT + 2;
+  constexpr uint32_t plane16 = (uint32_t)(Hd * Hh * Wh);
+  constexpr uint32_t kstep_a16 = 2u * plane16;
+  const uint64_t b_hi = make_planar_desc(0, (uint32_t)NF * 16u, 128u);
+  const uint32_t a_hi32 = (uint32_t)(a_hi >> 32), b_hi32 = (uint32_t)(b_hi >> 32);
+  const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)NF);
+  const uint32_t b_i = b_lo16 + (uint32_t)b_hi;
+#pragma unroll
+  for (int i = 1; i <= MT; ++i) {          // input slice i is the centre (kd = 1) of output slice i - 1
+    const uint32_t a_i = a_lo0 + (uint32_t)(i * Hh * Wh + Wh + 1) + (uint32_t)a_hi;
+#pragma unroll
+    for (int j = 0; j < KJ; ++j)
+      ptx::umma_bf16_off(d_tmem0, (uint32_t)((i - 1) * NF), a_i, (uint32_t)j * kstep_a16, a_hi32, b_i, (uint32_t)(2 * j * NF),
+                         b_hi32, idesc, 1u);
+  }
+}
+
 // Same schedule for layers whose weights do not fit shared memory (Cout_pad = 64): the weights of ONE (chunk, kh, kw)
 // for the three kd stacked along N are a ring stage [plane][2 - kd][co]; the stage's MMAs run over all input slices.
 // N = 192 is tensor-bound (96 cycles of math for 80 cycles of operand fetch) where N = 64 is fetch-bound (48 for 32).
@@ -277,12 +304,13 @@ __device__ __forceinline__ void issue_fold_stage(uint32_t a_lo, uint32_t b_lo, u
 // tcgen05.mma with immediate offsets (r01a: a generic loop cost ~240 issue cycles per MMA).
 template <int MT, int KJ, int NF>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvKernelParams p) {
+conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
+                     const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + 2 * (size_t)p.a_stage_bytes;
-  ConvShared* sh = reinterpret_cast<ConvShared*>(b_smem + (size_t)p.nsb * p.b_stage_bytes);
+  ConvShared* sh = reinterpret_cast<ConvShared*>(b_smem + (size_t)p.nsb * p.b_stage_bytes + p.skip_w_bytes);
   constexpr bool kFold = NF > 0;
 
   const int warp = threadIdx.x >> 5;
@@ -324,7 +352,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+        for (int kc = 0; kc < p.k_chunks + p.skip_chunks; ++kc, ++it) {
           const int s = it & 1;
           ptx::mbar_wait(&sh->a_empty[s], ((it >> 1) & 1) ^ 1);
           if ((p.debug_flags & 2) && it >= 2) {       // experiment: no halo traffic after the pipeline fill
@@ -332,9 +360,13 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             continue;
           }
           ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes_per_chunk * p.plane_bytes));
-          ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], (t.w0 - p.pad + p.x_shift) * 8,
-                           t.h0 - p.pad + p.x_shift, t.d0 - p.pad + p.x_shift,
-                           t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
+          if (kc < p.k_chunks)
+            ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], (t.w0 - p.pad + p.x_shift) * 8,
+                             t.h0 - p.pad + p.x_shift, t.d0 - p.pad + p.x_shift,
+                             t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
+          else   // skip-path tensor: same box (only its centre is multiplied), never circular
+            ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x2, &sh->a_full[s], (t.w0 - p.pad) * 8, t.h0 - p.pad,
+                             t.d0 - p.pad, t.b * p.x2_planes + p.x2_plane0 + (kc - p.k_chunks) * planes_per_chunk);
         }
       }
     }
@@ -366,7 +398,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
        } else {
         // resident, kd-folded order: [chunk][khw][plane][2 - kd][co] (see issue_fold_tile); n_split == 1
-        ptx::mbar_arrive_expect_tx(&sh->b_full[0], plane_copy_bytes * planes_per_chunk * (uint32_t)(n_taps * k_chunks));
+        ptx::mbar_arrive_expect_tx(&sh->b_full[0], plane_copy_bytes * planes_per_chunk * (uint32_t)(n_taps * k_chunks) +
+                                                       (uint32_t)p.skip_w_bytes);
         for (int kc = 0; kc < k_chunks; ++kc)
           for (int tap = 0; tap < n_taps; ++tap) {
             const int kd = p.tap_kd[tap], khw = p.tap_khw[tap];
@@ -376,6 +409,10 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                              p.w + (size_t)tap * tap_stride + (size_t)(kc * planes_per_chunk + pl) * plane_stride,
                              plane_copy_bytes, &sh->b_full[0]);
           }
+        // 1x1x1 skip-path weights: [plane][co] right after the main weights
+        for (int pl = 0; pl < p.skip_chunks * planes_per_chunk; ++pl)
+          ptx::bulk_load(b_smem + (size_t)p.b_stage_bytes + (size_t)pl * plane_copy_bytes, p.w2 + (size_t)pl * plane_stride,
+                         plane_copy_bytes, &sh->b_full[0]);
        }
       } else if (p.b_resident) {
         // Weights fit next to the halo stages: load every (chunk, tap) once.  Per-tile weight streaming was a
@@ -469,18 +506,23 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
         if (ti == 0) ptx::mbar_wait(&sh->b_full[0], 0);
         const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
-        for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
+        const int total_chunks = k_chunks + p.skip_chunks;
+        for (int kc = 0; kc < total_chunks; ++kc, ++ita) {
           const uint32_t sa = ita & 1;
           ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
           ptx::tc_fence_after();
           if (leader) {
             if (kc == 0)
               issue_fold_tile<MT, KJ, NF, true>(a_base16 + sa * a_stage16, b_base16, a_hi, b_hi, d_tmem0);
-            else
+            else if (kc < k_chunks)
               issue_fold_tile<MT, KJ, NF, false>(a_base16 + sa * a_stage16, b_base16 + (uint32_t)kc * chunk_b16, a_hi, b_hi,
                                                  d_tmem0);
+            else
+              issue_skip_chunk<MT, KJ, NF>(a_base16 + sa * a_stage16,
+                                           b_base16 + ((uint32_t)p.b_stage_bytes >> 4) + (uint32_t)(kc - k_chunks) * (2u * KJ * NF),
+                                           a_hi, d_tmem0);
             ptx::umma_commit(&sh->a_empty[sa]);
-            if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
+            if (kc == total_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
           }
           __syncwarp();
         }
@@ -899,6 +941,17 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     }
   p.pad = pad;
   const bool has_residual = epi && epi->residual;
+  const bool has_skip = epi && epi->skip_x;
+  if (has_skip) {
+    VDM_CHECK_ARG(epi->skip_w && epi->skip_c_in >= 16 && epi->skip_c_in % 16 == 0,
+                  "vdm_conv3d: fused skip conv needs packed weights and skip_c_in a multiple of 16, got %d", epi->skip_c_in);
+    if (epi->skip_c_in > 64 || d.circular || d.out_fp32) {
+      set_error("vdm_conv3d: the fused skip conv supports zero-padded bf16 layers with skip_c_in <= 64 only (got %d)",
+                epi->skip_c_in);
+      return VDM_E_UNSUPPORTED;
+    }
+  }
+  const int skip_w_bytes = has_skip ? epi->skip_c_in * d.c_out_pad * 2 : 0;
   // kd-folded schedule (issue_fold_tile): the full 3x3x3 stencil on a narrow layer
   bool fold = d.n_taps == 27 && pad == 1 && d.c_in % 16 == 0 && (d.c_out_pad == 16 || d.c_out_pad == 32 || d.c_out_pad == 64) &&
               d.depth >= 3 && g_debug_no_fold == 0 && g_debug_force_mt == 0 && g_debug_force_nsplit == 0;
@@ -911,10 +964,10 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     // all weights resident + two halo stages must fit; prefer tall tiles (halo efficiency), then wide chunks
     const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - (2 * 2 * 8 * d.c_out_pad * 4 + 2 * d.c_out_pad * 8) - 256 -
                        (has_residual ? 2 * kResSlotBytes : 0);      // room for at least two residual slots
-    const int w_bytes = 27 * d.c_in * d.c_out_pad * 2;
+    const int w_bytes = 27 * d.c_in * d.c_out_pad * 2 + skip_w_bytes;
     for (int m = 4; m >= 2 && !fold_mt; --m)
       for (int c = 32; c >= 16 && !fold_mt; c -= 16) {
-        if (d.c_in % c != 0) continue;
+        if (d.c_in % c != 0 || (has_skip && epi->skip_c_in % c != 0)) continue;
         const int a_stage = (((c / 8) * (m + 2) * (kTileH + 2) * (kTileW + 2) * 16) + 127) & ~127;
         if (2 * a_stage + w_bytes <= budget) { fold_mt = m; fold_kc = c; }
       }
@@ -1022,7 +1075,21 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     p.b_stage_bytes = d.n_taps * d.c_in * p.n_cta * 2;
     nsb = 1;
     p.b_resident = 1;
-    VDM_CHECK_ARG(2 * p.a_stage_bytes + p.b_stage_bytes <= smem_budget, "vdm_conv3d: folded layer does not fit shared memory");
+    VDM_CHECK_ARG(2 * p.a_stage_bytes + p.b_stage_bytes + skip_w_bytes <= smem_budget,
+                  "vdm_conv3d: folded layer does not fit shared memory");
+    if (has_skip) {
+      p.skip_chunks = epi->skip_c_in / kc;
+      p.skip_w_bytes = skip_w_bytes;
+      p.w2 = static_cast<const __nv_bfloat16*>(epi->skip_w);
+      p.x2_planes = epi->skip_planes > 0 ? epi->skip_planes : epi->skip_c_in / 8;
+      p.x2_plane0 = epi->skip_plane0;
+      VDM_CHECK_ARG(p.x2_plane0 >= 0 && p.x2_plane0 + epi->skip_c_in / 8 <= p.x2_planes, "vdm_conv3d: skip plane window out of range");
+    }
+  }
+  if (has_skip && !(fold && !fold_streamed)) {
+    set_error("vdm_conv3d: the fused skip conv needs the kd-folded schedule with resident weights "
+              "(3x3x3, c_out_pad 16 or 32, weights + skip weights fit shared memory); c_in=%d c_out=%d", d.c_in, d.c_out);
+    return VDM_E_UNSUPPORTED;
   }
   for (int o = 0; o < 3 && !fold; ++o) {
     const int c = kc_options[o];
@@ -1090,7 +1157,23 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     }
   }
 
-  const int used = 2 * p.a_stage_bytes + p.nsb * p.b_stage_bytes;
+  CUtensorMap tmx2 = tmx;
+  if (p.skip_chunks > 0) {
+    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
+    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * p.x2_planes};
+    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    cuuint32_t box[4] = {(cuuint32_t)p.Wh * 8, (cuuint32_t)p.Hh, (cuuint32_t)p.Hd, (cuuint32_t)(kc / 8)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmx2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(epi->skip_x), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d: cuTensorMapEncodeTiled(skip_x) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+  }
+
+  const int used = 2 * p.a_stage_bytes + p.nsb * p.b_stage_bytes + p.skip_w_bytes;
   if (has_residual) {
     int depth = (smem_total - used) / kResSlotBytes;
     p.res_depth = depth > 4 ? 4 : depth;
@@ -1109,7 +1192,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));          \
       configured = true;                                                                                       \
     }                                                                                                          \
-    conv3d_planar_kernel<MTv, KJv, NFv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, p);                   \
+    conv3d_planar_kernel<MTv, KJv, NFv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmx2, p);                   \
     rc = VDM_OK;                                                                                               \
   }
   VDM_LAUNCH(1, 1, 0) VDM_LAUNCH(1, 2, 0) VDM_LAUNCH(1, 4, 0)

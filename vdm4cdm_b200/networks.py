@@ -119,6 +119,7 @@ class CUNet(nn.Module):
         self.shape = tuple(shape)
         self.circular = conv_padding_mode == "circular"     # the cropsize == 256 models (src/utils.py:460)
         self.fuse_upsample = True       # inference: up blocks read the coarse tensor instead of its up-sampled copy
+        self._fused_skip_ok = {}        # per up block: False once vdm_conv3d declined the fused skip conv
         self.chs = list(chs)
         self.s_conditioning_channels = s_conditioning_channels
         self.v_conditioning_dims = list(v_conditioning_dims)
@@ -348,13 +349,24 @@ class CUNet(nn.Module):
             res, res_plane0 = x, x_plane0
         elif up_from is not None:
             xc, xc_plane0, c_up = up_from
-            res = ar.get(f"{own}r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+            # coarse half of the skip conv (with the skip conv's bias): a small 1x1x1 conv on the half-resolution grid
             rc = ar.get(f"rc.{co}.{b}x{grid[0] // 2}", (b, co // 8) + tuple(n // 2 for n in grid) + (8,), torch.bfloat16, dev)
             ops.conv3d(xc, self._packed_in_slice(name + ".skip.up", blk.skip_conv, 0, c_up), co, taps=ops.TAPS_1X1X1,
-                       x_plane0=xc_plane0, c_in=c_up, out=rc)
-            ops.conv3d(x, self._packed_in_slice(name + ".skip.skip", blk.skip_conv, c_up, ci - c_up), co,
-                       taps=ops.TAPS_1X1X1, x_plane0=x_plane0 + c_up // 8, c_in=ci - c_up, out=res,
-                       chan_add=rows[name + ".skip"], residual=rc, residual_upsample=True)
+                       x_plane0=xc_plane0, c_in=c_up, out=rc, chan_add=rows[name + ".skip"])
+            w_skip = self._packed_in_slice(name + ".skip.skip", blk.skip_conv, c_up, ci - c_up)
+            if self._fused_skip_ok.get(name, True):
+                # fine half fused into net2's conv as one more channel chunk (centre tap only): no separate 1x1x1 launch,
+                # and the residual the epilogue reads is the coarse tensor (1/8 of the bytes)
+                try:
+                    ops.conv3d(a2c, self._packed(name + ".net2", blk.net2[3]), co, out=out, out_plane0=out_plane0,
+                               chan_add=rows[name + ".net2"], residual=rc, residual_upsample=True, stats=out_stats,
+                               stats_c0=out_stats_c0, skip_x=x, skip_w=w_skip, skip_plane0=x_plane0 + c_up // 8)
+                    return
+                except ops.UnsupportedFusion:
+                    self._fused_skip_ok[name] = False          # wide layer: keep the skip conv as its own launch
+            res = ar.get(f"{own}r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
+            ops.conv3d(x, w_skip, co, taps=ops.TAPS_1X1X1, x_plane0=x_plane0 + c_up // 8, c_in=ci - c_up, out=res,
+                       residual=rc, residual_upsample=True)
             res_plane0 = 0
         else:
             res = ar.get(f"{own}r.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)

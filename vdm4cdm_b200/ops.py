@@ -134,14 +134,20 @@ def pack_conv_weight_into(w: torch.Tensor, out: torch.Tensor, transpose_flip: bo
     return out
 
 
+UnsupportedFusion = _C.UnsupportedFusion
+
+
 # ---- conv ------------------------------------------------------------------------------------------
 def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequence[Tuple[int, int, int]] = TAPS_3X3X3,
            x_plane0: int = 0, c_in: Optional[int] = None, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
            out_fp32: bool = False, chan_add: Optional[torch.Tensor] = None, step_ptr: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, residual_plane0: int = 0, stats: Optional[torch.Tensor] = None,
-           stats_c0: int = 0, circular: bool = False, residual_upsample: bool = False) -> torch.Tensor:
+           stats_c0: int = 0, circular: bool = False, residual_upsample: bool = False,
+           skip_x: Optional[torch.Tensor] = None, skip_w: Optional[torch.Tensor] = None, skip_plane0: int = 0) -> torch.Tensor:
     """``vdm_conv3d``: y = conv(x, w) [+ chan_add[b, co]] [+ residual], optional GroupNorm statistics.
     ``residual_upsample``: the residual lives on the half-resolution grid and is added through a nearest x2 up-sampling.
+    ``skip_x`` / ``skip_w``: y += conv1x1x1(skip_x[window at skip_plane0], skip_w) fused into the launch (narrow
+    kd-folded layers only; raises ``UnsupportedFusion`` when the layer cannot take it).
 
     x: planar buffer; the conv reads ``c_in`` channels starting at plane ``x_plane0``.
     w_packed: ``pack_conv_weight`` output, shape [taps, c_in/8, c_out_pad, 8].
@@ -197,6 +203,14 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
         epi.residual = residual.data_ptr()
         epi.residual_upsample = 1 if residual_upsample else 0
         desc.r_planes, desc.r_plane0 = residual.shape[1], residual_plane0
+    if skip_x is not None:
+        _planar_ok(skip_x, "conv3d skip_x")
+        _need(tuple(skip_x.shape[2:5]) == (d, h, w_) and skip_x.shape[0] == b, "conv3d: skip_x grid mismatch")
+        _need(skip_w is not None and skip_w.is_cuda and skip_w.dtype == torch.bfloat16 and skip_w.is_contiguous() and
+              skip_w.dim() == 4 and skip_w.shape[0] == 1 and skip_w.shape[2] == c_out_pad,
+              "conv3d: skip_w must be the packed (c_out, skip_c_in, 1, 1, 1) filter")
+        epi.skip_x, epi.skip_w = skip_x.data_ptr(), skip_w.data_ptr()
+        epi.skip_c_in, epi.skip_planes, epi.skip_plane0 = skip_w.shape[1] * 8, skip_x.shape[1], skip_plane0
     if stats is not None:
         _need(stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous() and stats.dim() == 3 and
               stats.shape[0] == b and stats.shape[2] == 2, "conv3d: stats must be double [B, C, 2]")
@@ -209,6 +223,8 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
         e0.record()
     rc = _C.lib().vdm_conv3d(ctypes.byref(desc), x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), ctypes.byref(epi),
                              _stream())
+    if rc == _C.E_UNSUPPORTED and skip_x is not None:
+        raise _C.UnsupportedFusion(_C.lib().vdm_last_error_string().decode("utf-8", "replace"))
     _C.check(rc, "vdm_conv3d")
     _launched(1)
     if prof is not None:
