@@ -10,9 +10,9 @@ $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 150 -c 330 --csv \
     --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
-# full capture of the conv kernels of one sampler step (first eager step of the session: 29 launches)
+# full capture of the conv kernels of one sampler step (first eager step of the session: 28 launches)
 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:conv3d_planar -s 0 -c 29 -f -o /tmp/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv3d_planar -s 0 -c 28 -f -o /tmp/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
 echo "ncu full rc=$?"
 # the report of 29 launches with source counters is ~75 MB (gpurun_out/ carries 64 MB back): summarise it here
 python tools/ncu_summary.py /tmp/${tag}_conv.ncu-rep > gpurun_out/${tag}_conv_ncu.txt 2> gpurun_out/${tag}_summary.err
