@@ -87,10 +87,10 @@ typedef struct VdmConvEpilogue {
   int32_t reserved;
   /* Fused 1x1x1 skip-path conv of a ResNet block (blocks.py ResNetBlock: h + skip_conv(x)): y += conv1x1x1(skip_x, skip_w)
    * inside the same launch, as one more channel chunk of which only the centre tap is multiplied.  Only for the
-   * kd-folded layers (3x3x3, c_out <= 32, zero padding, bf16 output) whose weights stay resident in shared memory;
+   * kd-folded layers (3x3x3, c_out <= 32, bf16 output) whose weights stay resident in shared memory;
    * VDM_E_UNSUPPORTED otherwise (the caller then runs the skip conv as its own launch).  The skip conv's bias goes
    * through chan_add or the residual. */
-  const void* skip_x;           /* bf16 channel-planar tensor on the same grid, or NULL */
+  const void* skip_x;           /* bf16 channel-planar tensor on the same grid (never halo-padded), or NULL */
   const void* skip_w;           /* vdm_pack_conv_weight of the (c_out, skip_c_in, 1, 1, 1) filter */
   int32_t skip_c_in;            /* 16, 32, 48 or 64; a multiple of the layer's channel chunk */
   int32_t skip_planes;          /* planes per sample of the skip_x buffer (0: skip_c_in/8) */

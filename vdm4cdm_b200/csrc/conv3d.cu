@@ -364,7 +364,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], (t.w0 - p.pad + p.x_shift) * 8,
                              t.h0 - p.pad + p.x_shift, t.d0 - p.pad + p.x_shift,
                              t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
-          else   // skip-path tensor: same box (only its centre is multiplied), never circular
+          else   // skip-path tensor, never padded: same box, of which only the centre (always inside the grid) is multiplied
             ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x2, &sh->a_full[s], (t.w0 - p.pad) * 8, t.h0 - p.pad,
                              t.d0 - p.pad, t.b * p.x2_planes + p.x2_plane0 + (kc - p.k_chunks) * planes_per_chunk);
         }
@@ -945,9 +945,8 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   if (has_skip) {
     VDM_CHECK_ARG(epi->skip_w && epi->skip_c_in >= 16 && epi->skip_c_in % 16 == 0,
                   "vdm_conv3d: fused skip conv needs packed weights and skip_c_in a multiple of 16, got %d", epi->skip_c_in);
-    if (epi->skip_c_in > 64 || d.circular || d.out_fp32) {
-      set_error("vdm_conv3d: the fused skip conv supports zero-padded bf16 layers with skip_c_in <= 64 only (got %d)",
-                epi->skip_c_in);
+    if (epi->skip_c_in > 64 || d.out_fp32) {
+      set_error("vdm_conv3d: the fused skip conv supports bf16 layers with skip_c_in <= 64 only (got %d)", epi->skip_c_in);
       return VDM_E_UNSUPPORTED;
     }
   }

@@ -360,7 +360,8 @@ class CUNet(nn.Module):
                 try:
                     ops.conv3d(a2c, self._packed(name + ".net2", blk.net2[3]), co, out=out, out_plane0=out_plane0,
                                chan_add=rows[name + ".net2"], residual=rc, residual_upsample=True, stats=out_stats,
-                               stats_c0=out_stats_c0, skip_x=x, skip_w=w_skip, skip_plane0=x_plane0 + c_up // 8)
+                               stats_c0=out_stats_c0, skip_x=x, skip_w=w_skip, skip_plane0=x_plane0 + c_up // 8,
+                               circular=self.circular)
                     return
                 except ops.UnsupportedFusion:
                     self._fused_skip_ok[name] = False          # wide layer: keep the skip conv as its own launch
@@ -459,7 +460,7 @@ class CUNet(nn.Module):
             cat, cst = cats[i], cat_stats[i]
             o = buf(f"up{i}", c[i], i)
             ost = self._stats(name + ".out", b, c[i], dev)
-            if self.fuse_upsample and tape is None and not self.circular and blk.skip_conv is not None:
+            if self.fuse_upsample and tape is None and blk.skip_conv is not None:
                 # the up-sampled channels are never written (see _run_block); their sums are 8x the coarse tensor's
                 torch.mul(x_stats, 8.0, out=cst[:, :c[i + 1]])
                 self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout, tape,
