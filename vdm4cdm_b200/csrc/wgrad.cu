@@ -104,7 +104,12 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
-  const int n_slices = p.n_sblocks * p.S;
+  // A CTA's jobs (job = operand block sb along d x (kh, kw)) touch only the halo slices of blocks sb_lo..sb_hi: wide
+  // layers (cpb = 128, S = 1, two or four jobs per CTA) mostly need ONE of the three slices, and loading all three
+  // made them TMA-bound (202 KB per tile for 16 MMAs of N = 256; r02t).
+  const int sb_lo = job0 / p.n_khw, sb_hi = (job0 + n_jobs - 1) / p.n_khw;
+  const int sl_lo = sb_lo * p.S;
+  const int n_slices = (sb_hi - sb_lo + 1) * p.S;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -122,7 +127,8 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         for (int sl = 0; sl < n_slices; ++sl)
           ptx::tma_load_4d(a_dst + (size_t)sl * p.slice_bytes, &tmap_a, &sh->full[s], (w0 - p.pad + p.a_shift) * 8,
-                           h0 - p.pad + p.a_shift, d - p.pad + sl + p.a_shift, b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
+                           h0 - p.pad + p.a_shift, d - p.pad + sl_lo + sl + p.a_shift,
+                           b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
         ptx::tma_load_4d(a_dst + p.a_stage_bytes, &tmap_g, &sh->full[s], w0 * 8, h0, d,
                          b * p.g_planes + p.g_plane0 + ns * (p.n >> 3));
       }
@@ -154,7 +160,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int job = job0 + j;
           const int sb = job / n_khw, khw = job % n_khw;
           const int kh = n_khw == 9 ? khw / 3 : 0, kw = n_khw == 9 ? khw % 3 : 0;
-          const uint32_t a_job = a0 + (uint32_t)sb * block16 + (uint32_t)(kh * Wh + kw);
+          const uint32_t a_job = a0 + (uint32_t)(sb - sb_lo) * block16 + (uint32_t)(kh * Wh + kw);
           const uint32_t d_tmem = tmem_u + (uint32_t)j * n;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
