@@ -199,3 +199,33 @@ def test_datamodule_file_lookup_cv_exclusion_and_split(tmp_path):
     with pytest.raises(FileNotFoundError, match="VDM4CDM_DATA_ROOT"):
         os.environ.pop("VDM4CDM_DATA_ROOT", None)
         dataset.get_dataset(dataset_name="CMD_16", set_name="1P", stage="test")
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in vdm4cdm_b200/_C.py must have the size and field offsets the C compiler gives the structs
+    of include/vdm4cdm_b200.h (the header is plain C: compiled here with gcc, no CUDA needed)."""
+    import ctypes
+    import subprocess
+    from vdm4cdm_b200 import _C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"VdmConvDesc": _C.ConvDesc, "VdmConvEpilogue": _C.ConvEpilogue, "VdmWgradDesc": _C.WgradDesc,
+             "VdmTensor": _C.Tensor}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vdm4cdm_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, what, value = line.split()
+        cls = pairs[cname]
+        want = ctypes.sizeof(cls) if what == "size" else getattr(cls, what).offset
+        assert int(value) == want, f"{cname}.{what}: C says {value}, ctypes says {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
