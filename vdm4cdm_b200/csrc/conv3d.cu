@@ -25,9 +25,12 @@
 //                        (chunk, 3 taps) stages
 //   warp 1  MMA issuer : generic path: chunk, tap, sub-tile s < MT, k16: tcgen05.mma M=128 N=n_cta K=16
 //                        into accumulator s (TMEM, fp32).
-//                        kd-folded path (narrow layers, NF = Cout_pad in {16, 32}): see issue_fold_tile.
+//                        kd-folded path (narrow layers, NF = Cout_pad in {16, 32, 64}): see issue_fold_tile /
+//                        issue_fold_stage; optionally one more channel chunk from a second tensor of which
+//                        only the centre tap is multiplied (the block's 1x1x1 skip conv, issue_skip_chunk).
 //                        2 accumulator sets: the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 3-10 epilogue: tcgen05.ld -> + bias/conditioning row + residual -> bf16 planar (or fp32
+//   warps 3-10 epilogue: tcgen05.ld -> + bias/conditioning row + residual (cp.async ring in shared memory,
+//                        optionally read through a nearest x2 up-sampling) -> bf16 planar (or fp32
 //                        NCDHW) store, per-channel (sum, sumsq) GroupNorm statistics by warp-shuffle
 //                        transpose reduction, kept per CTA in shared memory (fp64) and flushed with fp64
 //                        atomics when the CTA moves to another sample.  Two warps per TMEM lane quarter.
