@@ -133,3 +133,33 @@ def test_ddnm_inpainting_matches_oracle():
     assert err < 5e-2, err
     with pytest.raises(AssertionError):
         utils.get_ddnm_result(mod, y.cuda(), lambda x: x, lambda x: x, n_sampling_steps=4, l=[1, 2])
+
+
+def test_classifier_free_guidance_branch_matches_oracle():
+    """VDM.get_pred_noise with w_cfg (vdm_model.py:318-327): (1 + w) eps(cond) - w eps(parameters masked out), and a
+    guided chain samples through the generic (non-graph) loop."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_gpu_unet import _models, _rel_l2
+    from oracle.vdm_ref import VDM as RefVDM
+    from vdm4cdm_b200.vdm_model import VDM
+    shape, chs, batch = (1, 16, 16, 16), (16, 32), 2
+    ref_net, net = _models(shape, chs)
+    ref_vdm, vdm = RefVDM(ref_net, w_cfg=1.5).eval(), VDM(net, w_cfg=1.5).cuda().eval()
+    g = torch.Generator().manual_seed(12)
+    zt = torch.randn((batch,) + shape, generator=g)
+    cond = torch.randn((batch,) + shape, generator=g)
+    v = [torch.rand(batch, 6, generator=g)]
+    gamma_t = torch.full((batch,), 2.0)
+    with torch.no_grad():
+        want = ref_vdm.get_pred_noise(zt, gamma_t, s_conditioning=cond, v_conditionings=v)
+        plain = RefVDM(ref_net).eval().get_pred_noise(zt, gamma_t, s_conditioning=cond, v_conditionings=v)
+        got = vdm.get_pred_noise(zt.cuda(), gamma_t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()]).cpu()
+    # guidance extrapolates the difference of two network outputs, so their bf16 noise is amplified by (1 + 2w)
+    assert _rel_l2(got, want) < 4e-2, _rel_l2(got, want)
+    assert _rel_l2(want, plain) > 1e-3                  # the guided output is a different function
+    with pytest.raises(AssertionError, match="v_conditionings"):
+        vdm.get_pred_noise(zt.cuda(), gamma_t.cuda(), s_conditioning=cond.cuda())
+    xs = vdm.sample(batch, 3, "cuda:0", seed=3, s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()])
+    assert xs.shape == (batch,) + shape and torch.isfinite(xs).all()
