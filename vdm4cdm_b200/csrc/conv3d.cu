@@ -247,23 +247,26 @@ __device__ __forceinline__ void issue_fold_tile(uint32_t a_lo0, uint32_t b_base1
 }
 
 // Fused 1x1x1 skip-path conv of a ResNet block (h_out = conv3x3x3(a2) + conv1x1x1(x_skip) + ...): one more channel
-// chunk whose halo box comes from the skip tensor and of which only the centre tap (kd = kh = kw = 1) is multiplied,
-// MT*KJ MMAs of N = NF on top of the (MT+2)*9*KJ of a main chunk.  Weights: [plane][co] (LBO = NF*16 bytes).
+// chunk loaded from the skip tensor as a box WITHOUT halo, [plane][MT d][16 h][8 w][16 B] (a 1x1x1 filter needs the
+// tile's own voxels only: 32 KB instead of a 69 KB halo box), MT*KJ MMAs of N = NF on top of the (MT+2)*9*KJ of a main
+// chunk.  Weights: [plane][co] (LBO = NF*16 bytes).
 template <int MT, int KJ, int NF>
-__device__ __forceinline__ void issue_skip_chunk(uint32_t a_lo0, uint32_t b_lo16, uint64_t a_hi, uint32_t d_tmem0) {
-  constexpr int Hh = kTileH + 2, Wh = kTileW + 2, Hd = MT + 2;
-  constexpr uint32_t plane16 = (uint32_t)(Hd * Hh * Wh);
+__device__ __forceinline__ void issue_skip_chunk(uint32_t a_lo0, uint32_t b_lo16, uint32_t d_tmem0) {
+  constexpr uint32_t slice16 = (uint32_t)(kTileH * kTileW);          // one d-slice of a plane, 16-byte units
+  constexpr uint32_t plane16 = (uint32_t)MT * slice16;
   constexpr uint32_t kstep_a16 = 2u * plane16;
+  // A: K-major, 8 voxels along w = one core matrix, next h row (SBO) 128 B on, next 8 channels (LBO) one plane on
+  const uint64_t a_hi = make_planar_desc(0, plane16 * 16u, (uint32_t)kTileW * 16u);
   const uint64_t b_hi = make_planar_desc(0, (uint32_t)NF * 16u, 128u);
   const uint32_t a_hi32 = (uint32_t)(a_hi >> 32), b_hi32 = (uint32_t)(b_hi >> 32);
   const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)NF);
   const uint32_t b_i = b_lo16 + (uint32_t)b_hi;
 #pragma unroll
-  for (int i = 1; i <= MT; ++i) {          // input slice i is the centre (kd = 1) of output slice i - 1
-    const uint32_t a_i = a_lo0 + (uint32_t)(i * Hh * Wh + Wh + 1) + (uint32_t)a_hi;
+  for (int i = 0; i < MT; ++i) {
+    const uint32_t a_i = a_lo0 + (uint32_t)i * slice16 + (uint32_t)a_hi;
 #pragma unroll
     for (int j = 0; j < KJ; ++j)
-      ptx::umma_bf16_off(d_tmem0, (uint32_t)((i - 1) * NF), a_i, (uint32_t)j * kstep_a16, a_hi32, b_i, (uint32_t)(2 * j * NF),
+      ptx::umma_bf16_off(d_tmem0, (uint32_t)(i * NF), a_i, (uint32_t)j * kstep_a16, a_hi32, b_i, (uint32_t)(2 * j * NF),
                          b_hi32, idesc, 1u);
   }
 }
@@ -362,14 +365,16 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             ptx::mbar_arrive(&sh->a_full[s]);
             continue;
           }
-          ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes_per_chunk * p.plane_bytes));
-          if (kc < p.k_chunks)
+          if (kc < p.k_chunks) {
+            ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes_per_chunk * p.plane_bytes));
             ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x, &sh->a_full[s], (t.w0 - p.pad + p.x_shift) * 8,
                              t.h0 - p.pad + p.x_shift, t.d0 - p.pad + p.x_shift,
                              t.b * p.x_planes + p.x_plane0 + kc * planes_per_chunk);
-          else   // skip-path tensor, never padded: same box, of which only the centre (always inside the grid) is multiplied
-            ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x2, &sh->a_full[s], (t.w0 - p.pad) * 8, t.h0 - p.pad,
-                             t.d0 - p.pad, t.b * p.x2_planes + p.x2_plane0 + (kc - p.k_chunks) * planes_per_chunk);
+          } else {   // skip-path tensor (never halo-padded): the tile's own voxels, box (8 w, 16 h, MT d, planes)
+            ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes_per_chunk * MT * kTileH * kTileW * 16));
+            ptx::tma_load_4d(a_smem + (size_t)s * p.a_stage_bytes, &tmap_x2, &sh->a_full[s], t.w0 * 8, t.h0, t.d0,
+                             t.b * p.x2_planes + p.x2_plane0 + (kc - p.k_chunks) * planes_per_chunk);
+          }
         }
       }
     }
@@ -523,7 +528,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             else
               issue_skip_chunk<MT, KJ, NF>(a_base16 + sa * a_stage16,
                                            b_base16 + ((uint32_t)p.b_stage_bytes >> 4) + (uint32_t)(kc - k_chunks) * (2u * KJ * NF),
-                                           a_hi, d_tmem0);
+                                           d_tmem0);
             ptx::umma_commit(&sh->a_empty[sa]);
             if (kc == total_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
           }
@@ -1164,7 +1169,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
     cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * p.x2_planes};
     cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
-    cuuint32_t box[4] = {(cuuint32_t)p.Wh * 8, (cuuint32_t)p.Hh, (cuuint32_t)p.Hd, (cuuint32_t)(kc / 8)};
+    cuuint32_t box[4] = {(cuuint32_t)kTileW * 8, (cuuint32_t)kTileH, (cuuint32_t)mt, (cuuint32_t)(kc / 8)};   // no halo
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tmx2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(epi->skip_x), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
