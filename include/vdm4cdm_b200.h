@@ -103,7 +103,9 @@ typedef struct VdmConvEpilogue {
 VDM_API int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w, void* y,
                const VdmConvEpilogue* epi, void* stream);
 
-/* Tuning / bring-up knobs (0 = automatic): key 0 swap LBO/SBO roles, 1 force MT, 2 force KC, 3 force n_split. */
+/* Tuning / bring-up knobs of vdm_conv3d (value 0 = automatic): key 0 retired, 1 force MT, 2 force KC, 3 force n_split,
+ * 4 no resident weights, 5 ablation flags (timing experiments; results are wrong by construction, see
+ * tools/bench_epilogue.py), 6 no kd-folded schedule (1: resident variants off, 2: all off). */
 VDM_API int vdm_debug_set(int key, int value);
 
 /* ---- conv3d weight gradient (tcgen05, both operands MN-major straight from the planar tensors) ----

@@ -888,7 +888,6 @@ static int num_sms() {
   return n;
 }
 
-static int g_debug_swap_lbo_sbo = 0;
 static int g_debug_flags = 0;
 static int g_debug_force_mt = 0, g_debug_force_kc = 0, g_debug_force_nsplit = 0, g_debug_no_resident = 0, g_debug_no_fold = 0;
 
@@ -898,7 +897,7 @@ using namespace vdm;
 
 extern "C" int vdm_debug_set(int key, int value) {
   switch (key) {
-    case 0: g_debug_swap_lbo_sbo = value; return VDM_OK;   /* retired knob, kept for ABI stability */
+    case 0: return VDM_OK;   /* retired knob (LBO/SBO swap), accepted for ABI stability */
     case 1: g_debug_force_mt = value; return VDM_OK;
     case 2: g_debug_force_kc = value; return VDM_OK;
     case 3: g_debug_force_nsplit = value; return VDM_OK;

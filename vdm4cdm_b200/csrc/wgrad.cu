@@ -29,7 +29,6 @@ namespace vdm {
 
 constexpr int kWgThreads = 192;
 constexpr int kWgTileH = 16, kWgTileW = 8;
-constexpr int kWgMaxJobs = 27;
 constexpr int kWgMaxStages = 4;
 
 struct WgradParams {
@@ -637,8 +636,6 @@ extern "C" int vdm_conv3d_wgrad(const VdmWgradDesc* desc, const void* a, const v
     const cuuint64_t Da = d.depth + 2 * ah, Ha = d.height + 2 * ah, Wa = d.width + 2 * ah;
     cuuint64_t gdim[4] = {Wa * 8, Ha, Da, (cuuint64_t)d.batch * x_planes};
     cuuint64_t gstr_a[3] = {Wa * 16, Ha * Wa * 16, Da * Ha * Wa * 16};
-    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
-    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
     cuuint32_t box[4] = {(cuuint32_t)p.Wh * 8, (cuuint32_t)p.Hh, 1u, (cuuint32_t)(cpb / 8)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), gdim, gstr_a, box, estr,
