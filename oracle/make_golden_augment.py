@@ -37,5 +37,9 @@ for ci, (S, c, alpha, mean, std) in enumerate(cases):
     out[f"c{ci}_flip"] = flip_mask
     out[f"c{ci}_perm"] = pm.axes.numpy().astype(np.int32)
     out[f"c{ci}_meta"] = np.array([S, c, alpha, mean, std], dtype=np.float64)
+# order of the crop grid (AstroDataset.__getitem__: bidx, icrop = divmod(idx, ncrops); CAMELS_3D_dataset.py:53-56),
+# also for a box the crop size does not divide
+for S, c in ((16, 8), (24, 8), (24, 10)):
+    out[f"anchors_{S}_{c}"] = np.asarray(aug.Crop(3, c, 0, fullsize=S, do_augshift=False).anchors, dtype=np.int32)
 np.savez_compressed(os.path.join(HERE, "..", "tests", "golden", "augment_golden.npz"), **out)
 print("wrote", len(out), "arrays")
