@@ -229,3 +229,33 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(value) == want, f"{cname}.{what}: C says {value}, ctypes says {want}"
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
+
+
+def test_get_model_builds_what_the_reference_get_model_builds():
+    """tests/golden/get_model_kwargs.json holds the constructor arguments the REFERENCE's get_model (src/utils.py:434-471)
+    passes for every entry of its configs.yaml (oracle/make_golden_get_model.py); our get_model on our copy of the
+    registry must build the same networks."""
+    import json
+    from vdm4cdm_b200 import utils
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "get_model_kwargs.json")))
+    configs = yaml.safe_load(open(os.path.join(root, "configs.yaml")))
+    assert set(gold) <= set(configs), set(gold) - set(configs)
+    checked = 0
+    for name, want in gold.items():
+        cfg = {k: v for k, v in configs[name].items() if k != "ckpt_path"}
+        model = utils.get_model(cfg)
+        if want is None:
+            assert model is None, name                       # SFM entries: get_model returns None (src/utils.py:472-473)
+            continue
+        net, w = model.model.score_model, want["CUNet"]
+        assert list(net.shape) == w["shape"] and net.chs == w["chs"], name
+        assert net.s_conditioning_channels == w["s_conditioning_channels"], name
+        assert net.v_conditioning_dims == w["v_conditioning_dims"] and net.t_conditioning == w["t_conditioning"], name
+        assert net.norm_groups == w["norm_groups"] and net.dropout_prob == w["dropout_prob"], name
+        assert net.circular == (w["conv_padding_mode"] == "circular") and net.n_attention_heads == w["n_attention_heads"], name
+        assert w["mid_attn"] is False
+        assert model.model.gamma_max == want["LightVDM"]["gamma_max"], name
+        assert model.learning_rate == want["LightVDM"]["learning_rate"] and model.draw_figure is None, name
+        checked += 1
+    assert checked >= 8
