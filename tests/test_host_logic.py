@@ -259,3 +259,30 @@ def test_get_model_builds_what_the_reference_get_model_builds():
         assert model.learning_rate == want["LightVDM"]["learning_rate"] and model.draw_figure is None, name
         checked += 1
     assert checked >= 8
+
+
+def test_get_datamodule_passes_what_the_reference_passes(monkeypatch):
+    """tests/golden/get_datamodule_kwargs.json: the arguments the REFERENCE's get_datamodule (src/utils.py:401-432) hands
+    to get_dataset for every registry entry and three data_params variants, and its return_func's batch schema
+    (oracle/make_golden_get_datamodule.py).  Ours must hand the same to vdm4cdm_b200.dataset.get_dataset."""
+    import json
+    from vdm4cdm_b200 import dataset, utils
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "get_datamodule_kwargs.json")))
+    configs = yaml.safe_load(open(os.path.join(root, "configs.yaml")))
+    calls = []
+    monkeypatch.setattr(dataset, "get_dataset", lambda **kw: calls.append(kw) or "dm")
+    variants = {"default": {}, "cv_fit": {"set_name": "CV", "stage": "fit", "batch_size": 4},
+                "one_p": {"set_name": "1P", "stage": "test", "batch_size": 1}}
+    for key, want in gold.items():
+        name, variant = key.split("/")
+        cfg = dict(configs[name], data_params=dict(configs[name]["data_params"], **variants[variant]))
+        calls.clear()
+        assert utils.get_datamodule(cfg, data_root="/somewhere") == "dm"
+        kw = dict(calls[0])
+        rf = kw.pop("return_func")
+        assert kw.pop("data_root") == "/somewhere"            # the one argument the reference does not have
+        assert kw == want["kwargs"], (key, kw, want["kwargs"])
+        assert rf(fields=["F0", "F1"], params="P") == want["return_func"], key
+    with pytest.raises(AssertionError, match="data_params"):
+        utils.get_datamodule({"cropsize": 128})
