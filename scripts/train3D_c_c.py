@@ -24,11 +24,20 @@ from mltools.models import sfm_model, vdm_model
 from mltools.networks import networks
 from vdm4cdm_b200.trainer import Trainer
 
-# per-script hyper-parameters of the reference (trainVDM3D128_...:60-72, trainVDM3D224_...:60-72, trainSFM3D160_...:60-68)
-PRESETS = {"VDM": {64: ([16, 32, 64, 128], 2), 128: ([32, 64, 128, 256], 2), 160: ([32, 64, 128, 256], 2),
-                   192: ([32, 64, 128, 256], 2), 224: ([16, 32, 64, 128], 2)},
-           "SFM": {64: ([16, 32, 64, 128], 2), 128: ([32, 64, 128, 256], 4), 160: ([32, 64, 128, 256], 4),
-                   192: ([32, 64, 128, 256], 4)}}
+# Hyper-parameters of the reference's scripts (tests/golden/train_presets.json, read from their syntax trees by
+# oracle/make_golden_train_presets.py): the grid sizes with a dedicated script train on the re-gridded boxes CMD_{n};
+# every other cropsize is the base script (trainVDM3D_c_c_... / trainSFM3D_c_c_...: crops of the 256^3 "CMD" boxes).
+#   (model, cropsize) -> (chs, batch_size per GPU, dataset_name)
+PRESETS = {("VDM", 128): ([32, 64, 128, 256], 2, "CMD_128"), ("VDM", 160): ([32, 64, 128, 256], 2, "CMD_160"),
+           ("VDM", 192): ([32, 64, 128, 256], 2, "CMD_192"), ("VDM", 224): ([16, 32, 64, 128], 2, "CMD_224"),
+           ("SFM", 128): ([32, 64, 128, 256], 4, "CMD_128"), ("SFM", 160): ([32, 64, 128, 256], 4, "CMD_160"),
+           ("SFM", 192): ([32, 64, 128, 256], 2, "CMD_192")}
+BASE_PRESET = ([16, 32, 64, 128], 2, "CMD")
+NORM_GROUPS, DROPOUT_PROB, GAMMA_MAX, LEARNING_RATE, GRADIENT_CLIP_VAL = 8, 0.1, 13.3, 3.0e-4, 0.5
+
+
+def preset(model: str, cropsize: int):
+    return PRESETS.get((model, cropsize), BASE_PRESET)
 
 
 def main():
@@ -41,6 +50,7 @@ def main():
     ap.add_argument("--data-root", default=os.environ.get("VDM4CDM_DATA_ROOT"),
                     help="directory with the CAMELS grids (Grids_{field}_{suite}_LH_{res}_z=0.0.npy) and params_LH_{suite}.txt")
     ap.add_argument("--suite-name", default="Astrid")
+    ap.add_argument("--dataset-name", default=None, help="override the grid set (default: the reference script's, e.g. CMD_128)")
     ap.add_argument("--host-boxes", action="store_true", help="keep the boxes memory-mapped on the host (mmap=True)")
     ap.add_argument("--max-epochs", type=int, default=1000)
     ap.add_argument("--synthetic-boxes", action="store_true",
@@ -54,25 +64,26 @@ def main():
     args = ap.parse_args()
     rank, world, device = init_distributed()
     torch.manual_seed(42)                                     # seed_everything(42)
-    chs, batch_size = PRESETS[args.model].get(args.cropsize, ([32, 64, 128, 256], 2))
+    chs, batch_size, dataset_name = preset(args.model, args.cropsize)
     batch_size = args.batch_size or batch_size
+    dataset_name = args.dataset_name or dataset_name
     chs = args.chs or chs
     n = args.cropsize
     net = networks.CUNet(shape=(1, n, n, n), chs=chs, s_conditioning_channels=1, v_conditioning_dims=[6],
-                         t_conditioning=True, norm_groups=8, mid_attn=False, dropout_prob=0.1,
+                         t_conditioning=True, norm_groups=NORM_GROUPS, mid_attn=False, dropout_prob=DROPOUT_PROB,
                          conv_padding_mode="circular" if n == 256 else "zeros", n_attention_heads=4)
     if args.model == "VDM":
-        model = vdm_model.LightVDM(score_model=net, draw_figure=None, gamma_max=13.3, learning_rate=3.0e-4)
+        model = vdm_model.LightVDM(score_model=net, draw_figure=None, gamma_max=GAMMA_MAX, learning_rate=LEARNING_RATE)
     else:
-        model = sfm_model.LightSFM(velocity_model=net, draw_figure=None, learning_rate=3.0e-4)
+        model = sfm_model.LightSFM(velocity_model=net, draw_figure=None, learning_rate=LEARNING_RATE)
     model = model.to(device)
-    trainer = Trainer(model, gradient_clip_val=0.5)
+    trainer = Trainer(model, gradient_clip_val=GRADIENT_CLIP_VAL)
     stream = None
     if not args.synthetic:
         # trainVDM3D128_...:75-89: LH set of the re-gridded boxes, stage "fit", mmap=False (boxes resident in HBM)
         from vdm4cdm_b200.dataset import get_dataset
         key_c, key_x = ("conditioning", "x") if args.model == "VDM" else ("x0", "x1")
-        dm = get_dataset(dataset_name="CMD" if n == 256 else f"CMD_{n}", suite_name=args.suite_name,
+        dm = get_dataset(dataset_name=dataset_name, suite_name=args.suite_name,
                          return_func=lambda fields, params: {key_c: fields[0], key_x: fields[1], "conditioning_values": [params]},
                          set_name="LH", z_name="z_0.0", channel_names=[args.field_in, args.field_out], stage="fit",
                          batch_size=batch_size, cropsize=n, mmap=args.host_boxes, data_root=args.data_root, device=device,

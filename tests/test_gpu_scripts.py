@@ -78,7 +78,8 @@ def test_generate_scripts_on_a_camels_like_directory(tmp_path):
 
 def test_train_script_on_a_camels_like_directory(tmp_path):
     _camels_dir(tmp_path, {"LH": 6})
-    log = _run("train3D_c_c.py", "Mstar", "Mcdm", 16, "--model", "VDM", "--data-root", tmp_path, "--chs", 16, 32,
+    log = _run("train3D_c_c.py", "Mstar", "Mcdm", 16, "--model", "VDM", "--data-root", tmp_path, "--dataset-name", "CMD_16",
+               "--chs", 16, 32,
                "--max-steps", 6, "--log-every", 2, "--ckpt-dir", tmp_path / "ckpt")
     losses = [float(line.split("loss")[1].split()[0]) for line in log.splitlines() if line.startswith("step")]
     assert len(losses) == 3 and all(np.isfinite(losses))

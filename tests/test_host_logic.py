@@ -286,3 +286,32 @@ def test_get_datamodule_passes_what_the_reference_passes(monkeypatch):
         assert rf(fields=["F0", "F1"], params="P") == want["return_func"], key
     with pytest.raises(AssertionError, match="data_params"):
         utils.get_datamodule({"cropsize": 128})
+
+
+def test_train_script_presets_match_the_reference_scripts():
+    """tests/golden/train_presets.json: hyper-parameters read from the syntax trees of the reference's
+    train{VDM,SFM}3D*_c_c_..._lowbatch.py (oracle/make_golden_train_presets.py); scripts/train3D_c_c.py must carry them."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    spec = importlib.util.spec_from_file_location("train3D_c_c", os.path.join(root, "scripts", "train3D_c_c.py"))
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(os.path.join(root, "scripts"))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "train_presets.json")))
+    assert len(gold) == 9
+    for name, want in gold.items():
+        # scripts without a grid size in their name take it from the command line: any size without its own script
+        cropsize = want["cropsize_in_name"] or 64
+        chs, batch, dataset_name = mod.preset(want["model"], cropsize)
+        assert chs == want["chs"] and batch == want["batch_size"] and dataset_name == want["dataset_name"], name
+        assert mod.NORM_GROUPS == want["norm_groups"] and mod.DROPOUT_PROB == want["dropout_prob"], name
+        assert mod.LEARNING_RATE == want["learning_rate"] and mod.GRADIENT_CLIP_VAL == want["gradient_clip_val"], name
+        assert want["conditioning_values"] == 6 and want["conditioning_channels"] == 1, name      # CUNet(... [6], 1 ...)
+        assert want["set_name"] == "LH" and want["stage"] == "fit" and want["mmap"] is False, name
+        if want["model"] == "VDM":
+            assert mod.GAMMA_MAX == want["gamma_max"], name
+    assert mod.preset("VDM", 256) == mod.BASE_PRESET and mod.preset("SFM", 224) == mod.BASE_PRESET
