@@ -315,3 +315,80 @@ def test_train_script_presets_match_the_reference_scripts():
         if want["model"] == "VDM":
             assert mod.GAMMA_MAX == want["gamma_max"], name
     assert mod.preset("VDM", 256) == mod.BASE_PRESET and mod.preset("SFM", 224) == mod.BASE_PRESET
+
+
+def _run_our_generate(monkeypatch, tmp_path, script_mode, model_name, runtype, conditioning_values):
+    """scripts/generate_3D.py:main(mode) on the CPU with the same recording stand-ins oracle/make_golden_generate.py puts
+    under the reference's scripts."""
+    import importlib
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "scripts"))
+    import _common
+    from vdm4cdm_b200 import utils
+    gen = importlib.import_module("generate_3D")
+    draws, dms = [], []
+
+    class FakeModel:
+        def eval(self):
+            return self
+
+        def draw_samples(self, **kw):
+            field = int(kw["s_conditioning"].flatten()[0])
+            draws.append({"batch_size": kw["batch_size"], "field": field, "n_v_conditionings": len(kw["v_conditionings"]),
+                          "ids": list(kw["realisation_ids"])})
+            return torch.full((kw["batch_size"], 1, 2, 2, 2), float(field * 1000 + len(draws)))
+
+    class FakeDM:
+        def test_dataloader(self):
+            for i in range(40):
+                yield {"x": torch.full((1, 1, 2, 2, 2), float(i)), "conditioning": torch.full((1, 1, 2, 2, 2), float(i)),
+                       "conditioning_values": [torch.full((1, 6), float(i))]}
+
+    def fake_get_datamodule(config, **kw):
+        dms.append({k: config["data_params"].get(k) for k in ("set_name", "stage", "batch_size")})
+        return FakeDM()
+
+    monkeypatch.setattr(gen, "init_distributed", lambda: (0, 1, torch.device("cpu")))
+    monkeypatch.setattr(utils, "get_model", lambda config, device=None: FakeModel())
+    monkeypatch.setattr(utils, "get_datamodule", fake_get_datamodule)
+    cfg = {model_name: {"type": "VDM", "cropsize": 2, "conditioning_values": conditioning_values,
+                        "in_field_name": "Mstar", "out_field_name": "Mcdm", "data_params": {"dataset_name": "CMD"}}}
+    (tmp_path / "configs.yaml").write_text(yaml.safe_dump(cfg))
+    out = tmp_path / "out"
+    monkeypatch.setattr(sys, "argv", ["generate", model_name, str(out), runtype, "--configs", str(tmp_path / "configs.yaml"),
+                                      "--data-root", "unused", "--batch", "5"])
+    gen.main(script_mode)
+    files = {}
+    for f in sorted(os.listdir(out)):
+        a = np.load(out / f)
+        first = a.reshape(a.shape[0], -1)[:, 0].astype(int) // 1000
+        files[f] = {"shape": list(a.shape), "field": int(first[0]), "all_from_one_field": bool((first == first[0]).all())}
+    return files, dms, draws
+
+
+@pytest.mark.parametrize("key", ["generate_3D.py:VDM_Mstar_Mcdm_c_c_128:CV_12_12", "generate_3D.py:VDM_Mstar_Mcdm_c_c_128:CV_1_128",
+                                 "generate_3D.py:VDM_Mstar_Mcdm_c_uc_256:CV_1_128", "generate_3D_1P.py:VDM_Mstar_Mcdm_c_c_128:1P_24",
+                                 "generate_3D_1P.py:VDM_Mstar_Mcdm_c_c_256:1P_128"])
+def test_generate_scripts_behave_like_the_reference_scripts(monkeypatch, tmp_path, key):
+    """tests/golden/generate_scripts.json records what the reference's generate_3D.py / generate_3D_1P.py DO when run
+    (unmodified, under recording stand-ins: oracle/make_golden_generate.py): which test batches they sample, how many
+    realisations, the data_params they set, the files they write.  Ours must do the same (in batches of 5 here)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = json.load(open(os.path.join(root, "tests", "golden", "generate_scripts.json")))[key]
+    script, model_name, runtype = key.split(":")
+    ref_calls = [json.loads(c) for c in want["distinct_draw_calls"]]
+    n_v = ref_calls[0]["n_v_conditionings"]
+    files, dms, draws = _run_our_generate(monkeypatch, tmp_path, "1P" if "1P" in script else "CV", model_name, runtype,
+                                          conditioning_values=6 if n_v else 0)
+    assert files == want["files"]
+    assert dms == want["data_params"]
+    assert sum(d["batch_size"] for d in draws) == want["n_draw_calls"]          # reference: batch_size=1 per call
+    assert {d["n_v_conditionings"] for d in draws} == {n_v}
+    assert {d["field"] for d in draws} == {c["field"] for c in ref_calls}
+    rep = next(iter(want["files"].values()))["shape"][0]
+    by_field = {}
+    for d in draws:
+        by_field.setdefault(d["field"], []).extend(d["ids"])
+    assert all(sorted(ids) == list(range(rep)) for ids in by_field.values())     # every realisation exactly once
