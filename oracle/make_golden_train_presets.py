@@ -17,7 +17,8 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "..", "tests", "golden", "train_presets.json")
 NAMES = ("chs", "batch_size", "norm_groups", "dropout_prob", "gamma_max", "conditioning_values", "conditioning_channels")
-KEYWORDS = ("dataset_name", "learning_rate", "gradient_clip_val", "set_name", "stage", "mmap")
+KEYWORDS = ("dataset_name", "learning_rate", "gradient_clip_val", "set_name", "stage", "mmap", "max_steps",
+            "val_check_interval", "every_n_train_steps", "devices")
 
 
 def main():

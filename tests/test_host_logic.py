@@ -314,6 +314,10 @@ def test_train_script_presets_match_the_reference_scripts():
         assert want["set_name"] == "LH" and want["stage"] == "fit" and want["mmap"] is False, name
         if want["model"] == "VDM":
             assert mod.GAMMA_MAX == want["gamma_max"], name
+        # Trainer(max_steps=1_000_000, ModelCheckpoint(every_n_train_steps=10_000)): the script's defaults
+        assert want["max_steps"] == 1_000_000 and want["every_n_train_steps"] == 10_000, name
+    src = open(os.path.join(root, "scripts", "train3D_c_c.py")).read()
+    assert '"--max-steps", type=int, default=1_000_000' in src and '"--ckpt-every", type=int, default=10_000' in src
     assert mod.preset("VDM", 256) == mod.BASE_PRESET and mod.preset("SFM", 224) == mod.BASE_PRESET
 
 
