@@ -134,6 +134,114 @@ def cpu_oracle_rate(grid, chs, seconds_budget, steps, warmup, threads):
     return (n ** 3) / sec, sec, label, len(times)
 
 
+def parity_leg(net, vdm, dev, grid, chs):
+    """Parity of the BENCHMARKED configuration, measured in the bench run: the oracle (oracle/unet_ref.py + vdm_ref.py,
+    CPU fp32) gets the benchmarked network's weights and runs one denoiser call and one reverse step of one realisation
+    at the full grid with injected noise; the CUDA path runs the same.  Reported as relative L2 (tolerance 1e-2: bf16
+    activations, BASELINE.json north_star)."""
+    from oracle.unet_ref import CUNet as RefNet
+    from oracle.vdm_ref import VDM as RefVDM
+    net.invalidate_packed()
+    ref = RefNet(**model_kwargs(grid, chs)).eval()
+    ref.load_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()}, strict=True)
+    ref_vdm = RefVDM(ref).eval()
+    g = torch.Generator().manual_seed(7)
+    x, cond, params = synthetic_batch(1, grid, 4321)
+    noise = torch.randn(x.shape, generator=g)
+    t, s_ = torch.tensor(0.62), torch.tensor(0.616)
+    with torch.no_grad():
+        t_net = torch.tensor([0.37])
+        want = ref(x, t=t_net, s_conditioning=cond, v_conditionings=[params])
+        got = net(x.to(dev), t=t_net.to(dev), s_conditioning=cond.to(dev), v_conditionings=[params.to(dev)]).cpu()
+        zs_r = ref_vdm.sample_zs_given_zt(zt=x, t=t, s=s_, noise=noise, s_conditioning=cond, v_conditionings=[params])
+        zs = vdm.sample_zs_given_zt(zt=x.to(dev), t=t, s=s_, noise=noise.to(dev), s_conditioning=cond.to(dev),
+                                    v_conditionings=[params.to(dev)]).cpu()
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    return {"denoiser_rel_l2": rel(got, want), "step_rel_l2": rel(zs, zs_r), "tolerance": 1e-2,
+            "against": f"oracle/ (CPU fp32) with the benchmarked weights, 1 realisation at {grid}^3 chs={chs}"}
+
+
+def torch_gpu_leg(args, dev, ours_ms_per_step, ours_train_ms):
+    """Stock PyTorch on the SAME B200 (the bar a user of the reference would compare with): the
+    oracle's modules on cuda, bf16 autocast, channels_last_3d, TF32 allowed, cuDNN benchmark mode -- i.e. cuDNN conv3d +
+    ATen GroupNorm/SiLU.  Same work as our arms: one reverse step of `batch` realisations, and one VDM training step
+    (loss fwd + bwd + clip 0.5 + AdamW) of `train_batch` samples; CUDA events.  None of this repository's kernels run here."""
+    from oracle.unet_ref import CUNet as RefNet
+    from oracle.vdm_ref import LightVDM as RefLight
+    from oracle.vdm_ref import VDM as RefVDM
+    grid, chs = args.grid, args.chs
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    out = {"what": "oracle modules on cuda:0 under torch.autocast(bf16), channels_last_3d weights/activations, TF32 on, "
+                   "cudnn.benchmark (stock PyTorch: cuDNN conv3d + ATen GroupNorm/SiLU), eager launches",
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+
+    def timed(fn, warm, iters):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    try:
+        torch.manual_seed(42)
+        net = RefNet(**model_kwargs(grid, chs)).to(dev).to(memory_format=torch.channels_last_3d).eval()
+        vdm = RefVDM(net).to(dev).eval()
+        x, cond, params = synthetic_batch(args.batch, grid, 42, device=dev)
+        cond = cond.contiguous(memory_format=torch.channels_last_3d)
+        state = {"z": torch.randn_like(x)}
+        ts = torch.linspace(1.0, 0.0, 1001, device=dev)
+        it = [0]
+
+        def sample_step():
+            i = it[0] % 1000
+            it[0] += 1
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                state["z"] = vdm.sample_zs_given_zt(zt=state["z"], t=ts[i], s=ts[i + 1], s_conditioning=cond,
+                                                    v_conditionings=[params]).float()
+
+        ms = timed(sample_step, 3, 5)
+        out["sampling"] = {"ms_per_step": ms, "value": args.batch * grid ** 3 / (ms * 1e-3), "unit": UNIT,
+                           "realisations": args.batch}
+        out["vs_torch_gpu_sampling"] = ms / ours_ms_per_step
+        del vdm, net, state
+        torch.cuda.empty_cache()
+        if ours_train_ms is not None:
+            torch.manual_seed(42)
+            net = RefNet(**model_kwargs(grid, chs)).to(dev).to(memory_format=torch.channels_last_3d).train()
+            light = RefLight(net).to(dev).train()
+            opt = torch.optim.AdamW(light.parameters(), lr=3.0e-4, fused=True)
+            xb, cb, pb = synthetic_batch(args.train_batch, grid, 4242, device=dev)
+            batch = {"x": xb, "conditioning": cb.contiguous(memory_format=torch.channels_last_3d), "conditioning_values": [pb]}
+
+            def train_step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss, _ = light.get_loss(batch)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(light.parameters(), 0.5)
+                opt.step()
+
+            ms_t = timed(train_step, 3, 5)
+            out["training"] = {"ms_per_step": ms_t, "value": args.train_batch / (ms_t * 1e-3), "unit": "samples/s",
+                               "batch": args.train_batch}
+            out["vs_torch_gpu_training"] = ms_t / ours_train_ms
+            del light, net, opt
+    except Exception as exc:                         # e.g. cuDNN has no bf16 channels_last_3d engine for a layer
+        out["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -228,6 +336,8 @@ def run_b200(args, rank, world, local_rank):
     h2d = (cond_h.numel() * 4 + params_h.numel() * 4) / n_e2e
     d2h = out_h.numel() * 4 / n_e2e
 
+    # ---- BASELINE.json configs[4] scaled down: ensemble sampling -> calc_SS statistics gathered on rank 0 ----
+    pipeline = pipeline_leg(args, model, dev, rank, world, x, cond, params, rids)
     if rank != 0:
         if not args.no_train:
             train_leg(args, model, net, dev, rank, world, 1.0)
@@ -293,12 +403,24 @@ def run_b200(args, rank, world, local_rank):
     # ---- P(k) / r(k) of generated fields (SURVEY.md section 8d metric iii) ----
     pk = pk_leg(grid, dev, peaks)
 
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
-    cpu = None
+    # ---- other BASELINE.json configurations (configs[2], configs[3]): one training step each, 1 GPU ----
+    other = None
+    if world == 1 and not args.no_train and not args.no_other_configs:
+        other = other_configs_leg(dev)
+
+    # ---- stock PyTorch (cuDNN / ATen) on the same GPU: the oracle's modules under bf16 autocast ----
+    torch_gpu = None
+    if world == 1 and not args.no_torch_gpu_baseline:
+        torch_gpu = torch_gpu_leg(args, dev, ms_max / args.steps, None if train is None else train["ms_per_step"])
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample; parity of this very network ----
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, sec, label, k = cpu_oracle_rate(grid, chs, 30.0, 2, 1, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": label, "s_per_step": sec}
+        model.eval()
+        parity = parity_leg(net, vdm, dev, grid, chs)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -315,10 +437,171 @@ def run_b200(args, rank, world, local_rank):
             "conv_tflops": achieved}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if parity is not None:
+        line["parity"] = parity
     if train is not None:
         line["train"] = train
+        for k in ("replicas_identical", "grad_vs_1gpu_rel"):       # N > 1: correctness of the data-parallel step on hardware
+            if k in train:
+                line[k] = train[k]
     line["pk"] = pk
+    if pipeline is not None:
+        line["pipeline"] = pipeline
+    if other is not None:
+        line["other_configs"] = other
+    if torch_gpu is not None:
+        line["torch_gpu_baseline"] = torch_gpu
+        for k in ("vs_torch_gpu_sampling", "vs_torch_gpu_training"):
+            if k in torch_gpu:
+                line[k] = torch_gpu[k]
     emit(line)
+
+
+def pipeline_leg(args, model, dev, rank, world, x, cond, params, rids):
+    """BASELINE.json configs[4], scaled down to a bench-sized chain: every rank draws its `batch` realisations with
+    ``draw_samples`` (``--pipeline-steps`` reverse steps instead of 1000), computes calc_SS.py's P(k) of each sample and
+    r(k) against its truth field on the GPU, and rank 0 gathers the (kmax,) vectors of all world x batch realisations.
+    Wall time over the whole pipeline, max over ranks."""
+    import torch.distributed as dist
+
+    from vdm4cdm_b200 import utils
+    from vdm4cdm_b200.dataset import ALPHAS_3D, NORMALIZATIONS_3D, unnorm_func
+    n = args.pipeline_steps
+    if n <= 0:
+        return None
+    mu, sd = NORMALIZATIONS_3D["Mcdm"]
+    un = lambda f: unnorm_func(f, ALPHAS_3D["Mcdm"], mu, sd)
+    c, pv, truth = cond.to(dev), params.to(dev), x.to(dev)
+
+    def run():
+        xs = model.draw_samples(batch_size=args.batch, n_sampling_steps=n, s_conditioning=c, v_conditionings=[pv], seed=43,
+                                realisation_ids=rids)
+        s_un, t_un = un(xs), un(truth)
+        s_un = (s_un / s_un.sum((2, 3, 4), keepdim=True)).contiguous()          # calc_SS.py:67-70
+        t_un = (t_un / t_un.sum((2, 3, 4), keepdim=True)).contiguous()
+        _, pk_s, _ = utils.pk(s_un)
+        _, cc = utils.get_ccs(s_un, t_un)
+        stats = torch.stack([pk_s.float(), cc.float()], dim=1)                     # (batch, 2, kmax)
+        if world > 1:
+            out = [torch.empty_like(stats) for _ in range(world)] if rank == 0 else None
+            dist.gather(stats, out, dst=0)
+            stats = torch.cat(out) if rank == 0 else stats
+        return stats
+
+    run()                                               # builds the session / graph for this chain length
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    stats = run()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    return {"what": f"{world * args.batch} realisations x {n} reverse steps at {args.grid}^3 -> P(k) and r(k) vs truth per "
+                    "realisation (calc_SS.py) -> gathered on rank 0",
+            "realisations": world * args.batch, "steps": n, "wall_s": t.item(), "gathered_shape": list(stats.shape),
+            "finite": bool(torch.isfinite(stats).all()), "voxel_steps_per_s": world * args.batch * args.grid ** 3 * n / t.item()}
+
+
+def other_configs_leg(dev):
+    """One graph-replayed training step of BASELINE.json configs[2] (SFM 3D c_c at 160^3, chs [32,64,128,256], batch 4:
+    trainSFM3D160_...:60,68) and configs[3] (VDM 3D c_c at 224^3, chs [16,32,64,128], batch 2: trainVDM3D224_...:60,72):
+    samples/s, conv TFLOP/s against the sustained bf16 peak, peak memory.  Synthetic Gaussian fields."""
+    from vdm4cdm_b200.networks import CUNet
+    from vdm4cdm_b200.sfm_model import LightSFM
+    from vdm4cdm_b200.trainer import Trainer
+    from vdm4cdm_b200.vdm_model import LightVDM
+    peaks, _ = measured_peaks()
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    out = {}
+    for key, kind, n, chs, batch in (("sfm160", "SFM", 160, [32, 64, 128, 256], 4), ("vdm224", "VDM", 224, [16, 32, 64, 128], 2)):
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        torch.manual_seed(42)
+        net = CUNet(**model_kwargs(n, chs))
+        model = (LightVDM(score_model=net, gamma_max=13.3) if kind == "VDM" else LightSFM(velocity_model=net)).to(dev)
+        trainer = Trainer(model, gradient_clip_val=0.5)
+        x, cond, params = synthetic_batch(batch, n, 42, device=dev)
+        b = {"x": x, "conditioning": cond, "conditioning_values": [params]} if kind == "VDM" else \
+            {"x0": cond, "x1": x, "conditioning_values": [params]}
+        losses = [trainer.training_step(b).item() for _ in range(5)]            # 3 eager + capture + replay
+        steps = 8
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            loss = trainer.training_step(b)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        flops = 3.0 * net.conv_flops_per_sample() * batch        # fwd + dgrad + wgrad (conv_in's dgrad included: z needs it)
+        out[key] = {"config": f"{kind} 3D c_c {n}^3 chs={chs} batch {batch}", "ms_per_step": ms, "samples_per_s": batch / (ms * 1e-3),
+                    "steps": steps, "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                    "step_tflops_conv_algorithmic": flops / (ms * 1e-3) / 1e12,
+                    "step_frac_of_peak": flops / (ms * 1e-3) / 1e12 / peak,
+                    "first_loss": losses[0], "last_loss": loss.item(), "cuda_graph": trainer._graph is not None}
+        del trainer, model, net, b, x, cond, params
+    torch.cuda.empty_cache()
+    return out
+
+
+def ddp_check(model, trainer, batch, dev, rank, world):
+    """Correctness of the data-parallel training step ON THE HARDWARE (N > 1), after the timed steps:
+      * ``replicas_identical``: an exact integer checksum of every rank's flat parameter bucket (fp32 bit patterns summed
+        in int64) and of its AdamW moments is all-gathered and must be equal on all ranks;
+      * ``grad_vs_1gpu_rel``: every rank back-propagates ITS micro-batch (fixed times / noise, dropout off) and the flat
+        gradient bucket is all-reduced and averaged exactly as the step does; rank 0 then recomputes the same global
+        batch alone, micro-batch by micro-batch, accumulating into the same bucket.  Relative L2 of the difference (only
+        the summation order of fp32 atomics / the NCCL reduction tree differs)."""
+    import torch.distributed as dist
+
+    def checksum(t):
+        return t.view(torch.int32).to(torch.int64).sum()
+
+    mine = torch.stack([checksum(trainer.buckets.flat_param), checksum(trainer.exp_avg), checksum(trainer.exp_avg_sq)])
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    identical = all(torch.equal(c, allc[0]) for c in allc)
+
+    flat = {"x": batch["x"], "conditioning": batch["conditioning"], "conditioning_values": batch["conditioning_values"][0]}
+    gathered = {}
+    for k, v in flat.items():
+        parts = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(parts, v.contiguous())
+        gathered[k] = parts
+    g = torch.Generator(device=dev)
+    bsz = batch["x"].shape[0]
+
+    def micro_grad(r):
+        g.manual_seed(1000 + r)
+        xb = gathered["x"][r]
+        noise = torch.randn(xb.shape, generator=g, device=dev)
+        noise0 = torch.randn(xb.shape, generator=g, device=dev)
+        times = torch.remainder(torch.rand((), generator=g, device=dev) + torch.arange(bsz, device=dev) / bsz, 1.0)
+        b = {"x": xb, "conditioning": gathered["conditioning"][r], "conditioning_values": [gathered["conditioning_values"][r]]}
+        loss, _ = model.get_loss(b, noise=noise, noise0=noise0, times=times)
+        loss.backward()                                   # accumulates into the flat gradient bucket
+
+    model.eval()                                          # dropout off; gradients still flow (grad mode is on)
+    trainer.buckets.zero_grad()
+    micro_grad(rank)
+    dist.all_reduce(trainer.buckets.flat_grad, op=dist.ReduceOp.SUM)
+    g_multi = trainer.buckets.flat_grad.clone() / world
+    rel = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rank == 0:
+        trainer.buckets.zero_grad()
+        for r in range(world):
+            micro_grad(r)
+        g_single = trainer.buckets.flat_grad / world
+        rel[0] = ((g_multi - g_single).double().norm() / g_single.double().norm()).item()
+    dist.broadcast(rel, src=0)
+    trainer.buckets.zero_grad()
+    model.train()
+    return {"replicas_identical": bool(identical), "grad_vs_1gpu_rel": rel.item()}
 
 
 def pk_leg(grid, dev, peaks):
@@ -441,6 +724,7 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
     launches = ops.launch_count() - n0
     torch.cuda.synchronize(dev)
     ops.set_conv_profiler(None)
+    check = ddp_check(model, trainer, resident, dev, rank, world) if world > 1 else {}
     if rank != 0:
         return None
     kinds = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
@@ -466,7 +750,7 @@ def train_leg(args, model, net, dev, rank, world, peak_tflops):
             "parameters": trainer.buckets.numel,
             "conv": {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else None} for k, v in kinds.items()},
             "conv_tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "conv_frac_of_peak": conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tflops,
-            "conv_share_of_step": conv_ms / ms}
+            "conv_share_of_step": conv_ms / ms, **check}
 
 
 _REAL_STDOUT = None
@@ -502,7 +786,10 @@ def main():
     ap.add_argument("--e2e-chain", type=int, default=250, help="reverse steps of the end-to-end draw_samples call")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--train-batch", type=int, default=2, help="training samples per GPU (reference: batch_size = 2)")
-    ap.add_argument("--train-steps", type=int, default=5)
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true", help="skip the stock-PyTorch-on-GPU arm")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the SFM 160^3 / VDM 224^3 training steps")
+    ap.add_argument("--pipeline-steps", type=int, default=20, help="reverse steps of the scaled-down ensemble pipeline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -103,10 +103,15 @@ typedef struct VdmConvEpilogue {
 VDM_API int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w, void* y,
                const VdmConvEpilogue* epi, void* stream);
 
-/* Tuning / bring-up knobs of vdm_conv3d (value 0 = automatic): key 0 retired, 1 force MT, 2 force KC, 3 force n_split,
- * 4 no resident weights, 5 ablation flags (timing experiments; results are wrong by construction, see
- * tools/bench_epilogue.py), 6 no kd-folded schedule (1: resident variants off, 2: all off). */
-VDM_API int vdm_debug_set(int key, int value);
+#ifdef VDM_BRINGUP
+/* NOT part of the release library.  `make -C vdm4cdm_b200/csrc bringup` builds libvdm4cdm_b200_bringup.so with
+ * -DVDM_BRINGUP, the only build in which this symbol and the ablation branches of the conv kernel exist
+ * (tools/bench_epilogue.py, tools/bench_conv.py load it with VDM4CDM_BRINGUP=1).  Knobs (value 0 = automatic): 1 force
+ * MT, 2 force KC, 3 force n_split, 4 no resident weights, 5 ablation flags (timing experiments; results are wrong by
+ * construction), 6 no kd-folded schedule (1: resident variants off, 2: all off). */
+#define VDM_BRINGUP_API __attribute__((visibility("default")))
+VDM_BRINGUP_API int vdm_debug_set(int key, int value);
+#endif
 
 /* ---- conv3d weight gradient (tcgen05, both operands MN-major straight from the planar tensors) ----
  * Stands in for the cuDNN conv3d backward-filter autograd launches for every torch.nn.Conv3d of the

@@ -18,8 +18,7 @@ import torch.distributed as dist  # noqa: E402
 
 PARAM_LO = [0.1, 0.6, 0.25, 0.25, 0.5, 0.5]
 PARAM_HI = [0.5, 1.0, 4.0, 4.0, 2.0, 2.0]
-# Mcdm normalisation (normalizations_3d.json in the reference): x_norm = (log10(x + 1) - mean) / std
-MCDM_LOG_MEAN, MCDM_LOG_STD = 10.019, 0.552
+from vdm4cdm_b200.dataset import ALPHAS_3D, NORMALIZATIONS_3D, unnorm_func  # noqa: E402
 
 
 def init_distributed():
@@ -49,5 +48,8 @@ def synthetic_batch(batch, grid, seed, n_params=6, device="cpu"):
 
 
 def unnorm_mcdm(x):
-    """Normalised log field -> mass field (the consumer-side ``unnorm_func`` of calc_SS.py:146)."""
-    return 10.0 ** (x * MCDM_LOG_STD + MCDM_LOG_MEAN) - 1.0
+    """Normalised log field -> mass field: the consumer-side ``dm.unnorm_func(samples, i_channel=1)`` of calc_SS.py:146
+    with the SAME constants the data were normalised with (``vdm4cdm_b200.dataset.NORMALIZATIONS_3D["Mcdm"]``, the
+    reference's normalizations_3d.json) -- the one source of truth, not a rounded copy."""
+    mean, std = NORMALIZATIONS_3D["Mcdm"]
+    return unnorm_func(x, ALPHAS_3D["Mcdm"], mean, std)

@@ -5,7 +5,7 @@
     python scripts/calc_SS.py SAVE_PATH [--truth truth.npy]
 
 reads every ``gen_*.npy`` (rep, 1, N, N, N) written by scripts/generate_3D.py, un-normalises the fields
-(``10**(x*std+mean)-1``), and writes ``SAVE_PATH/summary.npz`` with, per file: the 3-D P(k) of every
+(``10**(x*std+mean)-1``), and writes ``SAVE_PATH/<file>_summary.npz`` next to every ensemble file with: the 3-D P(k) of every
 realisation, the projected 2-D P(k) of the half / quarter slabs, per-realisation mean/std, posterior mean/std of the
 3-D field over the ensemble (``post_means`` / ``post_stds``, calc_SS.py:150-152) and of the half slab and,
 when a truth field is given, the cross-correlation coefficient r(k) of every realisation with it.

@@ -46,6 +46,9 @@ def main(mode="CV"):
     ap.add_argument("--rep", type=int, default=None, help="override the number of realisations per field")
     ap.add_argument("--fields", type=int, default=None, help="override the number of test fields")
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--allow-random-init", action="store_true",
+                    help="smoke runs only: sample from random weights when the configured ckpt_path does not exist "
+                         "(default: raise, like the reference's torch.load)")
     ap.add_argument("--configs", default=os.path.join(ROOT, "configs.yaml"))
     args = ap.parse_args()
     if "SFM" in args.model_name:
@@ -57,7 +60,7 @@ def main(mode="CV"):
     rank, world, device = init_distributed()
     if rank == 0:
         os.makedirs(args.save_path, exist_ok=True)
-    model = utils.get_model(config, device=device).eval()
+    model = utils.get_model(config, device=device, allow_random_init=args.allow_random_init).eval()
     grid = int(config.get("cropsize", 128))
     n_params = int(config.get("conditioning_values", 6))
     if mode == "CV":
@@ -94,7 +97,16 @@ def main(mode="CV"):
         if rank == 0 and mode != "CV":
             print(name, "params", [v.tolist() for v in field["conditioning_values"]])
         mine = list(shard_indices(rep, rank, world))
-        gens = torch.zeros((rep, 1, grid, grid, grid), dtype=torch.float32, device=device)
+        # One .npy per field, shape (rep, 1, N, N, N) as the reference writes it.  Every rank writes the rows of its own
+        # realisations straight into the (memory-mapped) file: no dense ensemble buffer per rank and no collective over
+        # it (r01 all-reduced a zero-filled (rep, 1, N^3) tensor from every rank: 1 GB at 128^3 x 128, 8.6 GB at 256^3).
+        path = os.path.join(args.save_path, f"{name}.npy")
+        if rank == 0:
+            out = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=(rep, 1, grid, grid, grid))
+        if world > 1:
+            dist.barrier()
+        if rank != 0:
+            out = np.lib.format.open_memmap(path, mode="r+")
         for i0 in range(0, len(mine), args.batch):
             ids = mine[i0:i0 + args.batch]
             b = len(ids)
@@ -103,11 +115,12 @@ def main(mode="CV"):
             gen = model.draw_samples(batch_size=b, n_sampling_steps=args.n_sampling_steps, s_conditioning=cond,
                                      v_conditionings=vals, verbose=(rank == 0), seed=args.seed + count,
                                      realisation_ids=ids)
-            gens[ids] = gen
+            out[ids] = gen.cpu().numpy()
+        out.flush()
+        del out
         if world > 1:
-            dist.all_reduce(gens)                       # every realisation was written by exactly one rank
+            dist.barrier()
         if rank == 0:
-            np.save(os.path.join(args.save_path, f"{name}.npy"), gens.cpu().numpy())
             print(f"{name}: saved {rep} realisations")
     if world > 1:
         dist.barrier()

@@ -21,8 +21,8 @@ def test_version_and_error_string():
     lib = _C.lib()
     assert lib.vdm_version() >= 100
     assert isinstance(lib.vdm_last_error_string(), bytes)
-    assert lib.vdm_debug_set(99, 0) != 0
-    assert b"unknown key" in lib.vdm_last_error_string()
+    # the bring-up knobs ("results are wrong by construction") are not reachable from the release library
+    assert not hasattr(lib, "vdm_debug_set")
 
 
 def test_bad_arguments_are_rejected_without_touching_a_device():

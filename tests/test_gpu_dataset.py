@@ -108,7 +108,9 @@ def test_datamodule_batches_from_files_match_oracle(tmp_path):
     loader = dmf.train_dataloader()
     assert len(dmf.train_ids) == int(n_sims * 8 * 0.95)
     batch = next(iter(loader))
-    order = [dmr.train_ids[i] for i in torch.randperm(len(dmr.train_ids), generator=dmr.data.gen).tolist()][:4]
+    # epoch order: a function of (seed, epoch) shared by all ranks, separate from the augmentation generator
+    order = [dmr.train_ids[i] for i in dataset.epoch_permutation(len(dmr.train_ids), 9, 0)][:4]
+    assert order == loader.epoch_order(0)[:4]
     for j, idx in enumerate(order):
         bidx, anchor, flip, perm = dmr.data.draw(idx)
         want = augment_ref.prepare(raws["Mcdm"][bidx][None], anchor, (8, 8, 8), flip, perm, 1.0, m, s)

@@ -1,8 +1,11 @@
-"""Full-size (128^3, the BASELINE.json grid) checks through size-independent properties: the CPU oracle needs
-seconds to minutes per 128^3 call, so at this size the CUDA path is tested against identities that hold for the
-exact operator (SURVEY.md section 4 / prompt section 3): linearity and translation equivariance of the convolution
-on integer-valued inputs (bit-exact), Parseval and the delta-function / single-mode spectra for P(k), and
-reproducibility + batch independence of the sampler."""
+"""Full-size (128^3, the BASELINE.json grid) checks.
+
+  * DIRECT parity on the benchmarked configuration: the 128^3 ``chs=[32,64,128,256]`` conditional denoiser, its VDM
+    loss and every parameter gradient against the CPU oracle on identical weights, inputs, times and noise (a 128^3
+    oracle forward takes ~1.5 s on the box's host cores, forward + backward a few seconds more);
+  * size-independent properties that hold for the exact operator (SURVEY.md section 4 / prompt section 3): linearity and
+    translation equivariance of the convolution on integer-valued inputs (bit-exact), Parseval and the delta-function /
+    single-mode spectra for P(k), and reproducibility + batch independence of the sampler."""
 import math
 
 import pytest
@@ -108,3 +111,94 @@ def test_sampler_reproducible_and_batch_independent_128():
     rel = ((a[1:] - c).norm() / c.norm()).item()
     assert rel < 1e-2, rel            # same realisation in another batch: equal up to bf16 rounding noise
     assert ((a[:1] - c).norm() / c.norm()).item() > 0.3
+
+
+def _bench_models(train):
+    """The benchmarked network (bench.py: model_kwargs(128, [32, 64, 128, 256])) and the oracle with the same weights."""
+    from oracle.unet_ref import CUNet as RefNet
+    from vdm4cdm_b200.networks import CUNet
+    torch.manual_seed(42)
+    kw = dict(shape=(1, N, N, N), chs=[32, 64, 128, 256], s_conditioning_channels=1, v_conditioning_dims=[6],
+              t_conditioning=True, norm_groups=8, mid_attn=False, dropout_prob=0.0 if train else 0.1,
+              conv_padding_mode="zeros", n_attention_heads=4)
+    ref = RefNet(**kw)
+    with torch.no_grad():          # non-trivial biases / norm affines so that every epilogue term matters
+        for _, p in ref.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    net = CUNet(**kw)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    return (ref.train(), net.cuda().train()) if train else (ref.eval(), net.cuda().eval())
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def test_denoiser_matches_oracle_on_the_benchmarked_configuration_128():
+    """CUNet.forward at 128^3, chs=[32,64,128,256], B=1 vs oracle/unet_ref.py: relative L2 <= 1e-2 (bf16 activations;
+    BASELINE.json north_star tolerance), and one reverse step of the sampler with injected noise on top of it."""
+    from oracle.vdm_ref import VDM as RefVDM
+    from vdm4cdm_b200.vdm_model import VDM
+    ref, net = _bench_models(train=False)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((1, 1, N, N, N), generator=g)
+    cond = 0.7 * x + 0.3 * torch.randn((1, 1, N, N, N), generator=g)
+    t, v = torch.tensor([0.37]), [torch.rand(1, 6, generator=g)]
+    noise = torch.randn((1, 1, N, N, N), generator=g)
+    with torch.no_grad():
+        want = ref(x, t=t, s_conditioning=cond, v_conditionings=v)
+        got = net(x.cuda(), t=t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()]).cpu()
+    err = _rel(got, want)
+    print(f"128^3 denoiser: relative L2 {err:.3e}")
+    assert err < 1e-2, err
+    ref_vdm, vdm = RefVDM(ref).eval(), VDM(net).cuda().eval()
+    with torch.no_grad():
+        zs_r = ref_vdm.sample_zs_given_zt(zt=x, t=torch.tensor(0.6), s=torch.tensor(0.596), noise=noise, s_conditioning=cond,
+                                          v_conditionings=v)
+        zs = vdm.sample_zs_given_zt(zt=x.cuda(), t=torch.tensor(0.6), s=torch.tensor(0.596), noise=noise.cuda(),
+                                    s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()]).cpu()
+    err_s = _rel(zs, zs_r)
+    print(f"128^3 reverse step: relative L2 {err_s:.3e}")
+    assert err_s < 1e-2, err_s
+
+
+def test_vdm_loss_and_gradients_match_oracle_on_the_benchmarked_configuration_128():
+    """LightVDM.get_loss + backward at 128^3, chs=[32,64,128,256], B=1 vs autograd through the oracle: loss within 1e-2,
+    parameter gradients relative L2 <= 2e-2 over all parameters (the bar of tests/test_gpu_training.py at small grids)."""
+    from oracle.vdm_ref import LightVDM as RefLight
+    from vdm4cdm_b200.vdm_model import LightVDM
+    ref_net, net = _bench_models(train=True)
+    ref, mod = RefLight(ref_net).train(), LightVDM(net).cuda().train()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((1, 1, N, N, N), generator=g)
+    batch = {"x": x, "conditioning": 0.7 * x + 0.3 * torch.randn((1, 1, N, N, N), generator=g),
+             "conditioning_values": [torch.rand(1, 6, generator=g)]}
+    noise, noise0 = torch.randn((1, 1, N, N, N), generator=g), torch.randn((1, 1, N, N, N), generator=g)
+    times = torch.tensor([0.45])
+    loss_r, _ = ref.get_loss(batch, noise=noise, noise0=noise0, times=times)
+    loss_r.backward()
+    cb = {"x": x.cuda(), "conditioning": batch["conditioning"].cuda(), "conditioning_values": [batch["conditioning_values"][0].cuda()]}
+    loss, _ = mod.get_loss(cb, noise=noise.cuda(), noise0=noise0.cuda(), times=times.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"128^3 loss {loss.item():.6f} vs oracle {loss_r.item():.6f}")
+    assert abs(loss.item() - loss_r.item()) < 1e-2 * abs(loss_r.item())
+    num = den = 0.0
+    worst = (0.0, "")
+    refp = dict(ref.named_parameters())
+    for n_, p_ in mod.named_parameters():
+        gr = refp[n_].grad
+        assert (p_.grad is None) == (gr is None), n_
+        if gr is None:
+            continue
+        gc = p_.grad.detach().cpu()
+        assert torch.isfinite(gc).all(), n_
+        e = _rel(gc, gr)
+        worst = max(worst, (e, n_))
+        num += (gc - gr).double().pow(2).sum().item()
+        den += gr.double().pow(2).sum().item()
+    tot = (num / den) ** 0.5
+    print(f"128^3 gradients: overall relative L2 {tot:.3e}; worst tensor {worst[1]} {worst[0]:.3e}")
+    assert tot < 2e-2, tot
+    assert worst[0] < 8e-2, worst

@@ -58,14 +58,16 @@ def test_generate_scripts_on_a_camels_like_directory(tmp_path):
     _run("calc_SS.py", ss, "--chunk", 2)
     assert os.path.exists(ss / "gen_0_summary.npz")
     summ = np.load(ss / "fid_3_summary.npz")
-    fid = 10.0 ** (np.load(ss / "fid_3.npy").astype(np.float64) * 0.552 + 10.019) - 1.0
+    from vdm4cdm_b200.dataset import NORMALIZATIONS_3D
+    mu, sd = NORMALIZATIONS_3D["Mcdm"]            # calc_SS.py:146: dm.unnorm_func(samples, i_channel=1)
+    fid = 10.0 ** (np.load(ss / "fid_3.npy").astype(np.float64) * sd + mu) - 1.0
     assert summ["pk3d"].shape == (3, 8) and summ["pk2d_half"].shape == (3, 8) and summ["logpdf3d"].shape == (3, 99)
     assert np.allclose(summ["post_means"], fid.mean(0, keepdims=True), rtol=1e-3)
     assert np.allclose(summ["post_stds"], fid.std(0, ddof=1, keepdims=True), rtol=1e-3, atol=1e-3 * fid.std())
     assert np.allclose(summ["mean3d"], fid.reshape(3, -1).mean(1), rtol=1e-3)
     from oracle import power_ref
     field = np.load(ss / "fid_3.npy")[:1].astype(np.float32)
-    un = (10.0 ** (field * np.float32(0.552) + np.float32(10.019)) - 1.0).astype(np.float32)
+    un = (10.0 ** (field * np.float32(sd) + np.float32(mu)) - 1.0).astype(np.float32)
     k_ref, p_ref, _ = power_ref.power(un / un.sum())
     assert np.allclose(summ["pk3d"][0], p_ref, rtol=2e-3), (summ["pk3d"][0], p_ref)
     # same ensemble whatever the batch size
@@ -76,10 +78,61 @@ def test_generate_scripts_on_a_camels_like_directory(tmp_path):
     assert err < 1e-2, err                                        # bf16 tolerance (see test_philox_sampling_is_batch_independent)
 
 
+def _losses(log):
+    return {int(line.split(":")[0].split()[1]): float(line.split("loss")[1].split()[0])
+            for line in log.splitlines() if line.startswith("step") and " loss " in line}
+
+
 def test_train_script_on_a_camels_like_directory(tmp_path):
+    """The real-data path (AstroDataModule over files) through the launcher that carries the reference's file name:
+    checkpoints are written (trainVDM3D128_...:47 ModelCheckpoint), validation numbers land in the JSONL log
+    (:42 val_check_interval, :97-103 P(k) / r(k) of sample vs truth), and ``--resume`` continues the run
+    (trainVDM3D_c_c_...:133-135)."""
+    import json
+    import torch
     _camels_dir(tmp_path, {"LH": 6})
-    log = _run("train3D_c_c.py", "Mstar", "Mcdm", 16, "--model", "VDM", "--data-root", tmp_path, "--dataset-name", "CMD_16",
-               "--chs", 16, 32,
-               "--max-steps", 6, "--log-every", 2, "--ckpt-dir", tmp_path / "ckpt")
-    losses = [float(line.split("loss")[1].split()[0]) for line in log.splitlines() if line.startswith("step")]
-    assert len(losses) == 3 and all(np.isfinite(losses))
+    common = ["Mstar", "Mcdm", 16, "--data-root", tmp_path, "--dataset-name", "CMD_16", "--chs", 16, 32, "--log-every", 1,
+              "--val-check-interval", 4, "--val-sampling-steps", 5]
+    ck = tmp_path / "ckpt"
+    log = _run("trainVDM3D128_c_c_from_field_name_thick_lowbatch.py", *common, "--max-steps", 8, "--ckpt-every", 4,
+               "--ckpt-dir", ck)
+    losses = _losses(log)
+    assert sorted(losses) == list(range(1, 9)) and all(np.isfinite(list(losses.values())))
+    names = sorted(os.listdir(ck))
+    assert "VDM_Mstar_Mcdm_c_c_16_step=4.ckpt" in names and "VDM_Mstar_Mcdm_c_c_16_step=8.ckpt" in names, names
+    state = torch.load(ck / "VDM_Mstar_Mcdm_c_c_16_step=4.ckpt", map_location="cpu", weights_only=False)
+    assert state["global_step"] == 4 and state["optimizer"]["step"] == 4 and "model.score_model.conv_in.weight" in state["state_dict"]
+    assert state["optimizer"]["exp_avg"].abs().sum() > 0
+    # the checkpoint is what utils.get_model loads (src/utils.py:467-469)
+    from vdm4cdm_b200 import utils
+    model = utils.get_model({"type": "VDM", "cropsize": 16, "chs": [16, 32], "ckpt_path": str(ck / "VDM_Mstar_Mcdm_c_c_16_step=8.ckpt")})
+    final = torch.load(ck / "VDM_Mstar_Mcdm_c_c_16_step=8.ckpt", map_location="cpu", weights_only=False)["state_dict"]
+    assert torch.equal(model.state_dict()["model.score_model.conv_in.weight"], final["model.score_model.conv_in.weight"])
+    assert not torch.equal(final["model.score_model.conv_in.weight"], state["state_dict"]["model.score_model.conv_in.weight"])
+    # validation records: loss over the validation loader + P(k) / r(k) of a 5-step sample vs the truth
+    recs = [json.loads(l) for l in open(ck / "metrics.jsonl")]
+    vals = [r for r in recs if "val_loss" in r]
+    assert [r["step"] for r in vals] == [4, 8] and all(np.isfinite(r["val_loss"]) and r["val_batches"] >= 1 for r in vals)
+    assert len(vals[0]["pk_truth"]) == 8 and len(vals[0]["cc"]) == 8 and all(abs(c) <= 1.0 + 1e-4 for c in vals[0]["cc"])
+    assert [r["step"] for r in recs if "train_loss" in r] == list(range(1, 9))
+    # resume from step 4: steps 5..8 reproduce the uninterrupted run (same data order, RNG, optimizer state; the
+    # tolerance covers the unordered fp32 atomics of the weight-gradient and statistics reductions)
+    ck2 = tmp_path / "ckpt2"
+    log2 = _run("trainVDM3D128_c_c_from_field_name_thick_lowbatch.py", *common, "--max-steps", 8, "--ckpt-every", 100,
+                "--ckpt-dir", ck2, "--resume", ck / "VDM_Mstar_Mcdm_c_c_16_step=4.ckpt", "--val-check-interval", 1000)
+    again = _losses(log2)
+    assert sorted(again) == [5, 6, 7, 8], log2
+    assert os.path.exists(ck2 / "VDM_Mstar_Mcdm_c_c_16_step=8.ckpt")        # final checkpoint at loop exit
+    for k in (5, 6):
+        assert abs(again[k] - losses[k]) < 2e-2 * abs(losses[k]), (k, again[k], losses[k])
+
+
+def test_sfm_launcher_synthetic_boxes_writes_checkpoints(tmp_path):
+    """--synthetic-boxes (the data-stream path that skipped the checkpoint block in round 1) with the SFM launcher."""
+    ck = tmp_path / "ck"
+    log = _run("trainSFM3D128_c_c_from_field_name_thick_lowbatch.py", "Mstar", "Mcdm", 16, "--synthetic", "--synthetic-boxes",
+               "--chs", 16, 32, "--batch-size", 2, "--max-steps", 5, "--ckpt-every", 2, "--ckpt-dir", ck, "--log-every", 1,
+               "--val-check-interval", 3)
+    assert len(_losses(log)) == 5
+    assert sorted(os.listdir(ck)) == ["SFM_Mstar_Mcdm_c_c_16_step=2.ckpt", "SFM_Mstar_Mcdm_c_c_16_step=4.ckpt",
+                                      "SFM_Mstar_Mcdm_c_c_16_step=5.ckpt", "metrics.jsonl"]

@@ -56,7 +56,10 @@ def _compare_grads(ref_mod, mod, per_tensor=6e-2, overall=2e-2):
 
 @pytest.mark.parametrize("shape,chs,batch", [((1, 16, 16, 16), (16, 32), 2),
                                              ((1, 32, 32, 32), (16, 32, 64, 128), 2),
-                                             ((1, 16, 32, 48), (32, 64, 128), 1)])
+                                             ((1, 16, 32, 48), (32, 64, 128), 1),
+                                             # coarse sides 20 / 28 (deepest levels of the 160^3 / 224^3 configs)
+                                             ((1, 40, 40, 40), (16, 32), 1),
+                                             ((1, 56, 56, 56), (16, 32), 1)])
 def test_unet_backward_matches_oracle_autograd(shape, chs, batch):
     ref, net = _models(shape, chs)
     g = torch.Generator().manual_seed(1)

@@ -36,7 +36,11 @@ def _rel_l2(a, b):
 
 @pytest.mark.parametrize("shape,chs,batch", [((1, 32, 32, 32), (16, 32, 64, 128), 2),
                                              ((1, 16, 32, 48), (32, 64), 1),
-                                             ((1, 24, 24, 24), (16, 32, 64), 3)])
+                                             ((1, 24, 24, 24), (16, 32, 64), 3),
+                                             # coarse sides 20 and 28: the deepest levels of the 160^3 / 224^3 configs
+                                             # (160 -> 80 -> 40 -> 20, 224 -> 112 -> 56 -> 28): ragged 16 x 8 tiles
+                                             ((1, 80, 80, 80), (16, 32, 64), 1),
+                                             ((1, 56, 56, 56), (32, 64), 1)])
 def test_unet_forward_matches_oracle(shape, chs, batch):
     ref, net = _models(shape, chs)
     g = torch.Generator().manual_seed(1)

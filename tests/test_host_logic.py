@@ -41,13 +41,18 @@ def test_registry_and_model_factory():
                  "VDM_Mstar_Mcdm_c_c_224", "VDM_Mstar_Mcdm_c_c_256", "SFM_Mstar_Mcdm_c_c_128"]
     for n in ref_names:
         assert n in configs, n
-    m = utils.get_model(configs["VDM_Mstar_Mcdm_c_c_224"])
+    # the registry's checkpoint files are not shipped: a configured-but-missing ckpt_path raises like the reference's
+    # torch.load (src/utils.py:468-469) unless the caller explicitly asks for random weights
+    with pytest.raises(FileNotFoundError):
+        utils.get_model(configs["VDM_Mstar_Mcdm_c_c_224"])
+    with pytest.warns(UserWarning, match="RANDOM"):
+        m = utils.get_model(configs["VDM_Mstar_Mcdm_c_c_224"], allow_random_init=True)
     assert isinstance(m, LightVDM) and m.model.score_model.shape == (1, 224, 224, 224)
     assert m.model.score_model.chs == [16, 32, 64, 128] and m.learning_rate == 3.0e-4 and m.model.gamma_max == 13.3
     assert utils.get_model(configs["SFM_Mstar_Mcdm_c_c_128"]) is None          # src/utils.py:472-473 does `pass`
     with pytest.raises(ValueError):
         utils.get_model({"type": "GAN"})
-    m256 = utils.get_model(configs["VDM_Mstar_Mcdm_c_c_256"])                   # cropsize 256 -> circular padding (src/utils.py:460)
+    m256 = utils.get_model({k: v for k, v in configs["VDM_Mstar_Mcdm_c_c_256"].items() if k != "ckpt_path"})                 # cropsize 256 -> circular padding (src/utils.py:460)
     assert m256.model.score_model.circular and m256.model.score_model.conv_in.padding_mode == "circular"
     assert not m.model.score_model.circular
 
@@ -153,6 +158,40 @@ def test_flat_bucket_allreduce_over_gloo(tmp_path):
     assert sorted(r[0]["mine"] + r[1]["mine"]) == list(range(10))
 
 
+def test_loader_state_resumes_the_same_sample_stream():
+    """_Loader.state() / load_state(): a run resumed at (epoch, cursor) draws the same samples with the same augmentation
+    draws as the uninterrupted run (checkpoint resume of scripts/train3D_c_c.py), on every rank."""
+    from vdm4cdm_b200 import dataset
+
+    class FakeData:
+        def __init__(self, seed):
+            self.seed, self.gen = seed, torch.Generator().manual_seed(seed)
+
+        def draw(self, idx):
+            return (idx, torch.randint(1000, (3,), generator=self.gen).tolist())
+
+        def get_batch(self, chunk):
+            return [self.draw(i) for i in chunk]
+
+    def run(n_batches, state=None, rank=1):
+        ld = dataset._Loader(FakeData(11 + 7919 * rank), list(range(23)), 2, shuffle=True, rank=rank, world=2, seed=11)
+        if state is not None:
+            ld.load_state(state)
+        out = []
+        while len(out) < n_batches:
+            for b in ld:
+                out.append(b)
+                if len(out) == n_batches:
+                    return out, ld.state()
+        return out, ld.state()
+
+    full, _ = run(15)
+    for cut in (1, 5, 6, 7, 12):                       # 6 batches per epoch and rank: mid-epoch, at and across the boundary
+        head, st = run(cut)
+        tail, _ = run(15 - cut, state=st)
+        assert head + tail == full, cut
+
+
 def _write_camels_like(tmp_path, n_sims=20, size=16, set_name="CV", channels=("Mstar", "Mcdm"), res=16):
     import numpy as np
     rng = np.random.default_rng(0)
@@ -187,6 +226,20 @@ def test_datamodule_file_lookup_cv_exclusion_and_split(tmp_path):
     a = dataset._Loader(dm.data, dm.train_ids, 2, shuffle=False, rank=0, world=2)
     b = dataset._Loader(dm.data, dm.train_ids, 2, shuffle=False, rank=1, world=2)
     assert not set(a.ids[0::2]) & set(b.ids[1::2])
+    # ... and ALWAYS run the same number of full batches per epoch, whatever len(ids) % (world * batch) is (a rank
+    # that runs out of data early leaves the others hanging in the gradient all-reduce): 950 ids, 4 ranks, batch 2
+    for n_ids, world, bs in ((950, 4, 2), (129, 2, 2), (7, 8, 2), (16, 8, 2)):
+        loaders = [dataset._Loader(dm.data, list(range(n_ids)), bs, shuffle=True, rank=r, world=world, seed=5)
+                   for r in range(world)]
+        assert len({len(l) for l in loaders}) == 1
+        for epoch in (0, 1):
+            orders = [l.epoch_order(epoch) for l in loaders]
+            assert all(len(o) == len(loaders[0]) * bs for o in orders)
+            seen = [i for o in orders for i in o]
+            assert set(seen) == set(range(n_ids))                        # every sample is visited
+            assert len(seen) - n_ids < world * bs                        # at most one padding unit of repeats
+        assert loaders[0].epoch_order(0) != loaders[0].epoch_order(1)     # reshuffled per epoch, same on every rank
+        assert dataset.epoch_permutation(n_ids, 5, 1) == dataset.epoch_permutation(n_ids, 5, 1)
     # test stage: no exclusion for non-CV sets, deterministic ids, missing files are reported by name
     _write_camels_like(tmp_path, n_sims=5, set_name="1P")
     dmt = dataset.get_dataset(dataset_name="CMD_16", set_name="1P", channel_names=["Mstar", "Mcdm"], return_func=rf,
@@ -316,6 +369,12 @@ def test_train_script_presets_match_the_reference_scripts():
             assert mod.GAMMA_MAX == want["gamma_max"], name
         # Trainer(max_steps=1_000_000, ModelCheckpoint(every_n_train_steps=10_000)): the script's defaults
         assert want["max_steps"] == 1_000_000 and want["every_n_train_steps"] == 10_000, name
+        # the thin launcher that carries the reference's file name pins the script's own literals (a reference script
+        # takes chs / batch_size / dataset_name / val_check_interval from itself, not from the cropsize argument)
+        assert mod.script_preset(want["model"], want["cropsize_in_name"]) == \
+            (want["chs"], want["batch_size"], want["dataset_name"], want["val_check_interval"]), name
+        launcher = open(os.path.join(root, "scripts", name)).read()
+        assert f'model_kind="{want["model"]}", script_grid={want["cropsize_in_name"]!r}' in launcher, name
     src = open(os.path.join(root, "scripts", "train3D_c_c.py")).read()
     assert '"--max-steps", type=int, default=1_000_000' in src and '"--ckpt-every", type=int, default=10_000' in src
     assert mod.preset("VDM", 256) == mod.BASE_PRESET and mod.preset("SFM", 224) == mod.BASE_PRESET
@@ -354,7 +413,7 @@ def _run_our_generate(monkeypatch, tmp_path, script_mode, model_name, runtype, c
         return FakeDM()
 
     monkeypatch.setattr(gen, "init_distributed", lambda: (0, 1, torch.device("cpu")))
-    monkeypatch.setattr(utils, "get_model", lambda config, device=None: FakeModel())
+    monkeypatch.setattr(utils, "get_model", lambda config, device=None, allow_random_init=False: FakeModel())
     monkeypatch.setattr(utils, "get_datamodule", fake_get_datamodule)
     cfg = {model_name: {"type": "VDM", "cropsize": 2, "conditioning_values": conditioning_values,
                         "in_field_name": "Mstar", "out_field_name": "Mcdm", "data_params": {"dataset_name": "CMD"}}}

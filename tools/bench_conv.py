@@ -4,6 +4,7 @@ usage: python tools/bench_conv.py [--cin 32 --cout 32 --grid 128 --batch 2]"""
 import argparse
 import itertools
 import os
+os.environ["VDM4CDM_BRINGUP"] = "1"   # bring-up build of the library (make -C vdm4cdm_b200/csrc bringup)
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -3,6 +3,7 @@
 (vdm_debug_set key 5; results are wrong by construction).  usage: python tools/bench_epilogue.py [--taps 27|1]"""
 import argparse
 import os
+os.environ["VDM4CDM_BRINGUP"] = "1"   # bring-up build of the library (make -C vdm4cdm_b200/csrc bringup)
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -13,7 +13,10 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
     c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvdm4cdm_b200.so")
+# VDM4CDM_BRINGUP=1 selects the bring-up build (`make -C vdm4cdm_b200/csrc bringup`: ablation branches + vdm_debug_set);
+# tools/bench_epilogue.py and tools/bench_conv.py set it, nothing else does.
+BRINGUP = os.environ.get("VDM4CDM_BRINGUP", "0") == "1"
+LIB_PATH = os.path.join(_HERE, "lib", "libvdm4cdm_b200_bringup.so" if BRINGUP else "libvdm4cdm_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "vdm4cdm_b200.h")
 MAX_TAPS = 27
 
@@ -62,7 +65,6 @@ _SIGNATURES = {
     "vdm_last_error_string": (c_char_p, []),
     "vdm_device_supported": (c_int, [c_int]),
     "vdm_conv3d": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(ConvEpilogue), c_void_p]),
-    "vdm_debug_set": (c_int, [c_int, c_int]),
     "vdm_conv3d_wgrad": (c_int, [POINTER(WgradDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdm_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vdm_gn_silu_step": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -101,6 +103,9 @@ _SIGNATURES = {
     "vdm_pk_cross3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
+
+if BRINGUP:
+    _SIGNATURES["vdm_debug_set"] = (c_int, [c_int, c_int])
 
 _lib = None
 

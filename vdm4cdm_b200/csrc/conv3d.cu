@@ -41,6 +41,14 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+// Ablation branches (timing experiments whose results are wrong by construction) exist in bring-up builds only
+// (-DVDM_BRINGUP, `make bringup`); in the release library VDM_DBG is a compile-time false and the branches vanish.
+#ifdef VDM_BRINGUP
+#define VDM_DBG(p, f) (((p).debug_flags & (f)) != 0)
+#else
+#define VDM_DBG(p, f) (false)
+#endif
+
 namespace vdm {
 
 constexpr int kConvThreads = 352;       // 11 warps
@@ -361,7 +369,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         for (int kc = 0; kc < p.k_chunks + p.skip_chunks; ++kc, ++it) {
           const int s = it & 1;
           ptx::mbar_wait(&sh->a_empty[s], ((it >> 1) & 1) ^ 1);
-          if ((p.debug_flags & 2) && it >= 2) {       // experiment: no halo traffic after the pipeline fill
+          if (VDM_DBG(p, 2) && it >= 2) {       // experiment: no halo traffic after the pipeline fill
             ptx::mbar_arrive(&sh->a_full[s]);
             continue;
           }
@@ -719,7 +727,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       float* sp = stat_part + (ti & 1) * (16 * p.n_cta);   // this tile's partials (double-buffered by tile parity)
       ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
       ptx::tc_fence_after();
-      if (!(p.debug_flags & 1)) {
+      if (!VDM_DBG(p, 1)) {
         for (int ch = ch0; ch < n_chunks; ch += ch_step) {
           const int c0 = cbase + ch * 16;
           const bool full16 = (c0 + 16 <= p.c_out);
@@ -777,7 +785,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
               }
               const bf16x8 packed = pack8(g);
               if (valid) {
-                if (!(p.debug_flags & 8)) y_tile[(long long)(ch * 2 + hf) * V + (long long)s * HW] = packed;
+                if (!VDM_DBG(p, 8)) y_tile[(long long)(ch * 2 + hf) * V + (long long)s * HW] = packed;
                 unpack8(packed, g);  // statistics describe the stored (rounded) tensor
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {       // FADD2 / FFMA2: the epilogue is bound by its own arithmetic (r02n)
@@ -790,7 +798,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.n_cta + ch * 16);
           for (int s = s0; s < MT; s += s_step) {
             uint32_t raw0[16];
-            if (p.debug_flags & 4) {
+            if (VDM_DBG(p, 4)) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) raw0[j] = (uint32_t)(lane + j);     // experiment: no TMEM reads
             } else {
@@ -799,7 +807,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
             process(s, raw0);
           }
-          if (p.stats && c0 < p.c_out && !(p.debug_flags & 16)) {
+          if (p.stats && c0 < p.c_out && !VDM_DBG(p, 16)) {
             // one transpose-reduction per chunk and tile (r01j: per (slice, chunk) it cost 0.22 -> 0.30 ms on 32->32)
             warp_column_sums16(s1);
             warp_column_sums16(s2);
@@ -815,7 +823,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       // all TMEM reads of this accumulator set are complete (wait::ld above): hand it back
       ptx::tc_fence_before();
       ptx::mbar_arrive(&sh->tmem_empty[acc]);
-      if (p.stats && !(p.debug_flags & 32)) {
+      if (p.stats && !VDM_DBG(p, 32)) {
         // Fold this tile's per-warp fp32 partials into the CTA's fp64 running sums (fixed order: the result is
         // reproducible run to run up to the order of the final fp64 atomics); global atomics happen only when
         // this CTA moves on to another (sample, channel slice) or finishes.
@@ -888,16 +896,22 @@ static int num_sms() {
   return n;
 }
 
+#ifdef VDM_BRINGUP
 static int g_debug_flags = 0;
 static int g_debug_force_mt = 0, g_debug_force_kc = 0, g_debug_force_nsplit = 0, g_debug_no_resident = 0, g_debug_no_fold = 0;
+#else
+constexpr int g_debug_flags = 0;
+constexpr int g_debug_force_mt = 0, g_debug_force_kc = 0, g_debug_force_nsplit = 0, g_debug_no_resident = 0, g_debug_no_fold = 0;
+#endif
 
 }  // namespace vdm
 
 using namespace vdm;
 
+#ifdef VDM_BRINGUP
 extern "C" int vdm_debug_set(int key, int value) {
   switch (key) {
-    case 0: return VDM_OK;   /* retired knob (LBO/SBO swap), accepted for ABI stability */
+    case 0: return VDM_OK;   /* retired knob (LBO/SBO swap) */
     case 1: g_debug_force_mt = value; return VDM_OK;
     case 2: g_debug_force_kc = value; return VDM_OK;
     case 3: g_debug_force_nsplit = value; return VDM_OK;
@@ -907,6 +921,7 @@ extern "C" int vdm_debug_set(int key, int value) {
     default: set_error("vdm_debug_set: unknown key %d", key); return VDM_E_BADARG;
   }
 }
+#endif
 
 extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w, void* y,
                           const VdmConvEpilogue* epi, void* stream_) {

@@ -52,7 +52,8 @@ class DeviceAstroDataset:
         r = range(0, self.fullsize, self.crop)
         self.anchors = np.array([(a, b, c) for a in r for b in r for c in r], dtype=np.int64) if do_crop else np.zeros((1, 3), np.int64)
         self.ncrops = len(self.anchors)
-        self.gen = torch.Generator().manual_seed(seed)
+        self.seed = int(seed)
+        self.gen = torch.Generator().manual_seed(self.seed)
 
     def __len__(self):
         return self.n_sims * self.ncrops
@@ -86,13 +87,12 @@ class DeviceAstroDataset:
             samples.append(self.return_func(fields=[o[j] for o in outs], params=params[bidx]))
         return collate(samples)
 
-    def batches(self, batch_size: int, rank: int = 0, world: int = 1, shuffle: bool = True):
-        """Endless stream of batches; sample ids are sharded ``i -> rank i mod world`` over a shuffled epoch order."""
+    def batches(self, batch_size: int, rank: int = 0, world: int = 1, shuffle: bool = True, seed: int = 42):
+        """Endless stream of full batches; the epoch order is a function of (seed, epoch) shared by all ranks, padded to a
+        multiple of ``world * batch_size`` and sharded ``i -> rank i mod world`` (see ``_Loader``)."""
+        loader = _Loader(self, range(len(self)), batch_size, shuffle, rank=rank, world=world, drop_last=True, seed=seed)
         while True:
-            order = torch.randperm(len(self), generator=self.gen).tolist() if shuffle else list(range(len(self)))
-            mine = order[rank::world]
-            for i in range(0, len(mine) - batch_size + 1, batch_size):
-                yield self.get_batch(mine[i:i + batch_size])
+            yield from loader
 
 
 def collate(batch: List[dict]) -> dict:
@@ -143,30 +143,82 @@ def params_file_name(selection: dict) -> str:
     return f"params_{selection['set_name']}_{selection['suite_name']}.txt"     # CAMELS_3D_dataset.py:125
 
 
+def epoch_permutation(n: int, seed: int, epoch: int) -> List[int]:
+    """Shuffled order of ``n`` samples for one epoch: a function of (seed, epoch) ONLY, so every rank computes the same
+    order without talking to the others and without touching the generator the augmentation draws come from."""
+    g = torch.Generator().manual_seed((int(seed) * 1000003 + int(epoch)) % (2 ** 63 - 1))
+    return torch.randperm(n, generator=g).tolist()
+
+
 class _Loader:
     """Iterable of collated device batches over a fixed list of sample ids (what a ``DataLoader`` over a
-    ``Subset`` is for the reference): ``shuffle`` reshuffles every epoch, the last short batch is kept, samples are
-    sharded ``i -> rank i mod world`` AFTER shuffling so that ranks never see the same sample in one epoch."""
+    ``Subset`` is for the reference): ``shuffle`` reshuffles every epoch (``epoch_permutation``), a single rank keeps
+    the last short batch like the reference's ``DataLoader``.
+
+    With ``world > 1`` the (shuffled) epoch order is first padded, by wrapping around, to a multiple of
+    ``world * batch_size`` and then sharded ``i -> rank i mod world`` (``torch.utils.data.DistributedSampler``'s rule,
+    which Lightning applies to the reference under DDP, with the padding rounded up to whole batches): every rank runs
+    the SAME number of full batches per epoch, so the per-step gradient all-reduce can never be left waiting for a rank
+    that ran out of data, and the static-shape CUDA graph of the training step is never invalidated by a short batch."""
 
     def __init__(self, data: DeviceAstroDataset, ids: Sequence[int], batch_size: int, shuffle: bool, rank: int = 0,
-                 world: int = 1, drop_last: bool = False):
+                 world: int = 1, drop_last: bool = False, seed: int = 42):
         self.data, self.ids, self.batch_size, self.shuffle = data, list(ids), int(batch_size), shuffle
-        self.rank, self.world, self.drop_last = rank, world, drop_last
+        self.rank, self.world, self.drop_last, self.seed = rank, world, drop_last, seed
+        self.epoch, self.cursor, self._skip = 0, 0, 0
+
+    def _per_rank(self) -> int:
+        if self.world == 1:
+            return len(self.ids)
+        unit = self.world * self.batch_size
+        return -(-len(self.ids) // unit) * unit // self.world
 
     def __len__(self):
-        n = len(self.ids[self.rank::self.world])
+        n = self._per_rank()
         return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
 
-    def __iter__(self):
+    def epoch_order(self, epoch: int) -> List[int]:
+        """Sample ids of this rank for ``epoch``, in the order they are drawn."""
         order = self.ids
         if self.shuffle:
-            order = [self.ids[i] for i in torch.randperm(len(self.ids), generator=self.data.gen).tolist()]
-        mine = order[self.rank::self.world]
-        for i in range(0, len(mine), self.batch_size):
+            order = [self.ids[i] for i in epoch_permutation(len(self.ids), self.seed, epoch)]
+        if self.world > 1 and len(order) > 0:
+            total = self._per_rank() * self.world
+            order = (order * (-(-total // len(order))))[:total]
+        return order[self.rank::self.world]
+
+    def state(self) -> dict:
+        """Position in the sample stream, for checkpoints: (epoch, batches already drawn in it)."""
+        return {"epoch": self.epoch, "cursor": self.cursor}
+
+    def load_state(self, state: dict) -> None:
+        """Continue after ``state``: the next ``iter()`` replays the host-side augmentation draws of the batches that were
+        already consumed (no kernels) and yields the following ones -- the same stream as an uninterrupted run, on every
+        rank, because order and augmentation are functions of (seed, rank, epoch) only."""
+        self.epoch, self._skip = int(state["epoch"]), int(state["cursor"])
+
+    def __iter__(self):
+        mine = self.epoch_order(self.epoch)
+        # augmentation draws of epoch e come from a generator seeded by (dataset seed, e): epoch 0 continues the
+        # constructor's seeding, so a fresh dataset replays it (tests/test_gpu_dataset.py)
+        if self.epoch > 0 or self._skip:
+            self.data.gen.manual_seed(self.data.seed + 104729 * self.epoch)
+        skip, self._skip = self._skip, 0
+        self.cursor = 0
+        for bi, i in enumerate(range(0, len(mine), self.batch_size)):
             chunk = mine[i:i + self.batch_size]
             if len(chunk) < self.batch_size and self.drop_last:
-                return
-            yield self.data.get_batch(chunk)
+                break
+            if bi < skip:
+                for idx in chunk:
+                    self.data.draw(idx)
+                self.cursor = bi + 1
+                continue
+            batch = self.data.get_batch(chunk)
+            self.cursor = bi + 1
+            yield batch
+        self.epoch += 1
+        self.cursor = 0
 
 
 class AstroDataModule:
@@ -188,7 +240,7 @@ class AstroDataModule:
         assert stage in ["fit", "test"], f"stage {stage} not recognized"
         self.selection, self.channel_names, self.stage, self.batch_size = selection, list(channel_names), stage, batch_size
         self.do_crop, self.cropsize, self.ndim, self.num_workers, self.mmap = do_crop, cropsize, ndim, num_workers, mmap
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.seed, self._train_loader = rank, world, seed, None
         self.alphas = [ALPHAS_3D[c] for c in self.channel_names]
         self.means = [NORMALIZATIONS_3D[c][0] for c in self.channel_names]
         self.stds = [NORMALIZATIONS_3D[c][1] for c in self.channel_names]
@@ -220,7 +272,7 @@ class AstroDataModule:
             fields = [torch.from_numpy(np.ascontiguousarray(f, dtype=np.float32)).to(dev) for f in fields]
         self.data = DeviceAstroDataset(fields, torch.from_numpy(params), return_func, self.alphas, self.means, self.stds,
                                        do_crop=do_crop, crop=cropsize, aug_shift=(stage == "fit"), augment=(stage == "fit"),
-                                       seed=seed, device=device)
+                                       seed=seed + 7919 * rank, device=device)     # augmentation draws differ per rank
         if stage == "fit":
             n_train = int(len(self.data) * 0.95)                           # CAMELS_3D_dataset.py:137-139
             order = torch.randperm(len(self.data), generator=torch.Generator().manual_seed(seed)).tolist()
@@ -237,7 +289,10 @@ class AstroDataModule:
     collate_fn = staticmethod(collate)
 
     def train_dataloader(self):
-        return _Loader(self.data, self.train_ids, self.batch_size, shuffle=True, rank=self.rank, world=self.world, drop_last=self.world > 1)
+        if self._train_loader is None:           # one loader object: its epoch counter advances from epoch to epoch
+            self._train_loader = _Loader(self.data, self.train_ids, self.batch_size, shuffle=True, rank=self.rank,
+                                         world=self.world, seed=self.seed)
+        return self._train_loader
 
     def val_dataloader(self):
         return _Loader(self.data, self.valid_ids, self.batch_size, shuffle=False, rank=self.rank, world=self.world)

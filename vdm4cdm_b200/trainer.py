@@ -121,7 +121,7 @@ class Trainer:
 
     def __init__(self, model: torch.nn.Module, gradient_clip_val: float = 0.5, weight_decay: float = 0.01,
                  betas=(0.9, 0.999), eps: float = 1e-8, learning_rate: Optional[float] = None,
-                 use_cuda_graph: bool = True, graph_warmup_steps: int = 3):
+                 use_cuda_graph: bool = True, graph_warmup_steps: int = 3, seed: int = 42):
         self.model = model
         self.use_cuda_graph, self.graph_warmup_steps = use_cuda_graph, graph_warmup_steps
         self._graph, self._static_batch, self._static_loss, self._eager_steps = None, None, None, 0
@@ -131,6 +131,11 @@ class Trainer:
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.buckets = FlatBuckets(model)
         broadcast_parameters(self.buckets)
+        # dropout masks are keyed by (base seed + step counter, layer, element): fold the rank into the base seed so
+        # that the replicas of a data-parallel run draw DIFFERENT masks for their micro-batches
+        for m in model.modules():
+            if hasattr(m, "drop_counter"):
+                m.dropout_base_seed = int(seed) * self.world + self.rank
         self._nets_changed()
         dev = self.buckets.flat_param.device
         if dev.type != "cuda":
@@ -169,15 +174,8 @@ class Trainer:
                 loss = self._eager_step(self._static_batch)
             cur.wait_stream(self._stream)
             return loss
-        try:
-            self._capture()
-        except Exception as exc:                      # e.g. a collective the installed NCCL cannot capture
-            import warnings
-            warnings.warn(f"vdm4cdm_b200.Trainer: CUDA-graph capture of the training step failed ({exc}); "
-                          "continuing with eager launches")
-            self.use_cuda_graph, self._graph = False, None
-            torch.cuda.synchronize()
-            return self._eager_step(batch)
+        # A failed capture RAISES: there is no silent eager fallback (pass use_cuda_graph=False to ask for eager launches)
+        self._capture()
         self._graph.replay()
         self.step_count += 1
         return self._static_loss.clone()
@@ -217,6 +215,12 @@ class Trainer:
         self._optimizer_kernels()
         self.step_count += 1
 
+    def sync_inference_weights(self) -> None:
+        """Call before using the model for inference between training steps (validation, sampling): the captured step
+        re-packs the bf16 conv filters at its START, so after a replay they are one optimizer update behind the fp32
+        parameters; this marks them stale and the next forward re-packs them (in place, pointers stay valid)."""
+        self._nets_changed()
+
     def grad_norm(self) -> float:
         """Global gradient norm of the last step (after averaging over ranks, before clipping)."""
         return math.sqrt(self.grad_sumsq.item()) / self.world
@@ -230,15 +234,54 @@ class Trainer:
             if log is not None:
                 log(i, loss.item())
 
-    def state_dict(self) -> dict:
-        return {"state_dict": self.model.state_dict(), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "step": int(self.step_dev.item())}
+    def _dropout_nets(self):
+        return [(n, m) for n, m in self.model.named_modules() if hasattr(m, "drop_counter") and torch.is_tensor(m.drop_counter)]
 
-    def load_state_dict(self, state: dict) -> None:
+    def state_dict(self) -> dict:
+        """Everything a run needs to continue: ``state_dict`` (the key ``utils.get_model`` and Lightning checkpoints use,
+        src/utils.py:467), ``global_step``, the optimizer (AdamW moments + step number), the dropout-mask counters and
+        the RNG states the loss draws its times and noise from."""
+        dev = self.buckets.flat_param.device
+        return {"state_dict": self.model.state_dict(), "global_step": self.step_count,
+                "optimizer": {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                              "step": int(self.step_dev.item()), "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps,
+                              "weight_decay": self.wd, "gradient_clip_val": self.clip},
+                "drop_counters": {n: int(m.drop_counter.item()) for n, m in self._dropout_nets()},
+                "rng": {"cpu": torch.get_rng_state(), "cuda": torch.cuda.get_rng_state(dev)}}
+
+    def load_state_dict(self, state: dict, restore_rng: bool = True) -> None:
         self.model.load_state_dict(state["state_dict"])         # copies into the flat views in place
-        if "exp_avg" in state:
-            self.exp_avg.copy_(state["exp_avg"])
-            self.exp_avg_sq.copy_(state["exp_avg_sq"])
-            self.step_count = int(state["step"])
-            self.step_dev.fill_(self.step_count)
+        opt = state.get("optimizer")
+        if opt is None and "exp_avg" in state:                  # round-1 layout
+            opt = {"exp_avg": state["exp_avg"], "exp_avg_sq": state["exp_avg_sq"], "step": state["step"]}
+        if opt is not None:
+            self.exp_avg.copy_(opt["exp_avg"])
+            self.exp_avg_sq.copy_(opt["exp_avg_sq"])
+            self.step_dev.fill_(int(opt["step"]))
+        self.step_count = int(state.get("global_step", 0 if opt is None else opt["step"]))
+        nets = dict(self._dropout_nets())
+        for n, v in state.get("drop_counters", {}).items():
+            if n in nets:
+                nets[n].drop_counter.fill_(int(v))
+        if restore_rng and "rng" in state:
+            torch.set_rng_state(state["rng"]["cpu"].cpu())
+            torch.cuda.set_rng_state(state["rng"]["cuda"].cpu(), self.buckets.flat_param.device)
+        self._graph, self._eager_steps = None, 0                # pointers are unchanged, but re-capture from clean state
         self._nets_changed()
+
+    def save_checkpoint(self, path: str, extra: Optional[dict] = None) -> None:
+        """``torch.save`` of ``state_dict()`` (+ ``extra``, e.g. the data loader's position) -- written to a temporary
+        name first: a killed job never leaves a torn file."""
+        import os
+        state = self.state_dict()
+        if extra:
+            state.update(extra)
+        tmp = path + ".tmp"
+        torch.save(state, tmp)
+        os.replace(tmp, path)
+
+    def load_checkpoint(self, path: str, restore_rng: bool = True) -> dict:
+        """Restores weights, optimizer, step and RNG; returns the whole checkpoint dict (``global_step``, extras)."""
+        state = torch.load(path, map_location=self.buckets.flat_param.device, weights_only=False)
+        self.load_state_dict(state, restore_rng=restore_rng)
+        return state

@@ -167,10 +167,14 @@ def get_datamodule(config: dict, **kw):
                                cropsize=config["cropsize"], num_workers=8, mmap=False, **kw)
 
 
-def get_model(config: dict, device=None):
+def get_model(config: dict, device=None, allow_random_init: bool = False):
     """``CUNet`` + ``LightVDM`` from a ``configs.yaml`` entry (src/utils.py:434-471): ``chs`` default
     [32, 64, 128, 256], ``norm_groups=8``, ``dropout_prob=0.1``, ``gamma_max=13.3``, circular padding iff
-    ``cropsize == 256``; SFM entries return ``None`` exactly like the reference (src/utils.py:472-473)."""
+    ``cropsize == 256``; SFM entries return ``None`` exactly like the reference (src/utils.py:472-473).
+
+    A configured ``ckpt_path`` is loaded, and a missing file raises like the reference's ``torch.load`` does
+    (src/utils.py:468-469).  ``allow_random_init=True`` (the scripts' ``--allow-random-init``, smoke runs only) keeps
+    the random initialisation instead and says so."""
     from .networks import CUNet
     from .vdm_model import LightVDM
     if config["type"] == "SFM":
@@ -187,9 +191,18 @@ def get_model(config: dict, device=None):
                 n_attention_heads=4)
     model = LightVDM(score_model=net, draw_figure=None, gamma_max=13.3, learning_rate=3.0e-4)
     ckpt_path = config.get("ckpt_path")
-    if ckpt_path and os.path.exists(ckpt_path):   # the registry's paths live on the author's cluster
-        state = torch.load(ckpt_path, map_location="cpu")
-        model.load_state_dict(state["state_dict"])
+    if ckpt_path:
+        if os.path.exists(ckpt_path):
+            # trusted checkpoint ({"state_dict": ...}, Lightning's or scripts/train3D_c_c.py's): full unpickling
+            state = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+            model.load_state_dict(state["state_dict"])
+        elif allow_random_init:
+            import warnings
+            warnings.warn(f"vdm4cdm_b200.utils.get_model: checkpoint {ckpt_path!r} does not exist; the model keeps its "
+                          "RANDOM initialisation (allow_random_init=True)")
+        else:
+            raise FileNotFoundError(f"get_model: ckpt_path {ckpt_path!r} is configured but the file does not exist "
+                                    "(pass allow_random_init=True / --allow-random-init for a smoke run on random weights)")
     if device is not None:
         model = model.to(device)
     return model
