@@ -113,7 +113,10 @@ def test_train_script_on_a_camels_like_directory(tmp_path):
     recs = [json.loads(l) for l in open(ck / "metrics.jsonl")]
     vals = [r for r in recs if "val_loss" in r]
     assert [r["step"] for r in vals] == [4, 8] and all(np.isfinite(r["val_loss"]) and r["val_batches"] >= 1 for r in vals)
-    assert len(vals[0]["pk_truth"]) == 8 and len(vals[0]["cc"]) == 8 and all(abs(c) <= 1.0 + 1e-4 for c in vals[0]["cc"])
+    # (an UNTRAINED network's 5-step samples are amplified by alpha_0/alpha_1 ~ 770 and overflow 10**x: r(k) may be NaN
+    #  here exactly as it would be for the reference; the truth spectrum is always finite)
+    assert len(vals[0]["pk_truth"]) == 8 and len(vals[0]["cc"]) == 8 and np.isfinite(vals[0]["pk_truth"]).all()
+    assert all(np.isnan(c) or abs(c) <= 1.0 + 1e-4 for c in vals[0]["cc"]) and "sample_std" in vals[0]
     assert [r["step"] for r in recs if "train_loss" in r] == list(range(1, 9))
     # resume from step 4: steps 5..8 reproduce the uninterrupted run (same data order, RNG, optimizer state; the
     # tolerance covers the unordered fp32 atomics of the weight-gradient and statistics reductions)
