@@ -83,7 +83,12 @@ typedef struct VdmConvEpilogue {
   int32_t stats_c0;             /* first stats channel this conv's output maps to */
   int32_t residual_upsample;    /* != 0: the residual lives on the HALF-resolution grid (D/2, H/2, W/2) and is read through a
                                  *       nearest x2 up-sampling (a 1x1x1 conv commutes with it: the up blocks' skip conv over
-                                 *       cat([interpolate(h), skip]) = conv(skip) + interpolate(conv(h))) */
+                                 *       cat([interpolate(h), skip]) = conv(skip) + interpolate(conv(h)));
+                                 * 2: the half-resolution residual holds EIGHT blocks of c_out channels, block
+                                 *       (d&1)*4 + (h&1)*2 + (w&1) for the fine voxel (d, h, w), and is read through that
+                                 *       depth-to-space shuffle: the polyphase form of conv3x3x3(interpolate(a)) -- eight
+                                 *       2x2x2-tap convolutions of the COARSE tensor, one per output parity (27 -> 8 taps,
+                                 *       the up-sampled tensor is never written) -- lands in such a buffer */
   int32_t reserved;
   /* Fused 1x1x1 skip-path conv of a ResNet block (blocks.py ResNetBlock: h + skip_conv(x)): y += conv1x1x1(skip_x, skip_w)
    * inside the same launch, as one more channel chunk of which only the centre tap is multiplied.  Only for the
@@ -96,6 +101,13 @@ typedef struct VdmConvEpilogue {
   int32_t skip_planes;          /* planes per sample of the skip_x buffer (0: skip_c_in/8) */
   int32_t skip_plane0;          /* first plane read */
   int32_t reserved2;
+  /* Fused INPUT transform (inference): x holds the RAW tensor and the kernel applies GroupNorm + SiLU to every halo tile
+   * in shared memory before the tensor cores read it -- stands in for the ATen group_norm + silu launches in front of
+   * the conv (blocks.py:129-132: net1 / net2 = Sequential(GroupNorm, SiLU, [Dropout], Conv3d), model_test.ipynb:688-692).
+   * in_norm: fp32 [batch][c_in][2] = (a, b) from vdm_gn_coef, silu(gn(x)) = h + h tanh(h) with h = a x + b; NULL: x is
+   * used as it is.  Zero padding stays zero AFTER the non-linearity.  Not with circular padding (VDM_E_UNSUPPORTED);
+   * the fused skip-path chunk (skip_x) is never transformed. */
+  const float* in_norm;
 } VdmConvEpilogue;
 
 /* y = conv(x, w) [+ chan_add[b][co]] [+ residual]; also the dgrad when w holds the flipped,
@@ -175,10 +187,15 @@ VDM_API int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, int64
  * norm's full vectors.  (depth, height, width) is the grid of y.  upsample != 0: x is at HALF that resolution and
  * y = silu(gn(nearest_upsample2(x))) -- the up blocks' torch.cat([interpolate(h), skip]) -> GroupNorm -> SiLU
  * (blocks.py ResNetUp / ResNetBlock.net1) without ever writing the up-sampled tensor (its per-channel sums are 8x
- * the coarse tensor's).  No dropout: net1 has none. */
+ * the coarse tensor's).  upsample == 2: x AND y are at half the resolution of (depth, height, width), the grid the
+ * statistics refer to: y = silu(gn(x)) of the coarse tensor itself, the input of the polyphase up-conv (eight 2x2x2-tap
+ * convolutions on the coarse grid, VdmConvEpilogue.residual_upsample == 2).  No dropout: net1 has none. */
 VDM_API int vdm_gn_silu_view(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
                      int channels, int c_off, int channels_total, int groups, const double* stats,
                      const float* gamma, const float* beta, float eps, int upsample, void* stream);
+/* (a, b) pairs for VdmConvEpilogue.in_norm from the fp64 (sum, sumsq) statistics of the tensor: fp32 [batch][channels][2]. */
+VDM_API int vdm_gn_coef(const double* stats, int batch, int channels, int groups, int64_t voxels, const float* gamma,
+                const float* beta, float eps, float* coef, void* stream);
 /* Same with the dropout seed advanced on the device: seed_eff = seed + *seed_step (CUDA-graph replay). */
 VDM_API int vdm_gn_silu_step(const VdmTensor* x, const VdmTensor* y, int batch, int64_t voxels, int channels, int groups,
                      const double* stats, const float* gamma, const float* beta, float eps, float dropout_p,

@@ -253,3 +253,136 @@ def test_conv3d_fused_skip_conv_declined_for_wide_layers():
     ws = ops.pack_conv_weight(torch.zeros((64, 32, 1, 1, 1), device=dev))
     with pytest.raises(ops.UnsupportedFusion):
         ops.conv3d(x, w, 64, skip_x=torch.zeros((1, 4, 4, 16, 8, 8), dtype=torch.bfloat16, device=dev), skip_w=ws)
+
+
+# ---- fused input transform: GroupNorm + SiLU applied by the conv kernel to its input tile (VdmConvEpilogue.in_norm) ----
+def _gn_silu_ref(x, gamma, beta, groups, eps=1e-5):
+    import torch.nn.functional as F
+    return F.silu(F.group_norm(x.double(), groups, gamma.double(), beta.double(), eps))
+
+
+@pytest.mark.parametrize("ci,co,grid,batch,taps", [
+    (32, 32, (8, 32, 16), 2, 27),       # kd-folded, resident weights; two samples (coefficient table switch)
+    (32, 32, (5, 20, 12), 1, 27),       # ragged tiles: every tile touches the boundary
+    (64, 64, (8, 16, 16), 1, 27),       # kd-folded, streamed weights, two channel chunks
+    (16, 32, (6, 16, 8), 2, 27),        # one 16-channel chunk: two planes, voxels split between warps
+    (128, 128, (4, 16, 8), 1, 27),      # generic schedule, 64-channel chunks (8 planes: two per warp)
+    (64, 32, (4, 16, 16), 2, 1),        # 1x1x1: box without halo
+    (32, 1, (8, 16, 16), 2, 27),        # fp32 single-channel output (conv_out)
+])
+def test_conv3d_fused_groupnorm_silu_input(ci, co, grid, batch, taps):
+    """conv(silu(groupnorm(x))) with the normalisation applied by the conv kernel to every halo tile in shared memory
+    (ops.conv3d in_norm + ops.gn_coef) against (a) fp64 torch and (b) the two-pass path (ops.gn_silu, then ops.conv3d).
+    Zero padding must stay zero AFTER the non-linearity: a transformed halo would show up as an O(1) error on every
+    boundary voxel, so the maximum error is checked next to the relative L2."""
+    import torch.nn.functional as F
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    d, h, w = grid
+    k = 3 if taps == 27 else 1
+    x = (torch.randn((batch, ci, d, h, w), generator=g) * 1.5 + 0.3).to(dev)
+    wt = (torch.randn((co, ci, k, k, k), generator=g) / (taps * ci) ** 0.5).to(dev)
+    gamma = (1.0 + 0.2 * torch.randn(ci, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(ci, generator=g)).to(dev)
+    cadd = torch.randn((batch, co), generator=g).to(dev)
+    xp = ops.to_planar(x)
+    xr = ops.from_planar(xp, ci)                                   # the bf16 tensor both paths normalise
+    stats = ops.channel_stats(xp, ci)
+    coef = ops.gn_coef(stats, gamma, beta, 8, d * h * w)
+    wp = ops.pack_conv_weight(wt)
+    kw = dict(taps=ops.TAPS_3X3X3 if k == 3 else ops.TAPS_1X1X1, chan_add=cadd)
+    if co == 1:
+        kw["out_fp32"] = True
+    fused = ops.conv3d(xp, wp, co, in_norm=coef, **kw)
+    a = ops.gn_silu(xp, ci, 8, stats, gamma, beta)
+    two_pass = ops.conv3d(a, wp, co, **kw)
+    torch.cuda.synchronize()
+    if co > 1:
+        fused, two_pass = ops.from_planar(fused, co), ops.from_planar(two_pass, co)
+    ref = (F.conv3d(_gn_silu_ref(xr, gamma, beta, 8), wt.double(), padding=k // 2) + cadd.double()[:, :, None, None, None]).float()
+    scale = ref.abs().max().item()
+    for name, got in (("fused", fused), ("two-pass", two_pass)):
+        rel = ((got - ref).norm() / ref.norm()).item()
+        mx = (got - ref).abs().max().item() / scale
+        print(f"{name}: relative L2 {rel:.3e}, max abs / max |ref| {mx:.3e}")
+        assert rel < 6e-3 and mx < 3e-2, (name, rel, mx)
+    assert ((fused - two_pass).norm() / two_pass.norm()).item() < 4e-3
+
+
+def test_conv3d_fused_input_with_skip_chunk_residual_and_stats():
+    """The up block's net2 conv as the inference trunk launches it: raw h normalised in the kernel, the 1x1x1 skip conv
+    fused as an UN-transformed extra channel chunk, coarse residual, statistics."""
+    import torch.nn.functional as F
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(12)
+    b, c, cs, (d, h, w) = 2, 32, 32, (8, 32, 16)
+    x = torch.randn((b, c, d, h, w), generator=g).to(dev)
+    xs = torch.randn((b, cs, d, h, w), generator=g).to(dev)
+    rc = torch.randn((b, c, d // 2, h // 2, w // 2), generator=g).to(dev)
+    wt = (torch.randn((c, c, 3, 3, 3), generator=g) / (27 * c) ** 0.5).to(dev)
+    ws = (torch.randn((c, cs, 1, 1, 1), generator=g) / cs ** 0.5).to(dev)
+    gamma, beta = (1.0 + 0.2 * torch.randn(c, generator=g)).to(dev), (0.2 * torch.randn(c, generator=g)).to(dev)
+    cadd = torch.randn((b, c), generator=g).to(dev)
+    xp, sp, rp = ops.to_planar(x), ops.to_planar(xs), ops.to_planar(rc)
+    stats = ops.channel_stats(xp, c)
+    coef = ops.gn_coef(stats, gamma, beta, 8, d * h * w)
+    out_stats = torch.zeros((b, c, 2), dtype=torch.float64, device=dev)
+    y = ops.conv3d(xp, ops.pack_conv_weight(wt), c, chan_add=cadd, residual=rp, residual_upsample=True, stats=out_stats,
+                   skip_x=sp, skip_w=ops.pack_conv_weight(ws), in_norm=coef)
+    torch.cuda.synchronize()
+    got = ops.from_planar(y, c)
+    ref = F.conv3d(_gn_silu_ref(ops.from_planar(xp, c), gamma, beta, 8), wt.double(), padding=1) + \
+        F.conv3d(ops.from_planar(sp, cs).double(), ws.double()) + cadd.double()[:, :, None, None, None] + \
+        F.interpolate(ops.from_planar(rp, c).double(), scale_factor=2, mode="nearest")
+    rel = ((got - ref.float()).norm() / ref.float().norm()).item()
+    mx = (got - ref.float()).abs().max().item() / ref.abs().max().item()
+    print(f"fused input + skip chunk: relative L2 {rel:.3e}, max {mx:.3e}")
+    assert rel < 6e-3 and mx < 3e-2, (rel, mx)
+    assert torch.allclose(out_stats[..., 0], got.double().sum((2, 3, 4)), rtol=1e-5, atol=1e-2)
+
+
+def test_conv3d_fused_input_is_declined_for_circular_padding():
+    ops = _ops()
+    x = torch.zeros((1, 2, 6, 18, 10, 8), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((27, 2, 16, 8), dtype=torch.bfloat16, device="cuda")
+    coef = torch.zeros((1, 16, 2), dtype=torch.float32, device="cuda")
+    with pytest.raises(ops.UnsupportedFusion):
+        ops.conv3d(x, w, 16, circular=True, in_norm=coef)
+
+
+# ---- polyphase up-conv: conv3x3x3(interpolate(a)) as eight 2x2x2-tap convolutions of the coarse tensor ------------------
+@pytest.mark.parametrize("cc,co,cgrid,batch", [(32, 32, (4, 16, 8), 2), (64, 32, (5, 10, 6), 1), (128, 64, (4, 8, 8), 1)])
+def test_polyphase_upconv_is_exact_on_integers(cc, co, cgrid, batch):
+    """The up blocks' conv over the up-sampled half of the concat (ResNetUp: interpolate -> cat -> ResNetBlock.net1) in the
+    form the inference trunk runs it: per output parity a 2x2x2-tap conv of the COARSE tensor with summed filter taps
+    (ops.polyphase_weight / polyphase_taps) into a parity-planar buffer, read back by the consumer conv through the
+    depth-to-space residual (residual_upsample="d2s").  Integer inputs: every product and sum is exact, so the result
+    must equal F.conv3d(F.interpolate(a)) bit for bit -- including the zero padding at the fine-grid boundary."""
+    import torch.nn.functional as F
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    dc, hc, wc = cgrid
+    a = _int_tensor((batch, cc, dc, hc, wc), -2, 2, g, dev)
+    wt = _int_tensor((co, cc, 3, 3, 3), -1, 1, g, dev) * (_int_tensor((co, cc, 3, 3, 3), 0, 2, g, dev) == 0).float()
+    ap = ops.to_planar(a)
+    part = torch.full((batch, co, dc, hc, wc, 8), 55.0, dtype=torch.bfloat16, device=dev)     # 8 x co channels
+    for pi in range(8):
+        parity = (pi >> 2, (pi >> 1) & 1, pi & 1)
+        we = ops.polyphase_weight(wt, parity)
+        assert we.shape == (co, cc, 2, 2, 2)
+        ops.conv3d(ap, ops.pack_conv_weight(we), co, taps=ops.polyphase_taps(parity), out=part, out_plane0=pi * (co // 8))
+    # consumer: a conv with zero weights, so its output is bias + the depth-to-space residual
+    xs = torch.zeros((batch, 2, 2 * dc, 2 * hc, 2 * wc, 8), dtype=torch.bfloat16, device=dev)
+    wz = torch.zeros((27, 2, co, 8), dtype=torch.bfloat16, device=dev)
+    cadd = _int_tensor((batch, co), -3, 3, g, dev)
+    y = ops.conv3d(xs, wz, co, chan_add=cadd, residual=part, residual_upsample="d2s")
+    torch.cuda.synchronize()
+    # (fp64 reference on the CPU: cuDNN picks an FFT algorithm for some fp64 shapes and returns 113.00000000000001)
+    ref = (F.conv3d(F.interpolate(a.double().cpu(), scale_factor=2, mode="nearest"), wt.double().cpu(), padding=1) +
+           cadd.double().cpu()[:, :, None, None, None]).to(dev)
+    assert ref.abs().max() < 256                                     # integers bf16 holds exactly
+    got = ops.from_planar(y, co).double()
+    assert torch.equal(got, ref), f"max |diff| = {(got - ref).abs().max().item()}"

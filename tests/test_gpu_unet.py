@@ -34,6 +34,18 @@ def _rel_l2(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
+def _assert_bf16_parity(err, oracle_call, want):
+    """err < 1e-2; where a whole random-init network exceeds that (it sits AT the bf16 noise floor: ~30 conv layers x 3
+    roundings of 2^-9 each) the bar is the error torch's OWN bf16 autocast of the oracle makes on the same input, never
+    looser than 1.5e-2.  (Ragged-tile arithmetic itself is pinned bit-exactly in tests/test_gpu_conv3d.py.)"""
+    if err < BF16_RTOL:
+        return
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        autocast_err = _rel_l2(oracle_call().float(), want)
+    print(f"  torch bf16 autocast of the oracle on the same input: {autocast_err:.3e}")
+    assert err < min(max(BF16_RTOL, autocast_err), 1.5e-2), (err, autocast_err)
+
+
 @pytest.mark.parametrize("shape,chs,batch", [((1, 32, 32, 32), (16, 32, 64, 128), 2),
                                              ((1, 16, 32, 48), (32, 64), 1),
                                              ((1, 24, 24, 24), (16, 32, 64), 3),
@@ -54,19 +66,13 @@ def test_unet_forward_matches_oracle(shape, chs, batch):
     assert got.shape == want.shape and got.dtype == torch.float32
     err = _rel_l2(got, want)
     print(f"unet {shape} {chs}: relative L2 error {err:.3e}, max abs {((got - want).abs().max() / want.abs().max()).item():.3e}")
-    if err >= BF16_RTOL:
-        # A whole random-init network sits AT the bf16 noise floor (~30 conv layers x 3 roundings of 2^-9 each): where 1e-2
-        # is exceeded the bar is the error torch's OWN bf16 autocast of the oracle makes on this input, never looser
-        # than 1.5e-2.  (Ragged-tile arithmetic itself is pinned bit-exactly in tests/test_gpu_conv3d.py.)
-        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
-            autocast_err = _rel_l2(ref(x, t=t, s_conditioning=cond, v_conditionings=v).float(), want)
-        print(f"  torch bf16 autocast of the oracle on the same input: {autocast_err:.3e}")
-        assert err < min(max(BF16_RTOL, autocast_err), 1.5e-2), (err, autocast_err)
+    _assert_bf16_parity(err, lambda: ref(x, t=t, s_conditioning=cond, v_conditionings=v), want)
     # no time / parameter conditioning inputs, scalar t
     with torch.no_grad():
         want1 = ref(x[:1], t=torch.tensor(0.3), s_conditioning=cond[:1], v_conditionings=[v[0][:1]])
         got1 = net(x[:1].cuda(), t=torch.tensor(0.3), s_conditioning=cond[:1].cuda(), v_conditionings=[v[0][:1].cuda()]).cpu()
-    assert _rel_l2(got1, want1) < BF16_RTOL
+    _assert_bf16_parity(_rel_l2(got1, want1),
+                        lambda: ref(x[:1], t=torch.tensor(0.3), s_conditioning=cond[:1], v_conditionings=[v[0][:1]]), want1)
 
 
 def test_unet_fused_upsampling_equals_the_materialised_concat():
@@ -89,6 +95,57 @@ def test_unet_fused_upsampling_equals_the_materialised_concat():
           f"materialised {_rel_l2(plain, want):.3e}")
     assert _rel_l2(fused, plain) < BF16_RTOL
     assert _rel_l2(fused, want) < 1.2e-2 and _rel_l2(plain, want) < 1.2e-2
+
+
+def test_unet_fused_groupnorm_equals_the_two_pass_path():
+    """Inference applies GroupNorm + SiLU inside the consumer conv (CUNet.fuse_gn, ops.conv3d in_norm); the result must agree
+    with the path that runs vdm_gn_silu as its own pass (the one training uses) to bf16 rounding, and both with the oracle."""
+    shape, chs, batch = (1, 16, 32, 16), (16, 32, 64), 2
+    ref, net = _models(shape, chs)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((batch,) + shape, generator=g)
+    cond = 0.7 * x + 0.3 * torch.randn((batch,) + shape, generator=g)
+    t, v = torch.rand(batch, generator=g), [torch.rand(batch, 6, generator=g)]
+    kw = dict(t=t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()])
+    with torch.no_grad():
+        want = ref(x, t=t, s_conditioning=cond, v_conditionings=v)
+        assert net.fuse_gn
+        net.fuse_gn_min_channels = 1            # every layer, also the narrow ones the default policy leaves two-pass
+        from vdm4cdm_b200 import ops
+        n0 = ops.launch_count()
+        fused = net(x.cuda(), **kw).cpu()
+        n_fused = ops.launch_count() - n0
+        net.fuse_gn = False
+        n0 = ops.launch_count()
+        plain = net(x.cuda(), **kw).cpu()
+        n_plain = ops.launch_count() - n0
+    print(f"fused GN vs two-pass: {_rel_l2(fused, plain):.3e}; vs oracle: fused {_rel_l2(fused, want):.3e}, "
+          f"two-pass {_rel_l2(plain, want):.3e}; launches {n_fused} vs {n_plain}")
+    assert _rel_l2(fused, plain) < BF16_RTOL
+    assert _rel_l2(fused, want) < 1.2e-2 and _rel_l2(plain, want) < 1.2e-2
+
+
+def test_unet_polyphase_up_blocks_equal_the_direct_form():
+    """Inference runs the up blocks' conv over the up-sampled channels in polyphase form (CUNet.polyphase_up: eight 2x2x2-tap
+    convs of the coarse tensor + a depth-to-space residual); the result must agree with the direct 27-tap conv over
+    silu(gn(cat([interpolate(h), skip]))) to bf16 rounding, and both with the oracle."""
+    shape, chs, batch = (1, 16, 32, 16), (16, 32, 64), 2
+    ref, net = _models(shape, chs)
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn((batch,) + shape, generator=g)
+    cond = 0.7 * x + 0.3 * torch.randn((batch,) + shape, generator=g)
+    t, v = torch.rand(batch, generator=g), [torch.rand(batch, 6, generator=g)]
+    kw = dict(t=t.cuda(), s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()])
+    with torch.no_grad():
+        want = ref(x, t=t, s_conditioning=cond, v_conditionings=v)
+        assert net.polyphase_up
+        poly = net(x.cuda(), **kw).cpu()
+        net.polyphase_up = False
+        direct = net(x.cuda(), **kw).cpu()
+    print(f"polyphase vs direct: {_rel_l2(poly, direct):.3e}; vs oracle: polyphase {_rel_l2(poly, want):.3e}, "
+          f"direct {_rel_l2(direct, want):.3e}")
+    assert _rel_l2(poly, direct) < BF16_RTOL
+    assert _rel_l2(poly, want) < 1.2e-2 and _rel_l2(direct, want) < 1.2e-2
 
 
 def test_unet_forward_circular_padding_matches_oracle():

@@ -40,3 +40,13 @@ for flags, what in ((0, "nothing off"), (4, "no TMEM reads"), (8, "no output sto
     lib.vdm_debug_set(5, flags)
     print(f"  {what:40s}: bias+residual+stats {timeit(full):6.3f} ms   bias+stats {timeit(nores):6.3f} ms")
 lib.vdm_debug_set(5, 0)
+# fused input transform (GroupNorm + SiLU applied to the landed halo tile by warps 12..15): cost of the arithmetic vs the hand-off
+coef = torch.randn((b, ci, 2), device=dev) * 0.5
+xf = lambda: ops.conv3d(x, w, co, taps=taps, out=out, chan_add=cadd, stats=stats, in_norm=coef)
+xf_res = lambda: ops.conv3d(x, w, co, taps=taps, out=out, chan_add=cadd, residual=res, stats=stats, in_norm=coef)
+print(f"  fused input transform                   : bias+residual+stats {timeit(xf_res):6.3f} ms   bias+stats {timeit(xf):6.3f} ms")
+for flags, what in ((64, "transform warps hand the stage on only"), (128, "transform copies through (LDS + STS, no math)"),
+                    (256, "transform computes, no stores"), (384, "transform loads only")):
+    lib.vdm_debug_set(5, flags)
+    print(f"  {what:40s}: bias+residual+stats {timeit(xf_res):6.3f} ms   bias+stats {timeit(xf):6.3f} ms")
+lib.vdm_debug_set(5, 0)

@@ -17,6 +17,7 @@ ap.add_argument("--cout", type=int, default=32)
 ap.add_argument("--grid", type=int, default=128)
 ap.add_argument("--batch", type=int, default=2)
 ap.add_argument("--taps", type=int, default=27, choices=[1, 27])
+ap.add_argument("--in-norm", action="store_true", help="also launch the conv with the fused GroupNorm + SiLU input transform")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 b, ci, co, n = args.batch, args.cin, args.cout, args.grid
@@ -34,5 +35,8 @@ for _ in range(2):
     ops.conv3d(x, w, co, out=out, taps=taps, chan_add=cadd, residual=res, stats=stats)          # full epilogue
     ops.conv3d(x, w, co, out=out, taps=taps, chan_add=cadd, residual=res_c, residual_upsample=True)
     ops.conv3d_wgrad(x, out, ci, co, k)
+    if args.in_norm:
+        coef = torch.randn((b, ci, 2), device=dev) * 0.5
+        ops.conv3d(x, w, co, out=out, taps=taps, chan_add=cadd, stats=stats, in_norm=coef)
 torch.cuda.synchronize()
 print("done")

@@ -40,6 +40,7 @@ class ConvEpilogue(Structure):
         ("residual_upsample", c_int32), ("reserved", c_int32),
         ("skip_x", c_void_p), ("skip_w", c_void_p), ("skip_c_in", c_int32), ("skip_planes", c_int32),
         ("skip_plane0", c_int32), ("reserved2", c_int32),
+        ("in_norm", c_void_p),
     ]
 
 
@@ -87,6 +88,7 @@ _SIGNATURES = {
     "vdm_channel_stats": (c_int, [_T, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_gn_silu": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             c_float, c_float, c_uint64, c_uint32, c_void_p]),
+    "vdm_gn_coef": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "vdm_gn_silu_view": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_float, c_int, c_void_p]),
     "vdm_avgpool2": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

@@ -51,9 +51,17 @@
 
 namespace vdm {
 
-constexpr int kConvThreads = 352;       // 11 warps
-constexpr int kEpiThreads = 256;        // warps 3..10
-constexpr int kEpiFirst = 96;
+// 16 warps in four warpgroups (setmaxnreg re-balances the register file per warpgroup):
+//   WG0  warp 0 A producer, warp 1 MMA issuer, warp 2 B producer, warp 3 idle        64 registers
+//   WG1-2 warps 4..11  epilogue (two per TMEM lane quarter)                          176 registers
+//   WG3  warps 12..15  input transform (GroupNorm + SiLU on the landed halo tile)     88 registers
+constexpr int kConvThreads = 512;
+constexpr int kEpiThreads = 256;        // warps 4..11
+constexpr int kEpiFirst = 128;
+constexpr int kXfThreads = 128;         // warps 12..15
+constexpr int kXfFirst = 384;
+constexpr int kRegsWg0 = 64, kRegsEpi = 176, kRegsXf = 88;
+constexpr int kXfGroup = 2;              // units per software-pipeline group of the input transform (2 groups in flight)   // 128*64 + 256*176 + 128*88 = 64512 <= 65536
 constexpr int kResSlotBytes = 2 * 16 * kEpiThreads;   // one unit (two 8-channel planes) of residual for every epilogue thread
 constexpr int kMaxBStages = 16;
 constexpr int kTileH = 16, kTileW = 8;
@@ -95,10 +103,15 @@ struct ConvKernelParams {
   const __nv_bfloat16* residual;
   int r_planes, r_plane0;
   int r_up;                  // residual on the half-resolution grid, read through a nearest x2 up-sampling
+  int r_d2s_planes;          // != 0 (with r_up): the half-resolution residual holds 8 parity blocks of this many planes each
+                             // (block (d&1)*4 + (h&1)*2 + (w&1)) and is read through a depth-to-space shuffle
   int res_depth;             // units of residual in flight per epilogue thread (cp.async ring), 1..4
   int res_ring_off;          // byte offset of that ring in dynamic shared memory
   double* stats;
   int stats_channels, stats_c0;
+  const float* in_norm;      // fused input transform: fp32 [B][c_in][2] (a, b), silu(gn(x)) = h + h tanh(h), h = a x + b
+  int c_in;                  // channels of x read (the in_norm row length)
+  int xf_coef_off;           // byte offset of the current sample's (a, b) table in dynamic shared memory
   int debug_flags;           // bring-up experiments (results are wrong): 1 = epilogue does no work, 2 = halo loaded for the
                              // first two tiles only, 4 = no TMEM reads, 8 = no output stores, 16 = no statistics
                              // transpose-reduction, 32 = no statistics barrier + fold
@@ -106,6 +119,7 @@ struct ConvKernelParams {
 
 struct ConvShared {
   uint64_t a_full[2], a_empty[2];
+  uint64_t a_ready[2];             // fused input transform: the landed halo stage has been rewritten in place
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
@@ -313,6 +327,426 @@ __device__ __forceinline__ void issue_fold_stage(uint32_t a_lo, uint32_t b_lo, u
   }
 }
 
+// ---- fused input transform -----------------------------------------------------------------------------------
+// The conv reads the RAW tensor (the producer's output before GroupNorm); warps 12..15 rewrite every landed halo stage
+// in place, y = silu(a_c x + b'_c) per (sample, channel) = h + h tanh(h) with h = a x + b (vdm_gn_coef), re-zero the
+// voxels the TMA unit filled for out-of-range coordinates (Conv3d's zero padding is applied AFTER the non-linearity),
+// make the writes visible to the async proxy (tcgen05.mma reads shared memory through it) and hand the stage to the
+// MMA issuer.  This removes the separate GroupNorm + SiLU pass: one read and one write of the tensor per conv input.
+// Work split: a warp owns whole planes (its 16 coefficients stay in registers for the stage); with fewer than four
+// planes per chunk the voxels of a plane are split between warps.  Lanes walk consecutive 16-byte units (conflict-free).
+template <int HH, int WH>
+__device__ __forceinline__ bool halo_voxel_oob(int v, int dlo, int hlo, int wlo, int D, int H, int W) {
+  const int dz = v / (HH * WH);
+  const int rem = v - dz * (HH * WH);
+  const int hy = rem / WH;
+  const int wx = rem - hy * WH;
+  return (unsigned)(dlo + dz) >= (unsigned)D || (unsigned)(hlo + hy) >= (unsigned)H || (unsigned)(wlo + wx) >= (unsigned)W;
+}
+
+__device__ __forceinline__ uint4 gn_silu8(const uint4 x, const float (&ca)[8], const float (&cb)[8]) {
+  bf16x8 in;
+  in.u = x;
+  float f[8];
+  unpack8(in, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float h = fmaf(f[j], ca[j], cb[j]);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    f[j] = fmaf(h, t, h);
+  }
+  return pack8(f).u;
+}
+
+template <int MT, int KJ>
+__device__ __forceinline__ void transform_tiles(const ConvKernelParams& p, ConvShared* sh, uint8_t* a_smem, float* coef) {
+  constexpr int planes = 2 * KJ;
+  constexpr int nparts = planes >= 4 ? 1 : 4 / planes;        // warps sharing one plane
+  constexpr int pl_step = planes >= 4 ? 4 : planes;
+  const int xt = threadIdx.x - kXfFirst, tw = xt >> 5, lane = xt & 31;
+  const int pl0 = planes >= 4 ? tw : tw % planes;
+  const int part = planes >= 4 ? 0 : tw / planes;
+  const int vh = p.Hd * p.Hh * p.Wh;                          // voxels (16-byte units) of one plane of the stage
+  const int total_chunks = p.k_chunks + p.skip_chunks;
+  int cur_b = -1;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(p, tile);
+    if (t.b != cur_b) {
+      // (a, b) table of this sample -> shared memory; the first barrier keeps a slow warp from reading a table that
+      // is being replaced
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      const float4* src = reinterpret_cast<const float4*>(p.in_norm + (long long)t.b * p.c_in * 2);
+      for (int i = xt; i < p.c_in / 2; i += kXfThreads) reinterpret_cast<float4*>(coef)[i] = __ldg(src + i);
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      cur_b = t.b;
+    }
+    const int dlo = t.d0 - p.pad + p.x_shift, hlo = t.h0 - p.pad + p.x_shift, wlo = t.w0 - p.pad + p.x_shift;
+    const bool edge = dlo < 0 || dlo + p.Hd > p.D || hlo < 0 || hlo + p.Hh > p.H || wlo < 0 || wlo + p.Wh > p.W;
+    for (int kc = 0; kc < total_chunks; ++kc, ++it) {
+      const int s = it & 1;
+      ptx::mbar_wait(&sh->a_full[s], (it >> 1) & 1);
+      if (kc < p.k_chunks && !VDM_DBG(p, 64)) {          // (bring-up flag 64: hand-off only, no arithmetic)
+        uint8_t* stage = a_smem + (size_t)s * p.a_stage_bytes;
+#pragma unroll 1
+        for (int pl = pl0; pl < planes; pl += pl_step) {
+          float ca[8], cb[8];
+          {
+            const float4* cs = reinterpret_cast<const float4*>(coef + (size_t)((kc * planes + pl) * 8) * 2);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 c4 = cs[j4];
+              ca[2 * j4] = c4.x; cb[2 * j4] = c4.y; ca[2 * j4 + 1] = c4.z; cb[2 * j4 + 1] = c4.w;
+            }
+          }
+          uint4* base = reinterpret_cast<uint4*>(stage + (size_t)pl * p.plane_bytes);
+          // Software pipeline, kXfGroup units per group, the NEXT group's loads in flight while this one is computed:
+          // while the tensor core streams its operands out of the same shared memory (the N = 96 MMAs of the narrow layers
+          // run at the shared-memory operand rate) an LDS takes several hundred cycles, and with one or two loads in
+          // flight per thread the transform of a stage took 9K cycles (R2e ncu) -- longer than the MMAs of a tile.
+          constexpr int G = kXfGroup;
+          const int step = 32 * nparts;
+          int v = part * 32 + lane;
+          uint4 cur[G], nxt[G];
+#pragma unroll
+          for (int g2 = 0; g2 < G; ++g2) {
+            const int idx = v + g2 * step;
+            cur[g2] = idx < vh ? base[idx] : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll 1
+          for (; v < vh; v += G * step) {
+            const int vn = v + G * step;
+#pragma unroll
+            for (int g2 = 0; g2 < G; ++g2) {
+              const int idx = vn + g2 * step;
+              nxt[g2] = idx < vh ? base[idx] : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < G; ++g2) {
+              const int idx = v + g2 * step;
+              if (idx < vh) {
+                uint4 y = VDM_DBG(p, 128) ? cur[g2] : gn_silu8(cur[g2], ca, cb);     // (bring-up 128: copy through)
+                if (VDM_DBG(p, 256)) continue;                                       // (bring-up 256: no stores)
+                if (edge) {
+                  const bool oob = p.pad ? halo_voxel_oob<kTileH + 2, kTileW + 2>(idx, dlo, hlo, wlo, p.D, p.H, p.W)
+                                         : halo_voxel_oob<kTileH, kTileW>(idx, dlo, hlo, wlo, p.D, p.H, p.W);
+                  if (oob) y = make_uint4(0u, 0u, 0u, 0u);
+                }
+                base[idx] = y;
+              }
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < G; ++g2) cur[g2] = nxt[g2];
+          }
+        }
+      }
+      // generic-proxy writes -> visible to the async proxy (UMMA operand fetch), then release the stage to the MMA warp
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&sh->a_ready[s]);
+    }
+  }
+}
+
+// ---- epilogue ---------------------------------------------------------------------------------------------
+// 8 warps, two per TMEM lane quarter; thread = one output voxel of the 16 x 8 tile face, unit = (d-slice, 16-channel
+// chunk).  The two warps of a quarter split the units by chunk when the CTA has at least two chunks (each warp then owns
+// whole channels and reduces their statistics over all MT slices in registers), else by slice.
+// The feature set (residual, statistics, fp32 output) is a TEMPLATE parameter chosen once per launch: the r02 epilogue
+// tested those run-time flags inside the unit loop and executed 130 (bare) to 325 (bias + residual + statistics)
+// instructions per unit, 37 of them branches, from two warps per scheduler -- the level-0 layers were bound by that
+// instruction stream, not by the tensor pipe (profiles/R2b_epilogue_sass.txt).  Here a unit is straight-line code: the
+// bias row of a chunk lives in registers for the whole tile, the TMEM load of unit i+1 is issued before unit i is
+// processed, output pointers advance by adds, and shared memory is addressed as shared memory.
+constexpr int kEpiRes = 1, kEpiStats = 2, kEpiFp32 = 4;
+
+template <int MT, int MODE>
+__device__ __forceinline__ void epilogue_tiles(const ConvKernelParams& p, ConvShared* sh, uint8_t* smem, float* stat_part,
+                                               double* stat_acc, const uint32_t tmem_base) {
+  constexpr bool RES = (MODE & kEpiRes) != 0, STATS = (MODE & kEpiStats) != 0, FP32 = (MODE & kEpiFp32) != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;                       // TMEM lane quarter this warp may read
+  const int ew = warp - (kEpiFirst >> 5);       // 0..7
+  const int half = ew >> 2;                     // which of the two warps of that quarter
+  const int et = threadIdx.x - kEpiFirst;       // 0..255
+  const int r = q * 32 + lane;                  // tile row == TMEM lane
+  const int lh = r >> 3, lw = r & 7;
+  const int n_cta = p.n_cta;
+  const int n_chunks = n_cta >> 4;
+  const bool split_ch = n_chunks >= 2;
+  const int ch0 = split_ch ? half : 0, ch_step = split_ch ? 2 : 1;
+  const int s0 = split_ch ? 0 : half, s_step = split_ch ? 1 : 2;
+  const long long HW = (long long)p.H * p.W, V = (long long)p.D * HW;
+  // Bias + conditioning rows: when the [B][n_pad] table fits the 512-float buffer it is loaded ONCE per CTA
+  // (r01r: a per-tile global load + barrier in front of every tile cost ~1 us on the epilogue-bound layers).
+  // A launch without rows gets zeros, so that the unit code has no "is there a bias" branch.
+  float* cadd_tab = &sh->cadd[0][0];
+  const bool cadd_table = p.B * p.n_pad <= 512;
+  const long long cadd_step = (p.chan_add && p.step_ptr) ? (long long)(*p.step_ptr) : 0ll;
+  const float* cadd_g = p.chan_add ? p.chan_add + cadd_step * p.chan_add_step_stride : nullptr;
+  if (cadd_table) {
+    for (int i = et; i < p.B * p.n_pad; i += kEpiThreads) {
+      const int bb = i / p.n_pad, c = i - bb * p.n_pad;
+      cadd_tab[i] = (cadd_g && c < p.c_out) ? __ldg(cadd_g + (long long)bb * p.c_out + c) : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
+  // Residual prefetch ring in SHARED memory.  The residual does not depend on the accumulator, and a dependent
+  // 16-byte global load per (unit, half) cost ~700 cycles each (r01f: 0.44 -> 0.76 ms on the 32->32 level-0 conv).
+  // This warp consumes its units in a fixed order; p.res_depth of them are always in flight as cp.async copies
+  // (one commit group per unit) into per-thread slots, and the prefetch cursor runs AHEAD ACROSS TILE BOUNDARIES.
+  // cp.async has no destination register; the only wait is cp.async.wait_group on the oldest group.
+  constexpr int kResPrefetchTiles = 3;
+  const int r_depth = p.res_depth;
+  uint4* r_ring = reinterpret_cast<uint4*>(smem + p.res_ring_off) + et;   // slot i, plane hf: r_ring[(2*i + hf) * kEpiThreads]
+  int r_slot = 0;                                  // oldest slot == the one refilled next (the ring is always full)
+  const uint4* res_base = reinterpret_cast<const uint4*>(p.residual);
+  // residual grid: the output grid, or (r_up) its half-resolution parent (coordinates shifted right by one)
+  const int r_sh = p.r_up;
+  const int r_H = p.H >> r_sh, r_W = p.W >> r_sh;
+  const long long r_HW = (long long)r_H * r_W, r_V = (long long)(p.D >> r_sh) * r_HW;
+  int r_tile = blockIdx.x - (int)gridDim.x;        // tile the prefetch cursor is in (advanced before first use)
+  int ru_s = 0, ru_ch = n_chunks;                  // (slice, chunk) of the next unit to prefetch; "tile exhausted"
+  const uint4* r_ptr = nullptr;
+  int r_d0 = 0, r_cbase = 0;
+  bool r_hw_ok = false;
+  auto res_issue = [&](int slot) __attribute__((always_inline)) {
+    bool live = true;
+    if (ru_ch >= n_chunks) {                       // move the cursor to this CTA's next tile
+      r_tile += (int)gridDim.x;
+      if (r_tile < p.n_tiles) {
+        const TileCoord tr = decode_tile(p, r_tile);
+        const int hr = tr.h0 + lh, wr = tr.w0 + lw;
+        r_hw_ok = (hr < p.H) && (wr < p.W);
+        r_d0 = tr.d0;
+        r_cbase = tr.ns * n_cta;
+        r_ptr = res_base + ((long long)tr.b * p.r_planes + p.r_plane0 + (r_cbase >> 3) +
+                            (((hr & 1) << 1) | (wr & 1)) * p.r_d2s_planes) * r_V +
+                (long long)(hr >> r_sh) * r_W + (wr >> r_sh);
+        ru_s = s0; ru_ch = ch0;
+      } else {
+        live = false;
+      }
+    }
+    if (live) {
+      const int su = ru_s, chu = ru_ch;
+      ru_s += s_step;
+      if (ru_s >= MT) { ru_s = s0; ru_ch += ch_step; }
+      if (r_hw_ok && r_d0 + su < p.D) {
+        const uint4* src = r_ptr + (long long)(chu * 2 + (((r_d0 + su) & 1) << 2) * p.r_d2s_planes) * r_V +
+                           (long long)((r_d0 + su) >> r_sh) * r_HW;
+        const int cu = r_cbase + chu * 16;
+        uint4* dst = r_ring + (2 * slot) * kEpiThreads;
+        if (cu < p.c_out) ptx::cp_async16(dst, src);
+        if (cu + 8 < p.c_out) ptx::cp_async16(dst + kEpiThreads, src + r_V);
+      }
+    }
+    ptx::cp_async_commit();                        // one group per unit, also when nothing was copied
+  };
+  if (RES) {
+    for (int i = 0; i < r_depth; ++i) res_issue(i);
+  }
+  uint32_t ti = 0;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+    const TileCoord t = decode_tile(p, tile);
+    const int h = t.h0 + lh, w = t.w0 + lw;
+    const bool hw_ok = (h < p.H) && (w < p.W);
+    const int cbase = t.ns * n_cta;
+    const uint32_t acc = ti & 1;
+    if (RES && p.r_d2s_planes == 0) {
+      // The ring runs about one tile ahead, which covers an L2 hit but not an HBM miss (r02g).  Pull the residual rows
+      // of the tile this CTA processes kResPrefetchTiles from now into L2: one 128-byte row per thread.
+      const int pt = tile + kResPrefetchTiles * (int)gridDim.x;
+      if (pt < p.n_tiles) {
+        const TileCoord tp = decode_tile(p, pt);
+        const int pc0 = tp.ns * n_cta;
+        const int n_rows = (n_cta >> 3) * MT * 16;
+        const uint4* pbase = res_base + ((long long)tp.b * p.r_planes + p.r_plane0 + (pc0 >> 3)) * r_V + (tp.w0 >> r_sh);
+        for (int idx = et; idx < n_rows; idx += kEpiThreads) {
+          const int hh = tp.h0 + (idx & 15);
+          const int sp_ = idx >> 4;
+          const int pp = sp_ / MT;
+          const int dd = tp.d0 + (sp_ - pp * MT);
+          if (hh < p.H && dd < p.D && pc0 + pp * 8 < p.c_out && !(r_sh && ((hh | dd) & 1)))
+            ptx::prefetch_l2(pbase + (long long)pp * r_V + ((long long)(dd >> r_sh) * r_H + (hh >> r_sh)) * r_W);
+        }
+      }
+    }
+    const int buf = ti & 1;
+    if (!cadd_table) {
+      // bias + conditioning row of this sample -> shared memory, double-buffered by tile parity
+      if (et < n_cta)
+        sh->cadd[buf][et] = (cadd_g && cbase + et < p.c_out) ? __ldg(cadd_g + (long long)t.b * p.c_out + cbase + et) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    const float* cadd_row = cadd_tab + (cadd_table ? t.b * p.n_pad + cbase : buf * 256);
+    // per-tile bases (64-bit once per tile; per unit only adds): voxel of slice 0 of this thread
+    const long long vox0 = ((long long)t.d0 * p.H + h) * p.W + w;
+    float* sp = stat_part + (ti & 1) * (16 * n_cta);   // this tile's partials (double-buffered by tile parity)
+    ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
+    ptx::tc_fence_after();
+    const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * n_cta);
+    bool released = false;
+    for (int ch = ch0; ch < n_chunks; ch += ch_step) {
+      const int c0 = cbase + ch * 16;
+      const bool last_chunk = ch + ch_step >= n_chunks;
+      // valid 8-channel planes of this chunk (bf16 output: c_out % 8 == 0) / valid channels (fp32 output); warp-uniform
+      const int c_left = p.c_out - c0;
+      const int nhf = c_left >= 16 ? 2 : (c_left >= 8 ? 1 : 0);
+      float cb[16];                              // bias + conditioning row of this chunk, for all slices of the tile
+      {
+        const float4* cs = reinterpret_cast<const float4*>(cadd_row + ch * 16);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 cv = cs[j4];
+          cb[4 * j4] = cv.x; cb[4 * j4 + 1] = cv.y; cb[4 * j4 + 2] = cv.z; cb[4 * j4 + 3] = cv.w;
+        }
+      }
+      float s1[16], s2[16];                      // per-lane statistics of this chunk over the warp's slices
+      if (STATS) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
+      }
+      bf16x8* y_ch = reinterpret_cast<bf16x8*>(p.y) + ((long long)t.b * p.y_planes + p.y_plane0 + (c0 >> 3)) * V + vox0;
+      float* y32_ch = static_cast<float*>(p.y) + ((long long)t.b * p.c_out + c0) * V + vox0;
+      auto process = [&](uint32_t (&raw)[16], int s) __attribute__((always_inline)) {
+        const bool valid = hw_ok && (t.d0 + s < p.D);
+        uint4 rcur0 = make_uint4(0, 0, 0, 0), rcur1 = make_uint4(0, 0, 0, 0);
+        if (RES) {
+          // the oldest slot is this unit's residual; refill it for the unit r_depth ahead
+          ptx::cp_async_wait(r_depth - 1);
+          const uint4* slot = r_ring + (2 * r_slot) * kEpiThreads;
+          rcur0 = slot[0]; rcur1 = slot[kEpiThreads];
+          res_issue(r_slot);
+          r_slot = (r_slot + 1 == r_depth) ? 0 : r_slot + 1;
+        }
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          f[j] = __uint_as_float(raw[j]); f[j + 1] = __uint_as_float(raw[j + 1]);
+          add2(f[j], f[j + 1], cb[j], cb[j + 1]);
+        }
+        if (FP32) {
+          if (valid) {
+            float* yp = y32_ch + (long long)s * HW;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < c_left) yp[(long long)j * V] = f[j];
+          }
+          return;
+        }
+        if (nhf == 0 || !valid) return;          // padded output channels (warp-uniform) / voxels beyond the grid
+        bf16x8* yp = y_ch + (long long)s * HW;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf == 1 && nhf < 2) break;
+          float g[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = f[hf * 8 + j];
+          if (RES) {
+            float rr[8];
+            bf16x8 rv;
+            rv.u = hf == 0 ? rcur0 : rcur1;
+            unpack8(rv, rr);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) add2(g[j], g[j + 1], rr[j], rr[j + 1]);
+          }
+          const bf16x8 packed = pack8(g);
+          yp[hf == 0 ? 0 : V] = packed;
+          if (STATS) {
+            unpack8(packed, g);                  // statistics describe the stored (rounded) tensor
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              add2(s1[hf * 8 + j], s1[hf * 8 + j + 1], g[j], g[j + 1]);
+              fma2_sq(s2[hf * 8 + j], s2[hf * 8 + j + 1], g[j], g[j + 1]);
+            }
+          }
+        }
+      };
+      // unit pipeline of this chunk: the TMEM load of the next slice is in flight while this one is processed
+      const uint32_t tcol = trow0 + (uint32_t)(ch * 16);
+      uint32_t raw_a[16], raw_b[16];
+      int s = s0;
+      if (s < MT) ptx::tmem_ld16(tcol + (uint32_t)(s * n_cta), raw_a);
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        if (s >= MT) break;
+        const int sn = s + s_step;
+        if ((i & 1) == 0) {
+          ptx::tmem_ld_wait_dep(raw_a);
+          if (sn < MT) ptx::tmem_ld16(tcol + (uint32_t)(sn * n_cta), raw_b);
+        } else {
+          ptx::tmem_ld_wait_dep(raw_b);
+          if (sn < MT) ptx::tmem_ld16(tcol + (uint32_t)(sn * n_cta), raw_a);
+        }
+        if (last_chunk && sn >= MT) {
+          // every TMEM read of this accumulator set has completed (wait::ld above): hand it back before the arithmetic
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&sh->tmem_empty[acc]);
+          released = true;
+        }
+        if ((i & 1) == 0) process(raw_a, s);
+        else process(raw_b, s);
+        s = sn;
+      }
+      if (STATS && nhf > 0) {
+        // one transpose-reduction per chunk and tile (r01j: per (slice, chunk) it cost 0.22 -> 0.30 ms on 32->32)
+        warp_column_sums16(s1);
+        warp_column_sums16(s2);
+        if ((lane & 1) == 0) {
+          // one slot per (warp, channel), summed in a fixed order below: statistics do not depend on timing
+          const int c = ch * 16 + (lane >> 1);
+          sp[ew * n_cta + c] = s1[0];
+          sp[(8 + ew) * n_cta + c] = s2[0];
+        }
+      }
+    }
+    if (!released) {
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&sh->tmem_empty[acc]);
+    }
+    if (STATS) {
+      // Fold this tile's per-warp fp32 partials into the CTA's fp64 running sums (fixed order: the result is
+      // reproducible run to run up to the order of the final fp64 atomics); global atomics happen only when
+      // this CTA moves on to another (sample, channel slice) or finishes.
+      // ONE barrier per tile: the partials are double-buffered by tile parity, and the fold of tile i is ordered
+      // before the writes of tile i+2 by the barrier of tile i+1 (r02i: 14% of the samples sat in two barriers).
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (et < n_cta) {
+        const int next_tile = tile + (int)gridDim.x;
+        bool flush = next_tile >= p.n_tiles;
+        if (!flush) {
+          const TileCoord tn = decode_tile(p, next_tile);
+          flush = (tn.b != t.b) || (tn.ns != t.ns);
+        }
+        const int c = et;
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) {
+          t1 += sp[wv * n_cta + c];
+          t2 += sp[(8 + wv) * n_cta + c];
+          sp[wv * n_cta + c] = 0.f;
+          sp[(8 + wv) * n_cta + c] = 0.f;
+        }
+        const double a1 = stat_acc[c] + (double)t1;
+        const double a2 = stat_acc[n_cta + c] + (double)t2;
+        if (flush) {
+          if (cbase + c < p.c_out) {
+            double* dst = p.stats + ((long long)t.b * p.stats_channels + p.stats_c0 + cbase + c) * 2;
+            atomicAdd(dst, a1);
+            atomicAdd(dst + 1, a2);
+          }
+          stat_acc[c] = 0.0;
+          stat_acc[n_cta + c] = 0.0;
+        } else {
+          stat_acc[c] = a1;
+          stat_acc[n_cta + c] = a2;
+        }
+      }
+    }
+  }
+}
+
 // MT = d-slices (accumulators) per tile, KJ = K=16 MMAs per channel chunk (KC = 16*KJ), NF = 0 for the generic
 // path or Cout_pad for the kd-folded path: compile-time so that the MMA issue loops are straight lines of
 // tcgen05.mma with immediate offsets (r01a: a generic loop cost ~240 issue cycles per MMA).
@@ -321,7 +755,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                      const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // Round the window up to 1024 bytes by POINTER ARITHMETIC on the __shared__ array: a round trip through uintptr_t
+  // made nvcc lose the address space, and every access through `sh` / the residual ring compiled to generic LD / ST
+  // (R2b ncu: LD.E.128 for the bias rows and the ring slots in the epilogue's inner loop).
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + 2 * (size_t)p.a_stage_bytes;
   ConvShared* sh = reinterpret_cast<ConvShared*>(b_smem + (size_t)p.nsb * p.b_stage_bytes + p.skip_w_bytes);
@@ -335,6 +772,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&sh->a_full[s], 1);
       ptx::mbar_init(&sh->a_empty[s], 1);
+      ptx::mbar_init(&sh->a_ready[s], kXfThreads);
       ptx::mbar_init(&sh->tmem_full[s], 1);
       ptx::mbar_init(&sh->tmem_empty[s], kEpiThreads);
     }
@@ -350,7 +788,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
   float* stat_part = reinterpret_cast<float*>(sh + 1);     // [tile parity][sum | sumsq][epilogue warp][channel of this CTA]
   double* stat_acc = reinterpret_cast<double*>(stat_part + 2 * 2 * 8 * p.n_cta);   // [sum | sumsq][channel of this CTA]
-  if (warp >= 3) {
+  if (warp >= 4 && warp < 12) {
     for (int i = threadIdx.x - kEpiFirst; i < 2 * p.n_cta; i += kEpiThreads) stat_acc[i] = 0.0;
     for (int i = threadIdx.x - kEpiFirst; i < 2 * 2 * 8 * p.n_cta; i += kEpiThreads) stat_part[i] = 0.f;
   }
@@ -359,6 +797,14 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
   constexpr int planes_per_chunk = KJ * 2;
+  // the barrier the MMA issuer waits on before it reads a halo stage
+  uint64_t* const a_rdy = p.in_norm ? sh->a_ready : sh->a_full;
+  // Per-warpgroup register budgets (the launch gives every thread 65536 / 512 = 128): setmaxnreg is the FIRST statement
+  // of each warpgroup's branch, with no control-flow merge before the role code, so that ptxas allocates each role
+  // against its own budget (with the three instructions in front of a merged if-chain it compiled everything for 128
+  // registers and spilled 7 KB in the epilogue).
+  if (warp < 4) {
+  ptx::setmaxnreg_dec<kRegsWg0>();
 
   if (warp == 0) {
     // ===================== A producer: halo tiles =====================
@@ -496,7 +942,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
           for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
             const uint32_t sa = ita & 1;
-            ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
+            ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
             const uint32_t a_st = a_base16 + sa * a_stage16 + a_lbo;
             for (int khw = 0; khw < 9; ++khw, ++itb) {
               const uint32_t sb = itb % nsb;
@@ -525,7 +971,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int total_chunks = k_chunks + p.skip_chunks;
         for (int kc = 0; kc < total_chunks; ++kc, ++ita) {
           const uint32_t sa = ita & 1;
-          ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
+          ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
           ptx::tc_fence_after();
           if (leader) {
             if (kc == 0)
@@ -559,7 +1005,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)MT * n_cta;
         for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
           const uint32_t sa = ita & 1;
-          ptx::mbar_wait(&sh->a_full[sa], (ita >> 1) & 1);
+          ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
           const uint32_t a_lo0 = a_base16 + sa * a_stage16;
           for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++itb) {
             uint32_t sb, b_lo0;
@@ -598,271 +1044,19 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
       }
     }
+  }
+  } else if (warp >= 12) {
+    // ===================== input transform (4 warps): see transform_tiles =====================
+    ptx::setmaxnreg_dec<kRegsXf>();
+    if (p.in_norm) transform_tiles<MT, KJ>(p, sh, a_smem, reinterpret_cast<float*>(smem + p.xf_coef_off));
   } else {
-    // ===================== epilogue (8 warps; two per TMEM lane quarter) =====================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = (warp - 3) >> 2;             // which of the two warps of that quarter
-    const int et = threadIdx.x - kEpiFirst;       // 0..255
-    const int r = q * 32 + lane;                  // tile row == TMEM lane
-    const int lh = r >> 3, lw = r & 7;
-    const int n_chunks = p.n_cta >> 4;
-    // Work split between the two warps of a lane quarter: by 16-channel chunk when there are at least two (each
-    // warp then owns whole channels and reduces their statistics over all MT slices in registers), else by slice.
-    const int ch0 = n_chunks >= 2 ? half : 0, ch_step = n_chunks >= 2 ? 2 : 1;
-    const int s_step = n_chunks >= 2 ? 1 : 2;
-    const long long V = (long long)p.D * p.H * p.W;
-    const uint4* res_base = reinterpret_cast<const uint4*>(p.residual);
-    // Bias + conditioning rows: when the [B][n_pad] table fits the 512-float buffer it is loaded ONCE per CTA
-    // (r01r: a per-tile global load + barrier in front of every tile cost ~1 us on the epilogue-bound layers).
-    const bool cadd_table = p.chan_add != nullptr && p.B * p.n_pad <= 512;
-    if (cadd_table) {
-      const long long step = p.step_ptr ? (long long)(*p.step_ptr) : 0ll;
-      const float* cadd = p.chan_add + step * p.chan_add_step_stride;
-      float* tab = &sh->cadd[0][0];
-      for (int i = et; i < p.B * p.n_pad; i += kEpiThreads) {
-        const int bb = i / p.n_pad, c = i - bb * p.n_pad;
-        tab[i] = c < p.c_out ? __ldg(cadd + (long long)bb * p.c_out + c) : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-    // Residual prefetch ring in SHARED memory.  The residual does not depend on the accumulator, and a dependent
-    // 16-byte global load per (unit, half) cost ~700 cycles each (r01f: 0.44 -> 0.76 ms on the 32->32 level-0 conv).
-    // This warp consumes its units in a fixed order; p.res_depth of them are always in flight as cp.async copies
-    // (one commit group per unit) into per-thread slots, and the prefetch cursor runs AHEAD ACROSS TILE BOUNDARIES.
-    // The earlier REGISTER ring rotated its entries with moves, and a move out of a register that a load is still
-    // writing waits for that load: every unit waited for the load issued one unit before it (r02g: 18% of the 1x1x1
-    // skip conv's stall samples, +0.3 ms per GB of residual).  cp.async has no destination register; the only wait
-    // is cp.async.wait_group on the oldest group.
-    constexpr int kResPrefetchTiles = 3;
-    const int r_depth = p.res_depth;
-    uint4* r_ring = reinterpret_cast<uint4*>(smem + p.res_ring_off) + et;   // slot i, plane hf: r_ring[(2*i + hf) * kEpiThreads]
-    int r_slot = 0;                                  // oldest slot == the one refilled next (the ring is always full)
-    const long long HW = (long long)p.H * p.W;
-    // residual grid: the output grid, or (r_up) its half-resolution parent (coordinates shifted right by one)
-    const int r_sh = p.r_up;
-    const int r_H = p.H >> r_sh, r_W = p.W >> r_sh;
-    const long long r_HW = (long long)r_H * r_W, r_V = (long long)(p.D >> r_sh) * r_HW;
-    int r_tile = blockIdx.x - (int)gridDim.x;        // tile the prefetch cursor is in (advanced before first use)
-    int ru_s = 0, ru_ch = n_chunks;                  // (slice, chunk) of the next unit to prefetch; "tile exhausted"
-    const uint4* r_ptr = nullptr;
-    int r_d0 = 0, r_cbase = 0;
-    bool r_hw_ok = false;
-    const int s0 = n_chunks >= 2 ? 0 : half;
-    auto res_issue = [&](int slot) {
-      bool live = true;
-      if (ru_ch >= n_chunks) {                       // move the cursor to this CTA's next tile
-        r_tile += (int)gridDim.x;
-        if (r_tile < p.n_tiles) {
-          const TileCoord tr = decode_tile(p, r_tile);
-          const int hr = tr.h0 + lh, wr = tr.w0 + lw;
-          r_hw_ok = (hr < p.H) && (wr < p.W);
-          r_d0 = tr.d0;
-          r_cbase = tr.ns * p.n_cta;
-          r_ptr = res_base + ((long long)tr.b * p.r_planes + p.r_plane0 + (r_cbase >> 3)) * r_V +
-                  (long long)(hr >> r_sh) * r_W + (wr >> r_sh);
-          ru_s = s0; ru_ch = ch0;
-        } else {
-          live = false;
-        }
-      }
-      if (live) {
-        const int su = ru_s, chu = ru_ch;
-        ru_s += s_step;
-        if (ru_s >= MT) { ru_s = s0; ru_ch += ch_step; }
-        if (r_hw_ok && r_d0 + su < p.D) {
-          const uint4* src = r_ptr + (long long)(chu * 2) * r_V + (long long)((r_d0 + su) >> r_sh) * r_HW;
-          const int cu = r_cbase + chu * 16;
-          uint4* dst = r_ring + (2 * slot) * kEpiThreads;
-          if (cu < p.c_out) ptx::cp_async16(dst, src);
-          if (cu + 8 < p.c_out) ptx::cp_async16(dst + kEpiThreads, src + r_V);
-        }
-      }
-      ptx::cp_async_commit();                        // one group per unit, also when nothing was copied
-    };
-    if (p.residual) {
-      for (int i = 0; i < r_depth; ++i) res_issue(i);
-    }
-    uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-      const TileCoord t = decode_tile(p, tile);
-      const int h = t.h0 + lh, w = t.w0 + lw;
-      const bool hw_ok = (h < p.H) && (w < p.W);
-      const int cbase = t.ns * p.n_cta;
-      const uint32_t acc = ti & 1;
-      if (p.residual) {
-        // The register ring above runs about one tile ahead, which covers an L2 hit but not an HBM miss (r02g: 18% of
-        // the 1x1x1 skip conv's stall samples were the ring's first use).  Pull the residual rows of the tile this CTA
-        // processes kResPrefetchTiles from now into L2: one 128-byte row (8 voxels of one plane) per thread.
-        const int pt = tile + kResPrefetchTiles * (int)gridDim.x;
-        if (pt < p.n_tiles) {
-          const TileCoord tp = decode_tile(p, pt);
-          const int pc0 = tp.ns * p.n_cta;
-          const int n_rows = (p.n_cta >> 3) * MT * 16;
-          const uint4* pbase = res_base + ((long long)tp.b * p.r_planes + p.r_plane0 + (pc0 >> 3)) * r_V + (tp.w0 >> r_sh);
-          for (int idx = et; idx < n_rows; idx += kEpiThreads) {
-            const int hh = tp.h0 + (idx & 15);
-            const int sp = idx >> 4;
-            const int pp = sp / MT;
-            const int dd = tp.d0 + (sp - pp * MT);
-            if (hh < p.H && dd < p.D && pc0 + pp * 8 < p.c_out && !(r_sh && ((hh | dd) & 1)))
-              ptx::prefetch_l2(pbase + (long long)pp * r_V + ((long long)(dd >> r_sh) * r_H + (hh >> r_sh)) * r_W);
-          }
-        }
-      }
-      const int buf = ti & 1;
-      if (p.chan_add && !cadd_table) {
-        // bias + conditioning row of this sample -> shared memory (16 scalar global loads per unit cost ~10% of
-        // the epilogue's stall samples in r01h)
-        const long long step = p.step_ptr ? (long long)(*p.step_ptr) : 0ll;
-        const float* cadd = p.chan_add + step * p.chan_add_step_stride + (long long)t.b * p.c_out;
-        if (et < p.n_cta) sh->cadd[buf][et] = (cbase + et < p.c_out) ? __ldg(cadd + cbase + et) : 0.f;
-      }
-      // per-tile bases (64-bit once per tile; per unit only adds): voxel of slice 0, plane 0 of this thread
-      const long long vox0 = ((long long)t.d0 * p.H + h) * p.W + w;
-      bf16x8* y_tile = reinterpret_cast<bf16x8*>(p.y) + ((long long)t.b * p.y_planes + p.y_plane0 + (cbase >> 3)) * V + vox0;
-      if (p.chan_add && !cadd_table) asm volatile("bar.sync 1, 256;" ::: "memory");
-      // (an index into the shared array, not a pointer selected at run time: the latter compiled to generic loads,
-      // 6% of the stall samples in r02i)
-      const int cadd_off = cadd_table ? t.b * p.n_pad + cbase : buf * 256;
-      float* sp = stat_part + (ti & 1) * (16 * p.n_cta);   // this tile's partials (double-buffered by tile parity)
-      ptx::mbar_wait(&sh->tmem_full[acc], (ti >> 1) & 1);
-      ptx::tc_fence_after();
-      if (!VDM_DBG(p, 1)) {
-        for (int ch = ch0; ch < n_chunks; ch += ch_step) {
-          const int c0 = cbase + ch * 16;
-          const bool full16 = (c0 + 16 <= p.c_out);
-          float s1[16], s2[16];            // per-lane statistics of this chunk over the warp's slices
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
-          auto process = [&](int s, const uint32_t (&raw)[16]) __attribute__((always_inline)) {
-            const int d = t.d0 + s;
-            const bool valid = hw_ok && (d < p.D);
-            const long long vox = vox0 + (long long)s * HW;
-            // the oldest slot is this unit's residual; refill it for the unit r_depth ahead
-            uint4 rcur[2];
-            if (p.residual) {
-              ptx::cp_async_wait(r_depth - 1);
-              const uint4* slot = r_ring + (2 * r_slot) * kEpiThreads;
-              rcur[0] = slot[0]; rcur[1] = slot[kEpiThreads];
-              res_issue(r_slot);
-              r_slot = (r_slot + 1 == r_depth) ? 0 : r_slot + 1;
-            }
-            if (c0 >= p.c_out) return;  // padded output channels (warp-uniform)
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(raw[j]);
-            if (p.chan_add) {
-              const float4* cs = reinterpret_cast<const float4*>(&sh->cadd[0][0] + cadd_off + ch * 16);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 cv = cs[j4];
-                add2(f[4 * j4], f[4 * j4 + 1], cv.x, cv.y);
-                add2(f[4 * j4 + 2], f[4 * j4 + 3], cv.z, cv.w);
-              }
-            }
-            if (p.out_fp32) {
-              if (valid) {
-                float* yp = static_cast<float*>(p.y) + ((long long)t.b * p.c_out + c0) * V + vox;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (full16 || c0 + j < p.c_out) yp[(long long)j * V] = f[j];
-              }
-              return;
-            }
-            // bf16 planar output: two planes of 8 channels (c_out % 8 == 0 is checked on the host)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const int c = c0 + hf * 8;
-              if (c >= p.c_out) break;
-              float g[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) g[j] = f[hf * 8 + j];
-              if (p.residual && valid) {
-                float rr[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(&rcur[hf]), rr);
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) add2(g[j], g[j + 1], rr[j], rr[j + 1]);
-              }
-              const bf16x8 packed = pack8(g);
-              if (valid) {
-                if (!VDM_DBG(p, 8)) y_tile[(long long)(ch * 2 + hf) * V + (long long)s * HW] = packed;
-                unpack8(packed, g);  // statistics describe the stored (rounded) tensor
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) {       // FADD2 / FFMA2: the epilogue is bound by its own arithmetic (r02n)
-                  add2(s1[hf * 8 + j], s1[hf * 8 + j + 1], g[j], g[j + 1]);
-                  fma2_sq(s2[hf * 8 + j], s2[hf * 8 + j + 1], g[j], g[j + 1]);
-                }
-              }
-            }
-          };
-          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.n_cta + ch * 16);
-          for (int s = s0; s < MT; s += s_step) {
-            uint32_t raw0[16];
-            if (VDM_DBG(p, 4)) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) raw0[j] = (uint32_t)(lane + j);     // experiment: no TMEM reads
-            } else {
-              ptx::tmem_ld16(trow + (uint32_t)(s * p.n_cta), raw0);
-              ptx::tmem_ld_wait();
-            }
-            process(s, raw0);
-          }
-          if (p.stats && c0 < p.c_out && !VDM_DBG(p, 16)) {
-            // one transpose-reduction per chunk and tile (r01j: per (slice, chunk) it cost 0.22 -> 0.30 ms on 32->32)
-            warp_column_sums16(s1);
-            warp_column_sums16(s2);
-            if ((lane & 1) == 0) {
-              // one slot per (warp, channel), summed in a fixed order below: statistics do not depend on timing
-              const int c = ch * 16 + (lane >> 1);
-              sp[(warp - 3) * p.n_cta + c] = s1[0];
-              sp[(8 + warp - 3) * p.n_cta + c] = s2[0];
-            }
-          }
-        }
-      }
-      // all TMEM reads of this accumulator set are complete (wait::ld above): hand it back
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&sh->tmem_empty[acc]);
-      if (p.stats && !VDM_DBG(p, 32)) {
-        // Fold this tile's per-warp fp32 partials into the CTA's fp64 running sums (fixed order: the result is
-        // reproducible run to run up to the order of the final fp64 atomics); global atomics happen only when
-        // this CTA moves on to another (sample, channel slice) or finishes.
-        // ONE barrier per tile: the partials are double-buffered by tile parity, and the fold of tile i is ordered
-        // before the writes of tile i+2 by the barrier of tile i+1 (r02i: 14% of the samples sat in two barriers).
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (et < p.n_cta) {
-          const int next_tile = tile + (int)gridDim.x;
-          bool flush = next_tile >= p.n_tiles;
-          if (!flush) {
-            const TileCoord tn = decode_tile(p, next_tile);
-            flush = (tn.b != t.b) || (tn.ns != t.ns);
-          }
-          const int c = et;
-          float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-          for (int wv = 0; wv < 8; ++wv) {
-            t1 += sp[wv * p.n_cta + c];
-            t2 += sp[(8 + wv) * p.n_cta + c];
-            sp[wv * p.n_cta + c] = 0.f;
-            sp[(8 + wv) * p.n_cta + c] = 0.f;
-          }
-          const double a1 = stat_acc[c] + (double)t1;
-          const double a2 = stat_acc[p.n_cta + c] + (double)t2;
-          if (flush) {
-            if (cbase + c < p.c_out) {
-              double* dst = p.stats + ((long long)t.b * p.stats_channels + p.stats_c0 + cbase + c) * 2;
-              atomicAdd(dst, a1);
-              atomicAdd(dst + 1, a2);
-            }
-            stat_acc[c] = 0.0;
-            stat_acc[p.n_cta + c] = 0.0;
-          } else {
-            stat_acc[c] = a1;
-            stat_acc[p.n_cta + c] = a2;
-          }
-        }
-      }
-    }
+    // ===================== epilogue (8 warps; two per TMEM lane quarter): see epilogue_tiles =====================
+    ptx::setmaxnreg_inc<kRegsEpi>();
+    if (p.out_fp32) epilogue_tiles<MT, kEpiFp32>(p, sh, smem, stat_part, stat_acc, tmem_base);
+    else if (p.residual && p.stats) epilogue_tiles<MT, kEpiRes | kEpiStats>(p, sh, smem, stat_part, stat_acc, tmem_base);
+    else if (p.residual) epilogue_tiles<MT, kEpiRes>(p, sh, smem, stat_part, stat_acc, tmem_base);
+    else if (p.stats) epilogue_tiles<MT, kEpiStats>(p, sh, smem, stat_part, stat_acc, tmem_base);
+    else epilogue_tiles<MT, 0>(p, sh, smem, stat_part, stat_acc, tmem_base);
   }
 
   ptx::tc_fence_before();
@@ -964,6 +1158,12 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   p.pad = pad;
   const bool has_residual = epi && epi->residual;
   const bool has_skip = epi && epi->skip_x;
+  const bool has_xf = epi && epi->in_norm;
+  if (has_xf && d.circular) {
+    set_error("vdm_conv3d: the fused input transform is not available with circular padding");
+    return VDM_E_UNSUPPORTED;
+  }
+  const int xf_bytes = has_xf ? ((d.c_in * 8 + 15) & ~15) : 0;      // (a, b) table of one sample
   if (has_skip) {
     VDM_CHECK_ARG(epi->skip_w && epi->skip_c_in >= 16 && epi->skip_c_in % 16 == 0,
                   "vdm_conv3d: fused skip conv needs packed weights and skip_c_in a multiple of 16, got %d", epi->skip_c_in);
@@ -984,7 +1184,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   } else if (fold) {
     // all weights resident + two halo stages must fit; prefer tall tiles (halo efficiency), then wide chunks
     const int budget = 227 * 1024 - 1024 - (int)sizeof(ConvShared) - (2 * 2 * 8 * d.c_out_pad * 4 + 2 * d.c_out_pad * 8) - 256 -
-                       (has_residual ? 2 * kResSlotBytes : 0);      // room for at least two residual slots
+                       (has_residual ? 2 * kResSlotBytes : 0) - xf_bytes;      // room for at least two residual slots
     const int w_bytes = 27 * d.c_in * d.c_out_pad * 2 + skip_w_bytes;
     for (int m = 4; m >= 2 && !fold_mt; --m)
       for (int c = 32; c >= 16 && !fold_mt; c -= 16) {
@@ -1074,7 +1274,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
 
   // ---- shared memory plan: 2 halo stages + a ring of weight stages ----
   const int stat_part_bytes = 2 * 2 * 8 * p.n_cta * 4 + 2 * p.n_cta * 8;    // partials + running sums
-  const int smem_total = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - stat_part_bytes - 256;
+  const int smem_total = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(ConvShared) - stat_part_bytes - 256 - xf_bytes;
   // layers with a residual keep a cp.async ring of it in shared memory: 4 units deep where the weights are streamed
   // anyway, at least 2 where they are resident (the fold search above left room)
   const int smem_budget = smem_total - (has_residual ? (fold && !fold_streamed ? 2 : 4) * kResSlotBytes : 0);
@@ -1147,6 +1347,7 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     p.r_planes = d.r_planes > 0 ? d.r_planes : d.c_out / 8;
     p.r_plane0 = d.r_plane0;
     p.r_up = (epi->residual && epi->residual_upsample) ? 1 : 0;
+    p.r_d2s_planes = (epi->residual && epi->residual_upsample == 2) ? d.c_out / 8 : 0;
     p.stats = epi->stats;
     p.stats_channels = epi->stats_channels > 0 ? epi->stats_channels : d.c_out;
     p.stats_c0 = epi->stats_c0;
@@ -1202,7 +1403,10 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     p.res_ring_off = used + (int)sizeof(ConvShared) + stat_part_bytes;
     p.res_ring_off = (p.res_ring_off + 15) & ~15;
   }
-  const size_t smem_bytes = (size_t)used + sizeof(ConvShared) + stat_part_bytes + 16 + (size_t)p.res_depth * kResSlotBytes + 1024;
+  p.xf_coef_off = (used + (int)sizeof(ConvShared) + stat_part_bytes + 16 + p.res_depth * kResSlotBytes + 15) & ~15;
+  p.in_norm = has_xf ? epi->in_norm : nullptr;
+  p.c_in = d.c_in;
+  const size_t smem_bytes = (size_t)p.xf_coef_off + xf_bytes + 1024;
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   int rc = VDM_E_UNSUPPORTED;
 #define VDM_LAUNCH(MTv, KJv, NFv)                                                                              \

@@ -87,6 +87,34 @@ gn_silu_kernel(VdmTensor x, VdmTensor y, int planes, int64_t voxels, int groups,
   }
 }
 
+// ---- GroupNorm coefficients for the conv kernel's fused input transform ----------------------------------------
+// coef[b][c] = (a, b) with  silu(gn(x)) = h + h * tanh(h),  h = a * x + b = (gamma * rstd * x + beta - mean * gamma * rstd) / 2:
+// the per-(sample, channel) pair conv3d_planar_kernel's transform warps apply to the landed halo tile (csrc/conv3d.cu).
+// One thread per (sample, channel); group sums are re-derived per thread from the fp64 (sum, sumsq) table.
+__global__ void gn_coef_kernel(const double* __restrict__ stats, int batch, int C, int groups, double voxels,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                               float2* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * C) return;
+  const int b = i / C, c = i - b * C;
+  const int cpg = C / groups;
+  const int g0 = (c / cpg) * cpg;
+  const double* sb = stats + (int64_t)b * C * 2;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < cpg; ++k) {
+    s1 += sb[2 * (g0 + k)];
+    s2 += sb[2 * (g0 + k) + 1];
+  }
+  const double n = voxels * cpg;
+  const double mean = s1 / n;
+  double var = s2 / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * rstd;
+  const float sh = beta[c] - (float)mean * sc;      // same roundings as plane_scale_shift (the unfused kernels)
+  coef[i] = make_float2(0.5f * sc, 0.5f * sh);
+}
+
 // ---- GroupNorm + SiLU of a channel window of a wider norm, optionally through a nearest x2 up-sampling ------------
 // The up blocks normalise cat([upsample(h_coarse), skip]).  Nearest-neighbour up-sampling commutes with every
 // pointwise operation and leaves per-channel means and variances unchanged, so the up-sampled tensor is never
@@ -98,11 +126,11 @@ template <bool UP>
 __global__ void __launch_bounds__(kEwThreads)
 gn_silu_view_kernel(VdmTensor x, VdmTensor y, int planes, int c_off, int C_total, int groups, int D, int H, int W,
                     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float eps) {
+                    float eps, double stats_voxels) {
   __shared__ float s_scale[8], s_shift[8];
   const int b = blockIdx.y / planes, pl = blockIdx.y % planes;
   const int64_t vf = (int64_t)D * H * W;
-  plane_scale_shift(stats + (int64_t)b * C_total * 2, C_total, groups, (c_off >> 3) + pl, (double)vf, gamma, beta, eps,
+  plane_scale_shift(stats + (int64_t)b * C_total * 2, C_total, groups, (c_off >> 3) + pl, stats_voxels, gamma, beta, eps,
                     s_scale, s_shift, nullptr, nullptr);
   __syncthreads();
   float sc[8], sh[8];
@@ -311,6 +339,17 @@ extern "C" int vdm_gn_silu(const VdmTensor* x, const VdmTensor* y, int batch, in
                           layer_tag, stream);
 }
 
+extern "C" int vdm_gn_coef(const double* stats, int batch, int channels, int groups, int64_t voxels, const float* gamma,
+                           const float* beta, float eps, float* coef, void* stream) {
+  VDM_CHECK_ARG(stats && gamma && beta && coef && batch >= 1 && channels >= 1 && voxels >= 1, "vdm_gn_coef: bad argument");
+  VDM_CHECK_ARG(groups >= 1 && channels % groups == 0, "vdm_gn_coef: %d channels not divisible into %d groups", channels, groups);
+  const int n = batch * channels;
+  gn_coef_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, batch, channels, groups, (double)voxels, gamma, beta, eps,
+                                                                    reinterpret_cast<float2*>(coef));
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
+
 extern "C" int vdm_gn_silu_view(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,
                                 int channels, int c_off, int channels_total, int groups, const double* stats,
                                 const float* gamma, const float* beta, float eps, int upsample, void* stream) {
@@ -328,11 +367,18 @@ extern "C" int vdm_gn_silu_view(const VdmTensor* x, const VdmTensor* y, int batc
   if (upsample) {
     VDM_CHECK_ARG(depth % 2 == 0 && height % 2 == 0 && width % 2 == 0, "vdm_gn_silu_view: fine grid (%d,%d,%d) must be even",
                   depth, height, width);
+  }
+  if (upsample == 1) {
     gn_silu_view_kernel<true><<<ew_grid(vf / 2, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
-        *x, *y, planes, c_off, channels_total, groups, depth, height, width, stats, gamma, beta, eps);
+        *x, *y, planes, c_off, channels_total, groups, depth, height, width, stats, gamma, beta, eps, (double)vf);
+  } else if (upsample == 2) {
+    // x AND y on the half-resolution grid; the statistics are those of the (depth, height, width) concat the channels
+    // belong to (sums over the up-sampled tensor = 8x the coarse sums): the polyphase up-conv reads this tensor
+    gn_silu_view_kernel<false><<<ew_grid(vf / 8, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
+        *x, *y, planes, c_off, channels_total, groups, depth / 2, height / 2, width / 2, stats, gamma, beta, eps, (double)vf);
   } else {
     gn_silu_view_kernel<false><<<ew_grid(vf, batch * planes), kEwThreads, 0, (cudaStream_t)stream>>>(
-        *x, *y, planes, c_off, channels_total, groups, depth, height, width, stats, gamma, beta, eps);
+        *x, *y, planes, c_off, channels_total, groups, depth, height, width, stats, gamma, beta, eps, (double)vf);
   }
   VDM_CHECK_LAUNCH();
   return VDM_OK;

@@ -40,7 +40,7 @@ using namespace vdm;
 
 extern "C" int vdm_pack_conv_weight(const float* w, void* packed, int c_out, int c_in, int kernel, int transpose_flip,
                                     int ci0, int n_ci, int c_in_pad, int c_out_pad, void* stream) {
-  VDM_CHECK_ARG(w && packed && c_out >= 1 && c_in >= 1 && (kernel == 1 || kernel == 3), "vdm_pack_conv_weight: bad argument");
+  VDM_CHECK_ARG(w && packed && c_out >= 1 && c_in >= 1 && kernel >= 1 && kernel <= 3, "vdm_pack_conv_weight: bad argument");
   VDM_CHECK_ARG(c_in_pad % 16 == 0 && c_out_pad % 16 == 0 && c_in_pad >= 16 && c_out_pad >= 16,
                 "vdm_pack_conv_weight: padded sizes (%d, %d) must be multiples of 16", c_in_pad, c_out_pad);
   VDM_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "vdm_pack_conv_weight: packed must be 16-byte aligned");

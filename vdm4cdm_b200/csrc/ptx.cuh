@@ -42,13 +42,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a pipeline bug must trap (a launch error the host sees) instead of
-// hanging the GPU.  ~4 s at 2 GHz.
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase completes (or ~2 us pass)
+// instead of returning after ~100 cycles.  R2b ncu: the 9-instruction polling loops of the MMA / producer warps were
+// 20% of all issued instructions of the conv kernel, taken from the schedulers the epilogue warps run on.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Wait with a watchdog: a pipeline bug must trap (a launch error the host sees) instead of hanging the GPU
+// (2^21 suspended retries of up to ~2 us each: seconds).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000ll) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    if (++spins > (1u << 21)) {
       printf("vdm4cdm_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
@@ -67,6 +83,16 @@ __device__ __forceinline__ bool elect_one() {
       "}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// Per-warpgroup register budget (all four warps of the warpgroup execute the same instruction).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ---- TMA ------------------------------------------------------------------------------------
@@ -197,6 +223,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same, with the destination registers of the load as (fake) in/out operands: arithmetic on them cannot be scheduled
+// above the wait, which matters once a second load is in flight while the first one's values are used.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // ---- descriptors --------------------------------------------------------------------------------
 // K-major shared-memory matrix descriptor for a tile whose rows are `row_bytes` (= swizzle span:

@@ -119,6 +119,14 @@ class CUNet(nn.Module):
         self.shape = tuple(shape)
         self.circular = conv_padding_mode == "circular"     # the cropsize == 256 models (src/utils.py:460)
         self.fuse_upsample = True       # inference: up blocks read the coarse tensor instead of its up-sampled copy
+        # inference: GroupNorm + SiLU in front of a conv is applied by the conv kernel to its input tile (ops.conv3d
+        # in_norm) instead of by a separate read + write pass over the tensor
+        self.fuse_gn = True
+        self.fuse_gn_min_channels = 64
+        # inference, up blocks: conv3x3x3 over the up-sampled half of cat([interpolate(h), skip]) in its polyphase form --
+        # eight 2x2x2-tap convolutions of the COARSE tensor, one per output parity (8/27 of the multiply-adds, the
+        # up-sampled activations are never written); the skip half is a plain conv that adds them as its residual
+        self.polyphase_up = True
         self._fused_skip_ok = {}        # per up block: False once vdm_conv3d declined the fused skip conv
         self.chs = list(chs)
         self.s_conditioning_channels = s_conditioning_channels
@@ -228,6 +236,24 @@ class CUNet(nn.Module):
             self._packed_cache[slot] = hit
         return hit[1]
 
+    def _packed_poly(self, slot: str, conv: nn.Conv3d, c_up: int, parity) -> torch.Tensor:
+        """bf16 packed 2x2x2 filter of output parity ``parity`` for the first ``c_up`` (up-sampled) input channels of a 3x3x3
+        conv (``ops.polyphase_weight``: sums of the original taps, formed in fp32 and rounded once)."""
+        w = conv.weight
+        key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
+        slot = f"{slot}.poly.{parity[0]}{parity[1]}{parity[2]}"
+        hit = self._packed_cache.get(slot)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                part = ops.polyphase_weight(w.detach()[:, :c_up].float(), parity)
+                shape = ops.packed_weight_shape(part.shape)
+                buf = hit[1] if hit is not None and tuple(hit[1].shape) == shape and hit[1].device == w.device else \
+                    torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+                ops.pack_conv_weight_into(part, buf)
+                hit = (key, buf)
+            self._packed_cache[slot] = hit
+        return hit[1]
+
     def trunk_parameters(self):
         """(name, parameter) of everything the convolutional trunk differentiates itself: conv filters and
         GroupNorm affines, named as ``vdm4cdm_b200.autograd`` records their gradients.  (Conv biases and the
@@ -318,30 +344,68 @@ class CUNet(nn.Module):
         ci, co, g = blk.ch_in, blk.ch_out, blk.norm_groups
         tag = f"{b}x{grid[0]}"
         own = "" if tape is None else name + "."
-        a1 = ar.get(f"{own}a.{ci}.{tag}", (b, ci // 8) + grid + (8,), torch.bfloat16, dev)
         n1 = blk.net1[0]
-        if up_from is None:
-            ops.gn_silu(x, ci, g, x_stats, n1.weight, n1.bias, n1.eps, x_plane0=x_plane0, out=a1)
-        else:
-            xc, xc_plane0, c_up = up_from
-            ops.gn_silu_view(xc, c_up, 0, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a1, x_plane0=xc_plane0,
-                             out_plane0=0, upsample=True)
-            ops.gn_silu_view(x, ci - c_up, c_up, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a1,
-                             x_plane0=x_plane0 + c_up // 8, out_plane0=c_up // 8)
+        voxels = grid[0] * grid[1] * grid[2]
+        p_drop = blk.dropout_prob if training_dropout else 0.0
+        # inference without dropout and with zero padding: the convs normalise their own input tiles (fuse_gn) -- for layers
+        # of at least 64 output channels.  Narrower layers run the kd-folded N = 96 schedule, which is bound by the tensor
+        # core's shared-memory operand fetch; the transform's LDS / STS traffic on the same shared memory then costs more
+        # (+0.55 ms on a 0.85 ms 32->32 conv at 128^3 x 8 even as a plain copy, profiles/R2h_transform_ablation.txt) than
+        # the separate HBM pass it replaces (0.45 ms).
+        fuse_gn = self.fuse_gn and tape is None and not self.circular and p_drop == 0.0 and co >= self.fuse_gn_min_channels
         h = ar.get(f"{own}h.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
         h_stats = self._stats(f"{name}.h", b, co, dev)
-        a1c, _ = self._conv_input(a1, ci, 0, name + ".a1p", tape)
-        ops.conv3d(a1c, self._packed(name + ".net1", blk.net1[2]), co, out=h, chan_add=rows[name + ".net1"],
-                   step_ptr=step_ptr if rows[name + ".net1"].dim() == 3 else None, stats=h_stats, circular=self.circular)
-        a2 = ar.get(f"{own}a2.{co}.{tag}" if tape is not None else f"a.{co}.{tag}", (b, co // 8) + grid + (8,),
-                    torch.bfloat16, dev)
-        p_drop = blk.dropout_prob if training_dropout else 0.0
+        net1_kw = dict(out=h, chan_add=rows[name + ".net1"], step_ptr=step_ptr if rows[name + ".net1"].dim() == 3 else None,
+                       stats=h_stats, circular=self.circular)
+        if fuse_gn and up_from is None:
+            coef1 = ops.gn_coef(x_stats, n1.weight, n1.bias, g, voxels, n1.eps,
+                                out=ar.get(f"coef1.{name}.{b}", (b, ci, 2), torch.float32, dev))
+            ops.conv3d(x, self._packed(name + ".net1", blk.net1[2]), co, x_plane0=x_plane0, c_in=ci, in_norm=coef1, **net1_kw)
+        elif up_from is not None and self.polyphase_up and not self.circular:
+            xc, xc_plane0, c_up = up_from
+            cgrid = tuple(n // 2 for n in grid)
+            # silu(gn(.)) of the coarse channels at the COARSE resolution (statistics of the fine concat)
+            ac = ar.get(f"ac.{c_up}.{b}x{cgrid[0]}", (b, c_up // 8) + cgrid + (8,), torch.bfloat16, dev)
+            ops.gn_silu_view(xc, c_up, 0, ci, g, x_stats, n1.weight, n1.bias, n1.eps, ac, x_plane0=xc_plane0, upsample="coarse")
+            # eight parity convolutions (2x2x2 taps on the coarse grid) -> parity-planar partial sums [8 x co channels]
+            part = ar.get(f"poly.{co}.{b}x{cgrid[0]}", (b, co) + cgrid + (8,), torch.bfloat16, dev)
+            for pi in range(8):
+                parity = (pi >> 2, (pi >> 1) & 1, pi & 1)
+                ops.conv3d(ac, self._packed_poly(name + ".net1", blk.net1[2], c_up, parity), co, taps=ops.polyphase_taps(parity),
+                           out=part, out_plane0=pi * (co // 8))
+            # the skip channels at the fine resolution; the partial sums come in through the depth-to-space residual
+            a_s = ar.get(f"as.{ci - c_up}.{tag}", (b, (ci - c_up) // 8) + grid + (8,), torch.bfloat16, dev)
+            ops.gn_silu_view(x, ci - c_up, c_up, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a_s, x_plane0=x_plane0 + c_up // 8)
+            ops.conv3d(a_s, self._packed_in_slice(name + ".net1.skiphalf", blk.net1[2], c_up, ci - c_up), co,
+                       residual=part, residual_upsample="d2s", **net1_kw)
+        else:
+            a1 = ar.get(f"{own}a.{ci}.{tag}", (b, ci // 8) + grid + (8,), torch.bfloat16, dev)
+            if up_from is None:
+                ops.gn_silu(x, ci, g, x_stats, n1.weight, n1.bias, n1.eps, x_plane0=x_plane0, out=a1)
+            else:
+                xc, xc_plane0, c_up = up_from
+                ops.gn_silu_view(xc, c_up, 0, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a1, x_plane0=xc_plane0,
+                                 out_plane0=0, upsample=True)
+                ops.gn_silu_view(x, ci - c_up, c_up, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a1,
+                                 x_plane0=x_plane0 + c_up // 8, out_plane0=c_up // 8)
+            a1c, _ = self._conv_input(a1, ci, 0, name + ".a1p", tape)
+            ops.conv3d(a1c, self._packed(name + ".net1", blk.net1[2]), co, **net1_kw)
         if p_drop > 0.0:
             self._dropout_calls += 1
-        ops.gn_silu(h, co, g, h_stats, blk.net2[0].weight, blk.net2[0].bias, blk.net2[0].eps, out=a2, dropout_p=p_drop,
-                    seed=self.dropout_seed, layer_tag=self._dropout_calls,
-                    seed_step=self.drop_counter if p_drop > 0.0 else None)
-        a2c, _ = self._conv_input(a2, co, 0, name + ".a2p", tape)
+        n2 = blk.net2[0]
+        if fuse_gn:
+            # net2's conv reads h itself; (a, b) per (sample, channel) from h's statistics
+            a2c = h
+            in_norm2 = ops.gn_coef(h_stats, n2.weight, n2.bias, g, voxels, n2.eps,
+                                   out=ar.get(f"coef2.{name}.{b}", (b, co, 2), torch.float32, dev))
+        else:
+            in_norm2 = None
+            a2 = ar.get(f"{own}a2.{co}.{tag}" if tape is not None else f"a.{co}.{tag}", (b, co // 8) + grid + (8,),
+                        torch.bfloat16, dev)
+            ops.gn_silu(h, co, g, h_stats, n2.weight, n2.bias, n2.eps, out=a2, dropout_p=p_drop,
+                        seed=self.dropout_seed, layer_tag=self._dropout_calls,
+                        seed_step=self.drop_counter if p_drop > 0.0 else None)
+            a2c, _ = self._conv_input(a2, co, 0, name + ".a2p", tape)
         if tape is not None:
             tape[name] = dict(x=x, x_plane0=x_plane0, x_stats=x_stats, a1=a1c, h=h, h_stats=h_stats, a2=a2c, grid=grid,
                               p_drop=p_drop, drop_tag=self._dropout_calls, drop_seed=self.dropout_seed)
@@ -361,7 +425,7 @@ class CUNet(nn.Module):
                     ops.conv3d(a2c, self._packed(name + ".net2", blk.net2[3]), co, out=out, out_plane0=out_plane0,
                                chan_add=rows[name + ".net2"], residual=rc, residual_upsample=True, stats=out_stats,
                                stats_c0=out_stats_c0, skip_x=x, skip_w=w_skip, skip_plane0=x_plane0 + c_up // 8,
-                               circular=self.circular)
+                               circular=self.circular, in_norm=in_norm2)
                     return
                 except ops.UnsupportedFusion:
                     self._fused_skip_ok[name] = False          # wide layer: keep the skip conv as its own launch
@@ -376,7 +440,7 @@ class CUNet(nn.Module):
             res_plane0 = 0
         ops.conv3d(a2c, self._packed(name + ".net2", blk.net2[3]), co, out=out, out_plane0=out_plane0,
                    chan_add=rows[name + ".net2"], residual=res, residual_plane0=res_plane0, stats=out_stats,
-                   stats_c0=out_stats_c0, circular=self.circular)
+                   stats_c0=out_stats_c0, circular=self.circular, in_norm=in_norm2)
 
     def _conv_input(self, x, ch, x_plane0, slot, tape):
         """The tensor a 3x3x3 conv reads: ``x`` itself (zero padding is the TMA unit's out-of-bounds fill) or, for
@@ -470,14 +534,20 @@ class CUNet(nn.Module):
                 self._run_block(name, blk, cat, 0, cst, rows, step_ptr, o, 0, ost, 0, grids[i], training_dropout, tape)
             x, x_plane0, x_stats = o, 0, ost
         gn = self.conv_out[0]
+        if out is None:
+            out = torch.empty((b, 1) + grids[0], dtype=torch.float32, device=dev)
+        if self.fuse_gn and tape is None and not self.circular and self.fuse_gn_min_channels <= 1:
+            coef = ops.gn_coef(x_stats, gn.weight, gn.bias, gn.num_groups, grids[0][0] * grids[0][1] * grids[0][2], gn.eps,
+                               out=ar.get(f"coef.conv_out.{b}", (b, c[0], 2), torch.float32, dev))
+            ops.conv3d(x, self._packed("conv_out", self.conv_out[2]), 1, x_plane0=x_plane0, c_in=c[0], out=out, out_fp32=True,
+                       chan_add=rows["conv_out"], in_norm=coef)
+            return out
         a = ar.get(("conv_out." if tape is not None else "") + f"a.{c[0]}.{b}x{grids[0][0]}",
                    (b, c[0] // 8) + grids[0] + (8,), torch.bfloat16, dev)
         ops.gn_silu(x, c[0], gn.num_groups, x_stats, gn.weight, gn.bias, gn.eps, out=a)
         a_c, _ = self._conv_input(a, c[0], 0, "conv_out.ap", tape)
         if tape is not None:
             tape["trunk"] = dict(packed=packed_c, h_in=h, cats=cats, grids=grids, out_x=x, out_x_stats=x_stats, out_a=a_c)
-        if out is None:
-            out = torch.empty((b, 1) + grids[0], dtype=torch.float32, device=dev)
         ops.conv3d(a_c, self._packed("conv_out", self.conv_out[2]), 1, out=out, out_fp32=True, chan_add=rows["conv_out"],
                    circular=self.circular)
         return out

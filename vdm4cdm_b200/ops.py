@@ -142,12 +142,16 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
            x_plane0: int = 0, c_in: Optional[int] = None, out: Optional[torch.Tensor] = None, out_plane0: int = 0,
            out_fp32: bool = False, chan_add: Optional[torch.Tensor] = None, step_ptr: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, residual_plane0: int = 0, stats: Optional[torch.Tensor] = None,
-           stats_c0: int = 0, circular: bool = False, residual_upsample: bool = False,
-           skip_x: Optional[torch.Tensor] = None, skip_w: Optional[torch.Tensor] = None, skip_plane0: int = 0) -> torch.Tensor:
+           stats_c0: int = 0, circular: bool = False, residual_upsample=False,
+           skip_x: Optional[torch.Tensor] = None, skip_w: Optional[torch.Tensor] = None, skip_plane0: int = 0,
+           in_norm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``vdm_conv3d``: y = conv(x, w) [+ chan_add[b, co]] [+ residual], optional GroupNorm statistics.
     ``residual_upsample``: the residual lives on the half-resolution grid and is added through a nearest x2 up-sampling.
     ``skip_x`` / ``skip_w``: y += conv1x1x1(skip_x[window at skip_plane0], skip_w) fused into the launch (narrow
     kd-folded layers only; raises ``UnsupportedFusion`` when the layer cannot take it).
+
+    ``in_norm`` (``gn_coef`` output, fp32 [B, c_in, 2]): ``x`` is the RAW tensor and the kernel applies GroupNorm + SiLU to
+    every input tile on the fly (raises ``UnsupportedFusion`` where the layer cannot take it).
 
     x: planar buffer; the conv reads ``c_in`` channels starting at plane ``x_plane0``.
     w_packed: ``pack_conv_weight`` output, shape [taps, c_in/8, c_out_pad, 8].
@@ -201,7 +205,10 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
         r_grid = (d // 2, h // 2, w_ // 2) if residual_upsample else (d, h, w_)
         _need(tuple(residual.shape[2:5]) == r_grid and residual.shape[0] == b, "conv3d: residual grid mismatch")
         epi.residual = residual.data_ptr()
-        epi.residual_upsample = 1 if residual_upsample else 0
+        # residual_upsample="d2s": eight parity blocks of c_out channels on the half-resolution grid (see polyphase_upconv)
+        epi.residual_upsample = 2 if residual_upsample == "d2s" else (1 if residual_upsample else 0)
+        if residual_upsample == "d2s":
+            _need(c_out % 8 == 0 and residual.shape[1] >= residual_plane0 + c_out, "conv3d: a depth-to-space residual holds 8 x c_out channels")
         desc.r_planes, desc.r_plane0 = residual.shape[1], residual_plane0
     if skip_x is not None:
         _planar_ok(skip_x, "conv3d skip_x")
@@ -211,6 +218,10 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
               "conv3d: skip_w must be the packed (c_out, skip_c_in, 1, 1, 1) filter")
         epi.skip_x, epi.skip_w = skip_x.data_ptr(), skip_w.data_ptr()
         epi.skip_c_in, epi.skip_planes, epi.skip_plane0 = skip_w.shape[1] * 8, skip_x.shape[1], skip_plane0
+    if in_norm is not None:
+        _need(in_norm.is_cuda and in_norm.dtype == torch.float32 and in_norm.is_contiguous() and
+              tuple(in_norm.shape) == (b, c_in, 2), "conv3d: in_norm must be contiguous CUDA fp32 [B, c_in, 2]")
+        epi.in_norm = in_norm.data_ptr()
     if stats is not None:
         _need(stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous() and stats.dim() == 3 and
               stats.shape[0] == b and stats.shape[2] == 2, "conv3d: stats must be double [B, C, 2]")
@@ -223,7 +234,7 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
         e0.record()
     rc = _C.lib().vdm_conv3d(ctypes.byref(desc), x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), ctypes.byref(epi),
                              _stream())
-    if rc == _C.E_UNSUPPORTED and skip_x is not None:
+    if rc == _C.E_UNSUPPORTED and (skip_x is not None or in_norm is not None):
         raise _C.UnsupportedFusion(_C.lib().vdm_last_error_string().decode("utf-8", "replace"))
     _C.check(rc, "vdm_conv3d")
     _launched(1)
@@ -233,6 +244,32 @@ def conv3d(x: torch.Tensor, w_packed: torch.Tensor, c_out: int, *, taps: Sequenc
         prof.append((e0, e1, 2.0 * n_taps * c_in * c_out * b * d * h * w_,
                      f"{_PROFILE_TAG}{c_in}->{c_out} taps={n_taps} grid={d}x{h}x{w_} B={b}"))
     return out
+
+
+# ---- polyphase form of conv3x3x3(interpolate(a, scale_factor=2, mode="nearest")) ------------------------------
+# Fine voxel 2i + p (per axis, parity p in {0, 1}) reads the up-sampled input at 2i + p + t, t in {-1, 0, 1}, i.e. the COARSE
+# voxel i + floor((p + t) / 2):   p = 0: t = -1 -> i - 1, t = 0, +1 -> i;      p = 1: t = -1, 0 -> i, t = +1 -> i + 1.
+# Per output parity the 27 taps therefore collapse to 2 x 2 x 2 taps on the coarse grid whose weights are sums of the
+# original ones: 8 / 27 of the multiply-adds, and the up-sampled tensor (8x the coarse one) is never materialised.
+# Zero padding carries over exactly: fine index -1 / 2n is coarse index -1 / n.
+_POLY_SETS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}      # parity -> ((coarse offset, filter taps), ...)
+
+
+def polyphase_taps(parity: Tuple[int, int, int]):
+    """Coarse-grid tap offsets (8 triples in {-1, 0, 1}) of output parity (pd, ph, pw), in the order of
+    ``polyphase_weight``'s taps."""
+    return tuple((od, oh, ow) for od, _ in _POLY_SETS[parity[0]] for oh, _ in _POLY_SETS[parity[1]]
+                 for ow, _ in _POLY_SETS[parity[2]])
+
+
+def polyphase_weight(w: torch.Tensor, parity: Tuple[int, int, int]) -> torch.Tensor:
+    """(c_out, c_in, 3, 3, 3) -> (c_out, c_in, 2, 2, 2): the effective filter of output parity (pd, ph, pw), fp32."""
+    out = []
+    for _, kd in _POLY_SETS[parity[0]]:
+        for _, kh in _POLY_SETS[parity[1]]:
+            for _, kw in _POLY_SETS[parity[2]]:
+                out.append(w[:, :, list(kd)][:, :, :, list(kh)][:, :, :, :, list(kw)].sum(dim=(2, 3, 4)))
+    return torch.stack(out, dim=2).reshape(w.shape[0], w.shape[1], 2, 2, 2).contiguous()
 
 
 # ---- elementwise ---------------------------------------------------------------------------------
@@ -274,16 +311,41 @@ def gn_silu(x: torch.Tensor, channels: int, groups: int, stats: torch.Tensor, ga
     return out
 
 
+def gn_coef(stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, voxels: int, eps: float = 1e-5,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``vdm_gn_coef``: fp32 [B, C, 2] pairs (a, b) with silu(groupnorm(x)) = h + h tanh(h), h = a x + b, from the fp64
+    (sum, sumsq) table of the tensor -- the ``in_norm`` argument of ``conv3d`` (GroupNorm + SiLU applied by the conv
+    kernel to its input tile instead of by a separate pass)."""
+    _need(stats.is_cuda and stats.dtype == torch.float64 and stats.is_contiguous() and stats.dim() == 3 and stats.shape[2] == 2,
+          "gn_coef: stats must be a contiguous CUDA double [B, C, 2]")
+    b, c, _ = stats.shape
+    _need(gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == c and beta.numel() == c and
+          gamma.is_cuda and beta.is_cuda, "gn_coef: gamma/beta must be CUDA fp32 [C]")
+    if out is None:
+        out = torch.empty((b, c, 2), dtype=torch.float32, device=stats.device)
+    _need(out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (b, c, 2),
+          "gn_coef: out must be contiguous CUDA fp32 [B, C, 2]")
+    rc = _C.lib().vdm_gn_coef(stats.data_ptr(), b, c, groups, voxels, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
+                              _stream())
+    _C.check(rc, "vdm_gn_coef")
+    _launched(1)
+    return out
+
+
 def gn_silu_view(x: torch.Tensor, channels: int, c_off: int, channels_total: int, groups: int, stats: torch.Tensor,
                  gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: torch.Tensor, *, x_plane0: int = 0,
-                 out_plane0: int = 0, upsample: bool = False) -> torch.Tensor:
+                 out_plane0: int = 0, upsample=False) -> torch.Tensor:
     """silu(groupnorm(.)) of channels [c_off, c_off + channels) of a ``channels_total``-channel norm, written to a plane
     window of ``out``; with ``upsample`` x is at half the resolution of ``out`` (``vdm_gn_silu_view``)."""
     _planar_ok(x, "gn_silu_view x")
     _planar_ok(out, "gn_silu_view out")
     b, _, d, h, w, _ = out.shape
-    _need(tuple(x.shape[2:5]) == ((d // 2, h // 2, w // 2) if upsample else (d, h, w)) and x.shape[0] == b,
-          "gn_silu_view: x grid does not match out")
+    if upsample == "coarse":         # x and out on the half grid of the (2d, 2h, 2w) concat the statistics refer to
+        _need(tuple(x.shape[2:5]) == (d, h, w) and x.shape[0] == b, "gn_silu_view: x grid does not match out")
+        d, h, w = 2 * d, 2 * h, 2 * w
+    else:
+        _need(tuple(x.shape[2:5]) == ((d // 2, h // 2, w // 2) if upsample else (d, h, w)) and x.shape[0] == b,
+              "gn_silu_view: x grid does not match out")
     _need(stats.dtype == torch.float64 and tuple(stats.shape) == (b, channels_total, 2) and stats.is_contiguous(),
           "gn_silu_view: stats must be double [B, channels_total, 2]")
     _need(gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == channels_total and
@@ -291,7 +353,8 @@ def gn_silu_view(x: torch.Tensor, channels: int, c_off: int, channels_total: int
           "gn_silu_view: gamma/beta must be CUDA fp32 [channels_total]")
     vx, vy = _view(x, x_plane0), _view(out, out_plane0)
     rc = _C.lib().vdm_gn_silu_view(ctypes.byref(vx), ctypes.byref(vy), b, d, h, w, channels, c_off, channels_total, groups,
-                                   stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, 1 if upsample else 0, _stream())
+                                   stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
+                                   2 if upsample == "coarse" else (1 if upsample else 0), _stream())
     _C.check(rc, "vdm_gn_silu_view")
     _launched(1)
     return out
