@@ -353,8 +353,10 @@ def test_conv3d_fused_input_is_declined_for_circular_padding():
 
 
 # ---- polyphase up-conv: conv3x3x3(interpolate(a)) as eight 2x2x2-tap convolutions of the coarse tensor ------------------
-@pytest.mark.parametrize("cc,co,cgrid,batch", [(32, 32, (4, 16, 8), 2), (64, 32, (5, 10, 6), 1), (128, 64, (4, 8, 8), 1)])
-def test_polyphase_upconv_is_exact_on_integers(cc, co, cgrid, batch):
+@pytest.mark.parametrize("cc,co,cgrid,batch,n_par", [(32, 32, (4, 16, 8), 2, 1), (64, 32, (5, 10, 6), 1, 1), (128, 64, (4, 8, 8), 1, 1),
+                                                      (64, 32, (5, 10, 6), 2, 4), (128, 64, (4, 16, 8), 1, 4),
+                                                      (256, 128, (3, 8, 8), 1, 2), (32, 32, (4, 16, 8), 1, 8)])
+def test_polyphase_upconv_is_exact_on_integers(cc, co, cgrid, batch, n_par):
     """The up blocks' conv over the up-sampled half of the concat (ResNetUp: interpolate -> cat -> ResNetBlock.net1) in the
     form the inference trunk runs it: per output parity a 2x2x2-tap conv of the COARSE tensor with summed filter taps
     (ops.polyphase_weight / polyphase_taps) into a parity-planar buffer, read back by the consumer conv through the
@@ -366,14 +368,21 @@ def test_polyphase_upconv_is_exact_on_integers(cc, co, cgrid, batch):
     g = torch.Generator().manual_seed(21)
     dc, hc, wc = cgrid
     a = _int_tensor((batch, cc, dc, hc, wc), -2, 2, g, dev)
-    wt = _int_tensor((co, cc, 3, 3, 3), -1, 1, g, dev) * (_int_tensor((co, cc, 3, 3, 3), 0, 2, g, dev) == 0).float()
+    # sparse +-1 filter: every partial and final sum stays an integer bf16 holds exactly (|.| < 256)
+    wt = _int_tensor((co, cc, 3, 3, 3), -1, 1, g, dev) * (_int_tensor((co, cc, 3, 3, 3), 0, 2 if cc < 256 else 11, g, dev) == 0).float()
     ap = ops.to_planar(a)
     part = torch.full((batch, co, dc, hc, wc, 8), 55.0, dtype=torch.bfloat16, device=dev)     # 8 x co channels
-    for pi in range(8):
-        parity = (pi >> 2, (pi >> 1) & 1, pi & 1)
-        we = ops.polyphase_weight(wt, parity)
-        assert we.shape == (co, cc, 2, 2, 2)
-        ops.conv3d(ap, ops.pack_conv_weight(we), co, taps=ops.polyphase_taps(parity), out=part, out_plane0=pi * (co // 8))
+    if n_par == 1:                       # one launch per parity
+        for pi in range(8):
+            parity = (pi >> 2, (pi >> 1) & 1, pi & 1)
+            we = ops.polyphase_weight(wt, parity)
+            assert we.shape == (co, cc, 2, 2, 2)
+            ops.conv3d(ap, ops.pack_conv_weight(we), co, taps=ops.polyphase_taps(parity), out=part, out_plane0=pi * (co // 8))
+    else:                                # n_par parities per launch, stacked along N (what the inference trunk launches)
+        for grp in range(8 // n_par):
+            we, taps = ops.polyphase_group(wt, grp, n_par)
+            assert we.shape[0] == n_par * co and len(taps) == we.shape[2] * we.shape[3] * we.shape[4]
+            ops.conv3d(ap, ops.pack_conv_weight(we), n_par * co, taps=taps, out=part, out_plane0=grp * n_par * (co // 8))
     # consumer: a conv with zero weights, so its output is bias + the depth-to-space residual
     xs = torch.zeros((batch, 2, 2 * dc, 2 * hc, 2 * wc, 8), dtype=torch.bfloat16, device=dev)
     wz = torch.zeros((27, 2, co, 8), dtype=torch.bfloat16, device=dev)

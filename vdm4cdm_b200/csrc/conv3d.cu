@@ -935,7 +935,6 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const uint32_t a_lbo = (uint32_t)a_hi, b_lbo = (uint32_t)b_hi;       // LBO << 16: low descriptor words
         const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
         const int nsb = p.nsb;
-        uint32_t itb = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
           const uint32_t acc = ti & 1;
           ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
@@ -943,23 +942,23 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
             const uint32_t sa = ita & 1;
             ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
+            ptx::tc_fence_after();
             const uint32_t a_st = a_base16 + sa * a_stage16 + a_lbo;
-            for (int khw = 0; khw < 9; ++khw, ++itb) {
-              const uint32_t sb = itb % nsb;
-              ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
-              ptx::tc_fence_after();
-              if (leader) {
+            if (leader) {                      // one elected lane per chunk, weight-stage waits included (see the generic path)
+              uint32_t itb = ita * 9u;
+              for (int khw = 0; khw < 9; ++khw, ++itb) {
+                const uint32_t sb = itb % nsb;
+                ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
+                ptx::tc_fence_after();
                 const uint32_t kh = (uint32_t)khw / 3u, kw = (uint32_t)khw - 3u * kh;
                 issue_fold_stage<MT, KJ, NF>(a_st + kh * (uint32_t)(kTileW + 2) + kw, b_base16 + sb * b_stage16 + b_lbo, a_hi32,
                                              b_hi32, d_tmem0, kc == 0 && khw == 0);
                 ptx::umma_commit(&sh->b_empty[sb]);
-                if (khw == 8) {
-                  ptx::umma_commit(&sh->a_empty[sa]);
-                  if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
-                }
               }
-              __syncwarp();
+              ptx::umma_commit(&sh->a_empty[sa]);
+              if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
             }
+            __syncwarp();
           }
         }
       } else
@@ -997,7 +996,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const uint32_t btap16 = (uint32_t)planes_per_chunk * n_cta;  // one tap inside a B stage
       const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
       const bool resident = p.b_resident != 0;
-      uint32_t ita = 0, itb = 0, ti = 0;
+      const int steps_per_chunk = (n_taps + tps - 1) / tps;
+      uint32_t ita = 0, ti = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1;
         ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
@@ -1006,20 +1006,24 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
           const uint32_t sa = ita & 1;
           ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
+          if (resident && ita == 0) ptx::mbar_wait(&sh->b_full[0], 0);
+          ptx::tc_fence_after();
           const uint32_t a_lo0 = a_base16 + sa * a_stage16;
-          for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++itb) {
-            uint32_t sb, b_lo0;
-            if (resident) {
-              if (itb == 0) ptx::mbar_wait(&sh->b_full[0], 0);
-              sb = 0;
-              b_lo0 = b_base16 + (uint32_t)(kc * n_taps + tap0) * btap16;
-            } else {
-              sb = itb % nsb;
-              ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
-              b_lo0 = b_base16 + sb * b_stage16;
-            }
-            ptx::tc_fence_after();
-            if (leader) {
+          // ONE elected lane runs the whole chunk, weight-stage waits included: the per-stage warp-wide wait / fence /
+          // elect / __syncwarp sequence cost ~500 cycles per (chunk, tap stage) step (R2k: the time of an 8-tap conv
+          // scaled with the NUMBER of steps, 0.30 ms at KC = 16 vs 0.20 ms at KC = 32, not with its MMAs).
+          if (leader) {
+            uint32_t itb = ita * (uint32_t)steps_per_chunk;       // weight-stage counter, derived from the uniform chunk counter
+            for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++itb) {
+              uint32_t sb = 0, b_lo0;
+              if (resident) {
+                b_lo0 = b_base16 + (uint32_t)(kc * n_taps + tap0) * btap16;
+              } else {
+                sb = itb % nsb;
+                ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
+                ptx::tc_fence_after();
+                b_lo0 = b_base16 + sb * b_stage16;
+              }
               for (int q = 0; q < tps; ++q) {
                 const uint32_t a_lo = a_lo0 + (uint32_t)p.tap16[tap0 + q], b_lo = b_lo0 + (uint32_t)q * btap16;
                 const uint32_t first = (kc | tap0 | q) != 0 ? 1u : 0u;
@@ -1034,13 +1038,11 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
               }
               if (!resident) ptx::umma_commit(&sh->b_empty[sb]);
-              if (tap0 + tps >= n_taps) {
-                ptx::umma_commit(&sh->a_empty[sa]);
-                if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
-              }
             }
-            __syncwarp();
+            ptx::umma_commit(&sh->a_empty[sa]);
+            if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
           }
+          __syncwarp();
         }
       }
     }

@@ -236,23 +236,25 @@ class CUNet(nn.Module):
             self._packed_cache[slot] = hit
         return hit[1]
 
-    def _packed_poly(self, slot: str, conv: nn.Conv3d, c_up: int, parity) -> torch.Tensor:
-        """bf16 packed 2x2x2 filter of output parity ``parity`` for the first ``c_up`` (up-sampled) input channels of a 3x3x3
-        conv (``ops.polyphase_weight``: sums of the original taps, formed in fp32 and rounded once)."""
+    def _packed_poly(self, slot: str, conv: nn.Conv3d, c_up: int, group: int, n_par: int):
+        """(bf16 packed filter, taps) of the polyphase parity group ``group`` (``ops.polyphase_group``: ``n_par`` output
+        parities stacked along N) for the first ``c_up`` (up-sampled) input channels of a 3x3x3 conv; the effective taps
+        are sums of the original ones, formed in fp32 and rounded to bf16 once.  Re-packed in place when the parameter
+        changes (captured CUDA graphs keep the pointer)."""
         w = conv.weight
         key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
-        slot = f"{slot}.poly.{parity[0]}{parity[1]}{parity[2]}"
+        slot = f"{slot}.poly.{n_par}.{group}"
         hit = self._packed_cache.get(slot)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                part = ops.polyphase_weight(w.detach()[:, :c_up].float(), parity)
-                shape = ops.packed_weight_shape(part.shape)
-                buf = hit[1] if hit is not None and tuple(hit[1].shape) == shape and hit[1].device == w.device else \
-                    torch.empty(shape, dtype=torch.bfloat16, device=w.device)
-                ops.pack_conv_weight_into(part, buf)
-                hit = (key, buf)
+                part, taps = ops.polyphase_group(w.detach()[:, :c_up], group, n_par)
+                packed = ops.pack_conv_weight(part)
+                if hit is not None and tuple(hit[1].shape) == tuple(packed.shape) and hit[1].device == w.device:
+                    hit[1].copy_(packed)
+                    packed = hit[1]
+                hit = (key, packed, taps)
             self._packed_cache[slot] = hit
-        return hit[1]
+        return hit[1], hit[2]
 
     def trunk_parameters(self):
         """(name, parameter) of everything the convolutional trunk differentiates itself: conv filters and
@@ -367,12 +369,15 @@ class CUNet(nn.Module):
             # silu(gn(.)) of the coarse channels at the COARSE resolution (statistics of the fine concat)
             ac = ar.get(f"ac.{c_up}.{b}x{cgrid[0]}", (b, c_up // 8) + cgrid + (8,), torch.bfloat16, dev)
             ops.gn_silu_view(xc, c_up, 0, ci, g, x_stats, n1.weight, n1.bias, n1.eps, ac, x_plane0=xc_plane0, upsample="coarse")
-            # eight parity convolutions (2x2x2 taps on the coarse grid) -> parity-planar partial sums [8 x co channels]
+            # the eight parity convolutions (2x2x2 taps each on the coarse grid) -> parity-planar partial sums [8 x co
+            # channels], n_par parities per launch stacked along N (N = n_par * co <= 256)
             part = ar.get(f"poly.{co}.{b}x{cgrid[0]}", (b, co) + cgrid + (8,), torch.bfloat16, dev)
-            for pi in range(8):
-                parity = (pi >> 2, (pi >> 1) & 1, pi & 1)
-                ops.conv3d(ac, self._packed_poly(name + ".net1", blk.net1[2], c_up, parity), co, taps=ops.polyphase_taps(parity),
-                           out=part, out_plane0=pi * (co // 8))
+            # (measured at 128^3 x 8, profiles/R2k_poly_tiles.txt / R2m: 32 channels 1.35 ms in 2 launches vs 1.53 in 8;
+            #  64 channels 0.68 vs 0.62; 128 channels 0.30 in 4 launches vs 0.35 in 8)
+            n_par = {16: 4, 32: 4, 64: 1}.get(co, 2)
+            for grp in range(8 // n_par):
+                wp, taps = self._packed_poly(name + ".net1", blk.net1[2], c_up, grp, n_par)
+                ops.conv3d(ac, wp, n_par * co, taps=taps, out=part, out_plane0=grp * n_par * (co // 8))
             # the skip channels at the fine resolution; the partial sums come in through the depth-to-space residual
             a_s = ar.get(f"as.{ci - c_up}.{tag}", (b, (ci - c_up) // 8) + grid + (8,), torch.bfloat16, dev)
             ops.gn_silu_view(x, ci - c_up, c_up, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a_s, x_plane0=x_plane0 + c_up // 8)

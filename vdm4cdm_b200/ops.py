@@ -272,6 +272,37 @@ def polyphase_weight(w: torch.Tensor, parity: Tuple[int, int, int]) -> torch.Ten
     return torch.stack(out, dim=2).reshape(w.shape[0], w.shape[1], 2, 2, 2).contiguous()
 
 
+def polyphase_group(w: torch.Tensor, group: int, n_par: int):
+    """Several output parities in ONE conv launch: the ``n_par`` (2, 4 or 8) parities that share the leading parity bits
+    ``group`` (n_par = 4: group = pd; n_par = 2: group = pd * 2 + ph) are stacked along the output channels, block
+    ``j`` = parity ``group * n_par + j``, over the union of their coarse taps; a (tap, block) pair the parity does not use
+    holds zeros.  The parities of a group share the halo tile, so the coarse tensor is read once per group instead of
+    once per parity, and N = n_par * c_out keeps the tensor cores busy where a single parity (N = c_out) is bound by
+    the latency of its tile loads (profiles/R2k_poly_tiles.txt).
+    Returns (weight fp32 (n_par * c_out, c_in, Td, Th, Tw), taps as a tuple of coarse offsets in the weight's tap order)."""
+    co, ci = w.shape[0], w.shape[1]
+    if n_par == 1:
+        parity = (group >> 2, (group >> 1) & 1, group & 1)
+        return polyphase_weight(w.float(), parity), polyphase_taps(parity)
+    n_fixed = {8: 0, 4: 1, 2: 2}[n_par]
+    fixed = [(group >> (n_fixed - 1 - i)) & 1 for i in range(n_fixed)]
+    offs = [[p - 1, p] for p in fixed] + [[-1, 0, 1]] * (3 - n_fixed)
+    taps = tuple((od, oh, ow) for od in offs[0] for oh in offs[1] for ow in offs[2])
+    out = w.new_zeros((n_par * co, ci, len(offs[0]), len(offs[1]), len(offs[2])), dtype=torch.float32)
+    for j in range(n_par):
+        pi = group * n_par + j
+        parity = (pi >> 2, (pi >> 1) & 1, pi & 1)
+        sets = [dict(_POLY_SETS[p]) for p in parity]
+        for a, od in enumerate(offs[0]):
+            for b_, oh in enumerate(offs[1]):
+                for c, ow in enumerate(offs[2]):
+                    if od in sets[0] and oh in sets[1] and ow in sets[2]:
+                        kd, kh, kw = list(sets[0][od]), list(sets[1][oh]), list(sets[2][ow])
+                        out[j * co:(j + 1) * co, :, a, b_, c] = \
+                            w[:, :, kd][:, :, :, kh][:, :, :, :, kw].float().sum(dim=(2, 3, 4))
+    return out, taps
+
+
 # ---- elementwise ---------------------------------------------------------------------------------
 def channel_stats(x: torch.Tensor, channels: int, x_plane0: int = 0, stats: Optional[torch.Tensor] = None,
                   stats_c0: int = 0) -> torch.Tensor:
