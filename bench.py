@@ -406,6 +406,15 @@ def run_b200(args, rank, world, local_rank):
                 "algorithmic_flops_per_step": conv_flops, "conv_launches_per_step": len(records),
                 "conv_ms_per_step": conv_ms, "conv_share_of_eager_step": conv_ms / eager_step_ms}
 
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample; parity of this very network ----
+    cpu, parity = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sec, label, k = cpu_oracle_rate(grid, chs, 30.0, 2, 1, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": label, "s_per_step": sec}
+        model.eval()
+        parity = parity_leg(net, vdm, dev, grid, chs)
+
     # ---- training step (BASELINE.json configs[1]: trainVDM3D128..._lowbatch, batch_size=2 per GPU) ----
     train = None
     if not args.no_train:
@@ -423,15 +432,6 @@ def run_b200(args, rank, world, local_rank):
     torch_gpu = None
     if world == 1 and not args.no_torch_gpu_baseline:
         torch_gpu = torch_gpu_leg(args, dev, ms_max / args.steps, None if train is None else train["ms_per_step"])
-
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample; parity of this very network ----
-    cpu, parity = None, None
-    if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, sec, label, k = cpu_oracle_rate(grid, chs, 30.0, 2, 1, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": label, "s_per_step": sec}
-        model.eval()
-        parity = parity_leg(net, vdm, dev, grid, chs)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
