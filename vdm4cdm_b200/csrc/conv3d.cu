@@ -1235,7 +1235,11 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
         const long long tiles = (long long)p.tiles_w * p.tiles_h * ceil_div(d.depth, m) * d.batch * ns;
         const long long waves = (tiles + sms - 1) / sms;
         const double active = (double)(tiles < sms ? tiles : sms);
-        const double mma_cyc = (double)d.n_taps * (d.c_in / 16) * m * (ncta / 2 > 24 ? ncta / 2 : 24);
+        // one MMA (M = 128, K = 16): max(tensor time N/2, shared-memory operand fetch (4 KB of A + 32 B per row of B) at
+        // 128 B/clk): N = 32 / 64 are fetch-bound (40 / 48 cycles), N >= 128 tensor-bound (R2r sweep: with the old
+        // max(N/2, 24) the model preferred N = 64, MT = 4 over N = 128, MT = 2 and lost ~15% on every wide layer)
+        const double fetch_cyc = 32.0 + ncta / 4.0;
+        const double mma_cyc = (double)d.n_taps * (d.c_in / 16) * m * (ncta / 2.0 > fetch_cyc ? ncta / 2.0 : fetch_cyc);
         const double bytes = (double)(m + 2 * pad) * (kTileH + 2 * pad) * (kTileW + 2 * pad) * d.c_in * 2.0 +
                              (double)d.n_taps * d.c_in * ncta * 2.0;
         double bw = 5500.0 / active;  // L2 -> SM bytes per cycle per SM when `active` SMs pull at once

@@ -47,11 +47,11 @@ gn_silu_kernel(VdmTensor x, VdmTensor y, int planes, int64_t voxels, int groups,
   plane_scale_shift(stats + (int64_t)b * C * 2, C, groups, pl, (double)voxels, gamma, beta, eps, s_scale, s_shift,
                     nullptr, nullptr);
   __syncthreads();
-  float sc[8], sh[8];
+  float sc[8], sh[8];                      // halved: silu(y) = h + h tanh(h), h = y / 2 (silu_half)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc[j] = s_scale[j];
-    sh[j] = s_shift[j];
+    sc[j] = 0.5f * s_scale[j];
+    sh[j] = 0.5f * s_shift[j];
   }
   const bf16x8* xp = plane_ptr(x, b, pl, voxels);
   bf16x8* yp = plane_ptr_mut(y, b, pl, voxels);
@@ -75,7 +75,7 @@ gn_silu_kernel(VdmTensor x, VdmTensor y, int planes, int64_t voxels, int groups,
       float f[8];
       unpack8(k == 0 ? v0 : v1, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu(f[j] * sc[j] + sh[j]);
+      for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], sc[j], sh[j]));
       if (drop) {
         const uint32_t keep = dropout_keep8(chunk0 + (uint64_t)ii, layer_tag, seed, thresh16);
 #pragma unroll
@@ -133,11 +133,11 @@ gn_silu_view_kernel(VdmTensor x, VdmTensor y, int planes, int c_off, int C_total
   plane_scale_shift(stats + (int64_t)b * C_total * 2, C_total, groups, (c_off >> 3) + pl, stats_voxels, gamma, beta, eps,
                     s_scale, s_shift, nullptr, nullptr);
   __syncthreads();
-  float sc[8], sh[8];
+  float sc[8], sh[8];                      // halved: silu(y) = h + h tanh(h), h = y / 2 (silu_half)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc[j] = s_scale[j];
-    sh[j] = s_shift[j];
+    sc[j] = 0.5f * s_scale[j];
+    sh[j] = 0.5f * s_shift[j];
   }
   bf16x8* yp = plane_ptr_mut(y, b, pl, vf);
   const int64_t stride = (int64_t)gridDim.x * kEwThreads;
@@ -154,7 +154,7 @@ gn_silu_view_kernel(VdmTensor x, VdmTensor y, int planes, int c_off, int C_total
       float f[8];
       unpack8(cp[((int64_t)(d >> 1) * Hc + (h >> 1)) * Wc + wc], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu(f[j] * sc[j] + sh[j]);
+      for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], sc[j], sh[j]));
       const bf16x8 val = pack8(f);
       bf16x8* dst = yp + ((int64_t)d * H + h) * W + 2 * wc;
       st_stream(dst, val);
@@ -171,12 +171,12 @@ gn_silu_view_kernel(VdmTensor x, VdmTensor y, int planes, int c_off, int C_total
       float f[8];
       unpack8(v0, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu(f[j] * sc[j] + sh[j]);
+      for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], sc[j], sh[j]));
       st_stream(yp + i, pack8(f));
       if (two) {
         unpack8(v1, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = silu(f[j] * sc[j] + sh[j]);
+        for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], sc[j], sh[j]));
         st_stream(yp + i2, pack8(f));
       }
     }
