@@ -372,9 +372,10 @@ class CUNet(nn.Module):
             # the eight parity convolutions (2x2x2 taps each on the coarse grid) -> parity-planar partial sums [8 x co
             # channels], n_par parities per launch stacked along N (N = n_par * co <= 256)
             part = ar.get(f"poly.{co}.{b}x{cgrid[0]}", (b, co) + cgrid + (8,), torch.bfloat16, dev)
-            # (measured at 128^3 x 8, profiles/R2k_poly_tiles.txt / R2m: 32 channels 1.35 ms in 2 launches vs 1.53 in 8;
-            #  64 channels 0.68 vs 0.62; 128 channels 0.30 in 4 launches vs 0.35 in 8)
-            n_par = {16: 4, 32: 4, 64: 1}.get(co, 2)
+            # (measured at 128^3 x 8, R2t: N = 128 per launch where the layer is narrow -- 32 channels: 4 parities, 1.17 ms
+            #  in 2 launches vs 1.53 in 8; 64 channels: 2 parities, 0.42 ms in 4 launches vs 0.64 in 8 / 0.56 in 2; 128
+            #  channels: 2 parities (N = 256), 0.25 ms in 4 launches vs 0.30 in 8)
+            n_par = 4 if co <= 32 else 2
             for grp in range(8 // n_par):
                 wp, taps = self._packed_poly(name + ".net1", blk.net1[2], c_up, grp, n_par)
                 ops.conv3d(ac, wp, n_par * co, taps=taps, out=part, out_plane0=grp * n_par * (co // 8))
