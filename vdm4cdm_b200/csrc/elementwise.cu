@@ -59,21 +59,23 @@ gn_silu_kernel(VdmTensor x, VdmTensor y, int planes, int64_t voxels, int groups,
   const uint32_t thresh16 = (uint32_t)(dropout_p * 65536.0f + 0.5f);
   const float keep_scale = drop ? 1.0f / (1.0f - dropout_p) : 1.0f;
   const uint64_t chunk0 = ((uint64_t)b * planes + pl) * (uint64_t)voxels;
-  // two independent 16-byte loads in flight per thread (memory-level parallelism: r01f measured the
-  // one-load-per-trip version at ~50% of the HBM roofline)
+  // kGnUnroll independent 16-byte loads in flight per thread (memory-level parallelism: r01f measured the one-load-per-
+  // trip version at ~50% of the HBM roofline, two loads at ~73%)
+  constexpr int U = 4;
   const int64_t stride = (int64_t)gridDim.x * kEwThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < voxels; i += 2 * stride) {
-    const int64_t i2 = i + stride;
-    const bool two = i2 < voxels;
-    const bf16x8 v0 = STREAM ? ld_stream(xp + i) : xp[i];
-    bf16x8 v1 = v0;
-    if (two) v1 = STREAM ? ld_stream(xp + i2) : xp[i2];
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < voxels; i += U * stride) {
+    bf16x8 v[U];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k == 1 && !two) break;
-      const int64_t ii = k == 0 ? i : i2;
+    for (int k = 0; k < U; ++k) {
+      const int64_t ii = i + k * stride;
+      if (ii < voxels) v[k] = STREAM ? ld_stream(xp + ii) : xp[ii];
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t ii = i + k * stride;
+      if (ii >= voxels) break;
       float f[8];
-      unpack8(k == 0 ? v0 : v1, f);
+      unpack8(v[k], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], sc[j], sh[j]));
       if (drop) {
@@ -162,22 +164,21 @@ gn_silu_view_kernel(VdmTensor x, VdmTensor y, int planes, int c_off, int C_total
     }
   } else {
     const bf16x8* xp = plane_ptr(x, b, pl, vf);
-    for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vf; i += 2 * stride) {
-      const int64_t i2 = i + stride;
-      const bool two = i2 < vf;
-      const bf16x8 v0 = ld_stream(xp + i);
-      bf16x8 v1 = v0;
-      if (two) v1 = ld_stream(xp + i2);
-      float f[8];
-      unpack8(v0, f);
+    constexpr int U = 4;                       // independent 16-byte loads in flight per thread (see gn_silu_kernel)
+    for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < vf; i += U * stride) {
+      bf16x8 v[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], sc[j], sh[j]));
-      st_stream(yp + i, pack8(f));
-      if (two) {
-        unpack8(v1, f);
+      for (int k = 0; k < U; ++k)
+        if (i + k * stride < vf) v[k] = ld_stream(xp + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int64_t ii = i + k * stride;
+        if (ii >= vf) break;
+        float f[8];
+        unpack8(v[k], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = silu_half(fmaf(f[j], sc[j], sh[j]));
-        st_stream(yp + i2, pack8(f));
+        st_stream(yp + ii, pack8(f));
       }
     }
   }
