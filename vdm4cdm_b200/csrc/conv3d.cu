@@ -64,6 +64,7 @@ constexpr int kRegsWg0 = 64, kRegsEpi = 176, kRegsXf = 88;
 constexpr int kXfGroup = 2;              // units per software-pipeline group of the input transform (2 groups in flight)   // 128*64 + 256*176 + 128*88 = 64512 <= 65536
 constexpr int kResSlotBytes = 2 * 16 * kEpiThreads;   // one unit (two 8-channel planes) of residual for every epilogue thread
 constexpr int kMaxBStages = 16;
+constexpr int kMaxAStages = 4;
 constexpr int kTileH = 16, kTileW = 8;
 
 struct ConvKernelParams {
@@ -83,6 +84,7 @@ struct ConvKernelParams {
   int fast_div_ok;           // n_tiles < 2^22: tile decoding by float reciprocals
   float inv_n_split, inv_tiles_w, inv_tiles_h, inv_tiles_d;
   int a_stage_bytes, b_stage_bytes, nsb, taps_per_stage;
+  int nsa;                   // halo stages in flight (2..kMaxAStages): as many as fit next to the weights
   int b_resident;            // all weights of this CTA's channel slice stay in shared memory (loaded once)
   int plane_bytes;           // Hd*Hh*Wh*16
   int tmem_cols;
@@ -118,8 +120,8 @@ struct ConvKernelParams {
 };
 
 struct ConvShared {
-  uint64_t a_full[2], a_empty[2];
-  uint64_t a_ready[2];             // fused input transform: the landed halo stage has been rewritten in place
+  uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+  uint64_t a_ready[kMaxAStages];   // fused input transform: the landed halo stage has been rewritten in place
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
@@ -385,8 +387,8 @@ __device__ __forceinline__ void transform_tiles(const ConvKernelParams& p, ConvS
     const int dlo = t.d0 - p.pad + p.x_shift, hlo = t.h0 - p.pad + p.x_shift, wlo = t.w0 - p.pad + p.x_shift;
     const bool edge = dlo < 0 || dlo + p.Hd > p.D || hlo < 0 || hlo + p.Hh > p.H || wlo < 0 || wlo + p.Wh > p.W;
     for (int kc = 0; kc < total_chunks; ++kc, ++it) {
-      const int s = it & 1;
-      ptx::mbar_wait(&sh->a_full[s], (it >> 1) & 1);
+      const int s = (int)(it % (uint32_t)p.nsa);
+      ptx::mbar_wait(&sh->a_full[s], (it / (uint32_t)p.nsa) & 1);
       if (kc < p.k_chunks && !VDM_DBG(p, 64)) {          // (bring-up flag 64: hand-off only, no arithmetic)
         uint8_t* stage = a_smem + (size_t)s * p.a_stage_bytes;
 #pragma unroll 1
@@ -760,7 +762,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   // (R2b ncu: LD.E.128 for the bias rows and the ring slots in the epilogue's inner loop).
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + 2 * (size_t)p.a_stage_bytes;
+  uint8_t* b_smem = smem + (size_t)p.nsa * p.a_stage_bytes;
   ConvShared* sh = reinterpret_cast<ConvShared*>(b_smem + (size_t)p.nsb * p.b_stage_bytes + p.skip_w_bytes);
   constexpr bool kFold = NF > 0;
 
@@ -769,10 +771,12 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap_x);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxAStages; ++s) {
       ptx::mbar_init(&sh->a_full[s], 1);
       ptx::mbar_init(&sh->a_empty[s], 1);
       ptx::mbar_init(&sh->a_ready[s], kXfThreads);
+    }
+    for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&sh->tmem_full[s], 1);
       ptx::mbar_init(&sh->tmem_empty[s], kEpiThreads);
     }
@@ -813,8 +817,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         for (int kc = 0; kc < p.k_chunks + p.skip_chunks; ++kc, ++it) {
-          const int s = it & 1;
-          ptx::mbar_wait(&sh->a_empty[s], ((it >> 1) & 1) ^ 1);
+          const int s = (int)(it % (uint32_t)p.nsa);
+          ptx::mbar_wait(&sh->a_empty[s], ((it / (uint32_t)p.nsa) & 1) ^ 1);
           if (VDM_DBG(p, 2) && it >= 2) {       // experiment: no halo traffic after the pipeline fill
             ptx::mbar_arrive(&sh->a_full[s]);
             continue;
@@ -920,6 +924,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // per-thread registers compiled to an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall around every MMA.)
     const uint32_t n_cta = (uint32_t)p.n_cta;
     const uint32_t a_base16 = ptx::smem_u32(a_smem) >> 4, a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t nsa_u = (uint32_t)p.nsa;
     const uint32_t b_base16 = ptx::smem_u32(b_smem) >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const bool leader = ptx::elect_one();
@@ -940,8 +945,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
           const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
           for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
-            const uint32_t sa = ita & 1;
-            ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
+            const uint32_t sa = ita % nsa_u;
+            ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
             ptx::tc_fence_after();
             const uint32_t a_st = a_base16 + sa * a_stage16 + a_lbo;
             if (leader) {                      // one elected lane per chunk, weight-stage waits included (see the generic path)
@@ -969,8 +974,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
         const int total_chunks = k_chunks + p.skip_chunks;
         for (int kc = 0; kc < total_chunks; ++kc, ++ita) {
-          const uint32_t sa = ita & 1;
-          ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
+          const uint32_t sa = ita % nsa_u;
+          ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
           ptx::tc_fence_after();
           if (leader) {
             if (kc == 0)
@@ -1004,8 +1009,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         ptx::tc_fence_after();
         const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)MT * n_cta;
         for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
-          const uint32_t sa = ita & 1;
-          ptx::mbar_wait(&a_rdy[sa], (ita >> 1) & 1);
+          const uint32_t sa = ita % nsa_u;
+          ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
           if (resident && ita == 0) ptx::mbar_wait(&sh->b_full[0], 0);
           ptx::tc_fence_after();
           const uint32_t a_lo0 = a_base16 + sa * a_stage16;
@@ -1401,7 +1406,15 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
     }
   }
 
-  const int used = 2 * p.a_stage_bytes + p.nsb * p.b_stage_bytes + p.skip_w_bytes;
+  // Halo stages: two are planned above; layers whose weights leave room get up to kMaxAStages.  A TMA box takes
+  // several thousand cycles to arrive from L2 / HBM, and where a chunk's MMAs are shorter than that (conv_in: 54 MMAs per
+  // tile, the 1x1x1 convs) two stages left the tensor core waiting for loads.
+  p.nsa = 2;
+  {
+    const int fixed = p.nsb * p.b_stage_bytes + p.skip_w_bytes + (has_residual ? 4 * kResSlotBytes : 0);
+    while (p.nsa < kMaxAStages && (p.nsa + 1) * p.a_stage_bytes + fixed <= smem_total) ++p.nsa;
+  }
+  const int used = p.nsa * p.a_stage_bytes + p.nsb * p.b_stage_bytes + p.skip_w_bytes;
   if (has_residual) {
     int depth = (smem_total - used) / kResSlotBytes;
     p.res_depth = depth > 4 ? 4 : depth;
