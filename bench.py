@@ -398,11 +398,15 @@ def run_b200(args, rank, world, local_rank):
         with open(tpath) as f:
             tj = json.load(f)
         # DRAM read + write of one step's conv launches (ncu --set full), valid for the workload it was captured on
-        if tj.get("grid", 128) == args.grid and tj.get("realisations_per_gpu") == args.batch:
+        # (a capture of another grid / batch / set of conv launches does not apply: traffic stays null)
+        if tj.get("grid", 128) == args.grid and tj.get("realisations_per_gpu") == args.batch and \
+                tj.get("conv_launches_per_step") == len(records):
             traffic = tj.get("conv_dram_bytes_per_step")
     roofline = {"kernel": "conv3d_planar_kernel (all conv launches of one step)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": traffic,
+                "traffic_source": "profiles/roofline_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the conv "
+                                  "launches of one step of this workload; not measurable inside the timed run)" if traffic else None,
                 "algorithmic_flops_per_step": conv_flops, "conv_launches_per_step": len(records),
                 "conv_ms_per_step": conv_ms, "conv_share_of_eager_step": conv_ms / eager_step_ms}
 
