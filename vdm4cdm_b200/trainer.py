@@ -181,10 +181,15 @@ class Trainer:
         return self._static_loss.clone()
 
     def _eager_step(self, batch) -> torch.Tensor:
-        self.buckets.zero_grad()
-        loss = self.model.training_step(batch)
-        loss.backward()
-        self.optimizer_step()
+        nvtx = torch.cuda.nvtx.range          # no-ops without a profiler attached
+        with nvtx("vdm.train_step"):
+            self.buckets.zero_grad()
+            with nvtx("vdm.forward_loss"):
+                loss = self.model.training_step(batch)
+            with nvtx("vdm.backward"):
+                loss.backward()
+            with nvtx("vdm.allreduce_clip_adamw"):
+                self.optimizer_step()
         return loss.detach()
 
     def _capture(self) -> None:

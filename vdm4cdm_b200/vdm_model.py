@@ -329,13 +329,19 @@ class SamplerSession:
 
     def _one_step(self):
         n0 = ops.launch_count()
-        self.net.run_packed(self.packed, self.rows, step_ptr=self.step_idx, out=self.eps)
+        # NVTX ranges (no-ops without a profiler): `ncu --nvtx --nvtx-include "vdm.sampler_step/"` / Nsight Systems timelines
+        with torch.cuda.nvtx.range("vdm.sampler_step"):
+            with torch.cuda.nvtx.range("vdm.denoiser"):
+                self.net.run_packed(self.packed, self.rows, step_ptr=self.step_idx, out=self.eps)
+            self._update()
+        self.kernels_per_step = ops.launch_count() - n0
+
+    def _update(self):
         ops.sampler_step(self.z, self.eps, self.coef, out=self.z, step_ptr=self.step_idx, seed=self.seed,
                          realisation_id=self.rid_buf, draw_base=1,
                          noise=self.noise_buf if self.noise_fn is not None else None, cond=self.cond_buf,
                          packed_out=self.packed)
         ops.increment(self.step_idx)
-        self.kernels_per_step = ops.launch_count() - n0
 
     @torch.no_grad()
     def step(self):
