@@ -107,6 +107,45 @@ def test_pack_conv_weight_kernel_matches_host_packing(co, ci, k):
     torch.cuda.synchronize()
 
 
+def test_batched_pack_equals_the_single_filter_launches():
+    """vdm_pack_conv_weight_batched: every filter of a job table (forward and dgrad variants, 3x3x3 and 1x1x1) in one
+    launch gives bit for bit what the per-filter launches give; CUNet.repack_all re-packs exactly the stale filters."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(11)
+    jobs, want = [], []
+    for co, ci, k in ((32, 2, 3), (1, 32, 3), (64, 32, 3), (128, 384, 1), (32, 96, 3), (256, 256, 3)):
+        w = torch.randn((co, ci, k, k, k), generator=gen).to(dev)
+        variants = [(False, 0, ci)] + ([(True, 0, ci)] if ci <= 256 else [(True, 0, ci // 2), (True, ci // 2, ci // 2)])
+        for tf, c0, n in variants:
+            out = torch.zeros(ops.packed_weight_shape(w.shape, tf, n), dtype=torch.bfloat16, device=dev)
+            ref = torch.empty_like(out)
+            ops.pack_conv_weight_into(w, ref, tf, c0, n)
+            jobs.append((w, out, tf, c0, n))
+            want.append(ref)
+    table = ops.pack_job_table(jobs, dev)
+    ops.pack_conv_weights_batched(table, len(jobs))
+    torch.cuda.synchronize()
+    for (w, out, tf, c0, n), ref in zip(jobs, want):
+        assert torch.equal(out, ref), (tuple(w.shape), tf, c0, n)
+
+    from vdm4cdm_b200.networks import CUNet
+    net = CUNet(shape=(1, 16, 16, 16), chs=[16, 32], s_conditioning_channels=1, v_conditioning_dims=[], t_conditioning=True).to(dev)
+    net.refresh_packed()
+    before = {slot: hit[1].clone() for slot, hit in net._packed_cache.items()}
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.mul_(1.5)
+    net.invalidate_packed()
+    launches0 = ops.launch_count()
+    net.repack_all()
+    assert ops.launch_count() - launches0 == 1
+    torch.cuda.synchronize()
+    for name, conv in net._convs():
+        assert torch.equal(net._packed_cache[name][1], ops.pack_conv_weight(conv.weight.detach()))
+        assert not torch.equal(net._packed_cache[name][1], before[name])
+
+
 def test_dgrad_wide_input_in_two_launches():
     """dgrad of a 384 -> 128 conv: 384 output channels exceed one launch (N <= 256) -> two plane windows."""
     ops = _ops()

@@ -262,7 +262,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     from vdm4cdm_b200 import _C
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = {"VdmConvDesc": _C.ConvDesc, "VdmConvEpilogue": _C.ConvEpilogue, "VdmWgradDesc": _C.WgradDesc,
-             "VdmTensor": _C.Tensor}
+             "VdmTensor": _C.Tensor, "VdmPackJob": _C.PackJob}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vdm4cdm_b200.h"', "int main(void) {"]
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')

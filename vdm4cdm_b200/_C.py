@@ -33,6 +33,14 @@ class ConvDesc(Structure):
     ]
 
 
+class PackJob(Structure):
+    _fields_ = [
+        ("w", c_void_p), ("packed", c_void_p),
+        ("c_out", c_int32), ("c_in", c_int32), ("k3", c_int32), ("transpose_flip", c_int32),
+        ("ci0", c_int32), ("n_ci", c_int32), ("c_in_pad", c_int32), ("c_out_pad", c_int32),
+    ]
+
+
 class ConvEpilogue(Structure):
     _fields_ = [
         ("chan_add", c_void_p), ("step_ptr", c_void_p), ("chan_add_step_stride", c_int64),
@@ -68,6 +76,7 @@ _SIGNATURES = {
     "vdm_conv3d": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(ConvEpilogue), c_void_p]),
     "vdm_conv3d_wgrad": (c_int, [POINTER(WgradDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdm_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vdm_pack_conv_weight_batched": (c_int, [c_void_p, c_int, c_void_p]),
     "vdm_gn_silu_step": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_float, c_float, c_uint64, c_void_p, c_uint32, c_void_p]),
     "vdm_gn_silu_bwd_reduce": (c_int, [_T, _T, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,

@@ -114,6 +114,7 @@ struct ConvKernelParams {
   const float* in_norm;      // fused input transform: fp32 [B][c_in][2] (a, b), silu(gn(x)) = h + h tanh(h), h = a x + b
   int c_in;                  // channels of x read (the in_norm row length)
   int xf_coef_off;           // byte offset of the current sample's (a, b) table in dynamic shared memory
+  int m_units, m_nseg, m_seglen;   // d-marching schedule (conv3d_march.cuh): units = columns x d-segments of m_seglen slices
   int debug_flags;           // bring-up experiments (results are wrong): 1 = epilogue does no work, 2 = halo loaded for the
                              // first two tiles only, 4 = no TMEM reads, 8 = no output stores, 16 = no statistics
                              // transpose-reduction, 32 = no statistics barrier + fold
@@ -1074,6 +1075,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
 }
 
+#include "conv3d_march.cuh"
+
 // ---- host side ------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
@@ -1100,10 +1103,84 @@ static int num_sms() {
 #ifdef VDM_BRINGUP
 static int g_debug_flags = 0;
 static int g_debug_force_mt = 0, g_debug_force_kc = 0, g_debug_force_nsplit = 0, g_debug_no_resident = 0, g_debug_no_fold = 0;
+static int g_debug_no_march = 0;
 #else
 constexpr int g_debug_flags = 0;
 constexpr int g_debug_force_mt = 0, g_debug_force_kc = 0, g_debug_force_nsplit = 0, g_debug_no_resident = 0, g_debug_no_fold = 0;
+constexpr int g_debug_no_march = 0;
 #endif
+
+// Launch of the d-marching schedule (conv3d_march.cuh).  `p` carries the grid, the plane windows and the epilogue; this
+// fills in the unit decomposition, the shared-memory plan and the one-slice tensor map.
+static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x, int kc, int halo, int x_planes, bool has_residual,
+                        PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t stream) {
+  const int NF = p.n_cta, planes = kc / 8, sms = num_sms();
+  // Segment length: static round-robin over equal units, so the launch takes ceil(units / SMs) rounds of (seglen + 2) slices
+  // (+1: per-unit fixed costs); short segments balance the SMs, long ones amortise the two halo slices.
+  const long long cols = (long long)d.batch * p.tiles_h * p.tiles_w;
+  int nseg_best = 1;
+  double best = -1.0;
+  for (int nseg = 1; nseg <= ceil_div(d.depth, 4); ++nseg) {
+    const int seglen = ceil_div(d.depth, nseg);
+    if (ceil_div(d.depth, seglen) != nseg) continue;
+    const long long rounds = (cols * nseg + sms - 1) / sms;
+    const double cost = (double)rounds * (seglen + 3);
+    if (best < 0.0 || cost < best * 0.999) { best = cost; nseg_best = nseg; }
+  }
+  p.m_nseg = nseg_best;
+  p.m_seglen = ceil_div(d.depth, nseg_best);
+  const long long units = cols * p.m_nseg;
+  VDM_CHECK_ARG(units < (1ll << 31), "vdm_conv3d: too many units");
+  p.m_units = (int)units;
+  const int stage_bytes = planes * (kTileH + 2) * (kTileW + 2) * 16;
+  int off = kMarchStages * stage_bytes + 27 * planes * NF * 16 + (int)sizeof(MarchShared) + 2 * kMEpiWarps * NF * 4 + 2 * NF * 8 +
+            kMarchCaddMax * 4;
+  off = (off + 15) & ~15;
+  p.res_depth = 0;
+  if (has_residual) {
+    p.res_ring_off = off;
+    p.res_depth = kMarchResDepth;
+    off += kMarchResDepth * (NF / 8) * kMEpiThreads * 16;
+  }
+  const size_t smem_bytes = (size_t)off + 1024;
+  VDM_CHECK_ARG(smem_bytes <= 227 * 1024, "vdm_conv3d: marching layer does not fit shared memory");
+  CUtensorMap tmx;
+  {
+    const cuuint64_t Dx = d.depth + 2 * halo, Hx = d.height + 2 * halo, Wx = d.width + 2 * halo;
+    cuuint64_t gdim[4] = {Wx * 8, Hx, Dx, (cuuint64_t)d.batch * x_planes};
+    cuuint64_t gstr[3] = {Wx * 16, Hx * Wx * 16, Dx * Hx * Wx * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(kTileW + 2) * 8, (cuuint32_t)(kTileH + 2), 1u, (cuuint32_t)planes};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d: cuTensorMapEncodeTiled(x, marching) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+  }
+  const int grid = p.m_units < sms ? p.m_units : sms;
+  int rc = VDM_E_UNSUPPORTED;
+#define VDM_LAUNCH_MARCH(KJv, NFv)                                                                             \
+  if (kc == 16 * KJv && NF == NFv) {                                                                           \
+    static bool configured = false;                                                                            \
+    if (!configured) {                                                                                         \
+      VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_march_kernel<KJv, NFv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          227 * 1024));                                                        \
+      configured = true;                                                                                       \
+    }                                                                                                          \
+    conv3d_march_kernel<KJv, NFv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, p);                         \
+    rc = VDM_OK;                                                                                               \
+  }
+  VDM_LAUNCH_MARCH(1, 16) VDM_LAUNCH_MARCH(1, 32) VDM_LAUNCH_MARCH(2, 16) VDM_LAUNCH_MARCH(2, 32)
+#undef VDM_LAUNCH_MARCH
+  if (rc != VDM_OK) {
+    set_error("vdm_conv3d: no marching kernel instance for KC=%d N=%d", kc, NF);
+    return rc;
+  }
+  VDM_CHECK_LAUNCH();
+  return VDM_OK;
+}
 
 }  // namespace vdm
 
@@ -1119,6 +1196,7 @@ extern "C" int vdm_debug_set(int key, int value) {
     case 4: g_debug_no_resident = value; return VDM_OK;
     case 5: g_debug_flags = value; return VDM_OK;
     case 6: g_debug_no_fold = value; return VDM_OK;
+    case 7: g_debug_no_march = value; return VDM_OK;
     default: set_error("vdm_debug_set: unknown key %d", key); return VDM_E_BADARG;
   }
 }
@@ -1368,6 +1446,10 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   VDM_CHECK_ARG(!p.r_up || (d.depth % 2 == 0 && d.height % 2 == 0 && d.width % 2 == 0),
                 "vdm_conv3d: an up-sampled residual needs an even grid, got (%d,%d,%d)", d.depth, d.height, d.width);
   p.debug_flags = g_debug_flags;
+
+  // d-marching schedule for the narrow layers whose input channels are one chunk (conv3d_march.cuh)
+  if (fold && !fold_streamed && p.k_chunks == 1 && !has_skip && !has_xf && g_debug_no_march == 0)
+    return launch_march(d, p, x, kc, halo, x_planes, has_residual, encode, stream);
 
   // activations: 4-D (W*8 channels-in-plane, H, D, B*planes), box (Wh*8, Hh, Hd, KC/8); out-of-bounds -> zeros.
   // The (w, 8ch) pair is ONE tensor-map dimension on purpose: the TMA unit issues requests per

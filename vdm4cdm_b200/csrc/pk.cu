@@ -3,9 +3,9 @@
 // Stands in for power() at src/utils.py:16-83 of the reference (pk :85-102, get_ccs :110-128):
 // rfftn -> X conj(X2) -> batch mean / channel sum -> ceil(|k|) bins with Hermitian weights.
 // The reference builds ~10 full-size temporaries and calls torch.bincount three times; here the
-// wave number is recomputed from the flat mode index, equal-bin runs inside a warp are combined
-// with a segmented shuffle scan (warp-aggregated atomics), blocks accumulate in shared memory
-// and flush once with fp64 global atomics.  k-mean and mode counts depend on the grid only and
+// wave number is recomputed from the mode's coordinates, every mode goes to its bin with one native
+// fp32 shared-memory atomic into bins private to the warp, the warps' bins are folded into fp64 block
+// bins every few thousand values, and blocks flush once with fp64 global atomics.  k-mean and mode counts depend on the grid only and
 // are produced by a separate read-free geometry kernel.
 //
 // HBM roofline: the binning kernel reads each complex mode once: 8 (auto) or 16 (cross) bytes
@@ -27,164 +27,170 @@ struct PkGeom {
   int64_t modes;        // n0*n1*n2h
 };
 
-__device__ __forceinline__ void mode_bin(const PkGeom& g, int64_t m, int& bin, int& weight, float& kmag) {
-  const int i2 = (int)(m % g.n2h);
-  const int64_t r = m / g.n2h;
-  const int i1 = (int)(r % g.n1);
-  const int i0 = (int)(r / g.n1);
-  const int f0 = i0 > g.n0 / 2 ? i0 - g.n0 : i0;
-  const int f1 = i1 > g.n1 / 2 ? i1 - g.n1 : i1;
-  const int k2 = f0 * f0 + f1 * f1 + i2 * i2;
-  kmag = sqrtf((float)k2);
-  bin = (int)ceilf(kmag);
-  weight = (i2 == 0 || (g.last_even && i2 == g.n2h - 1)) ? 1 : 2;
-}
-
-// Segmented inclusive scan over runs of equal `bin` in a warp; returns true on the tail lane of a run.
-template <int NV>
-__device__ __forceinline__ bool warp_run_sum(int bin, float (&v)[NV]) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int prev = __shfl_up_sync(full, bin, 1);
-  int head = (lane == 0) || (prev != bin);
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    float up[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) up[i] = __shfl_up_sync(full, v[i], o);
-    const int head_up = __shfl_up_sync(full, head, o);
-    if (lane >= o && !head) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] += up[i];
-      head |= head_up;
-    }
+// Position of a thread in the half spectrum, advanced by a fixed stride without divisions: m = (i0 * n1 + i1) * n2h + i2.
+struct ModeCursor {
+  int i0, i1, i2;
+  int ds, d1, d0;     // the stride in (i2, i1, i0) digits
+  __device__ __forceinline__ void init(const PkGeom& g, int64_t m, int64_t stride) {
+    i2 = (int)(m % g.n2h);
+    const int64_t row = m / g.n2h;
+    i1 = (int)(row % g.n1);
+    i0 = (int)(row / g.n1);
+    ds = (int)(stride % g.n2h);
+    const int64_t drow = stride / g.n2h;
+    d1 = (int)(drow % g.n1);
+    d0 = (int)(drow / g.n1);
   }
-  const int next = __shfl_down_sync(full, bin, 1);
-  return (lane == 31) || (next != bin);
+  __device__ __forceinline__ void advance(const PkGeom& g) {
+    i2 += ds;
+    const int c2 = i2 >= g.n2h ? 1 : 0;
+    i2 -= c2 ? g.n2h : 0;
+    i1 += d1 + c2;                     // <= 2 * n1 - 1
+    const int c1 = i1 >= g.n1 ? 1 : 0;
+    i1 -= c1 ? g.n1 : 0;
+    i0 += d0 + c1;
+  }
+  // bin = ceil(|k|) (src/utils.py:53-56), Hermitian weight (src/utils.py:59-66); bin = -1 outside 1..kmax
+  __device__ __forceinline__ int bin(const PkGeom& g, float& weight, float& kmag) const {
+    const int f0 = i0 > g.n0 / 2 ? i0 - g.n0 : i0;
+    const int f1 = i1 > g.n1 / 2 ? i1 - g.n1 : i1;
+    kmag = sqrtf((float)(f0 * f0 + f1 * f1 + i2 * i2));
+    const int b = (int)ceilf(kmag);
+    weight = (i2 == 0 || (g.last_even && i2 == g.n2h - 1)) ? 1.f : 2.f;
+    return (b >= 1 && b <= g.kmax) ? b : -1;
+  }
+};
+
+constexpr int kPkThreads = 256, kPkWarps = kPkThreads / 32;
+constexpr int kPkUnroll = 4;          // modes (independent 8-byte loads) in flight per thread
+constexpr int kPkFoldEvery = 32;      // trips between folds of the fp32 warp bins into the block's fp64 bins
+
+// Fold the warps' private fp32 bins into the block's fp64 bins in a fixed order and clear them (all threads call).
+__device__ __forceinline__ void pk_fold_bins(float* s_bins, double* s_acc, int n) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kPkThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kPkWarps; ++wv) {
+      s += (double)s_bins[wv * n + i];
+      s_bins[wv * n + i] = 0.f;
+    }
+    s_acc[i] += s;
+  }
+  __syncthreads();
 }
 
 // acc: double [n_fields][NSPEC][kmax+1], zero-initialised.
 // NSPEC == 1: Re(X conj(X2)) (X2 may alias X).  NSPEC == 3: |X|^2, |X2|^2, Re(X conj(X2)).
+//
+// One mode per thread and trip, kPkUnroll trips' loads in flight, coordinates advanced without divisions, and every mode
+// added to its bin with ONE native fp32 shared-memory atomic per spectrum into bins PRIVATE to the warp (no contention
+// between warps; lanes of one instruction that hit the same bin are serialised by the hardware in a fixed order).  A
+// warp bin collects at most kPkFoldEvery * kPkUnroll * 32 = 4096 values in fp32 before it is folded into the block's
+// fp64 bins, and blocks flush once with fp64 global atomics.
+// (Round 2: the previous version merged equal-bin runs with a 5-round segmented shuffle scan per 32 modes -- ~120
+// instructions per trip, 0.14 ms per 16 fields of 128^3 against a 0.02 ms HBM floor.  Bins are NOT nearly constant
+// along a row (b = ceil(sqrt(k01 + i2^2)) takes ~10-30 values over the 65 modes of a 128^3 row), so there is little
+// to merge; the atomic unit does the same work in one instruction.)
 template <int NSPEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPkThreads)
 pk_bin_kernel(const float2* __restrict__ X, const float2* __restrict__ X2, PkGeom g, int n_transforms,
               double* __restrict__ acc) {
-  extern __shared__ double s_acc[];  // [warp][NSPEC][kmax+1]: private bins per warp
-  const int nb = g.kmax + 1;
-  const int n_warps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < n_warps * NSPEC * nb; i += blockDim.x) s_acc[i] = 0.0;
+  extern __shared__ double s_acc[];   // [NSPEC][kmax+1] fp64 block bins, then [warp][NSPEC][kmax+1] fp32 warp bins
+  const int nb = g.kmax + 1, n = NSPEC * nb;
+  float* s_bins = reinterpret_cast<float*>(s_acc + n);
+  for (int i = threadIdx.x; i < n; i += kPkThreads) s_acc[i] = 0.0;
+  for (int i = threadIdx.x; i < kPkWarps * n; i += kPkThreads) s_bins[i] = 0.f;
   __syncthreads();
-  double* my = s_acc + (threadIdx.x >> 5) * NSPEC * nb;
+  float* my = s_bins + (threadIdx.x >> 5) * n;
 
-  // One warp per (i0, i1) row of the half spectrum: the row's n2h modes are contiguous, (f0, f1) are computed once
-  // per row instead of two 64-bit divisions per mode, and |k| grows along the row, so equal-bin runs are long.
-  // Four 32-mode trips are loaded before any is reduced (four 8-byte loads in flight per lane).
-  // (r02l: the one-mode-per-thread version ran at 0.9 TB/s, instruction-bound.)
   const int field = blockIdx.y;
   const float2* x = X + (int64_t)field * n_transforms * g.modes;
   const float2* x2 = X2 + (int64_t)field * n_transforms * g.modes;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int rows = g.n0 * g.n1;
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
-    const int i1 = row % g.n1, i0 = row / g.n1;
-    const int f0 = i0 > g.n0 / 2 ? i0 - g.n0 : i0;
-    const int f1 = i1 > g.n1 / 2 ? i1 - g.n1 : i1;
-    const int k01 = f0 * f0 + f1 * f1;
-    const float2* xr = x + (int64_t)row * g.n2h;
-    const float2* xr2 = x2 + (int64_t)row * g.n2h;
-    for (int base = 0; base < g.n2h; base += 128) {
-      int bins[4];
-      float v[4][NSPEC];
+  const int64_t stride = (int64_t)gridDim.x * kPkThreads;
+  int64_t m = (int64_t)blockIdx.x * kPkThreads + threadIdx.x;
+  ModeCursor cur;
+  cur.init(g, m, stride);
+  const int trips = (int)((g.modes + stride * kPkUnroll - 1) / (stride * kPkUnroll));   // the same for every thread
+  for (int it = 0; it < trips; ++it) {
+    int bins[kPkUnroll];
+    float v[kPkUnroll][NSPEC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i2 = base + u * 32 + lane;
-        bins[u] = -1;
+    for (int u = 0; u < kPkUnroll; ++u) {
+      float w, kmag;
+      bins[u] = (m < g.modes) ? cur.bin(g, w, kmag) : -1;
 #pragma unroll
-        for (int i = 0; i < NSPEC; ++i) v[u][i] = 0.f;
-        if (i2 < g.n2h) {
-          const int b = (int)ceilf(sqrtf((float)(k01 + i2 * i2)));
-          if (b >= 1 && b <= g.kmax) {
-            bins[u] = b;
-            for (int t = 0; t < n_transforms; ++t) {
-              const float2 a = __ldg(xr + (int64_t)t * g.modes + i2);
-              const float2 c = __ldg(xr2 + (int64_t)t * g.modes + i2);
-              if constexpr (NSPEC == 1) {
-                v[u][0] += a.x * c.x + a.y * c.y;
-              } else {
-                v[u][0] += a.x * a.x + a.y * a.y;
-                v[u][NSPEC - 2] += c.x * c.x + c.y * c.y;
-                v[u][NSPEC - 1] += a.x * c.x + a.y * c.y;
-              }
-            }
-            const float w = (i2 == 0 || (g.last_even && i2 == g.n2h - 1)) ? 1.f : 2.f;
-#pragma unroll
-            for (int i = 0; i < NSPEC; ++i) v[u][i] *= w;
+      for (int i = 0; i < NSPEC; ++i) v[u][i] = 0.f;
+      if (bins[u] >= 1) {
+        for (int t = 0; t < n_transforms; ++t) {
+          const float2 a = __ldg(x + (int64_t)t * g.modes + m);
+          const float2 c = __ldg(x2 + (int64_t)t * g.modes + m);
+          if constexpr (NSPEC == 1) {
+            v[u][0] += a.x * c.x + a.y * c.y;
+          } else {
+            v[u][0] += a.x * a.x + a.y * a.y;
+            v[u][NSPEC - 2] += c.x * c.x + c.y * c.y;
+            v[u][NSPEC - 1] += a.x * c.x + a.y * c.y;
           }
         }
+#pragma unroll
+        for (int i = 0; i < NSPEC; ++i) v[u][i] *= w;
       }
+      m += stride;
+      cur.advance(g);
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (base + u * 32 >= g.n2h) break;           // warp-uniform
-        // |k| grows along a row, so after the run merge every bin has at most ONE tail lane in this trip: the
-        // warp's private bins take plain read-modify-writes (fp64 shared-memory atomics are compare-and-swap loops;
-        // with eight warps of neighbouring rows hitting the same few bins they were the cost of this kernel, r02m)
-        const bool tail = warp_run_sum<NSPEC>(bins[u], v[u]);
-        if (tail && bins[u] >= 1) {
+    for (int u = 0; u < kPkUnroll; ++u) {
+      if (bins[u] >= 1) {
 #pragma unroll
-          for (int i = 0; i < NSPEC; ++i) my[i * nb + bins[u]] += (double)v[u][i];
-        }
-        __syncwarp();
+        for (int i = 0; i < NSPEC; ++i) atomicAdd(&my[i * nb + bins[u]], v[u][i]);
       }
     }
+    if ((it & (kPkFoldEvery - 1)) == kPkFoldEvery - 1) pk_fold_bins(s_bins, s_acc, n);
   }
-  __syncthreads();
-  double* out = acc + (int64_t)field * NSPEC * nb;
-  for (int i = threadIdx.x; i < NSPEC * nb; i += blockDim.x) {
-    double s = 0.0;
-    for (int wv = 0; wv < n_warps; ++wv) s += s_acc[wv * NSPEC * nb + i];
-    if (s != 0.0) atomicAdd(out + i, s);
-  }
+  pk_fold_bins(s_bins, s_acc, n);
+  double* out = acc + (int64_t)field * n;
+  for (int i = threadIdx.x; i < n; i += kPkThreads)
+    if (s_acc[i] != 0.0) atomicAdd(out + i, s_acc[i]);
 }
 
-// geometry: ksum[bin] += w*|k| (double), cnt[bin] += w (unsigned long long). No memory reads.
-__global__ void __launch_bounds__(256)
+// geometry: ksum[bin] += w*|k| (double), cnt[bin] += w (unsigned long long). No memory reads; same traversal.
+__global__ void __launch_bounds__(kPkThreads)
 pk_geometry_kernel(PkGeom g, double* __restrict__ ksum, unsigned long long* __restrict__ cnt) {
-  extern __shared__ double s_k[];  // [kmax+1] doubles then [kmax+1] uint64
+  extern __shared__ double s_acc[];   // [kmax+1] fp64 k sums, then [warp][kmax+1] fp32 warp bins, then [kmax+1] counts
   const int nb = g.kmax + 1;
-  unsigned long long* s_c = reinterpret_cast<unsigned long long*>(s_k + nb);
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-    s_k[i] = 0.0;
-    s_c[i] = 0ull;
+  float* s_bins = reinterpret_cast<float*>(s_acc + nb);
+  unsigned int* s_c = reinterpret_cast<unsigned int*>(s_bins + kPkWarps * nb);
+  for (int i = threadIdx.x; i < nb; i += kPkThreads) {
+    s_acc[i] = 0.0;
+    s_c[i] = 0u;
   }
+  for (int i = threadIdx.x; i < kPkWarps * nb; i += kPkThreads) s_bins[i] = 0.f;
   __syncthreads();
-  const int64_t span = (int64_t)gridDim.x * blockDim.x;
-  const int64_t iters = (g.modes + span - 1) / span;
-  for (int64_t it = 0; it < iters; ++it) {
-    const int64_t m = it * span + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int bin = -1, w = 0;
-    float kmag = 0.f;
-    float v[2] = {0.f, 0.f};
+  float* my = s_bins + (threadIdx.x >> 5) * nb;
+  const int64_t stride = (int64_t)gridDim.x * kPkThreads;
+  int64_t m = (int64_t)blockIdx.x * kPkThreads + threadIdx.x;
+  ModeCursor cur;
+  cur.init(g, m, stride);
+  const int trips = (int)((g.modes + stride - 1) / stride);
+  for (int it = 0; it < trips; ++it) {
     if (m < g.modes) {
-      mode_bin(g, m, bin, w, kmag);
-      if (bin >= 1 && bin <= g.kmax) {
-        v[0] = kmag * (float)w;
-        v[1] = (float)w;  // <= 64 per run: exact in fp32
-      } else {
-        bin = -1;
+      float w, kmag;
+      const int b = cur.bin(g, w, kmag);
+      if (b >= 1) {
+        atomicAdd(&my[b], kmag * w);
+        atomicAdd(&s_c[b], (unsigned int)w);      // < 2^32 per block: at most 2 * trips * 256
       }
     }
-    const bool tail = warp_run_sum<2>(bin, v);
-    if (tail && bin >= 1) {
-      atomicAdd(&s_k[bin], (double)v[0]);
-      atomicAdd(&s_c[bin], (unsigned long long)(v[1] + 0.5f));
-    }
+    m += stride;
+    cur.advance(g);
+    if ((it & 127) == 127) pk_fold_bins(s_bins, s_acc, nb);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-    if (s_c[i] != 0ull) {
-      atomicAdd(ksum + i, s_k[i]);
-      atomicAdd(cnt + i, s_c[i]);
+  pk_fold_bins(s_bins, s_acc, nb);
+  for (int i = threadIdx.x; i < nb; i += kPkThreads) {
+    if (s_c[i] != 0u) {
+      atomicAdd(ksum + i, s_acc[i]);
+      atomicAdd(cnt + i, (unsigned long long)s_c[i]);
     }
   }
 }
@@ -302,15 +308,15 @@ static int pk_run(const float* f1, const float* f2, int n_fields, int batch, int
   VDM_CHECK_CUDA(cudaMemsetAsync(base + L.acc_off, 0, L.total - L.acc_off, stream));
 
   const int nb = L.g.kmax + 1;
-  const int threads = 256;
-  // enough blocks to fill the 148 SMs a few times over, bounded so per-block flushes stay cheap
-  int64_t want = (L.g.modes + threads * 4 - 1) / (threads * 4);
+  const int threads = kPkThreads;
+  // enough blocks to fill the 148 SMs (8 resident blocks each), bounded so per-block flushes stay cheap
+  int64_t want = (L.g.modes + threads * kPkUnroll - 1) / (threads * kPkUnroll);
   int bx = (int)(want < 1 ? 1 : want);
-  const int cap = (kNumSMs * 8 + n_fields - 1) / n_fields;
+  const int cap = (kNumSMs * 4 + n_fields - 1) / n_fields;   // 64 registers x 256 threads: four blocks per SM
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, n_fields);
   const int ntr = batch * chan;
-  const size_t bin_smem = (size_t)(threads / 32) * nspec * nb * sizeof(double);     // private bins per warp
+  const size_t bin_smem = (size_t)nspec * nb * (sizeof(double) + kPkWarps * sizeof(float));   // block bins + private warp bins
   VDM_CHECK_ARG(bin_smem <= 200 * 1024, "vdm_pk: grid too large for the shared-memory bins (kmax = %d)", L.g.kmax);
   if (nspec == 1) {
     if (bin_smem > 48 * 1024)
@@ -324,7 +330,8 @@ static int pk_run(const float* f1, const float* f2, int n_fields, int batch, int
   VDM_CHECK_LAUNCH();
   int gx = (int)((L.g.modes + threads * 8 - 1) / (threads * 8));
   gx = gx < 1 ? 1 : (gx > kNumSMs * 4 ? kNumSMs * 4 : gx);
-  pk_geometry_kernel<<<gx, threads, nb * (sizeof(double) + sizeof(unsigned long long)), stream>>>(L.g, ksum, cnt);
+  const size_t geo_smem = (size_t)nb * (sizeof(double) + kPkWarps * sizeof(float) + sizeof(unsigned int));
+  pk_geometry_kernel<<<gx, threads, geo_smem, stream>>>(L.g, ksum, cnt);
   VDM_CHECK_LAUNCH();
   const int total = n_fields * L.g.kmax;
   pk_finalize_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(acc, ksum, cnt, n_fields, nspec, L.g.kmax,

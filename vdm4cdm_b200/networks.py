@@ -166,6 +166,8 @@ class CUNet(nn.Module):
         self._arena = _Arena()
         self._train_arena = _Arena()
         self._packed_cache: Dict[str, tuple] = {}
+        self._pack_meta: Dict[str, tuple] = {}        # slot -> (conv, transpose_flip, c0, n) of the filters repack_all handles
+        self._pack_tables: Dict[tuple, torch.Tensor] = {}
         self.dropout_seed = 0
         self._dropout_calls = 0
         # device-side training-step counter added to the dropout seed (a captured CUDA graph draws new masks)
@@ -217,7 +219,34 @@ class CUNet(nn.Module):
                 ops.pack_conv_weight_into(w.detach().contiguous(), buf, transpose_flip, c0, n)
                 hit = (key, buf)
             self._packed_cache[slot] = hit
+            self._pack_meta[slot] = (conv, transpose_flip, c0, n)
         return hit[1]
+
+    def repack_all(self) -> None:
+        """Re-pack EVERY stale filter the trunk has used so far (forward and dgrad variants) in one
+        ``vdm_pack_conv_weight_batched`` launch -- the training step calls this after each optimizer update instead of
+        letting ~56 lazy single-filter launches happen.  Filters seen for the first time are still packed lazily."""
+        stale = []
+        for slot, (conv, transpose_flip, c0, n) in self._pack_meta.items():
+            w = conv.weight
+            key = (w.data_ptr(), w._version, w.device, getattr(self, "_weights_epoch", 0))
+            hit = self._packed_cache.get(slot)
+            if hit is None or not w.is_cuda or not w.is_contiguous() or hit[1].device != w.device:
+                continue
+            if hit[0] != key:
+                stale.append((slot, key, w, hit[1], transpose_flip, c0, n))
+        if not stale:
+            return
+        tkey = tuple((slot, key[0], buf.data_ptr()) for slot, key, _, buf, _, _, _ in stale)
+        table = self._pack_tables.get(tkey)
+        if table is None:
+            self._pack_tables.clear()
+            table = ops.pack_job_table([(w.detach(), buf, tf, c0, n) for _, _, w, buf, tf, c0, n in stale], stale[0][2].device)
+            self._pack_tables[tkey] = table
+        with torch.no_grad():
+            ops.pack_conv_weights_batched(table, len(stale))
+        for slot, key, _, buf, _, _, _ in stale:
+            self._packed_cache[slot] = (key, buf)
 
     def _packed_in_slice(self, slot: str, conv: nn.Conv3d, c0: int, n: int) -> torch.Tensor:
         """bf16 filter of the conv restricted to INPUT channels [c0, c0 + n) (the two halves of an up block's 1x1x1
@@ -280,7 +309,9 @@ class CUNet(nn.Module):
         return out
 
     def refresh_packed(self) -> None:
-        """Re-pack (in place) every conv filter whose fp32 parameter changed since it was packed."""
+        """Re-pack (in place) every conv filter whose fp32 parameter changed since it was packed: one batched launch for
+        the filters packed before (``repack_all``), single launches for new ones."""
+        self.repack_all()
         for name, conv in self._convs():
             self._packed(name, conv)
 

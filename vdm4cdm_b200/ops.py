@@ -134,6 +134,29 @@ def pack_conv_weight_into(w: torch.Tensor, out: torch.Tensor, transpose_flip: bo
     return out
 
 
+def pack_job_table(jobs, device) -> torch.Tensor:
+    """Device copy of a ``VdmPackJob`` array for ``pack_conv_weights_batched``.  ``jobs``: (w fp32 CUDA (Cout, Cin, k, k, k)
+    contiguous, out bf16 packed buffer, transpose_flip, ci0, n_ci) tuples; the tensors must outlive the table."""
+    arr = (_C.PackJob * len(jobs))()
+    for j, (w, out, transpose_flip, ci0, n_ci) in zip(arr, jobs):
+        _need(w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 5, "pack_job_table: bad weight")
+        _need(out.is_cuda and out.dtype == torch.bfloat16 and out.is_contiguous() and
+              tuple(out.shape) == packed_weight_shape(w.shape, transpose_flip, n_ci), "pack_job_table: bad out tensor")
+        j.w, j.packed = w.data_ptr(), out.data_ptr()
+        j.c_out, j.c_in, j.k3 = w.shape[0], w.shape[1], w.shape[2] ** 3
+        j.transpose_flip, j.ci0, j.n_ci = (1 if transpose_flip else 0), ci0, n_ci
+        j.c_in_pad, j.c_out_pad = out.shape[1] * 8, out.shape[2]
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return raw.to(device)
+
+
+def pack_conv_weights_batched(table: torch.Tensor, n_jobs: int) -> None:
+    """``vdm_pack_conv_weight_batched``: every job of ``pack_job_table`` in one launch."""
+    rc = _C.lib().vdm_pack_conv_weight_batched(table.data_ptr(), n_jobs, _stream())
+    _C.check(rc, "vdm_pack_conv_weight_batched")
+    _launched(1)
+
+
 UnsupportedFusion = _C.UnsupportedFusion
 
 
