@@ -211,6 +211,31 @@ def test_conv3d_residual_read_through_upsampling():
                    residual_upsample=True)
 
 
+@pytest.mark.parametrize("ci,co", [(16, 16), (32, 32), (96, 32), (64, 64)])
+def test_conv3d_circular_is_shift_equivariant_bit_for_bit(ci, co):
+    """Periodic padding: conv(roll(x)) == roll(conv(x)) BIT FOR BIT on random bf16 data for shifts that are not multiples of
+    the tile (every output voxel sums the same products in the same order wherever it sits -- tile and marching schedules
+    alike), and the GroupNorm statistics of the two runs agree to fp32 summation order."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    b, d, h, w = 2, 16, 32, 16
+    x = torch.randn((b, ci // 8, d, h, w, 8), device=dev, generator=g).to(torch.bfloat16)
+    wt = ops.pack_conv_weight(torch.randn((co, ci, 3, 3, 3), device=dev, generator=g) / (27 * ci) ** 0.5)
+    cadd = torch.randn((b, co), device=dev, generator=g)
+    outs = []
+    for sh in ((0, 0, 0), (3, 5, 4), (4, 8, 4)):
+        st = torch.zeros((b, co, 2), dtype=torch.float64, device=dev)
+        y = ops.conv3d(ops.pad_circular(torch.roll(x, sh, (2, 3, 4)), ci), wt, co, chan_add=cadd, stats=st, circular=True)
+        torch.cuda.synchronize()
+        outs.append((sh, y, st))
+    for sh, y, st in outs[1:]:
+        assert torch.equal(y, torch.roll(outs[0][1], sh, (2, 3, 4))), sh
+        scale = outs[0][2][..., 1:].sqrt() * (d * h * w) ** 0.5          # ~ sum |y|: the sums' natural scale
+        assert float(((st[..., 0] - outs[0][2][..., 0]).abs() / scale[..., 0]).max()) < 1e-6
+        assert float(((st[..., 1] - outs[0][2][..., 1]).abs() / outs[0][2][..., 1]).max()) < 1e-6
+
+
 @pytest.mark.parametrize("case", [(2, 32, 32, 32, 6, 20, 12), (1, 16, 16, 16, 5, 16, 8), (1, 32, 32, 64, 4, 16, 16),
                                   (1, 64, 32, 32, 8, 16, 8), (1, 16, 32, 48, 3, 9, 7)], ids=lambda c: "x".join(map(str, c)))
 def test_conv3d_fused_skip_conv_exact_integers(case):

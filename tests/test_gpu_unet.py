@@ -169,14 +169,21 @@ def test_unet_forward_circular_padding_matches_oracle():
     print(f"circular unet: relative L2 error {err:.3e} (torch bf16 autocast of the oracle: {autocast_err:.3e}; "
           f"zero-padded network differs by {_rel_l2(zero_pad, want):.3e})")
     assert err < min(max(BF16_RTOL, autocast_err), 2e-2), (err, autocast_err)
-    # periodic boundaries make the network equivariant under shifts by a multiple of the coarsest cell (4 voxels)
+    # periodic boundaries make the network equivariant under shifts by a multiple of the coarsest cell (4 voxels) -- to the
+    # bf16 noise floor: every conv output is bit-for-bit equivariant (tests/test_gpu_conv3d.py::
+    # test_conv3d_circular_is_shift_equivariant_bit_for_bit), but the GroupNorm sums are added in an order that depends on
+    # the position (per-lane fp32 sums along d in the marching schedule), they move by ~1e-7, a few bf16 roundings of the
+    # normalised tensor flip, and a random-init network amplifies single flips to every element within ~3 layers
+    # (tools/check_equivariance_per_layer.py: 0.3% of the elements differ after the first block, 16% after the third).
+    # The bar is therefore the parity bar; a wrong halo shows up at the 1e-1 level (zero padding: 0.89).
     shift = dict(shifts=(4, 8, 4), dims=(2, 3, 4))
     with torch.no_grad():
         rolled = net(torch.roll(x, **shift).cuda(), t=t.cuda(), s_conditioning=torch.roll(cond, **shift).cuda(),
                      v_conditionings=[v[0].cuda()]).cpu()
     eq = _rel_l2(rolled, torch.roll(got, **shift))
     print(f"circular unet: shift equivariance defect {eq:.3e}")
-    assert eq < 1e-4, eq          # measured 1.1e-7: same kernels, same per-voxel summation order
+    assert eq < min(max(BF16_RTOL, autocast_err), 2e-2), eq
+    assert _rel_l2(rolled, torch.roll(want, **shift)) < min(max(BF16_RTOL, autocast_err), 2e-2)
     # the sampler works on top of it (packed input is re-padded every step)
     from vdm4cdm_b200.vdm_model import VDM
     xs = VDM(net).cuda().eval().sample(batch, 3, "cuda:0", seed=1, s_conditioning=cond.cuda(), v_conditionings=[v[0].cuda()])

@@ -1112,8 +1112,8 @@ constexpr int g_debug_no_march = 0;
 
 // Launch of the d-marching schedule (conv3d_march.cuh).  `p` carries the grid, the plane windows and the epilogue; this
 // fills in the unit decomposition, the shared-memory plan and the one-slice tensor map.
-static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x, int kc, int halo, int x_planes, bool has_residual,
-                        PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t stream) {
+static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x, const void* skip_x, int kc, int halo, int x_planes,
+                        bool has_residual, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t stream) {
   const int NF = p.n_cta, planes = kc / 8, sms = num_sms();
   // Segment length: static round-robin over equal units, so the launch takes ceil(units / SMs) rounds of (seglen + 2) slices
   // (+1: per-unit fixed costs); short segments balance the SMs, long ones amortise the two halo slices.
@@ -1133,8 +1133,8 @@ static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x
   VDM_CHECK_ARG(units < (1ll << 31), "vdm_conv3d: too many units");
   p.m_units = (int)units;
   const int stage_bytes = planes * (kTileH + 2) * (kTileW + 2) * 16;
-  int off = kMarchStages * stage_bytes + 27 * planes * NF * 16 + (int)sizeof(MarchShared) + 2 * kMEpiWarps * NF * 4 + 2 * NF * 8 +
-            kMarchCaddMax * 4;
+  int off = kMarchStages * stage_bytes + 27 * planes * NF * 16 + p.skip_w_bytes + (int)sizeof(MarchShared) + 2 * kMEpiWarps * NF * 4 +
+            2 * NF * 8 + kMarchCaddMax * 4;
   off = (off + 15) & ~15;
   p.res_depth = 0;
   if (has_residual) {
@@ -1159,6 +1159,21 @@ static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x
       return VDM_E_DRIVER;
     }
   }
+  CUtensorMap tmx2 = tmx;
+  if (p.skip_chunks > 0) {     // fused 1x1x1 skip conv: one d-slice of the tile's own face per stage (no halo)
+    const cuuint64_t V = (cuuint64_t)d.depth * d.height * d.width;
+    cuuint64_t gdim[4] = {(cuuint64_t)d.width * 8, (cuuint64_t)d.height, (cuuint64_t)d.depth, (cuuint64_t)d.batch * p.x2_planes};
+    cuuint64_t gstr[3] = {(cuuint64_t)d.width * 16, (cuuint64_t)d.height * d.width * 16, V * 16};
+    cuuint32_t box[4] = {(cuuint32_t)kTileW * 8, (cuuint32_t)kTileH, 1u, (cuuint32_t)planes};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmx2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(skip_x), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("vdm_conv3d: cuTensorMapEncodeTiled(skip_x, marching) failed with %d", (int)r);
+      return VDM_E_DRIVER;
+    }
+  }
   const int grid = p.m_units < sms ? p.m_units : sms;
   int rc = VDM_E_UNSUPPORTED;
 #define VDM_LAUNCH_MARCH(KJv, NFv)                                                                             \
@@ -1169,7 +1184,7 @@ static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x
                                           227 * 1024));                                                        \
       configured = true;                                                                                       \
     }                                                                                                          \
-    conv3d_march_kernel<KJv, NFv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, p);                         \
+    conv3d_march_kernel<KJv, NFv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmx2, p);                      \
     rc = VDM_OK;                                                                                               \
   }
   VDM_LAUNCH_MARCH(1, 16) VDM_LAUNCH_MARCH(1, 32) VDM_LAUNCH_MARCH(2, 16) VDM_LAUNCH_MARCH(2, 32)
@@ -1448,8 +1463,8 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   p.debug_flags = g_debug_flags;
 
   // d-marching schedule for the narrow layers whose input channels are one chunk (conv3d_march.cuh)
-  if (fold && !fold_streamed && p.k_chunks == 1 && !has_skip && !has_xf && g_debug_no_march == 0)
-    return launch_march(d, p, x, kc, halo, x_planes, has_residual, encode, stream);
+  if (fold && !fold_streamed && p.k_chunks == 1 && !has_xf && g_debug_no_march == 0)
+    return launch_march(d, p, x, has_skip ? epi->skip_x : nullptr, kc, halo, x_planes, has_residual, encode, stream);
 
   // activations: 4-D (W*8 channels-in-plane, H, D, B*planes), box (Wh*8, Hh, Hd, KC/8); out-of-bounds -> zeros.
   // The (w, 8ch) pair is ONE tensor-map dimension on purpose: the TMA unit issues requests per

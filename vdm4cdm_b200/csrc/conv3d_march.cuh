@@ -53,8 +53,7 @@ __device__ __forceinline__ MarchUnit decode_unit(const ConvKernelParams& p, int 
 // a_st / b_lo: low descriptor words (start address in 16-byte units | LBO << 16); b_lo already points at the first weight
 // row block of the span; d_col: TMEM column of the span's first block.
 template <int KJ, int NF, bool FRESH, int K0, int K1, int NBLK = 0>
-__device__ __forceinline__ void issue_march_span(uint32_t a_st, uint32_t b_lo, uint32_t a_hi32, uint32_t b_hi32, uint32_t d_col,
-                                                 int nblk_rt) {
+__device__ __forceinline__ void issue_march_span(uint64_t a_desc, uint64_t b_desc, uint32_t d_col, int nblk_rt) {
   const int nblk = NBLK > 0 ? NBLK : nblk_rt;     // compile-time on the steady-state path (three blocks, immediate descriptors)
   constexpr int Wh = kTileW + 2;
   constexpr uint32_t kstep_a16 = 2u * (uint32_t)((kTileH + 2) * Wh);
@@ -67,28 +66,28 @@ __device__ __forceinline__ void issue_march_span(uint32_t a_st, uint32_t b_lo, u
       const uint32_t b_off = (uint32_t)((khw * 2 * KJ + 2 * j) * 3 * NF);
       if (FRESH && khw == 0 && j == 0) {
         if (nblk > 1)
-          ptx::umma_bf16_off(d_col, 0u, a_st, a_off, a_hi32, b_lo, b_off, b_hi32, ptx::make_idesc_bf16(128, (uint32_t)((nblk - 1) * NF)), 1u);
-        ptx::umma_bf16_off(d_col, (uint32_t)((nblk - 1) * NF), a_st, a_off, a_hi32, b_lo, b_off + (uint32_t)((nblk - 1) * NF), b_hi32,
-                           ptx::make_idesc_bf16(128, (uint32_t)NF), 0u);
+          ptx::umma_bf16_off64(d_col, 0u, a_desc, a_off, b_desc, b_off, ptx::make_idesc_bf16(128, (uint32_t)((nblk - 1) * NF)), 1u);
+        ptx::umma_bf16_off64(d_col, (uint32_t)((nblk - 1) * NF), a_desc, a_off, b_desc, b_off + (uint32_t)((nblk - 1) * NF),
+                             ptx::make_idesc_bf16(128, (uint32_t)NF), 0u);
       } else {
-        ptx::umma_bf16_off(d_col, 0u, a_st, a_off, a_hi32, b_lo, b_off, b_hi32, idesc, 1u);
+        ptx::umma_bf16_off64(d_col, 0u, a_desc, a_off, b_desc, b_off, idesc, 1u);
       }
     }
   }
 }
 
 // One input slice's MMAs for (kh, kw) in [K0, K1): output slices s_lo..s_hi = accumulator blocks g_lo.. (mod R) = weight row
-// blocks starting at b_st; the span is split in two where the ring wraps (2 of every 16 slices).
+// blocks starting at b_desc; the span is split in two where the ring wraps (2 of every 16 slices).
 template <int KJ, int NF, int K0, int K1>
-__device__ __forceinline__ void issue_march_slice(uint32_t a_st, uint32_t b_st, uint32_t a_hi32, uint32_t b_hi32, uint32_t tmem_u,
-                                                  uint32_t g_lo, int n, int n1, bool fresh) {
+__device__ __forceinline__ void issue_march_slice(uint64_t a_desc, uint64_t b_desc, uint32_t tmem_u, uint32_t g_lo, int n, int n1,
+                                                  bool fresh) {
   if (n1 == n) {
-    if (fresh) issue_march_span<KJ, NF, true, K0, K1>(a_st, b_st, a_hi32, b_hi32, tmem_u + g_lo * (uint32_t)NF, n);
-    else issue_march_span<KJ, NF, false, K0, K1>(a_st, b_st, a_hi32, b_hi32, tmem_u + g_lo * (uint32_t)NF, n);
+    if (fresh) issue_march_span<KJ, NF, true, K0, K1>(a_desc, b_desc, tmem_u + g_lo * (uint32_t)NF, n);
+    else issue_march_span<KJ, NF, false, K0, K1>(a_desc, b_desc, tmem_u + g_lo * (uint32_t)NF, n);
   } else {
-    issue_march_span<KJ, NF, false, K0, K1>(a_st, b_st, a_hi32, b_hi32, tmem_u + g_lo * (uint32_t)NF, n1);
-    if (fresh) issue_march_span<KJ, NF, true, K0, K1>(a_st, b_st + (uint32_t)(n1 * NF), a_hi32, b_hi32, tmem_u, n - n1);
-    else issue_march_span<KJ, NF, false, K0, K1>(a_st, b_st + (uint32_t)(n1 * NF), a_hi32, b_hi32, tmem_u, n - n1);
+    issue_march_span<KJ, NF, false, K0, K1>(a_desc, b_desc, tmem_u + g_lo * (uint32_t)NF, n1);
+    if (fresh) issue_march_span<KJ, NF, true, K0, K1>(a_desc, b_desc + (uint64_t)(n1 * NF), tmem_u, n - n1);
+    else issue_march_span<KJ, NF, false, K0, K1>(a_desc, b_desc + (uint64_t)(n1 * NF), tmem_u, n - n1);
   }
 }
 
@@ -302,7 +301,8 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
 
 template <int KJ, int NF>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvKernelParams p) {
+conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
+                    const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int planes = 2 * KJ;
@@ -312,7 +312,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   constexpr int R = kMarchBlocks, S = kMarchStages;
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + (size_t)S * kStageBytes;
-  MarchShared* sh = reinterpret_cast<MarchShared*>(b_smem + kWBytes);
+  MarchShared* sh = reinterpret_cast<MarchShared*>(b_smem + kWBytes + p.skip_w_bytes);   // (1x1x1 skip weights after the main ones)
   float* stat_part = reinterpret_cast<float*>(sh + 1);                 // [sum | sumsq][epilogue warp][channel]
   double* stat_acc = reinterpret_cast<double*>(stat_part + 2 * kMEpiWarps * NF);   // [sum | sumsq][channel]: this sample so far
   float* cadd_s = reinterpret_cast<float*>(stat_acc + 2 * NF);         // [B][NF] bias + conditioning rows
@@ -352,16 +352,29 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         uint32_t it = 0;
         for (int u = blockIdx.x; u < p.m_units; u += gridDim.x) {
           const MarchUnit m = decode_unit(p, u);
-          for (int i = 0; i < m.len + 2; ++i, ++it) {
-            const int s = (int)(it % (uint32_t)S);
-            ptx::mbar_wait(&sh->a_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
-            if (VDM_DBG(p, 2) && it >= (uint32_t)S) {      // (bring-up: no halo traffic after the pipeline fill)
-              ptx::mbar_arrive(&sh->a_full[s]);
-              continue;
+          for (int i = 0; i < m.len + 2; ++i) {
+            {
+              const int s = (int)(it % (uint32_t)S);
+              ptx::mbar_wait(&sh->a_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
+              if (VDM_DBG(p, 2) && it >= (uint32_t)S) {      // (bring-up: no halo traffic after the pipeline fill)
+                ptx::mbar_arrive(&sh->a_full[s]);
+              } else {
+                ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)kStageBytes);
+                ptx::tma_load_4d(a_smem + (size_t)s * kStageBytes, &tmap_x, &sh->a_full[s], (m.w0 - 1 + p.x_shift) * 8,
+                                 m.h0 - 1 + p.x_shift, m.d0 - 1 + i + p.x_shift, m.b * p.x_planes + p.x_plane0);
+              }
+              ++it;
             }
-            ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)kStageBytes);
-            ptx::tma_load_4d(a_smem + (size_t)s * kStageBytes, &tmap_x, &sh->a_full[s], (m.w0 - 1 + p.x_shift) * 8,
-                             m.h0 - 1 + p.x_shift, m.d0 - 1 + i + p.x_shift, m.b * p.x_planes + p.x_plane0);
+            // fused 1x1x1 skip conv: the face of output slice i of the skip tensor (never halo-padded), one stage per chunk
+            if (i < m.len) {
+              for (int c = 0; c < p.skip_chunks; ++c, ++it) {
+                const int s = (int)(it % (uint32_t)S);
+                ptx::mbar_wait(&sh->a_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes * kTileH * kTileW * 16));
+                ptx::tma_load_4d(a_smem + (size_t)s * kStageBytes, &tmap_x2, &sh->a_full[s], m.w0 * 8, m.h0, m.d0 + i,
+                                 m.b * p.x2_planes + p.x2_plane0 + c * planes);
+              }
+            }
           }
         }
       }
@@ -369,7 +382,10 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       // ===================== B producer: all weights once, kd-folded order [khw][plane][2 - kd][co] =====================
       if (lane == 0 && blockIdx.x < (unsigned)p.m_units) {
         const size_t tap_stride = (size_t)p.c_in8 * p.n_pad * 8, plane_stride = (size_t)p.n_pad * 8;
-        ptx::mbar_arrive_expect_tx(&sh->b_full, (uint32_t)kWBytes);
+        ptx::mbar_arrive_expect_tx(&sh->b_full, (uint32_t)kWBytes + (uint32_t)p.skip_w_bytes);
+        // 1x1x1 skip-path weights: [plane][co] right after the main weights
+        for (int pl = 0; pl < p.skip_chunks * planes; ++pl)
+          ptx::bulk_load(b_smem + kWBytes + (size_t)pl * (NF * 16), p.w2 + (size_t)pl * plane_stride, (uint32_t)(NF * 16), &sh->b_full);
         for (int tap = 0; tap < 27; ++tap) {
           const int kd = p.tap_kd[tap], khw = p.tap_khw[tap];
 #pragma unroll
@@ -386,8 +402,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const bool leader = ptx::elect_one();
       const uint64_t a_hi = make_planar_desc(0, (uint32_t)kSliceBytes, (uint32_t)(kTileW + 2) * 16u);
       const uint64_t b_hi = make_planar_desc(0, 3u * (uint32_t)NF * 16u, 128u);
-      const uint32_t a_hi32 = (uint32_t)(a_hi >> 32), b_hi32 = (uint32_t)(b_hi >> 32);
-      const uint32_t a_lbo = (uint32_t)a_hi, b_lbo = (uint32_t)b_hi;       // LBO << 16: low descriptor words
+      const uint64_t b_desc0 = b_hi | (uint64_t)b_base16;                  // kd-folded weights, row block 0
       // ONE elected lane runs the whole schedule, barrier waits included (a warp-wide wait / fence / elect / __syncwarp
       // sequence per slice cost ~750 cycles: R3c, 32->32 took 1686 cycles per slice for 1008 cycles of MMAs and the time did
       // not change with the epilogue or the loads switched off).  The waits of slice i+1 sit in the MIDDLE of slice i's MMAs:
@@ -397,15 +412,25 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         ptx::mbar_wait(&sh->b_full, 0);
         int u = blockIdx.x;
         MarchUnit m = decode_unit(p, u);
-        uint32_t ita = 0, ob = 0;                 // input-slice counter, output-slice counter at the start of the unit
+        const int skip_chunks = p.skip_chunks;
+        uint32_t ita = 0, ob = 0;                 // stage counter, output-slice counter at the start of the unit
+        // look-ahead waits: the stage with counter ita_ has landed (and, for input slice ii of a unit that starts output
+        // slice ii with it, that accumulator block has been drained by the epilogue)
+        auto wait_stage = [&](uint32_t ita_) __attribute__((always_inline)) {
+          ptx::mbar_wait(&sh->a_full[ita_ % (uint32_t)S], (ita_ / (uint32_t)S) & 1);
+          ptx::tc_fence_after();
+        };
         auto wait_slice = [&](int ii, uint32_t ita_, uint32_t ob_, int len_) __attribute__((always_inline)) {
           if (ii < len_) {                        // output slice ii receives its first contribution (kd = 0) from input slice ii
             const uint32_t o = ob_ + (uint32_t)ii;
             ptx::mbar_wait(&sh->t_empty[o % (uint32_t)R], ((o / (uint32_t)R) & 1) ^ 1);
           }
-          ptx::mbar_wait(&sh->a_full[ita_ % (uint32_t)S], (ita_ / (uint32_t)S) & 1);
-          ptx::tc_fence_after();
+          wait_stage(ita_);
         };
+        // skip-path descriptors: A = the slice's own face [plane][16 h][8 w][16 B] (LBO one plane, SBO one h row), B = [plane][co]
+        const uint64_t a2_hi = make_planar_desc(0, (uint32_t)(kTileH * kTileW * 16), (uint32_t)kTileW * 16u);
+        const uint64_t b2_hi = make_planar_desc(0, (uint32_t)NF * 16u, 128u);
+        const uint32_t b2_base16 = b_base16 + ((uint32_t)kWBytes >> 4);
         wait_slice(0, 0u, 0u, m.len);
         while (true) {
           const int len = m.len;
@@ -414,32 +439,52 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           const bool more_units = nu < p.m_units;
           MarchUnit nm = m;
           if (more_units) nm = decode_unit(p, nu);
-          for (int i = 0; i < len + 2; ++i, ++ita) {
+          for (int i = 0; i < len + 2; ++i) {
             const uint32_t sa = ita % (uint32_t)S;
-            const uint32_t a_st = a_base16 + sa * a_stage16 + a_lbo;
+            const uint64_t a_desc = a_hi | (uint64_t)(a_base16 + sa * a_stage16);
             const bool last = i == len + 1;
+            const bool skip_next = skip_chunks > 0 && i < len;                  // the next stage is this slice's skip chunk
             const uint32_t g_st = (ob + (uint32_t)(i - 2)) % (uint32_t)R;       // first block of the steady-state span
             if (i >= 2 && i < len && g_st <= (uint32_t)(R - 3)) {
               // steady state: output slices i-2, i-1, i (kd = 2, 1, 0), the last one starts here, no ring wrap
               const uint32_t d_col = tmem_u + g_st * (uint32_t)NF;
-              issue_march_span<KJ, NF, true, 0, 5, 3>(a_st, b_base16 + b_lbo, a_hi32, b_hi32, d_col, 3);
-              wait_slice(i + 1, ita + 1u, ob, len);
-              issue_march_span<KJ, NF, true, 5, 9, 3>(a_st, b_base16 + b_lbo, a_hi32, b_hi32, d_col, 3);
+              issue_march_span<KJ, NF, true, 0, 5, 3>(a_desc, b_desc0, d_col, 3);
+              if (skip_next) wait_stage(ita + 1u);
+              else wait_slice(i + 1, ita + 1u, ob, len);
+              issue_march_span<KJ, NF, true, 5, 9, 3>(a_desc, b_desc0, d_col, 3);
             } else {
               const int s_lo = i - 2 > 0 ? i - 2 : 0, s_hi = i < len - 1 ? i : len - 1;
               const bool fresh = i < len;
               const uint32_t g_lo = (ob + (uint32_t)s_lo) % (uint32_t)R;
               const int n = s_hi - s_lo + 1;
               const int n1 = n < R - (int)g_lo ? n : R - (int)g_lo;
-              const uint32_t b_st = b_base16 + b_lbo + (uint32_t)((2 - i + s_lo) * NF);
-              issue_march_slice<KJ, NF, 0, 5>(a_st, b_st, a_hi32, b_hi32, tmem_u, g_lo, n, n1, fresh);
-              // the next slice (possibly of this CTA's next unit): its barriers are waited for here
-              if (!last) wait_slice(i + 1, ita + 1u, ob, len);
+              const uint64_t b_desc = b_desc0 + (uint64_t)((2 - i + s_lo) * NF);
+              issue_march_slice<KJ, NF, 0, 5>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
+              // the next stage (possibly of this CTA's next unit): its barriers are waited for here
+              if (skip_next) wait_stage(ita + 1u);
+              else if (!last) wait_slice(i + 1, ita + 1u, ob, len);
               else if (more_units) wait_slice(0, ita + 1u, ob + (uint32_t)len, nm.len);
-              issue_march_slice<KJ, NF, 5, 9>(a_st, b_st, a_hi32, b_hi32, tmem_u, g_lo, n, n1, fresh);
+              issue_march_slice<KJ, NF, 5, 9>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
             }
             ptx::umma_commit(&sh->a_empty[sa]);
             if (i >= 2) ptx::umma_commit(&sh->t_full[g_st]);
+            ++ita;
+            if (skip_next) {
+              // y += conv1x1x1(x_skip): KJ MMAs of N = NF per chunk into the accumulator of output slice i
+              const uint32_t d_s = tmem_u + ((ob + (uint32_t)i) % (uint32_t)R) * (uint32_t)NF;
+              for (int c = 0; c < skip_chunks; ++c, ++ita) {
+                const uint32_t s2 = ita % (uint32_t)S;
+                const uint64_t a2 = a2_hi | (uint64_t)(a_base16 + s2 * a_stage16);
+                const uint64_t b2 = b2_hi | (uint64_t)(b2_base16 + (uint32_t)(c * planes * NF));
+#pragma unroll
+                for (int j = 0; j < KJ; ++j)
+                  ptx::umma_bf16_off64(d_s, 0u, a2, (uint32_t)(j * 2 * kTileH * kTileW), b2, (uint32_t)(2 * j * NF),
+                                       ptx::make_idesc_bf16(128, (uint32_t)NF), 1u);
+                if (c + 1 < skip_chunks) wait_stage(ita + 1u);
+                else wait_slice(i + 1, ita + 1u, ob, len);                     // (i < len: the next stage is input slice i + 1)
+                ptx::umma_commit(&sh->a_empty[s2]);
+              }
+            }
           }
           if (!more_units) break;
           ob += (uint32_t)len;

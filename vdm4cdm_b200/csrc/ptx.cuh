@@ -200,6 +200,25 @@ __device__ __forceinline__ void umma_bf16_off(uint32_t d_tmem, uint32_t d_off, u
       "r"(a_lo), "r"(a_off), "r"(a_hi32), "r"(b_lo), "r"(b_off), "r"(b_hi32), "r"(idesc), "r"(accumulate), "r"(d_off)
       : "memory");
 }
+// Same with whole 64-bit descriptors plus per-MMA offsets: ONE UIADD3.64 per descriptor in SASS (the 32-bit form above costs an
+// add for the low word and a move for the high word of every descriptor pair: R3e, 6 uniform instructions per MMA from a single
+// issuing thread that has ~56 cycles per MMA).  The low words (address >> 4 | LBO << 16) never carry into the high ones.
+__device__ __forceinline__ void umma_bf16_off64(uint32_t d_tmem, uint32_t d_off, uint64_t a_desc, uint32_t a_off, uint64_t b_desc,
+                                                uint32_t b_off, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 dd;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "add.u64 da, %1, %2;\n\t"
+      "add.u64 db, %3, %4;\n\t"
+      "add.u32 dd, %0, %7;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [dd], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"((uint64_t)a_off), "l"(b_desc), "l"((uint64_t)b_off), "r"(idesc), "r"(accumulate), "r"(d_off)
+      : "memory");
+}
 // Arrive on `bar` when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
