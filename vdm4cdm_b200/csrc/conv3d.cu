@@ -1176,18 +1176,19 @@ static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x
   }
   const int grid = p.m_units < sms ? p.m_units : sms;
   int rc = VDM_E_UNSUPPORTED;
-#define VDM_LAUNCH_MARCH(KJv, NFv)                                                                             \
-  if (kc == 16 * KJv && NF == NFv) {                                                                           \
+#define VDM_LAUNCH_MARCH(KJv, NFv, SKv)                                                                        \
+  if (kc == 16 * KJv && NF == NFv && (p.skip_chunks > 0) == SKv) {                                             \
     static bool configured = false;                                                                            \
     if (!configured) {                                                                                         \
-      VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_march_kernel<KJv, NFv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_march_kernel<KJv, NFv, SKv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           227 * 1024));                                                        \
       configured = true;                                                                                       \
     }                                                                                                          \
-    conv3d_march_kernel<KJv, NFv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmx2, p);                      \
+    conv3d_march_kernel<KJv, NFv, SKv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmx2, p);              \
     rc = VDM_OK;                                                                                               \
   }
-  VDM_LAUNCH_MARCH(1, 16) VDM_LAUNCH_MARCH(1, 32) VDM_LAUNCH_MARCH(2, 16) VDM_LAUNCH_MARCH(2, 32)
+  VDM_LAUNCH_MARCH(1, 16, false) VDM_LAUNCH_MARCH(1, 32, false) VDM_LAUNCH_MARCH(2, 16, false) VDM_LAUNCH_MARCH(2, 32, false)
+  VDM_LAUNCH_MARCH(1, 16, true) VDM_LAUNCH_MARCH(1, 32, true) VDM_LAUNCH_MARCH(2, 16, true) VDM_LAUNCH_MARCH(2, 32, true)
 #undef VDM_LAUNCH_MARCH
   if (rc != VDM_OK) {
     set_error("vdm_conv3d: no marching kernel instance for KC=%d N=%d", kc, NF);

@@ -299,7 +299,7 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
   }
 }
 
-template <int KJ, int NF>
+template <int KJ, int NF, bool SKIP>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                     const __grid_constant__ ConvKernelParams p) {
@@ -367,7 +367,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             }
             // fused 1x1x1 skip conv: the face of output slice i of the skip tensor (never halo-padded), one stage per chunk
             if (i < m.len) {
-              for (int c = 0; c < p.skip_chunks; ++c, ++it) {
+              for (int c = 0; c < (SKIP ? p.skip_chunks : 0); ++c, ++it) {
                 const int s = (int)(it % (uint32_t)S);
                 ptx::mbar_wait(&sh->a_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(planes * kTileH * kTileW * 16));
@@ -403,34 +403,50 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const uint64_t a_hi = make_planar_desc(0, (uint32_t)kSliceBytes, (uint32_t)(kTileW + 2) * 16u);
       const uint64_t b_hi = make_planar_desc(0, 3u * (uint32_t)NF * 16u, 128u);
       const uint64_t b_desc0 = b_hi | (uint64_t)b_base16;                  // kd-folded weights, row block 0
-      // ONE elected lane runs the whole schedule, barrier waits included (a warp-wide wait / fence / elect / __syncwarp
-      // sequence per slice cost ~750 cycles: R3c, 32->32 took 1686 cycles per slice for 1008 cycles of MMAs and the time did
-      // not change with the epilogue or the loads switched off).  The waits of slice i+1 sit in the MIDDLE of slice i's MMAs:
-      // the issuing thread would be blocked on the tensor core's queue there anyway, and the queue is too short to cover them
-      // at a slice boundary.
+      // ONE elected lane runs the whole schedule, barrier waits included.  What bounds these layers is this thread: the tensor
+      // core's queue holds only a few MMAs, so every stretch of bookkeeping longer than that many x 56 cycles is a bubble
+      // (R3o: 125 instructions per slice at ~7 cycles each around 19 MMAs; the pipe was busy 61% of the time).  The steady-state
+      // slice therefore issues its MMAs in groups of four with one piece of the bookkeeping between groups: the look-ahead
+      // waits for the next stage's barriers, the commits, the index arithmetic.
       if (leader && blockIdx.x < (unsigned)p.m_units) {
         ptx::mbar_wait(&sh->b_full, 0);
         int u = blockIdx.x;
         MarchUnit m = decode_unit(p, u);
-        const int skip_chunks = p.skip_chunks;
+        const int skip_chunks = SKIP ? p.skip_chunks : 0;
         uint32_t ita = 0, ob = 0;                 // stage counter, output-slice counter at the start of the unit
-        // look-ahead waits: the stage with counter ita_ has landed (and, for input slice ii of a unit that starts output
-        // slice ii with it, that accumulator block has been drained by the epilogue)
         auto wait_stage = [&](uint32_t ita_) __attribute__((always_inline)) {
           ptx::mbar_wait(&sh->a_full[ita_ % (uint32_t)S], (ita_ / (uint32_t)S) & 1);
           ptx::tc_fence_after();
         };
+        auto wait_block = [&](uint32_t o) __attribute__((always_inline)) {      // accumulator block of output slice o drained
+          ptx::mbar_wait(&sh->t_empty[o % (uint32_t)R], ((o / (uint32_t)R) & 1) ^ 1);
+        };
+        // input slice ii of a unit: its stage has landed and, if it starts output slice ii (kd = 0), that block is free
         auto wait_slice = [&](int ii, uint32_t ita_, uint32_t ob_, int len_) __attribute__((always_inline)) {
-          if (ii < len_) {                        // output slice ii receives its first contribution (kd = 0) from input slice ii
-            const uint32_t o = ob_ + (uint32_t)ii;
-            ptx::mbar_wait(&sh->t_empty[o % (uint32_t)R], ((o / (uint32_t)R) & 1) ^ 1);
-          }
+          if (ii < len_) wait_block(ob_ + (uint32_t)ii);
           wait_stage(ita_);
         };
         // skip-path descriptors: A = the slice's own face [plane][16 h][8 w][16 B] (LBO one plane, SBO one h row), B = [plane][co]
         const uint64_t a2_hi = make_planar_desc(0, (uint32_t)(kTileH * kTileW * 16), (uint32_t)kTileW * 16u);
         const uint64_t b2_hi = make_planar_desc(0, (uint32_t)NF * 16u, 128u);
         const uint32_t b2_base16 = b_base16 + ((uint32_t)kWBytes >> 4);
+        // y += conv1x1x1(x_skip) for output slice i: KJ MMAs of N = NF per chunk into its accumulator, then the look-ahead for
+        // input slice i + 1 (i < len, so that slice exists)
+        auto skip_stages = [&](int i, int len) __attribute__((always_inline)) {
+          const uint32_t d_s = tmem_u + ((ob + (uint32_t)i) % (uint32_t)R) * (uint32_t)NF;
+          for (int c = 0; c < skip_chunks; ++c, ++ita) {
+            const uint32_t s2 = ita % (uint32_t)S;
+            const uint64_t a2 = a2_hi | (uint64_t)(a_base16 + s2 * a_stage16);
+            const uint64_t b2 = b2_hi | (uint64_t)(b2_base16 + (uint32_t)(c * planes * NF));
+#pragma unroll
+            for (int j = 0; j < KJ; ++j)
+              ptx::umma_bf16_off64(d_s, 0u, a2, (uint32_t)(j * 2 * kTileH * kTileW), b2, (uint32_t)(2 * j * NF),
+                                   ptx::make_idesc_bf16(128, (uint32_t)NF), 1u);
+            if (c + 1 < skip_chunks) wait_stage(ita + 1u);
+            else wait_slice(i + 1, ita + 1u, ob, len);
+            ptx::umma_commit(&sh->a_empty[s2]);
+          }
+        };
         wait_slice(0, 0u, 0u, m.len);
         while (true) {
           const int len = m.len;
@@ -439,53 +455,53 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           const bool more_units = nu < p.m_units;
           MarchUnit nm = m;
           if (more_units) nm = decode_unit(p, nu);
-          for (int i = 0; i < len + 2; ++i) {
+          // any slice: edges of a unit (fewer than three output slices, or none of them new) and ring wraps
+          auto general_slice = [&](int i) __attribute__((always_inline)) {
             const uint32_t sa = ita % (uint32_t)S;
             const uint64_t a_desc = a_hi | (uint64_t)(a_base16 + sa * a_stage16);
             const bool last = i == len + 1;
-            const bool skip_next = skip_chunks > 0 && i < len;                  // the next stage is this slice's skip chunk
-            const uint32_t g_st = (ob + (uint32_t)(i - 2)) % (uint32_t)R;       // first block of the steady-state span
-            if (i >= 2 && i < len && g_st <= (uint32_t)(R - 3)) {
-              // steady state: output slices i-2, i-1, i (kd = 2, 1, 0), the last one starts here, no ring wrap
-              const uint32_t d_col = tmem_u + g_st * (uint32_t)NF;
-              issue_march_span<KJ, NF, true, 0, 5, 3>(a_desc, b_desc0, d_col, 3);
-              if (skip_next) wait_stage(ita + 1u);
-              else wait_slice(i + 1, ita + 1u, ob, len);
-              issue_march_span<KJ, NF, true, 5, 9, 3>(a_desc, b_desc0, d_col, 3);
-            } else {
-              const int s_lo = i - 2 > 0 ? i - 2 : 0, s_hi = i < len - 1 ? i : len - 1;
-              const bool fresh = i < len;
-              const uint32_t g_lo = (ob + (uint32_t)s_lo) % (uint32_t)R;
-              const int n = s_hi - s_lo + 1;
-              const int n1 = n < R - (int)g_lo ? n : R - (int)g_lo;
-              const uint64_t b_desc = b_desc0 + (uint64_t)((2 - i + s_lo) * NF);
-              issue_march_slice<KJ, NF, 0, 5>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
-              // the next stage (possibly of this CTA's next unit): its barriers are waited for here
-              if (skip_next) wait_stage(ita + 1u);
-              else if (!last) wait_slice(i + 1, ita + 1u, ob, len);
-              else if (more_units) wait_slice(0, ita + 1u, ob + (uint32_t)len, nm.len);
-              issue_march_slice<KJ, NF, 5, 9>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
-            }
+            const bool skip_next = SKIP && i < len;                             // the next stage is this slice's skip chunk
+            const int s_lo = i - 2 > 0 ? i - 2 : 0, s_hi = i < len - 1 ? i : len - 1;
+            const bool fresh = i < len;
+            const uint32_t g_lo = (ob + (uint32_t)s_lo) % (uint32_t)R;
+            const int n = s_hi - s_lo + 1;
+            const int n1 = n < R - (int)g_lo ? n : R - (int)g_lo;
+            const uint64_t b_desc = b_desc0 + (uint64_t)((2 - i + s_lo) * NF);
+            issue_march_slice<KJ, NF, 0, 5>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
+            // the next stage (possibly of this CTA's next unit): its barriers are waited for here
+            if (skip_next) wait_stage(ita + 1u);
+            else if (!last) wait_slice(i + 1, ita + 1u, ob, len);
+            else if (more_units) wait_slice(0, ita + 1u, ob + (uint32_t)len, nm.len);
+            issue_march_slice<KJ, NF, 5, 9>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
             ptx::umma_commit(&sh->a_empty[sa]);
-            if (i >= 2) ptx::umma_commit(&sh->t_full[g_st]);
+            if (i >= 2) ptx::umma_commit(&sh->t_full[(ob + (uint32_t)(i - 2)) % (uint32_t)R]);
             ++ita;
-            if (skip_next) {
-              // y += conv1x1x1(x_skip): KJ MMAs of N = NF per chunk into the accumulator of output slice i
-              const uint32_t d_s = tmem_u + ((ob + (uint32_t)i) % (uint32_t)R) * (uint32_t)NF;
-              for (int c = 0; c < skip_chunks; ++c, ++ita) {
-                const uint32_t s2 = ita % (uint32_t)S;
-                const uint64_t a2 = a2_hi | (uint64_t)(a_base16 + s2 * a_stage16);
-                const uint64_t b2 = b2_hi | (uint64_t)(b2_base16 + (uint32_t)(c * planes * NF));
-#pragma unroll
-                for (int j = 0; j < KJ; ++j)
-                  ptx::umma_bf16_off64(d_s, 0u, a2, (uint32_t)(j * 2 * kTileH * kTileW), b2, (uint32_t)(2 * j * NF),
-                                       ptx::make_idesc_bf16(128, (uint32_t)NF), 1u);
-                if (c + 1 < skip_chunks) wait_stage(ita + 1u);
-                else wait_slice(i + 1, ita + 1u, ob, len);                     // (i < len: the next stage is input slice i + 1)
-                ptx::umma_commit(&sh->a_empty[s2]);
-              }
+            if (skip_next) skip_stages(i, len);
+          };
+          int i = 0;
+          for (; i < 2 && i < len + 2; ++i) general_slice(i);
+          for (; i < len; ++i) {
+            const uint32_t g_st = (ob + (uint32_t)(i - 2)) % (uint32_t)R;       // block of output slice i - 2
+            if (g_st > (uint32_t)(R - 3)) {
+              general_slice(i);
+              continue;
             }
+            // steady state: output slices i-2, i-1, i (kd = 2, 1, 0), the last one starts here, no ring wrap
+            const uint32_t sa = ita % (uint32_t)S;
+            const uint64_t a_desc = a_hi | (uint64_t)(a_base16 + sa * a_stage16);
+            const uint32_t d_col = tmem_u + g_st * (uint32_t)NF;
+            issue_march_span<KJ, NF, true, 0, 2, 3>(a_desc, b_desc0, d_col, 3);
+            if (!SKIP && i + 1 < len) wait_block(ob + (uint32_t)(i + 1));
+            issue_march_span<KJ, NF, true, 2, 4, 3>(a_desc, b_desc0, d_col, 3);
+            wait_stage(ita + 1u);
+            issue_march_span<KJ, NF, true, 4, 6, 3>(a_desc, b_desc0, d_col, 3);
+            issue_march_span<KJ, NF, true, 6, 9, 3>(a_desc, b_desc0, d_col, 3);
+            ptx::umma_commit(&sh->a_empty[sa]);
+            ptx::umma_commit(&sh->t_full[g_st]);
+            ++ita;
+            if (SKIP) skip_stages(i, len);
           }
+          for (; i < len + 2; ++i) general_slice(i);
           if (!more_units) break;
           ob += (uint32_t)len;
           u = nu;
