@@ -279,6 +279,28 @@ VDM_API int vdm_adamw_step_dev(float* param, const float* grad, float* exp_avg, 
                        float beta1, float beta2, float eps, float weight_decay, int step, const int32_t* step_ptr,
                        const double* grad_sumsq, float max_norm, float grad_scale, void* stream);
 
+/* ---- continuous-time VDM training loss around the denoiser call (mltools vdm_model.py:429-442 in model_test.ipynb:680;
+ *      restated in oracle/vdm_ref.py:158-184).  gamma(t) = *gamma_b + |*gamma_w| t when learned != 0 (LearnedLinearSchedule),
+ *      *gamma_b + *gamma_w t otherwise; the schedule parameters are read from DEVICE memory (CUDA-graph replay of a training
+ *      step).  All tensors fp32 [batch][n], n % 4 == 0, 16-byte aligned. ---- */
+
+/* z_t = alpha_t x + sigma_t noise with alpha^2 = sigmoid(-gamma(times[b])), sigma^2 = sigmoid(gamma(times[b])). */
+VDM_API int vdm_loss_zt(const float* x, const float* noise, const float* times, const float* gamma_b, const float* gamma_w,
+                int learned, float* zt, int batch, int64_t n, void* stream);
+/* Backward of vdm_loss_zt with respect to the schedule: grads2 = (d b, d w) from g_zt = dL/dz_t.
+ * work: 2 * batch doubles of scratch. */
+VDM_API int vdm_loss_zt_bwd(const float* g_zt, const float* x, const float* noise, const float* times, const float* gamma_b,
+                    const float* gamma_w, int learned, double* work, float* grads2, int batch, int64_t n, void* stream);
+/* out8 = (loss, diffusion, latent, reconstruction) in bits per dimension (batch means), then k gamma' (the scalar of
+ * d eps_hat, k = 1 / (batch n log 2)), d b and d w of the three terms at fixed eps_hat, and one unused float.
+ * work: 3 * batch doubles of scratch. */
+VDM_API int vdm_loss_terms(const float* pred, const float* noise, const float* x, const float* noise0, const float* gamma_b,
+                   const float* gamma_w, int learned, double data_noise, double* work, float* out8, int batch, int64_t n,
+                   void* stream);
+/* d_pred = *g_loss * *coef * (pred - noise)  (coef = out8[4] of vdm_loss_terms; g_loss = dL/dloss), total elements. */
+VDM_API int vdm_loss_dpred(const float* pred, const float* noise, const float* coef, const float* g_loss, float* d_pred,
+                   int64_t total, void* stream);
+
 /* Periodic one-voxel halo: y[b][p][dp][hp][wp] = x[b][p][(dp-1) mod D][(hp-1) mod H][(wp-1) mod W] for
  * dp in [0, D+2) etc.  x: [B][planes][D][H][W][8] view, y: [B][planes][D+2][H+2][W+2][8] view. */
 VDM_API int vdm_pad_circular(const VdmTensor* x, const VdmTensor* y, int batch, int depth, int height, int width,

@@ -104,6 +104,51 @@ def test_unet_backward_circular_padding_matches_oracle_autograd():
     assert _rel(xc.grad.cpu(), xr.grad) < 3e-2
 
 
+class _StandInScore(torch.nn.Module):
+    """A tiny differentiable stand-in for the denoiser: eps_hat = a z + c tanh(z) (1 + t)."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Parameter(torch.tensor(0.3))
+        self.c = torch.nn.Parameter(torch.tensor(-0.7))
+
+    def forward(self, z, t=None, **kw):
+        return self.a * z + self.c * torch.tanh(z) * (1.0 + t.reshape(-1, *([1] * (z.dim() - 1))))
+
+
+@pytest.mark.parametrize("schedule,w_sign", [("learned_linear", 1.0), ("learned_linear", -1.0), ("fixed_linear", 1.0)])
+def test_vdm_loss_kernels_match_the_oracle_formulas(schedule, w_sign):
+    """csrc/vdm_loss.cu (z_t, the three sums, d eps_hat, the hand-derived schedule gradients) against autograd through the
+    oracle's get_loss (oracle/vdm_ref.py:158-184, fp32 CPU) with a stand-in denoiser: loss and terms to 1e-5, every
+    gradient to 1e-4 -- including a NEGATIVE slope parameter (gamma' = |w|)."""
+    from oracle.vdm_ref import VDM as RefVDM
+    from vdm4cdm_b200.vdm_model import VDM
+    g = torch.Generator().manual_seed(9)
+    shape, batch = (1, 8, 12, 16), 3
+    x = torch.randn((batch,) + shape, generator=g)
+    noise, noise0 = torch.randn((batch,) + shape, generator=g), torch.randn((batch,) + shape, generator=g)
+    times = torch.tensor([0.05, 0.5, 0.93])
+    ref = RefVDM(_StandInScore(), noise_schedule=schedule, gamma_min=-8.0, gamma_max=6.0).double()
+    mod = VDM(_StandInScore(), noise_schedule=schedule, gamma_min=-8.0, gamma_max=6.0).cuda()
+    if w_sign < 0:
+        with torch.no_grad():
+            ref.gamma.w.neg_()
+            mod.gamma.w.neg_()
+    loss_r, terms_r = ref.get_loss(x.double(), noise=noise.double(), noise0=noise0.double(), times=times.double())
+    loss_r.backward()
+    loss, terms = mod.get_loss(x.cuda(), noise=noise.cuda(), noise0=noise0.cuda(), times=times.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_r.item()) < 1e-5 * abs(loss_r.item())
+    for k in terms_r:
+        assert abs(terms[k].item() - terms_r[k].item()) < 1e-5 * abs(terms_r[k].item()) + 1e-9, k
+    pr, pm = dict(ref.named_parameters()), dict(mod.named_parameters())
+    assert set(pr) == set(pm)
+    for n in pr:
+        a, b = pm[n].grad.item(), pr[n].grad.item()
+        assert abs(a - b) < 1e-4 * abs(b) + 1e-9, (n, a, b)
+
+
 def test_vdm_loss_and_gradients_match_oracle():
     from oracle.vdm_ref import LightVDM as RefLight
     from vdm4cdm_b200.vdm_model import LightVDM

@@ -86,6 +86,12 @@ _SIGNATURES = {
                                       c_int, c_int, c_void_p]),
     "vdm_adamw_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                    c_float, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p]),
+    "vdm_loss_zt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
+    "vdm_loss_zt_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                c_int64, c_void_p]),
+    "vdm_loss_terms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p,
+                               c_int, c_int64, c_void_p]),
+    "vdm_loss_dpred": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vdm_avgpool2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_upsample2_bwd": (c_int, [_T, _T, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vdm_augment_crop": (c_int, [c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),

@@ -157,6 +157,63 @@ def pack_conv_weights_batched(table: torch.Tensor, n_jobs: int) -> None:
     _launched(1)
 
 
+# ---- VDM training loss (csrc/vdm_loss.cu) ---------------------------------------------------------------
+def _loss_args_ok(*tensors):
+    n = tensors[0][0].numel()
+    for t in tensors:
+        _need(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == tensors[0].shape,
+              "VDM loss kernels take contiguous fp32 CUDA tensors of one shape")
+    _need(n % 4 == 0, "VDM loss kernels need a multiple of 4 elements per sample")
+    return tensors[0].shape[0], n
+
+
+def loss_zt(x, noise, times, gamma_b, gamma_w, learned: bool) -> torch.Tensor:
+    """``vdm_loss_zt``: z_t = alpha_t x + sigma_t noise, schedule parameters read on the device."""
+    b, n = _loss_args_ok(x, noise)
+    zt = torch.empty_like(x)
+    rc = _C.lib().vdm_loss_zt(x.data_ptr(), noise.data_ptr(), times.data_ptr(), gamma_b.data_ptr(), gamma_w.data_ptr(),
+                              1 if learned else 0, zt.data_ptr(), b, n, _stream())
+    _C.check(rc, "vdm_loss_zt")
+    _launched(1)
+    return zt
+
+
+def loss_zt_bwd(g_zt, x, noise, times, gamma_b, gamma_w, learned: bool) -> torch.Tensor:
+    """``vdm_loss_zt_bwd``: fp32 [2] = (d b, d w) of the schedule through z_t."""
+    b, n = _loss_args_ok(g_zt, x, noise)
+    work = torch.empty(2 * b, dtype=torch.float64, device=x.device)
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    rc = _C.lib().vdm_loss_zt_bwd(g_zt.data_ptr(), x.data_ptr(), noise.data_ptr(), times.data_ptr(), gamma_b.data_ptr(),
+                                  gamma_w.data_ptr(), 1 if learned else 0, work.data_ptr(), out.data_ptr(), b, n, _stream())
+    _C.check(rc, "vdm_loss_zt_bwd")
+    _launched(2)
+    return out
+
+
+def loss_terms(pred, noise, x, noise0, gamma_b, gamma_w, learned: bool, data_noise: float) -> torch.Tensor:
+    """``vdm_loss_terms``: fp32 [8] = (loss, diffusion, latent, reconstruction, k gamma', d b, d w, -)."""
+    b, n = _loss_args_ok(pred, noise, x, noise0)
+    work = torch.empty(3 * b, dtype=torch.float64, device=x.device)
+    out = torch.empty(8, dtype=torch.float32, device=x.device)
+    rc = _C.lib().vdm_loss_terms(pred.data_ptr(), noise.data_ptr(), x.data_ptr(), noise0.data_ptr(), gamma_b.data_ptr(),
+                                 gamma_w.data_ptr(), 1 if learned else 0, float(data_noise), work.data_ptr(), out.data_ptr(),
+                                 b, n, _stream())
+    _C.check(rc, "vdm_loss_terms")
+    _launched(2)
+    return out
+
+
+def loss_dpred(pred, noise, coef, g_loss) -> torch.Tensor:
+    """``vdm_loss_dpred``: d eps_hat = g_loss * coef * (eps_hat - eps) (coef, g_loss: one-element fp32 CUDA tensors)."""
+    _loss_args_ok(pred, noise)
+    d = torch.empty_like(pred)
+    rc = _C.lib().vdm_loss_dpred(pred.data_ptr(), noise.data_ptr(), coef.data_ptr(), g_loss.data_ptr(), d.data_ptr(),
+                                 pred.numel(), _stream())
+    _C.check(rc, "vdm_loss_dpred")
+    _launched(1)
+    return d
+
+
 UnsupportedFusion = _C.UnsupportedFusion
 
 

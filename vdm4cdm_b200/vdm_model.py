@@ -52,6 +52,48 @@ class FixedLinearSchedule(nn.Module):
         return self.w
 
 
+class _ZtFn(torch.autograd.Function):
+    """z_t = alpha_t x + sigma_t eps in one kernel; backward = (d b, d w) of the schedule from dL/dz_t (two reductions +
+    a one-block finalize), no gradient for the data or the noise."""
+
+    @staticmethod
+    def forward(ctx, x, noise, times, gamma_b, gamma_w, learned):
+        ctx.save_for_backward(x, noise, times, gamma_b, gamma_w)
+        ctx.learned = learned
+        return ops.loss_zt(x, noise, times, gamma_b.detach(), gamma_w.detach(), learned)
+
+    @staticmethod
+    def backward(ctx, g_zt):
+        x, noise, times, gamma_b, gamma_w = ctx.saved_tensors
+        if not (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
+            return None, None, None, None, None, None
+        g = ops.loss_zt_bwd(g_zt.contiguous(), x, noise, times, gamma_b.detach(), gamma_w.detach(), ctx.learned)
+        return None, None, None, g[0].reshape(gamma_b.shape), g[1].reshape(gamma_w.shape), None
+
+
+class _LossTermsFn(torch.autograd.Function):
+    """(loss, [diffusion, latent, reconstruction]) from eps_hat in two kernels; backward = one elementwise kernel for
+    d eps_hat and two scalar products for the schedule parameters."""
+
+    @staticmethod
+    def forward(ctx, pred, noise, x, noise0, gamma_b, gamma_w, learned, data_noise):
+        out = ops.loss_terms(pred, noise, x, noise0, gamma_b.detach(), gamma_w.detach(), learned, data_noise)
+        ctx.save_for_backward(pred, noise, out)
+        ctx.shapes = (gamma_b.shape, gamma_w.shape)
+        terms = out[1:4]
+        ctx.mark_non_differentiable(terms)
+        return out[0], terms
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms):
+        pred, noise, out = ctx.saved_tensors
+        g = g_loss.reshape(1).float().contiguous()
+        d_pred = ops.loss_dpred(pred, noise, out[4:5], g) if ctx.needs_input_grad[0] else None
+        db = (g * out[5:6]).reshape(ctx.shapes[0]) if ctx.needs_input_grad[4] else None
+        dw = (g * out[6:7]).reshape(ctx.shapes[1]) if ctx.needs_input_grad[5] else None
+        return d_pred, None, None, None, db, dw, None, None
+
+
 class VDM(nn.Module):
     def __init__(self, score_model, noise_schedule: str = "learned_linear", gamma_min: float = -13.3,
                  gamma_max: float = 13.3, antithetic_time_sampling: bool = True, data_noise: float = 1.0e-3,
@@ -227,32 +269,26 @@ class VDM(nn.Module):
         return torch.rand(batch_size, device=device)
 
     def get_loss(self, x, noise=None, noise0=None, times=None, **kwargs):
-        """Continuous-time VDM loss in bits per dimension, plus its three terms (batch means)."""
+        """Continuous-time VDM loss in bits per dimension, plus its three terms (batch means).
+
+        Everything that touches a B x N^3 tensor runs in the kernels of csrc/vdm_loss.cu (z_t, the three per-sample sums,
+        d eps_hat, the schedule gradients through z_t); torch autograd only carries gamma(t) into the time embedding."""
         bsz = x.shape[0]
-        red = tuple(range(1, x.dim()))
+        x = x.float().contiguous()
         if times is None:
             times = self.sample_times(bsz, x.device)
         if noise is None:
             noise = torch.randn_like(x)
         if noise0 is None:
             noise0 = torch.randn_like(x)
-        zt, gamma_t = self.sample_zt_given_x(x, times, noise)
-        pred = self.get_pred_noise(zt, gamma_t, **kwargs)
-        diffusion = 0.5 * self.gamma.slope() * ((noise - pred) ** 2).sum(dim=red)
-
-        gamma_1 = self._gamma5(1.0, x)
-        var_1 = torch.sigmoid(gamma_1)
-        latent = 0.5 * (var_1 + torch.sigmoid(-gamma_1) * x * x - torch.log(var_1) - 1.0).sum(dim=red)
-
-        gamma_0 = self._gamma5(0.0, x)
-        z0_rescaled = x + torch.exp(0.5 * gamma_0) * noise0
-        dn = self.data_noise
-        recons = (0.5 * ((x - z0_rescaled) / dn) ** 2 + math.log(dn) + 0.5 * math.log(2.0 * math.pi)).sum(dim=red)
-
-        bpd = 1.0 / (x[0].numel() * math.log(2.0))
-        loss = (diffusion + latent + recons).mean() * bpd
-        return loss, {"diffusion_loss": diffusion.mean() * bpd, "latent_loss": latent.mean() * bpd,
-                      "reconstruction_loss": recons.mean() * bpd}
+        times = times.to(device=x.device, dtype=torch.float32).contiguous()
+        noise, noise0 = noise.float().contiguous(), noise0.float().contiguous()
+        learned = isinstance(self.gamma, LearnedLinearSchedule)
+        gb, gw = self.gamma.b, self.gamma.w
+        zt = _ZtFn.apply(x, noise, times, gb, gw, learned)
+        pred = self.get_pred_noise(zt, self._gamma5(times, x), **kwargs)
+        loss, terms = _LossTermsFn.apply(pred.float().contiguous(), noise, x, noise0, gb, gw, learned, float(self.data_noise))
+        return loss, {"diffusion_loss": terms[0], "latent_loss": terms[1], "reconstruction_loss": terms[2]}
 
 
 class SamplerSession:
