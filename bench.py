@@ -353,7 +353,7 @@ def run_b200(args, rank, world, local_rank):
         if not args.no_train:
             train_leg(args, model, net, dev, rank, world, 1.0)
         return
-    # ---- roofline of the dominant kernel (conv3d_planar_kernel): CUDA events around every conv launch ----
+    # ---- roofline of the dominant kernels (conv3d_planar_kernel, conv3d_march_kernel): CUDA events around every conv launch ----
     peaks, peak_kind = measured_peaks()
     vdm.use_cuda_graph = False
     sess2 = vdm.session(batch, n_chain, dev, seed=42, realisation_ids=rids, s_conditioning=cond.to(dev),
@@ -402,7 +402,7 @@ def run_b200(args, rank, world, local_rank):
         if tj.get("grid", 128) == args.grid and tj.get("realisations_per_gpu") == args.batch and \
                 tj.get("conv_launches_per_step") == len(records):
             traffic = tj.get("conv_dram_bytes_per_step")
-    roofline = {"kernel": "conv3d_planar_kernel (all conv launches of one step)", "bound": "tensor",
+    roofline = {"kernel": "conv3d_planar_kernel + conv3d_march_kernel (all conv launches of one step)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": traffic,
                 "traffic_source": "profiles/roofline_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the conv "

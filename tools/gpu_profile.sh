@@ -13,7 +13,7 @@ echo "ncu launches rc=$?"
 python tools/launch_share.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launch_share.txt 2> gpurun_out/${tag}_summary.err
 head -30 gpurun_out/${tag}_launch_share.txt
 # 3. full capture of the conv kernels of one sampler step (the first eager step of the session)
-ncu --set full --clock-control none --import-source on -k regex:conv3d_planar -s 0 -c 38 -f -o /tmp/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:conv3d_(planar|march)" -s 0 -c 38 -f -o /tmp/${tag}_conv $CMD > gpurun_out/${tag}_ncu2.log 2>&1
 echo "ncu full rc=$?"
 python tools/ncu_summary.py /tmp/${tag}_conv.ncu-rep > gpurun_out/${tag}_conv_ncu.txt 2>> gpurun_out/${tag}_summary.err
 python tools/ncu_stalls.py /tmp/${tag}_conv.ncu-rep 12 > gpurun_out/${tag}_conv_stalls.txt 2>> gpurun_out/${tag}_summary.err

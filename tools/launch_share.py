@@ -27,11 +27,11 @@ print(f"# {sys.argv[1]}: {sum(cnt.values())} launches, {tot:.3f} ms of kernel ti
 print(f"{'kernel':72s} {'launches':>8s} {'ms':>9s} {'share':>7s} {'DRAM rd MB':>11s} {'DRAM wr MB':>11s}")
 for k in sorted(t, key=lambda k: -t[k]):
     print(f"{k:72s} {cnt[k]:8d} {t[k]:9.3f} {100 * t[k] / tot:6.1f}% {rd.get(k, 0) / 1e6:11.1f} {wr.get(k, 0) / 1e6:11.1f}")
-conv = [k for k in t if "conv3d_planar" in k]
+conv = [k for k in t if "conv3d_planar" in k or "conv3d_march" in k]
 summary = {"conv_launches": sum(cnt[k] for k in conv), "conv_ms_under_ncu": sum(t[k] for k in conv),
            "conv_dram_bytes_read": sum(rd.get(k, 0) for k in conv), "conv_dram_bytes_written": sum(wr.get(k, 0) for k in conv),
            "all_launches": sum(cnt.values()), "all_ms_under_ncu": tot, "all_dram_bytes": sum(rd.values()) + sum(wr.values())}
-print(f"# conv3d_planar_kernel: {summary['conv_launches']} launches, {summary['conv_ms_under_ncu']:.3f} ms = "
+print(f"# conv3d_planar_kernel + conv3d_march_kernel: {summary['conv_launches']} launches, {summary['conv_ms_under_ncu']:.3f} ms = "
       f"{100 * summary['conv_ms_under_ncu'] / tot:.1f}% of the window, DRAM {summary['conv_dram_bytes_read'] / 1e9:.2f} GB read + "
       f"{summary['conv_dram_bytes_written'] / 1e9:.2f} GB written")
 if "--json" in sys.argv:
