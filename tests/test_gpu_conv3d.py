@@ -101,6 +101,42 @@ def test_conv3d_epilogue_bias_residual_stats_and_windows():
     assert stats[:, :8].abs().sum().item() == 0 and stats[:, 40:].abs().sum().item() == 0
 
 
+@pytest.mark.parametrize("b,ci,co,d,h,w", [
+    (1, 32, 32, 37, 16, 8),       # one long column: ring wraps twice, segments of unequal length
+    (40, 16, 16, 3, 16, 8),       # more samples than the shared-memory bias table holds (rows read from global memory)
+    (2, 32, 16, 19, 20, 12),      # ragged faces, depth not a multiple of the segment length
+    (3, 16, 32, 5, 9, 7),         # tiny odd grid: a segment shorter than the three-slice span
+    (1, 32, 32, 130, 16, 8),      # the 128^3 regime: 130 slices in one column
+    (2, 32, 32, 20, 32, 16),      # even grid: also with the coarse (nearest x2) residual
+])
+def test_conv3d_marching_schedule_edges_exact_integers(b, ci, co, d, h, w):
+    """The d-marching schedule (conv3d_march.cuh: narrow 3x3x3 layers) on the cases specific to it: TMEM ring wrap, unit /
+    segment boundaries, segments shorter than the kd span, ragged faces, the bias-row fallback, with bias + residual +
+    statistics and a coarse (up-sampled) residual -- exact on integers."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(500 + d + b)
+    x = _int_tensor((b, ci, d, h, w), -2, 2, g, dev)
+    wt = _int_tensor((co, ci, 3, 3, 3), -1, 1, g, dev)
+    cadd = _int_tensor((b, co), -3, 3, g, dev)
+    res = _int_tensor((b, co, d, h, w), -4, 4, g, dev)
+    ref = _reference(x, wt, cadd, res).to(torch.bfloat16).float()
+    stats = torch.zeros((b, co, 2), dtype=torch.float64, device=dev)
+    y = ops.conv3d(ops.to_planar(x), ops.pack_conv_weight(wt), co, chan_add=cadd, residual=ops.to_planar(res), stats=stats)
+    torch.cuda.synchronize()
+    got = ops.from_planar(y, co)
+    assert (got != ref).sum().item() == 0, f"max |diff| = {(got - ref).abs().max().item()}"
+    assert torch.allclose(stats[..., 0], ref.double().sum(dim=(2, 3, 4)), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(stats[..., 1], (ref.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-6, atol=1e-3)
+    if d % 2 == 0 and h % 2 == 0 and w % 2 == 0:
+        rc = _int_tensor((b, co, d // 2, h // 2, w // 2), -4, 4, g, dev)
+        ref2 = _reference(x, wt, cadd, F.interpolate(rc, scale_factor=2, mode="nearest")).to(torch.bfloat16).float()
+        y2 = ops.conv3d(ops.to_planar(x), ops.pack_conv_weight(wt), co, chan_add=cadd, residual=ops.to_planar(rc),
+                        residual_upsample=True)
+        torch.cuda.synchronize()
+        assert (ops.from_planar(y2, co) != ref2).sum().item() == 0
+
+
 def test_conv3d_fp32_single_channel_output():
     """conv_out of the UNet: C -> 1, fp32 NCDHW result."""
     ops = _ops()

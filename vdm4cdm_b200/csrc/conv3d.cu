@@ -750,6 +750,80 @@ __device__ __forceinline__ void epilogue_tiles(const ConvKernelParams& p, ConvSh
   }
 }
 
+// ---- generic issue schedule (wide layers, tap subsets, 1x1x1) ----------------------------------------------------------
+// chunk -> weight stage (one (kd, kh) row of taps, or one tap) -> tap -> sub-tile s < MT -> k16, N = n_cta.  The issuing
+// thread has ~64 cycles per MMA at N = 128: the r02 loop built every descriptor from run-time loop indices in vector
+// registers (12 instructions per MMA, two of them R2UR: ~84 cycles, R3 SASS) and the wide layers sat at 66 % of the tensor
+// rate while L2 ran at 8 %.  Here the run-time part is per TAP (its halo offset from the tap table, its weight block: one
+// 64-bit descriptor for A and KJ for B), and the MT x KJ MMAs of a tap differ by IMMEDIATE offsets (PAD fixes the halo
+// geometry at compile time): one UIADD3.64 and the UTCHMMA per MMA.
+template <int MT, int KJ, int PAD>
+__device__ __forceinline__ void issue_generic_tiles(const ConvKernelParams& p, ConvShared* sh, uint64_t* a_rdy, uint32_t a_base16,
+                                                    uint32_t b_base16, uint32_t tmem_u, bool leader) {
+  constexpr uint32_t Hh = kTileH + 2 * PAD, Wh = kTileW + 2 * PAD, Hd = MT + 2 * PAD;
+  constexpr uint32_t slice16 = Hh * Wh;                      // one d-slice of a plane, 16-byte units
+  constexpr uint32_t kstep_a16 = 2u * Hd * Hh * Wh;          // two planes (K = 16)
+  const uint32_t n_cta = (uint32_t)p.n_cta;
+  const uint32_t idesc = ptx::make_idesc_bf16(128, n_cta);
+  const uint64_t a_hi = make_planar_desc(0, Hd * Hh * Wh * 16u, Wh * 16u);
+  const uint64_t b_hi = make_planar_desc(0, n_cta * 16u, 128u);
+  const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+  const uint32_t nsa_u = (uint32_t)p.nsa;
+  const uint32_t kstep_b16 = 2u * n_cta;
+  const uint32_t btap16 = (uint32_t)(2 * KJ) * n_cta;          // one tap inside a B stage
+  const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
+  const bool resident = p.b_resident != 0;
+  const int steps_per_chunk = (n_taps + tps - 1) / tps;
+  uint32_t ita = 0, ti = 0;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+    const uint32_t acc = ti & 1;
+    ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
+    ptx::tc_fence_after();
+    const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)MT * n_cta;
+    for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
+      const uint32_t sa = ita % nsa_u;
+      ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
+      if (resident && ita == 0) ptx::mbar_wait(&sh->b_full[0], 0);
+      ptx::tc_fence_after();
+      const uint32_t a_lo0 = a_base16 + sa * a_stage16;
+      // ONE elected lane runs the whole chunk, weight-stage waits included (R2k: the per-stage warp-wide wait / fence / elect /
+      // __syncwarp sequence cost ~500 cycles per step)
+      if (leader) {
+        uint32_t itb = ita * (uint32_t)steps_per_chunk;       // weight-stage counter, derived from the uniform chunk counter
+        for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++itb) {
+          uint32_t sb = 0, b_lo0;
+          if (resident) {
+            b_lo0 = b_base16 + (uint32_t)(kc * n_taps + tap0) * btap16;
+          } else {
+            sb = itb % nsb;
+            ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
+            ptx::tc_fence_after();
+            b_lo0 = b_base16 + sb * b_stage16;
+          }
+          for (int q = 0; q < tps; ++q) {
+            const uint64_t a_tap = a_hi | (uint64_t)(a_lo0 + (uint32_t)p.tap16[tap0 + q]);
+            const uint32_t first = (kc | tap0 | q) != 0 ? 1u : 0u;
+            uint64_t b_tap[KJ];
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) b_tap[j] = b_hi | (uint64_t)(b_lo0 + (uint32_t)q * btap16 + (uint32_t)j * kstep_b16);
+#pragma unroll
+            for (int s = 0; s < MT; ++s) {
+#pragma unroll
+              for (int j = 0; j < KJ; ++j)
+                ptx::umma_bf16_off64(d_tmem0, (uint32_t)s * n_cta, a_tap, (uint32_t)s * slice16 + (uint32_t)j * kstep_a16, b_tap[j], 0u,
+                                     idesc, j == 0 ? first : 1u);
+            }
+          }
+          if (!resident) ptx::umma_commit(&sh->b_empty[sb]);
+        }
+        ptx::umma_commit(&sh->a_empty[sa]);
+        if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // MT = d-slices (accumulators) per tile, KJ = K=16 MMAs per channel chunk (KC = 16*KJ), NF = 0 for the generic
 // path or Cout_pad for the kd-folded path: compile-time so that the MMA issue loops are straight lines of
 // tcgen05.mma with immediate offsets (r01a: a generic loop cost ~240 issue cycles per MMA).
@@ -995,62 +1069,8 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
       }
     } else {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, n_cta);
-      const uint64_t b_hi = make_planar_desc(0, n_cta * 16u, 128u);
-      const uint32_t slice16 = (uint32_t)(p.Hh * p.Wh);          // one d-slice of a plane
-      const uint32_t kstep_a16 = 2u * ((uint32_t)p.plane_bytes >> 4), kstep_b16 = 2u * n_cta;
-      const uint32_t btap16 = (uint32_t)planes_per_chunk * n_cta;  // one tap inside a B stage
-      const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
-      const bool resident = p.b_resident != 0;
-      const int steps_per_chunk = (n_taps + tps - 1) / tps;
-      uint32_t ita = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t acc = ti & 1;
-        ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)MT * n_cta;
-        for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
-          const uint32_t sa = ita % nsa_u;
-          ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
-          if (resident && ita == 0) ptx::mbar_wait(&sh->b_full[0], 0);
-          ptx::tc_fence_after();
-          const uint32_t a_lo0 = a_base16 + sa * a_stage16;
-          // ONE elected lane runs the whole chunk, weight-stage waits included: the per-stage warp-wide wait / fence /
-          // elect / __syncwarp sequence cost ~500 cycles per (chunk, tap stage) step (R2k: the time of an 8-tap conv
-          // scaled with the NUMBER of steps, 0.30 ms at KC = 16 vs 0.20 ms at KC = 32, not with its MMAs).
-          if (leader) {
-            uint32_t itb = ita * (uint32_t)steps_per_chunk;       // weight-stage counter, derived from the uniform chunk counter
-            for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++itb) {
-              uint32_t sb = 0, b_lo0;
-              if (resident) {
-                b_lo0 = b_base16 + (uint32_t)(kc * n_taps + tap0) * btap16;
-              } else {
-                sb = itb % nsb;
-                ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
-                ptx::tc_fence_after();
-                b_lo0 = b_base16 + sb * b_stage16;
-              }
-              for (int q = 0; q < tps; ++q) {
-                const uint32_t a_lo = a_lo0 + (uint32_t)p.tap16[tap0 + q], b_lo = b_lo0 + (uint32_t)q * btap16;
-                const uint32_t first = (kc | tap0 | q) != 0 ? 1u : 0u;
-#pragma unroll
-                for (int s = 0; s < MT; ++s) {
-#pragma unroll
-                  for (int j = 0; j < KJ; ++j) {
-                    const uint64_t a_desc = a_hi | (uint64_t)(a_lo + (uint32_t)s * slice16 + (uint32_t)j * kstep_a16);
-                    const uint64_t b_desc = b_hi | (uint64_t)(b_lo + (uint32_t)j * kstep_b16);
-                    ptx::umma_bf16(d_tmem0 + (uint32_t)s * n_cta, a_desc, b_desc, idesc, j == 0 ? first : 1u);
-                  }
-                }
-              }
-              if (!resident) ptx::umma_commit(&sh->b_empty[sb]);
-            }
-            ptx::umma_commit(&sh->a_empty[sa]);
-            if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
-          }
-          __syncwarp();
-        }
-      }
+      if (p.pad) issue_generic_tiles<MT, KJ, 1>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+      else issue_generic_tiles<MT, KJ, 0>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
     }
   }
   } else if (warp >= 12) {
