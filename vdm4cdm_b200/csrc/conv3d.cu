@@ -197,6 +197,28 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
   return t;
 }
 
+// Position in a ring of `n` pipeline stages and the mbarrier phase parity of that lap, advanced without divisions.
+// (R3w ncu of a 128 -> 128 layer: the issuing thread spent half of every 12-MMA weight stage on `it % nsb`, `it / nsb` with a
+// run-time nsb -- an I2F / MUFU.RCP sequence -- and on re-loading loop-invariant kernel parameters from the constant bank;
+// the tensor pipe was active 48 % of the time with L2 at 12 %.)  Consumers wait full[s] with parity ph, producers empty[s]
+// with parity ph ^ 1.
+struct Ring {
+  uint32_t s, ph, n;
+  __device__ __forceinline__ explicit Ring(uint32_t n_) : s(0u), ph(0u), n(n_) {}
+  __device__ __forceinline__ void next() {
+    if (++s == n) {
+      s = 0u;
+      ph ^= 1u;
+    }
+  }
+};
+// A copy of a kernel parameter the compiler has to keep in a register (it otherwise re-materialises loop-invariant
+// parameters with LDCU inside the issue loops, ~30 cycles of latency each on the single issuing thread).
+__device__ __forceinline__ uint32_t hold_u32(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
+}
+
 // Un-swizzled K-major descriptor: rows 16 B apart inside a core matrix, `sbo` between 8-row groups,
 // `lbo` between the two K core matrices of one K=16 MMA (cute::UMMA::SmemDescriptor, version 1).
 __device__ __forceinline__ uint64_t make_planar_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
@@ -373,7 +395,7 @@ __device__ __forceinline__ void transform_tiles(const ConvKernelParams& p, ConvS
   const int vh = p.Hd * p.Hh * p.Wh;                          // voxels (16-byte units) of one plane of the stage
   const int total_chunks = p.k_chunks + p.skip_chunks;
   int cur_b = -1;
-  uint32_t it = 0;
+  Ring ra((uint32_t)p.nsa);
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const TileCoord t = decode_tile(p, tile);
     if (t.b != cur_b) {
@@ -387,9 +409,9 @@ __device__ __forceinline__ void transform_tiles(const ConvKernelParams& p, ConvS
     }
     const int dlo = t.d0 - p.pad + p.x_shift, hlo = t.h0 - p.pad + p.x_shift, wlo = t.w0 - p.pad + p.x_shift;
     const bool edge = dlo < 0 || dlo + p.Hd > p.D || hlo < 0 || hlo + p.Hh > p.H || wlo < 0 || wlo + p.Wh > p.W;
-    for (int kc = 0; kc < total_chunks; ++kc, ++it) {
-      const int s = (int)(it % (uint32_t)p.nsa);
-      ptx::mbar_wait(&sh->a_full[s], (it / (uint32_t)p.nsa) & 1);
+    for (int kc = 0; kc < total_chunks; ++kc, ra.next()) {
+      const int s = (int)ra.s;
+      ptx::mbar_wait(&sh->a_full[s], ra.ph);
       if (kc < p.k_chunks && !VDM_DBG(p, 64)) {          // (bring-up flag 64: hand-off only, no arithmetic)
         uint8_t* stage = a_smem + (size_t)s * p.a_stage_bytes;
 #pragma unroll 1
@@ -763,42 +785,42 @@ __device__ __forceinline__ void issue_generic_tiles(const ConvKernelParams& p, C
   constexpr uint32_t Hh = kTileH + 2 * PAD, Wh = kTileW + 2 * PAD, Hd = MT + 2 * PAD;
   constexpr uint32_t slice16 = Hh * Wh;                      // one d-slice of a plane, 16-byte units
   constexpr uint32_t kstep_a16 = 2u * Hd * Hh * Wh;          // two planes (K = 16)
-  const uint32_t n_cta = (uint32_t)p.n_cta;
+  const uint32_t n_cta = hold_u32((uint32_t)p.n_cta);
   const uint32_t idesc = ptx::make_idesc_bf16(128, n_cta);
   const uint64_t a_hi = make_planar_desc(0, Hd * Hh * Wh * 16u, Wh * 16u);
   const uint64_t b_hi = make_planar_desc(0, n_cta * 16u, 128u);
-  const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
-  const uint32_t nsa_u = (uint32_t)p.nsa;
+  const uint32_t a_stage16 = hold_u32((uint32_t)p.a_stage_bytes >> 4), b_stage16 = hold_u32((uint32_t)p.b_stage_bytes >> 4);
   const uint32_t kstep_b16 = 2u * n_cta;
   const uint32_t btap16 = (uint32_t)(2 * KJ) * n_cta;          // one tap inside a B stage
-  const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
+  const int tps = (int)hold_u32((uint32_t)p.taps_per_stage), n_taps = (int)hold_u32((uint32_t)p.n_taps);
+  const int k_chunks = (int)hold_u32((uint32_t)p.k_chunks);
   const bool resident = p.b_resident != 0;
-  const int steps_per_chunk = (n_taps + tps - 1) / tps;
-  uint32_t ita = 0, ti = 0;
+  Ring ra((uint32_t)p.nsa), rb((uint32_t)p.nsb);               // rb is advanced by the issuing lane only
+  uint32_t ti = 0;
+  bool first_chunk = true;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
     const uint32_t acc = ti & 1;
     ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
     ptx::tc_fence_after();
     const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)MT * n_cta;
-    for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
-      const uint32_t sa = ita % nsa_u;
-      ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
-      if (resident && ita == 0) ptx::mbar_wait(&sh->b_full[0], 0);
+    for (int kc = 0; kc < k_chunks; ++kc, ra.next()) {
+      const uint32_t sa = ra.s;
+      ptx::mbar_wait(&a_rdy[sa], ra.ph);
+      if (resident && first_chunk) ptx::mbar_wait(&sh->b_full[0], 0);
+      first_chunk = false;
       ptx::tc_fence_after();
       const uint32_t a_lo0 = a_base16 + sa * a_stage16;
       // ONE elected lane runs the whole chunk, weight-stage waits included (R2k: the per-stage warp-wide wait / fence / elect /
       // __syncwarp sequence cost ~500 cycles per step)
       if (leader) {
-        uint32_t itb = ita * (uint32_t)steps_per_chunk;       // weight-stage counter, derived from the uniform chunk counter
-        for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++itb) {
-          uint32_t sb = 0, b_lo0;
+        for (int tap0 = 0; tap0 < n_taps; tap0 += tps) {
+          uint32_t b_lo0;
           if (resident) {
             b_lo0 = b_base16 + (uint32_t)(kc * n_taps + tap0) * btap16;
           } else {
-            sb = itb % nsb;
-            ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
+            ptx::mbar_wait(&sh->b_full[rb.s], rb.ph);
             ptx::tc_fence_after();
-            b_lo0 = b_base16 + sb * b_stage16;
+            b_lo0 = b_base16 + rb.s * b_stage16;
           }
           for (int q = 0; q < tps; ++q) {
             const uint64_t a_tap = a_hi | (uint64_t)(a_lo0 + (uint32_t)p.tap16[tap0 + q]);
@@ -814,7 +836,10 @@ __device__ __forceinline__ void issue_generic_tiles(const ConvKernelParams& p, C
                                      idesc, j == 0 ? first : 1u);
             }
           }
-          if (!resident) ptx::umma_commit(&sh->b_empty[sb]);
+          if (!resident) {
+            ptx::umma_commit(&sh->b_empty[rb.s]);
+            rb.next();
+          }
         }
         ptx::umma_commit(&sh->a_empty[sa]);
         if (kc == k_chunks - 1) ptx::umma_commit(&sh->tmem_full[acc]);
@@ -889,11 +914,12 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // ===================== A producer: halo tiles =====================
     if (lane == 0) {
       uint32_t it = 0;
+      Ring ra((uint32_t)p.nsa);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        for (int kc = 0; kc < p.k_chunks + p.skip_chunks; ++kc, ++it) {
-          const int s = (int)(it % (uint32_t)p.nsa);
-          ptx::mbar_wait(&sh->a_empty[s], ((it / (uint32_t)p.nsa) & 1) ^ 1);
+        for (int kc = 0; kc < p.k_chunks + p.skip_chunks; ++kc, ++it, ra.next()) {
+          const int s = (int)ra.s;
+          ptx::mbar_wait(&sh->a_empty[s], ra.ph ^ 1u);
           if (VDM_DBG(p, 2) && it >= 2) {       // experiment: no halo traffic after the pipeline fill
             ptx::mbar_arrive(&sh->a_full[s]);
             continue;
@@ -920,12 +946,12 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       if constexpr (kFold) {
        if (p.fold_streamed) {
         // one ring stage per (tile, chunk, kh, kw): [plane][2 - kd][co] (see issue_fold_stage); n_split == 1
-        uint32_t it = 0;
+        Ring rb((uint32_t)nsb);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
           for (int kc = 0; kc < k_chunks; ++kc)
-            for (int khw = 0; khw < 9; ++khw, ++it) {
-              const int s = it % nsb;
-              ptx::mbar_wait(&sh->b_empty[s], ((it / nsb) & 1) ^ 1);
+            for (int khw = 0; khw < 9; ++khw, rb.next()) {
+              const int s = (int)rb.s;
+              ptx::mbar_wait(&sh->b_empty[s], rb.ph ^ 1u);
               ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk * 3u);
               uint8_t* dst = b_smem + (size_t)s * p.b_stage_bytes;
 #pragma unroll
@@ -970,13 +996,13 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                              &sh->b_full[0]);
           }
       } else {
-        uint32_t it = 0;
+        Ring rb((uint32_t)nsb);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           const TileCoord t = decode_tile(p, tile);
           for (int kc = 0; kc < k_chunks; ++kc) {
-            for (int tap0 = 0; tap0 < n_taps; tap0 += tps, ++it) {
-              const int s = it % nsb;
-              ptx::mbar_wait(&sh->b_empty[s], ((it / nsb) & 1) ^ 1);
+            for (int tap0 = 0; tap0 < n_taps; tap0 += tps, rb.next()) {
+              const int s = (int)rb.s;
+              ptx::mbar_wait(&sh->b_empty[s], rb.ph ^ 1u);
               ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk * tps);
               uint8_t* dst = b_smem + (size_t)s * p.b_stage_bytes;
               const __nv_bfloat16* src = p.w + (size_t)tap0 * tap_stride +
@@ -1009,26 +1035,25 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const uint64_t b_hi = make_planar_desc(0, 3u * (uint32_t)NF * 16u, 128u);
       constexpr uint32_t chunk_b16 = 9u * 2u * KJ * 3u * NF;       // one channel chunk of the folded weights, 16-byte units
       const int k_chunks = p.k_chunks;
-      uint32_t ti = 0, ita = 0;
+      uint32_t ti = 0;
       if (p.fold_streamed) {
         const uint32_t a_hi32 = (uint32_t)(a_hi >> 32), b_hi32 = (uint32_t)(b_hi >> 32);
         const uint32_t a_lbo = (uint32_t)a_hi, b_lbo = (uint32_t)b_hi;       // LBO << 16: low descriptor words
-        const uint32_t b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
-        const int nsb = p.nsb;
+        const uint32_t b_stage16 = hold_u32((uint32_t)p.b_stage_bytes >> 4);
+        Ring ra(nsa_u), rb((uint32_t)p.nsb);                 // rb is advanced by the issuing lane only
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
           const uint32_t acc = ti & 1;
           ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
           const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
-          for (int kc = 0; kc < k_chunks; ++kc, ++ita) {
-            const uint32_t sa = ita % nsa_u;
-            ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
+          for (int kc = 0; kc < k_chunks; ++kc, ra.next()) {
+            const uint32_t sa = ra.s;
+            ptx::mbar_wait(&a_rdy[sa], ra.ph);
             ptx::tc_fence_after();
             const uint32_t a_st = a_base16 + sa * a_stage16 + a_lbo;
             if (leader) {                      // one elected lane per chunk, weight-stage waits included (see the generic path)
-              uint32_t itb = ita * 9u;
-              for (int khw = 0; khw < 9; ++khw, ++itb) {
-                const uint32_t sb = itb % nsb;
-                ptx::mbar_wait(&sh->b_full[sb], (itb / nsb) & 1);
+              for (int khw = 0; khw < 9; ++khw, rb.next()) {
+                const uint32_t sb = rb.s;
+                ptx::mbar_wait(&sh->b_full[sb], rb.ph);
                 ptx::tc_fence_after();
                 const uint32_t kh = (uint32_t)khw / 3u, kw = (uint32_t)khw - 3u * kh;
                 issue_fold_stage<MT, KJ, NF>(a_st + kh * (uint32_t)(kTileW + 2) + kw, b_base16 + sb * b_stage16 + b_lbo, a_hi32,
@@ -1041,16 +1066,17 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             __syncwarp();
           }
         }
-      } else
+      } else {
+      Ring ra(nsa_u);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1;
         ptx::mbar_wait(&sh->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
         if (ti == 0) ptx::mbar_wait(&sh->b_full[0], 0);
         const uint32_t d_tmem0 = tmem_u + acc * (uint32_t)(MT * NF);
         const int total_chunks = k_chunks + p.skip_chunks;
-        for (int kc = 0; kc < total_chunks; ++kc, ++ita) {
-          const uint32_t sa = ita % nsa_u;
-          ptx::mbar_wait(&a_rdy[sa], (ita / nsa_u) & 1);
+        for (int kc = 0; kc < total_chunks; ++kc, ra.next()) {
+          const uint32_t sa = ra.s;
+          ptx::mbar_wait(&a_rdy[sa], ra.ph);
           ptx::tc_fence_after();
           if (leader) {
             if (kc == 0)
@@ -1067,6 +1093,7 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           }
           __syncwarp();
         }
+      }
       }
     } else {
       if (p.pad) issue_generic_tiles<MT, KJ, 1>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
