@@ -779,7 +779,7 @@ __device__ __forceinline__ void epilogue_tiles(const ConvKernelParams& p, ConvSh
 // rate while L2 ran at 8 %.  Here the run-time part is per TAP (its halo offset from the tap table, its weight block: one
 // 64-bit descriptor for A and KJ for B), and the MT x KJ MMAs of a tap differ by IMMEDIATE offsets (PAD fixes the halo
 // geometry at compile time): one UIADD3.64 and the UTCHMMA per MMA.
-template <int MT, int KJ, int PAD>
+template <int MT, int KJ, int PAD, int TPS, bool RESIDENT>
 __device__ __forceinline__ void issue_generic_tiles(const ConvKernelParams& p, ConvShared* sh, uint64_t* a_rdy, uint32_t a_base16,
                                                     uint32_t b_base16, uint32_t tmem_u, bool leader) {
   constexpr uint32_t Hh = kTileH + 2 * PAD, Wh = kTileW + 2 * PAD, Hd = MT + 2 * PAD;
@@ -792,10 +792,11 @@ __device__ __forceinline__ void issue_generic_tiles(const ConvKernelParams& p, C
   const uint32_t a_stage16 = hold_u32((uint32_t)p.a_stage_bytes >> 4), b_stage16 = hold_u32((uint32_t)p.b_stage_bytes >> 4);
   const uint32_t kstep_b16 = 2u * n_cta;
   const uint32_t btap16 = (uint32_t)(2 * KJ) * n_cta;          // one tap inside a B stage
-  const int tps = (int)hold_u32((uint32_t)p.taps_per_stage), n_taps = (int)hold_u32((uint32_t)p.n_taps);
+  constexpr int tps = TPS;                                     // taps per weight stage: one (kd, kh) row of three, or one
+  constexpr bool resident = RESIDENT;                          // all weights stay in shared memory (loaded once)
+  const int n_taps = (int)hold_u32((uint32_t)p.n_taps);
   const int k_chunks = (int)hold_u32((uint32_t)p.k_chunks);
-  const bool resident = p.b_resident != 0;
-  Ring ra((uint32_t)p.nsa), rb((uint32_t)p.nsb);               // rb is advanced by the issuing lane only
+  Ring ra(hold_u32((uint32_t)p.nsa)), rb(hold_u32((uint32_t)p.nsb));   // rb is advanced by the issuing lane only
   uint32_t ti = 0;
   bool first_chunk = true;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
@@ -822,6 +823,7 @@ __device__ __forceinline__ void issue_generic_tiles(const ConvKernelParams& p, C
             ptx::tc_fence_after();
             b_lo0 = b_base16 + rb.s * b_stage16;
           }
+#pragma unroll
           for (int q = 0; q < tps; ++q) {
             const uint64_t a_tap = a_hi | (uint64_t)(a_lo0 + (uint32_t)p.tap16[tap0 + q]);
             const uint32_t first = (kc | tap0 | q) != 0 ? 1u : 0u;
@@ -1096,8 +1098,18 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
       }
     } else {
-      if (p.pad) issue_generic_tiles<MT, KJ, 1>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
-      else issue_generic_tiles<MT, KJ, 0>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+      // (pad == 0 is the 1x1x1 conv: one tap per stage; tap subsets whose count is not a multiple of three too)
+      const bool res = p.b_resident != 0;
+      if (!p.pad) {
+        if (res) issue_generic_tiles<MT, KJ, 0, 1, true>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+        else issue_generic_tiles<MT, KJ, 0, 1, false>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+      } else if (p.taps_per_stage == 3) {
+        if (res) issue_generic_tiles<MT, KJ, 1, 3, true>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+        else issue_generic_tiles<MT, KJ, 1, 3, false>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+      } else {
+        if (res) issue_generic_tiles<MT, KJ, 1, 1, true>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+        else issue_generic_tiles<MT, KJ, 1, 1, false>(p, sh, a_rdy, a_base16, b_base16, tmem_u, leader);
+      }
     }
   }
   } else if (warp >= 12) {

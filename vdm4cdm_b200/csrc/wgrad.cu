@@ -61,6 +61,7 @@ struct WgradShared {
   uint64_t full[kWgMaxStages], empty[kWgMaxStages];
   uint64_t done;
   uint32_t tmem_base;
+  uint32_t job_off[32];      // per job of this CTA: offset of its A operand inside a stage (16-byte units), computed once
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -94,6 +95,14 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     ptx::mbar_init(&sh->done, 1);
     ptx::fence_barrier_init();
+    // (the issue loop used to divide job by n_khw and khw by 3 for every job of every 128-voxel tile)
+    const int sb0 = job0 / p.n_khw;
+    for (int j = 0; j < n_jobs && j < 32; ++j) {
+      const int job = job0 + j;
+      const int sb = job / p.n_khw, khw = job % p.n_khw;
+      const int kh = p.n_khw == 9 ? khw / 3 : 0, kw = p.n_khw == 9 ? khw % 3 : 0;
+      sh->job_off[j] = (uint32_t)(sb - sb0) * 16u * (uint32_t)(p.Hh * p.Wh) + (uint32_t)(kh * p.Wh + kw);
+    }
   }
   if (warp == 1) {
     ptx::tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
@@ -113,15 +122,17 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-        int t = tile;
-        const int d = t % p.D; t /= p.D;
-        const int w0 = (t % p.tiles_w) * kWgTileW; t /= p.tiles_w;
-        const int h0 = (t % p.tiles_h) * kWgTileH;
-        const int b = t / p.tiles_h;
-        const int s = it % p.stages;
-        ptx::mbar_wait(&sh->empty[s], ((it / p.stages) & 1) ^ 1);
+      // tile -> (b, h0, w0, d), d fastest: decoded once, then advanced (four run-time divisions per 128-voxel tile before)
+      int t = tile_begin;
+      int d = t % p.D; t /= p.D;
+      int tw = t % p.tiles_w; t /= p.tiles_w;
+      int th = t % p.tiles_h;
+      int b = t / p.tiles_h;
+      uint32_t s = 0, ph = 0;
+      const uint32_t stages = (uint32_t)p.stages;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int w0 = tw * kWgTileW, h0 = th * kWgTileH;
+        ptx::mbar_wait(&sh->empty[s], ph ^ 1u);
         ptx::mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(n_slices * p.slice_bytes + p.g_stage_bytes));
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         for (int sl = 0; sl < n_slices; ++sl)
@@ -130,6 +141,14 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                            b * p.x_planes + p.x_plane0 + cb * (p.cpb >> 3));
         ptx::tma_load_4d(a_dst + p.a_stage_bytes, &tmap_g, &sh->full[s], w0 * 8, h0, d,
                          b * p.g_planes + p.g_plane0 + ns * (p.n >> 3));
+        if (++s == stages) { s = 0; ph ^= 1u; }
+        if (++d == p.D) {
+          d = 0;
+          if (++tw == p.tiles_w) {
+            tw = 0;
+            if (++th == p.tiles_h) { th = 0; ++b; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -146,24 +165,22 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t smem16 = ptx::smem_u32(smem) >> 4;
     const uint32_t stage16 = (uint32_t)stage_bytes >> 4, a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t block16 = 16u * plane16;                 // one 128-row operand block
-    const int Wh = p.Wh, n_khw = p.n_khw, stages = p.stages;
-    uint32_t it = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-      const uint32_t s = it % stages;
-      ptx::mbar_wait(&sh->full[s], (it / stages) & 1);
+    const uint32_t Wh2 = 2u * (uint32_t)p.Wh;
+    const uint32_t stages = (uint32_t)p.stages;
+    uint32_t s = 0, ph = 0;
+    bool first = true;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      ptx::mbar_wait(&sh->full[s], ph);
       ptx::tc_fence_after();
       if (leader) {
         const uint32_t a0 = smem16 + s * stage16, g0 = a0 + a_stage16;
-        const uint32_t acc = it != 0 ? 1u : 0u;
+        const uint32_t acc = first ? 0u : 1u;
         for (int j = 0; j < n_jobs; ++j) {
-          const int job = job0 + j;
-          const int sb = job / n_khw, khw = job % n_khw;
-          const int kh = n_khw == 9 ? khw / 3 : 0, kw = n_khw == 9 ? khw % 3 : 0;
-          const uint32_t a_job = a0 + (uint32_t)(sb - sb_lo) * block16 + (uint32_t)(kh * Wh + kw);
+          const uint32_t a_job = a0 + sh->job_off[j];
           const uint32_t d_tmem = tmem_u + (uint32_t)j * n;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint64_t a_desc = a_hi | (uint64_t)((a_job + (uint32_t)(2 * k * Wh)) & 0x3FFFu);
+            const uint64_t a_desc = a_hi | (uint64_t)((a_job + (uint32_t)k * Wh2) & 0x3FFFu);
             const uint64_t b_desc = b_hi | (uint64_t)((g0 + (uint32_t)(16 * k)) & 0x3FFFu);
             ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, k == 0 ? acc : 1u);
           }
@@ -172,6 +189,8 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (tile == tile_end - 1) ptx::umma_commit(&sh->done);
       }
       __syncwarp();
+      first = false;
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
   } else if (tile_end > tile_begin) {
     // ===================== final epilogue: TMEM -> fp32 atomics into dW =====================
