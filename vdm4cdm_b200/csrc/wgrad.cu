@@ -367,32 +367,38 @@ conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     const uint64_t b_hi = ((uint64_t)8u << 16) | ((uint64_t)128u << 32) | ((uint64_t)1 << 46);
     const uint32_t a_base16 = ptx::smem_u32(a_smem) >> 4, g_base16 = ptx::smem_u32(g_smem) >> 4;
     const uint32_t slice16 = (uint32_t)p.slice_bytes >> 4, gstage16 = (uint32_t)p.g_stage_bytes >> 4;
-    uint32_t it = 0;
-    for (int i = 0; i < n_my; ++i) {
-      int b, d0, h0, w0;
-      seg_coord(i, b, d0, h0, w0);
-      const int len_eff = min(kWnLen, p.D - d0);
-      ptx::mbar_wait(&sh->slot_full[0], i & 1);
-      ptx::mbar_wait(&sh->slot_full[1], i & 1);
-      for (int j = 0; j < kWnLen; ++j, ++it) {
-        const uint32_t gs = it % kWnGStages;
-        ptx::mbar_wait(&sh->slot_full[j + 2], i & 1);
-        ptx::mbar_wait(&sh->g_full[gs], (it / kWnGStages) & 1);
-        ptx::tc_fence_after();
-        if (leader) {
+    // ONE elected lane runs the whole schedule, barrier waits included, with 64-bit descriptors and immediate per-MMA
+    // offsets (the lessons of conv3d.cu section "issuing thread": a warp-wide wait / fence / elect / __syncwarp per
+    // output slice and ~8 instructions per MMA kept this kernel at 815 TFLOP/s where its N = 96 MMAs allow ~1250)
+    if (leader) {
+      const uint64_t a_desc0 = a_hi | (uint64_t)(a_base16 + 1u);         // + 1: centre column of the halo
+      const uint64_t b_desc0 = b_hi | (uint64_t)g_base16;
+      uint32_t gs = 0, gph = 0;
+      bool first = true;
+      for (int i = 0; i < n_my; ++i) {
+        const int seg = split + i * p.n_splits;
+        const int d0 = (seg % p.segs_d) * kWnLen;
+        const int len_eff = min(kWnLen, p.D - d0);
+        const uint32_t par = (uint32_t)(i & 1);
+        ptx::mbar_wait(&sh->slot_full[0], par);
+        ptx::mbar_wait(&sh->slot_full[1], par);
+#pragma unroll 1
+        for (int j = 0; j < kWnLen; ++j) {
+          ptx::mbar_wait(&sh->slot_full[j + 2], par);
+          ptx::mbar_wait(&sh->g_full[gs], gph);
+          ptx::tc_fence_after();
           if (j < len_eff) {
-            const uint32_t a0 = a_base16 + (uint32_t)j * slice16 + 1u;       // + 1: centre column of the halo
-            const uint32_t g0 = g_base16 + gs * gstage16;
-            const uint32_t acc = it != 0 ? 1u : 0u;
+            const uint64_t a_j = a_desc0 + (uint64_t)((uint32_t)j * slice16);
+            const uint64_t b_j = b_desc0 + (uint64_t)(gs * gstage16);
+            const uint32_t acc = first ? 0u : 1u;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const uint64_t a_desc = a_hi | (uint64_t)(a0 + (uint32_t)((kh + 2 * k) * Wh));
-                const uint64_t b_desc = b_hi | (uint64_t)(g0 + (uint32_t)(16 * k));
-                ptx::umma_bf16(tmem_u + (uint32_t)kh * n3, a_desc, b_desc, idesc, k == 0 ? acc : 1u);
-              }
+              for (int k = 0; k < 8; ++k)
+                ptx::umma_bf16_off64(tmem_u, (uint32_t)kh * n3, a_j, (uint32_t)((kh + 2 * k) * Wh), b_j, (uint32_t)(16 * k), idesc,
+                                     k == 0 ? acc : 1u);
             }
+            first = false;
           }
           ptx::umma_commit(&sh->slot_empty[j]);
           ptx::umma_commit(&sh->g_empty[gs]);
@@ -401,10 +407,11 @@ conv3d_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
             ptx::umma_commit(&sh->slot_empty[kWnLen + 1]);
             if (i == n_my - 1) ptx::umma_commit(&sh->done);
           }
+          if (++gs == (uint32_t)kWnGStages) { gs = 0; gph ^= 1u; }
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else if (n_my > 0) {
     // ===================== final epilogue: TMEM -> fp32 atomics into dW =====================
     const int q = warp & 3;
