@@ -3,9 +3,9 @@
 // Stands in for power() at src/utils.py:16-83 of the reference (pk :85-102, get_ccs :110-128):
 // rfftn -> X conj(X2) -> batch mean / channel sum -> ceil(|k|) bins with Hermitian weights.
 // The reference builds ~10 full-size temporaries and calls torch.bincount three times; here the
-// wave number is recomputed from the mode's coordinates, every mode goes to its bin with one native
-// fp32 shared-memory atomic into bins private to the warp, the warps' bins are folded into fp64 block
-// bins every few thousand values, and blocks flush once with fp64 global atomics.  k-mean and mode counts depend on the grid only and
+// wave number is recomputed from the mode's coordinates, the 32 consecutive modes of a warp trip are
+// summed per run of equal bins (one ballot + a five-round segmented shuffle scan) and the run tails go to
+// fp64 bins private to the warp with plain read-modify-writes; blocks flush once with fp64 global atomics.  k-mean and mode counts depend on the grid only and
 // are produced by a separate read-free geometry kernel.
 //
 // HBM roofline: the binning kernel reads each complex mode once: 8 (auto) or 16 (cross) bytes
@@ -63,71 +63,119 @@ struct ModeCursor {
 
 constexpr int kPkThreads = 256, kPkWarps = kPkThreads / 32;
 constexpr int kPkUnroll = 4;          // modes (independent 8-byte loads) in flight per thread
-constexpr int kPkFoldEvery = 32;      // trips between folds of the fp32 warp bins into the block's fp64 bins
 
-// Fold the warps' private fp32 bins into the block's fp64 bins in a fixed order and clear them (all threads call).
-__device__ __forceinline__ void pk_fold_bins(float* s_bins, double* s_acc, int n) {
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += kPkThreads) {
-    double s = 0.0;
+// Sum the values of every maximal run of equal `bin` among the 32 consecutive modes of a warp trip, without atomics: the
+// run starts come from ONE ballot, a lane's run start from a count-leading-zeros of that mask, and the segmented inclusive
+// scan is five rounds of NV shuffles + predicated adds ("is the source lane still inside my run").  Returns true on the
+// last lane of a run, which then holds the run's sums.  (Round 1-2: a generic segmented scan that also shuffled the head
+// flags, ~120 instructions per trip; R3: fp32 shared-memory atomicAdd instead -- which is NOT a native instruction on
+// sm_100: ptxas emits an ATOMS.CAST.SPIN compare-and-swap loop, 0.11 ms per 16 fields of 128^3, R4e.)
+template <int NV>
+__device__ __forceinline__ bool warp_run_sums(int bin, float (&v)[NV]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int prev = __shfl_up_sync(full, bin, 1);
+  const unsigned starts = __ballot_sync(full, lane == 0 || prev != bin);
+  const int my_start = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));      // highest run start at or below this lane
 #pragma unroll
-    for (int wv = 0; wv < kPkWarps; ++wv) {
-      s += (double)s_bins[wv * n + i];
-      s_bins[wv * n + i] = 0.f;
+  for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float up = __shfl_up_sync(full, v[i], o);
+      if (lane - o >= my_start) v[i] += up;
     }
-    s_acc[i] += s;
   }
-  __syncthreads();
+  return lane == 31 || ((starts >> (lane + 1)) & 1u);
+}
+
+// Add the run sums of a trip to the warp's PRIVATE fp64 bins.  Bins grow along a spectrum row, so a bin normally has one run
+// (one tail lane) per trip and the tails do plain read-modify-writes.  A trip that spans a row boundary holds a descent; then
+// the same bin can occur on both sides only if the largest bin after the boundary reaches the smallest before it (two integer
+// warp reductions, REDUX) -- those trips, and trips with several boundaries (short rows of small grids), take the
+// compare-and-swap path.  (match.any over the tail lanes instead of this test cost 0.08 ms per 16 fields: R4f.)
+template <int NV>
+__device__ __forceinline__ void warp_bins_add(double* my, int nb, int bin, bool tail, const float (&v)[NV]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int key = bin >= 1 ? bin : 0x7fffffff;            // modes outside 1..kmax: neutral for the order test
+  const int prev = __shfl_up_sync(full, key, 1);
+  const unsigned desc = __ballot_sync(full, lane > 0 && prev > key);
+  bool dup = false;
+  if (desc != 0u) {                                        // warp-uniform
+    if ((desc & (desc - 1u)) != 0u) {
+      dup = true;
+    } else {
+      const int p = __ffs(desc) - 1;                       // first lane after the boundary
+      const int max_after = __reduce_max_sync(full, (lane >= p && bin >= 1) ? bin : -1);
+      const int min_before = __reduce_min_sync(full, (lane < p && bin >= 1) ? bin : 0x7fffffff);
+      dup = max_after >= min_before;
+    }
+  }
+  if (tail && bin >= 1) {
+    if (!dup) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) my[i * nb + bin] += (double)v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) atomicAdd(&my[i * nb + bin], (double)v[i]);
+    }
+  }
+  __syncwarp();
 }
 
 // acc: double [n_fields][NSPEC][kmax+1], zero-initialised.
 // NSPEC == 1: Re(X conj(X2)) (X2 may alias X).  NSPEC == 3: |X|^2, |X2|^2, Re(X conj(X2)).
 //
-// One mode per thread and trip, kPkUnroll trips' loads in flight, coordinates advanced without divisions, and every mode
-// added to its bin with ONE native fp32 shared-memory atomic per spectrum into bins PRIVATE to the warp (no contention
-// between warps; lanes of one instruction that hit the same bin are serialised by the hardware in a fixed order).  A
-// warp bin collects at most kPkFoldEvery * kPkUnroll * 32 = 4096 values in fp32 before it is folded into the block's
-// fp64 bins, and blocks flush once with fp64 global atomics.
-// (Round 2: the previous version merged equal-bin runs with a 5-round segmented shuffle scan per 32 modes -- ~120
-// instructions per trip, 0.14 ms per 16 fields of 128^3 against a 0.02 ms HBM floor.  Bins are NOT nearly constant
-// along a row (b = ceil(sqrt(k01 + i2^2)) takes ~10-30 values over the 65 modes of a 128^3 row), so there is little
-// to merge; the atomic unit does the same work in one instruction.)
-template <int NSPEC>
+// One mode per thread and trip, kPkUnroll trips' loads in flight, coordinates advanced without divisions (ModeCursor); the
+// 32 consecutive modes of a warp trip are reduced per run of equal bins (warp_run_sums) and the run tails go to fp64 bins
+// private to the warp; blocks fold their warps' bins in a fixed order and flush once with fp64 global atomics.
+// AUTO: X2 aliases X (auto-spectrum: one load per mode).  SINGLE: one transform per field (no batch / channel loop).  Mode
+// indices are 32-bit inside a field (checked by the host).  (R4g: with a run-time transform loop, two loads per mode even
+// for the auto-spectrum and 64-bit index arithmetic the loop body was ~500 instructions per mode and the pass took 0.12 ms
+// per 16 fields of 128^3 whatever the reduction scheme -- it was issue-bound on its own addressing.)
+template <int NSPEC, bool AUTO, bool SINGLE>
 __global__ void __launch_bounds__(kPkThreads)
 pk_bin_kernel(const float2* __restrict__ X, const float2* __restrict__ X2, PkGeom g, int n_transforms,
               double* __restrict__ acc) {
-  extern __shared__ double s_acc[];   // [NSPEC][kmax+1] fp64 block bins, then [warp][NSPEC][kmax+1] fp32 warp bins
+  extern __shared__ double s_acc[];   // [warp][NSPEC][kmax+1]
   const int nb = g.kmax + 1, n = NSPEC * nb;
-  float* s_bins = reinterpret_cast<float*>(s_acc + n);
-  for (int i = threadIdx.x; i < n; i += kPkThreads) s_acc[i] = 0.0;
-  for (int i = threadIdx.x; i < kPkWarps * n; i += kPkThreads) s_bins[i] = 0.f;
+  for (int i = threadIdx.x; i < kPkWarps * n; i += kPkThreads) s_acc[i] = 0.0;
   __syncthreads();
-  float* my = s_bins + (threadIdx.x >> 5) * n;
+  double* my = s_acc + (threadIdx.x >> 5) * n;
 
   const int field = blockIdx.y;
   const float2* x = X + (int64_t)field * n_transforms * g.modes;
   const float2* x2 = X2 + (int64_t)field * n_transforms * g.modes;
-  const int64_t stride = (int64_t)gridDim.x * kPkThreads;
-  int64_t m = (int64_t)blockIdx.x * kPkThreads + threadIdx.x;
+  const int modes = (int)g.modes;
+  const int stride = (int)gridDim.x * kPkThreads;
+  int m = (int)blockIdx.x * kPkThreads + (int)threadIdx.x;
   ModeCursor cur;
   cur.init(g, m, stride);
-  const int trips = (int)((g.modes + stride * kPkUnroll - 1) / (stride * kPkUnroll));   // the same for every thread
+  const int trips = (modes + stride * kPkUnroll - 1) / (stride * kPkUnroll);   // the same for every thread
   for (int it = 0; it < trips; ++it) {
     int bins[kPkUnroll];
     float v[kPkUnroll][NSPEC];
 #pragma unroll
     for (int u = 0; u < kPkUnroll; ++u) {
       float w, kmag;
-      bins[u] = (m < g.modes) ? cur.bin(g, w, kmag) : -1;
+      bins[u] = (m < modes) ? cur.bin(g, w, kmag) : -1;
 #pragma unroll
       for (int i = 0; i < NSPEC; ++i) v[u][i] = 0.f;
       if (bins[u] >= 1) {
-        for (int t = 0; t < n_transforms; ++t) {
-          const float2 a = __ldg(x + (int64_t)t * g.modes + m);
-          const float2 c = __ldg(x2 + (int64_t)t * g.modes + m);
+        const int nt = SINGLE ? 1 : n_transforms;
+        const float2* xa = x + m;
+        const float2* xc = x2 + m;
+        for (int t = 0; t < nt; ++t, xa += modes, xc += modes) {
+          const float2 a = __ldg(xa);
           if constexpr (NSPEC == 1) {
-            v[u][0] += a.x * c.x + a.y * c.y;
+            if constexpr (AUTO) {
+              v[u][0] += a.x * a.x + a.y * a.y;
+            } else {
+              const float2 c = __ldg(xc);
+              v[u][0] += a.x * c.x + a.y * c.y;
+            }
           } else {
+            const float2 c = __ldg(xc);
             v[u][0] += a.x * a.x + a.y * a.y;
             v[u][NSPEC - 2] += c.x * c.x + c.y * c.y;
             v[u][NSPEC - 1] += a.x * c.x + a.y * c.y;
@@ -141,55 +189,60 @@ pk_bin_kernel(const float2* __restrict__ X, const float2* __restrict__ X2, PkGeo
     }
 #pragma unroll
     for (int u = 0; u < kPkUnroll; ++u) {
-      if (bins[u] >= 1) {
-#pragma unroll
-        for (int i = 0; i < NSPEC; ++i) atomicAdd(&my[i * nb + bins[u]], v[u][i]);
-      }
+      const bool tail = warp_run_sums<NSPEC>(bins[u], v[u]);
+      warp_bins_add<NSPEC>(my, nb, bins[u], tail, v[u]);
     }
-    if ((it & (kPkFoldEvery - 1)) == kPkFoldEvery - 1) pk_fold_bins(s_bins, s_acc, n);
   }
-  pk_fold_bins(s_bins, s_acc, n);
+  __syncthreads();
   double* out = acc + (int64_t)field * n;
-  for (int i = threadIdx.x; i < n; i += kPkThreads)
-    if (s_acc[i] != 0.0) atomicAdd(out + i, s_acc[i]);
+  for (int i = threadIdx.x; i < n; i += kPkThreads) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kPkWarps; ++wv) t += s_acc[wv * n + i];
+    if (t != 0.0) atomicAdd(out + i, t);
+  }
 }
 
 // geometry: ksum[bin] += w*|k| (double), cnt[bin] += w (unsigned long long). No memory reads; same traversal.
 __global__ void __launch_bounds__(kPkThreads)
 pk_geometry_kernel(PkGeom g, double* __restrict__ ksum, unsigned long long* __restrict__ cnt) {
-  extern __shared__ double s_acc[];   // [kmax+1] fp64 k sums, then [warp][kmax+1] fp32 warp bins, then [kmax+1] counts
+  extern __shared__ double s_acc[];   // [warp][kmax+1] fp64 k sums, then [kmax+1] counts
   const int nb = g.kmax + 1;
-  float* s_bins = reinterpret_cast<float*>(s_acc + nb);
-  unsigned int* s_c = reinterpret_cast<unsigned int*>(s_bins + kPkWarps * nb);
-  for (int i = threadIdx.x; i < nb; i += kPkThreads) {
-    s_acc[i] = 0.0;
-    s_c[i] = 0u;
-  }
-  for (int i = threadIdx.x; i < kPkWarps * nb; i += kPkThreads) s_bins[i] = 0.f;
+  unsigned int* s_c = reinterpret_cast<unsigned int*>(s_acc + kPkWarps * nb);
+  for (int i = threadIdx.x; i < kPkWarps * nb; i += kPkThreads) s_acc[i] = 0.0;
+  for (int i = threadIdx.x; i < nb; i += kPkThreads) s_c[i] = 0u;
   __syncthreads();
-  float* my = s_bins + (threadIdx.x >> 5) * nb;
+  double* my = s_acc + (threadIdx.x >> 5) * nb;
   const int64_t stride = (int64_t)gridDim.x * kPkThreads;
   int64_t m = (int64_t)blockIdx.x * kPkThreads + threadIdx.x;
   ModeCursor cur;
   cur.init(g, m, stride);
   const int trips = (int)((g.modes + stride - 1) / stride);
   for (int it = 0; it < trips; ++it) {
+    int b = -1;
+    float v[2] = {0.f, 0.f};
     if (m < g.modes) {
       float w, kmag;
-      const int b = cur.bin(g, w, kmag);
+      b = cur.bin(g, w, kmag);
       if (b >= 1) {
-        atomicAdd(&my[b], kmag * w);
-        atomicAdd(&s_c[b], (unsigned int)w);      // < 2^32 per block: at most 2 * trips * 256
+        v[0] = kmag * w;
+        v[1] = w;                                  // <= 64 per run: exact in fp32
       }
     }
+    const bool tail = warp_run_sums<2>(b, v);
+    const float one[1] = {v[0]};
+    warp_bins_add<1>(my, nb, b, tail, one);
+    if (tail && b >= 1) atomicAdd(&s_c[b], (unsigned int)(v[1] + 0.5f));      // integer shared atomics are native
     m += stride;
     cur.advance(g);
-    if ((it & 127) == 127) pk_fold_bins(s_bins, s_acc, nb);
   }
-  pk_fold_bins(s_bins, s_acc, nb);
+  __syncthreads();
   for (int i = threadIdx.x; i < nb; i += kPkThreads) {
     if (s_c[i] != 0u) {
-      atomicAdd(ksum + i, s_acc[i]);
+      double t = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < kPkWarps; ++wv) t += s_acc[wv * nb + i];
+      atomicAdd(ksum + i, t);
       atomicAdd(cnt + i, (unsigned long long)s_c[i]);
     }
   }
@@ -316,21 +369,30 @@ static int pk_run(const float* f1, const float* f2, int n_fields, int batch, int
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, n_fields);
   const int ntr = batch * chan;
-  const size_t bin_smem = (size_t)nspec * nb * (sizeof(double) + kPkWarps * sizeof(float));   // block bins + private warp bins
+  const size_t bin_smem = (size_t)kPkWarps * nspec * nb * sizeof(double);     // fp64 bins private to each warp
   VDM_CHECK_ARG(bin_smem <= 200 * 1024, "vdm_pk: grid too large for the shared-memory bins (kmax = %d)", L.g.kmax);
-  if (nspec == 1) {
-    if (bin_smem > 48 * 1024)
-      VDM_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
-    pk_bin_kernel<1><<<grid, threads, bin_smem, stream>>>(X, X2, L.g, ntr, acc);
-  } else {
-    if (bin_smem > 48 * 1024)
-      VDM_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
-    pk_bin_kernel<3><<<grid, threads, bin_smem, stream>>>(X, X2, L.g, ntr, acc);
+  VDM_CHECK_ARG(L.g.modes + (int64_t)bx * threads * kPkUnroll < ((int64_t)1 << 31), "vdm_pk: field too large for 32-bit mode indices");
+  const bool aut = f2 == nullptr, single = ntr == 1;
+#define VDM_PK_LAUNCH(NS, AU, SI)                                                                                        \
+  {                                                                                                                      \
+    if (bin_smem > 48 * 1024)                                                                                            \
+      VDM_CHECK_CUDA(cudaFuncSetAttribute(pk_bin_kernel<NS, AU, SI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem)); \
+    pk_bin_kernel<NS, AU, SI><<<grid, threads, bin_smem, stream>>>(X, X2, L.g, ntr, acc);                                 \
   }
+  if (nspec == 1) {
+    if (aut && single) VDM_PK_LAUNCH(1, true, true)
+    else if (aut) VDM_PK_LAUNCH(1, true, false)
+    else if (single) VDM_PK_LAUNCH(1, false, true)
+    else VDM_PK_LAUNCH(1, false, false)
+  } else {
+    if (single) VDM_PK_LAUNCH(3, false, true)
+    else VDM_PK_LAUNCH(3, false, false)
+  }
+#undef VDM_PK_LAUNCH
   VDM_CHECK_LAUNCH();
   int gx = (int)((L.g.modes + threads * 8 - 1) / (threads * 8));
   gx = gx < 1 ? 1 : (gx > kNumSMs * 4 ? kNumSMs * 4 : gx);
-  const size_t geo_smem = (size_t)nb * (sizeof(double) + kPkWarps * sizeof(float) + sizeof(unsigned int));
+  const size_t geo_smem = (size_t)nb * (kPkWarps * sizeof(double) + sizeof(unsigned int));
   pk_geometry_kernel<<<gx, threads, geo_smem, stream>>>(L.g, ksum, cnt);
   VDM_CHECK_LAUNCH();
   const int total = n_fields * L.g.kmax;
