@@ -1171,8 +1171,10 @@ constexpr int g_debug_no_march = 0;
 
 // Launch of the d-marching schedule (conv3d_march.cuh).  `p` carries the grid, the plane windows and the epilogue; this
 // fills in the unit decomposition, the shared-memory plan and the one-slice tensor map.
-static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x, const void* skip_x, int kc, int halo, int x_planes,
-                        bool has_residual, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t stream) {
+static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x, const void* skip_x, const float* in_norm, int kc,
+                        int halo, int x_planes, bool has_residual, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t stream) {
+  p.in_norm = in_norm;                 // fused GroupNorm + SiLU of the input: warps 12..15 transform, eight epilogue warps
+  p.c_in = d.c_in;
   const int NF = p.n_cta, planes = kc / 8, sms = num_sms();
   // Segment length: static round-robin over equal units, so the launch takes ceil(units / SMs) rounds of (seglen + 2) slices
   // (+1: per-unit fixed costs); short segments balance the SMs, long ones amortise the two halo slices.
@@ -1235,19 +1237,21 @@ static int launch_march(const VdmConvDesc& d, ConvKernelParams& p, const void* x
   }
   const int grid = p.m_units < sms ? p.m_units : sms;
   int rc = VDM_E_UNSUPPORTED;
-#define VDM_LAUNCH_MARCH(KJv, NFv, SKv)                                                                        \
-  if (kc == 16 * KJv && NF == NFv && (p.skip_chunks > 0) == SKv) {                                             \
+#define VDM_LAUNCH_MARCH(KJv, NFv, SKv, XFv)                                                                   \
+  if (kc == 16 * KJv && NF == NFv && (p.skip_chunks > 0) == SKv && (in_norm != nullptr) == XFv) {              \
     static bool configured = false;                                                                            \
     if (!configured) {                                                                                         \
-      VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_march_kernel<KJv, NFv, SKv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          227 * 1024));                                                        \
+      VDM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_march_kernel<KJv, NFv, SKv, XFv>,                             \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));          \
       configured = true;                                                                                       \
     }                                                                                                          \
-    conv3d_march_kernel<KJv, NFv, SKv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmx2, p);              \
+    conv3d_march_kernel<KJv, NFv, SKv, XFv><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmx2, p);         \
     rc = VDM_OK;                                                                                               \
   }
-  VDM_LAUNCH_MARCH(1, 16, false) VDM_LAUNCH_MARCH(1, 32, false) VDM_LAUNCH_MARCH(2, 16, false) VDM_LAUNCH_MARCH(2, 32, false)
-  VDM_LAUNCH_MARCH(1, 16, true) VDM_LAUNCH_MARCH(1, 32, true) VDM_LAUNCH_MARCH(2, 16, true) VDM_LAUNCH_MARCH(2, 32, true)
+#define VDM_LAUNCH_MARCH4(SKv, XFv)                                                                            \
+  VDM_LAUNCH_MARCH(1, 16, SKv, XFv) VDM_LAUNCH_MARCH(1, 32, SKv, XFv) VDM_LAUNCH_MARCH(2, 16, SKv, XFv) VDM_LAUNCH_MARCH(2, 32, SKv, XFv)
+  VDM_LAUNCH_MARCH4(false, false) VDM_LAUNCH_MARCH4(true, false) VDM_LAUNCH_MARCH4(false, true) VDM_LAUNCH_MARCH4(true, true)
+#undef VDM_LAUNCH_MARCH4
 #undef VDM_LAUNCH_MARCH
   if (rc != VDM_OK) {
     set_error("vdm_conv3d: no marching kernel instance for KC=%d N=%d", kc, NF);
@@ -1523,8 +1527,9 @@ extern "C" int vdm_conv3d(const VdmConvDesc* desc, const void* x, const void* w,
   p.debug_flags = g_debug_flags;
 
   // d-marching schedule for the narrow layers whose input channels are one chunk (conv3d_march.cuh)
-  if (fold && !fold_streamed && p.k_chunks == 1 && !has_xf && g_debug_no_march == 0)
-    return launch_march(d, p, x, has_skip ? epi->skip_x : nullptr, kc, halo, x_planes, has_residual, encode, stream);
+  if (fold && !fold_streamed && p.k_chunks == 1 && g_debug_no_march == 0)
+    return launch_march(d, p, x, has_skip ? epi->skip_x : nullptr, has_xf ? epi->in_norm : nullptr, kc, halo, x_planes, has_residual,
+                        encode, stream);
 
   // activations: 4-D (W*8 channels-in-plane, H, D, B*planes), box (Wh*8, Hh, Hd, KC/8); out-of-bounds -> zeros.
   // The (w, 8ch) pair is ONE tensor-map dimension on purpose: the TMA unit issues requests per

@@ -28,6 +28,7 @@ constexpr int kMarchCaddMax = 1024; // floats of the bias + conditioning table k
 
 struct MarchShared {
   uint64_t a_full[kMarchStages], a_empty[kMarchStages];
+  uint64_t a_ready[kMarchStages];     // fused input transform: the landed slice has been rewritten in place
   uint64_t b_full;
   uint64_t t_full[kMarchBlocks], t_empty[kMarchBlocks];
   uint32_t tmem_base;
@@ -97,9 +98,11 @@ __device__ __forceinline__ void issue_march_slice(uint64_t a_desc, uint64_t b_de
 // a cp.async ring in shared memory (kMarchResDepth slices of THIS warp in flight, the cursor runs ahead across units).
 // Statistics: per-lane fp32 sums over the warp's slices of a unit, one transpose reduction per unit, per-warp slots folded
 // in a fixed order into the CTA's fp64 running sums, fp64 atomics when the CTA moves on to another sample.
-template <int NF, int MODE>
+template <int NF, int MODE, int EW>
 __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchShared* sh, uint8_t* smem, float* stat_part,
                                                double* stat_acc, float* cadd_s, const uint32_t tmem_base) {
+  // EW = epilogue warps per TMEM lane quarter: 3 (warps 4..15), or 2 (warps 4..11) when warps 12..15 transform the input
+  constexpr int kThreadsE = 128 * EW;
   constexpr bool RES = (MODE & kEpiRes) != 0, STATS = (MODE & kEpiStats) != 0, FP32 = (MODE & kEpiFp32) != 0;
   constexpr int R = kMarchBlocks, n_chunks = NF / 16, n_planes = NF / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,11 +117,11 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
   const float* cadd_g = p.chan_add ? p.chan_add + cadd_step * p.chan_add_step_stride : nullptr;
   const bool cadd_table = p.B * NF <= kMarchCaddMax;
   if (cadd_table) {
-    for (int i = et; i < p.B * NF; i += kMEpiThreads) {
+    for (int i = et; i < p.B * NF; i += kThreadsE) {
       const int bb = i / NF, c = i - bb * NF;
       cadd_s[i] = (cadd_g && c < p.c_out) ? __ldg(cadd_g + (long long)bb * p.c_out + c) : 0.f;
     }
-    asm volatile("bar.sync 1, 384;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreadsE) : "memory");
   }
   // valid 8-channel planes (bf16 output: c_out % 8 == 0)
   const int n_valid_planes = (p.c_out >> 3) < n_planes ? (p.c_out >> 3) : n_planes;
@@ -151,7 +154,7 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
     }
     if (live) {
       const int dz = r_d0 + ru_s;
-      ru_s += 3;
+      ru_s += EW;
       if (r_hw_ok) {
         const uint4* src = r_ptr + (long long)(((dz & 1) << 2) * p.r_d2s_planes) * r_V + (long long)(dz >> r_sh) * r_HW;
         uint4* dst = r_ring + (slot * n_planes) * kMEpiThreads;
@@ -181,7 +184,7 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
     }
     bf16x8* y_b = reinterpret_cast<bf16x8*>(p.y) + ((long long)m.b * p.y_planes + p.y_plane0) * V + vox0;
     float* y32_b = static_cast<float*>(p.y) + (long long)m.b * p.c_out * V + vox0;
-    for (int s = k3; s < m.len; s += 3) {
+    for (int s = k3; s < m.len; s += EW) {
       const uint32_t o = ob + (uint32_t)s;
       const uint32_t g = o % (uint32_t)R;
       ptx::mbar_wait(&sh->t_full[g], (o / (uint32_t)R) & 1);
@@ -267,7 +270,7 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
           stat_part[(kMEpiWarps + ew) * NF + ch] = s2[c][0];
         }
       }
-      asm volatile("bar.sync 2, 384;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(kThreadsE) : "memory");
       if (et < NF) {
         const int next_u = u + (int)gridDim.x;
         bool flush = next_u >= p.m_units;
@@ -275,7 +278,7 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
         const int c = et;
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int wv = 0; wv < kMEpiWarps; ++wv) {
+        for (int wv = 0; wv < 4 * EW; ++wv) {
           t1 += stat_part[wv * NF + c];
           t2 += stat_part[(kMEpiWarps + wv) * NF + c];
         }
@@ -294,12 +297,80 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
           stat_acc[NF + c] = a2;
         }
       }
-      asm volatile("bar.sync 2, 384;" ::: "memory");     // the slots are read before the next unit overwrites them
+      asm volatile("bar.sync 2, %0;" ::"n"(kThreadsE) : "memory");     // the slots are read before the next unit overwrites them
     }
   }
 }
 
-template <int KJ, int NF, bool SKIP>
+// ---- fused GroupNorm + SiLU of the input (XF): warps 12..15 rewrite every landed input slice in place ------------------
+// y = h + h tanh(h), h = a_c x + b_c ((a, b) per (sample, channel) from vdm_gn_coef, the 1/2 of silu(2h) folded in), voxels
+// outside the grid back to zero (Conv3d's zero padding applies AFTER the non-linearity), fence.proxy.async, arrive on
+// a_ready[s] -- the barrier the MMA issuer then waits on instead of a_full[s].  Warp j takes every fourth stage of the main
+// tensor WHOLE (so its wait -> LDS -> arithmetic -> STS chain may last four slices: in the tile kernel four warps shared every
+// stage and the chain, not the bandwidth, made the transform slower than the MMAs, R2h); a lane owns one 8-channel plane,
+// its 16 coefficients stay in registers while the sample does not change.  Skip-tensor stages are not transformed.
+template <int KJ, bool SKIP>
+__device__ __forceinline__ void march_transform(const ConvKernelParams& p, MarchShared* sh, uint8_t* a_smem) {
+  constexpr int planes = 2 * KJ, S = kMarchStages;
+  constexpr int kSliceBytes = (kTileH + 2) * (kTileW + 2) * 16, kStageBytes = planes * kSliceBytes;
+  constexpr int lpp = 32 / planes;                         // lanes per plane
+  constexpr int nvox = (kTileH + 2) * (kTileW + 2);
+  const int lane = threadIdx.x & 31, j = (threadIdx.x >> 5) - 12;
+  const int pl = lane / lpp, l0 = lane % lpp;
+  const int skip_chunks = SKIP ? p.skip_chunks : 0;
+  float ca[8], cb[8];
+  int cur_b = -1;
+  uint32_t it = 0, n_main = 0, n_skip = 0;                 // stage counter (all stages), main / skip-tensor stages so far
+  for (int u = blockIdx.x; u < p.m_units; u += gridDim.x) {
+    const MarchUnit m = decode_unit(p, u);
+    if (m.b != cur_b) {
+      cur_b = m.b;
+      const float4* cs = reinterpret_cast<const float4*>(p.in_norm + ((long long)m.b * p.c_in + pl * 8) * 2);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 c4 = __ldg(cs + j4);
+        ca[2 * j4] = c4.x; cb[2 * j4] = c4.y; ca[2 * j4 + 1] = c4.z; cb[2 * j4 + 1] = c4.w;
+      }
+    }
+    for (int i = 0; i < m.len + 2; ++i, ++n_main) {
+      if ((int)(n_main & 3u) == j) {
+        const uint32_t s = it % (uint32_t)S;
+        ptx::mbar_wait(&sh->a_full[s], (it / (uint32_t)S) & 1);
+        const int dz = m.d0 - 1 + i;
+        if (dz >= 0 && dz < p.D) {                         // (a slice beyond the grid is all zero padding: nothing to do)
+          uint4* base = reinterpret_cast<uint4*>(a_smem + (size_t)s * kStageBytes + (size_t)pl * kSliceBytes);
+          const bool edge = m.h0 == 0 || m.h0 + kTileH >= p.H || m.w0 == 0 || m.w0 + kTileW >= p.W;
+#pragma unroll 4
+          for (int v = l0; v < nvox; v += lpp) {
+            uint4 y = gn_silu8(base[v], ca, cb);
+            if (edge) {
+              const int hy = v / (kTileW + 2), wx = v - hy * (kTileW + 2);
+              if ((unsigned)(m.h0 - 1 + hy) >= (unsigned)p.H || (unsigned)(m.w0 - 1 + wx) >= (unsigned)p.W) y = make_uint4(0u, 0u, 0u, 0u);
+            }
+            base[v] = y;
+          }
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sh->a_ready[s]);
+      }
+      ++it;
+      // the skip-tensor stages of this output slice are not transformed, but a_ready has to complete one phase per use of a
+      // stage like a_full does (the issuer waits on a_ready for every stage): forward the arrival
+      if (i < m.len) {
+        for (int c = 0; c < skip_chunks; ++c, ++it, ++n_skip) {
+          if ((int)(n_skip & 3u) == j) {
+            const uint32_t s = it % (uint32_t)S;
+            ptx::mbar_wait(&sh->a_full[s], (it / (uint32_t)S) & 1);
+            if (lane == 0) ptx::mbar_arrive(&sh->a_ready[s]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int KJ, int NF, bool SKIP, bool XF>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                     const __grid_constant__ ConvKernelParams p) {
@@ -324,6 +395,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&sh->a_full[s], 1);
       ptx::mbar_init(&sh->a_empty[s], 1);
+      ptx::mbar_init(&sh->a_ready[s], 1);
     }
     ptx::mbar_init(&sh->b_full, 1);
     for (int g = 0; g < R; ++g) {
@@ -414,10 +486,12 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         MarchUnit m = decode_unit(p, u);
         const int skip_chunks = SKIP ? p.skip_chunks : 0;
         uint32_t ita = 0, ob = 0;                 // stage counter, output-slice counter at the start of the unit
+        // (landed and, with the fused input transform, rewritten / passed on by the transform warps)
         auto wait_stage = [&](uint32_t ita_) __attribute__((always_inline)) {
-          ptx::mbar_wait(&sh->a_full[ita_ % (uint32_t)S], (ita_ / (uint32_t)S) & 1);
+          ptx::mbar_wait(XF ? &sh->a_ready[ita_ % (uint32_t)S] : &sh->a_full[ita_ % (uint32_t)S], (ita_ / (uint32_t)S) & 1);
           ptx::tc_fence_after();
         };
+        auto wait_skip_stage = [&](uint32_t ita_) __attribute__((always_inline)) { wait_stage(ita_); };
         auto wait_block = [&](uint32_t o) __attribute__((always_inline)) {      // accumulator block of output slice o drained
           ptx::mbar_wait(&sh->t_empty[o % (uint32_t)R], ((o / (uint32_t)R) & 1) ^ 1);
         };
@@ -442,7 +516,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             for (int j = 0; j < KJ; ++j)
               ptx::umma_bf16_off64(d_s, 0u, a2, (uint32_t)(j * 2 * kTileH * kTileW), b2, (uint32_t)(2 * j * NF),
                                    ptx::make_idesc_bf16(128, (uint32_t)NF), 1u);
-            if (c + 1 < skip_chunks) wait_stage(ita + 1u);
+            if (c + 1 < skip_chunks) wait_skip_stage(ita + 1u);
             else wait_slice(i + 1, ita + 1u, ob, len);
             ptx::umma_commit(&sh->a_empty[s2]);
           }
@@ -469,7 +543,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const uint64_t b_desc = b_desc0 + (uint64_t)((2 - i + s_lo) * NF);
             issue_march_slice<KJ, NF, 0, 5>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
             // the next stage (possibly of this CTA's next unit): its barriers are waited for here
-            if (skip_next) wait_stage(ita + 1u);
+            if (skip_next) wait_skip_stage(ita + 1u);
             else if (!last) wait_slice(i + 1, ita + 1u, ob, len);
             else if (more_units) wait_slice(0, ita + 1u, ob + (uint32_t)len, nm.len);
             issue_march_slice<KJ, NF, 5, 9>(a_desc, b_desc, tmem_u, g_lo, n, n1, fresh);
@@ -493,7 +567,8 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             issue_march_span<KJ, NF, true, 0, 2, 3>(a_desc, b_desc0, d_col, 3);
             if (!SKIP && i + 1 < len) wait_block(ob + (uint32_t)(i + 1));
             issue_march_span<KJ, NF, true, 2, 4, 3>(a_desc, b_desc0, d_col, 3);
-            wait_stage(ita + 1u);
+            if (SKIP) wait_skip_stage(ita + 1u);
+            else wait_stage(ita + 1u);
             issue_march_span<KJ, NF, true, 4, 6, 3>(a_desc, b_desc0, d_col, 3);
             issue_march_span<KJ, NF, true, 6, 9, 3>(a_desc, b_desc0, d_col, 3);
             ptx::umma_commit(&sh->a_empty[sa]);
@@ -511,13 +586,19 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       __syncwarp();
     }
   } else {
-    // ===================== epilogue (12 warps; three per TMEM lane quarter): see march_epilogue =====================
+    // ===================== epilogue (12 warps, three per TMEM lane quarter; with the fused input transform eight, and
+    // warps 12..15 transform): see march_epilogue / march_transform =====================
     ptx::setmaxnreg_inc<kRegsMEpi>();
-    if (p.out_fp32) march_epilogue<NF, kEpiFp32>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
-    else if (p.residual && p.stats) march_epilogue<NF, kEpiRes | kEpiStats>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
-    else if (p.residual) march_epilogue<NF, kEpiRes>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
-    else if (p.stats) march_epilogue<NF, kEpiStats>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
-    else march_epilogue<NF, 0>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
+    if (XF && warp >= 12) {
+      march_transform<KJ, SKIP>(p, sh, a_smem);
+    } else {
+      constexpr int EW = XF ? 2 : 3;
+      if (p.out_fp32) march_epilogue<NF, kEpiFp32, EW>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
+      else if (p.residual && p.stats) march_epilogue<NF, kEpiRes | kEpiStats, EW>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
+      else if (p.residual) march_epilogue<NF, kEpiRes, EW>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
+      else if (p.stats) march_epilogue<NF, kEpiStats, EW>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
+      else march_epilogue<NF, 0, EW>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
+    }
   }
 
   ptx::tc_fence_before();

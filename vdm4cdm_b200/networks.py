@@ -21,6 +21,7 @@ fallback for the convolutional path; autograd support lives in ``vdm4cdm_b200.au
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -123,6 +124,10 @@ class CUNet(nn.Module):
         # in_norm) instead of by a separate read + write pass over the tensor
         self.fuse_gn = True
         self.fuse_gn_min_channels = 64
+        # ... and for the narrow layers that run the d-marching schedule (at most 32 channels in and out), where warps 12..15
+        # transform whole input slices (R4k, 128^3 x 8: 12.40 -> 11.81 ms per step; the convs get 0.2 ms slower each, the
+        # 0.34 ms GroupNorm passes go).  VDM4CDM_FUSE_GN_NARROW=0 switches it off (A/B measurements).
+        self.fuse_gn_narrow = os.environ.get("VDM4CDM_FUSE_GN_NARROW", "1") != "0"
         # inference, up blocks: conv3x3x3 over the up-sampled half of cat([interpolate(h), skip]) in its polyphase form --
         # eight 2x2x2-tap convolutions of the COARSE tensor, one per output parity (8/27 of the multiply-adds, the
         # up-sampled activations are never written); the skip half is a plain conv that adds them as its residual
@@ -381,16 +386,18 @@ class CUNet(nn.Module):
         voxels = grid[0] * grid[1] * grid[2]
         p_drop = blk.dropout_prob if training_dropout else 0.0
         # inference without dropout and with zero padding: the convs normalise their own input tiles (fuse_gn) -- for layers
-        # of at least 64 output channels.  Narrower layers run the kd-folded N = 96 schedule, which is bound by the tensor
-        # core's shared-memory operand fetch; the transform's LDS / STS traffic on the same shared memory then costs more
-        # (+0.55 ms on a 0.85 ms 32->32 conv at 128^3 x 8 even as a plain copy, profiles/R2h_transform_ablation.txt) than
-        # the separate HBM pass it replaces (0.45 ms).
-        fuse_gn = self.fuse_gn and tape is None and not self.circular and p_drop == 0.0 and co >= self.fuse_gn_min_channels
+        # of at least 64 output channels (tile kernel, four warps share every halo stage) and for the narrow layers of the
+        # marching schedule (four warps take whole slices in turn).  In between (narrow output, more than 32 input channels:
+        # the kd-folded TILE schedule) the transform's LDS / STS traffic costs more than the HBM pass it replaces
+        # (+0.55 ms on a 0.85 ms conv even as a plain copy, profiles/R2h_transform_ablation.txt).
+        fuse_ok = self.fuse_gn and tape is None and not self.circular and p_drop == 0.0
+        fuse_gn = fuse_ok and (co >= self.fuse_gn_min_channels or (self.fuse_gn_narrow and co <= 32))      # net2 reads h (co channels)
+        fuse_gn1 = fuse_ok and (co >= self.fuse_gn_min_channels or (self.fuse_gn_narrow and ci <= 32 and co <= 32))
         h = ar.get(f"{own}h.{co}.{tag}", (b, co // 8) + grid + (8,), torch.bfloat16, dev)
         h_stats = self._stats(f"{name}.h", b, co, dev)
         net1_kw = dict(out=h, chan_add=rows[name + ".net1"], step_ptr=step_ptr if rows[name + ".net1"].dim() == 3 else None,
                        stats=h_stats, circular=self.circular)
-        if fuse_gn and up_from is None:
+        if fuse_gn1 and up_from is None:
             coef1 = ops.gn_coef(x_stats, n1.weight, n1.bias, g, voxels, n1.eps,
                                 out=ar.get(f"coef1.{name}.{b}", (b, ci, 2), torch.float32, dev))
             ops.conv3d(x, self._packed(name + ".net1", blk.net1[2]), co, x_plane0=x_plane0, c_in=ci, in_norm=coef1, **net1_kw)
@@ -573,7 +580,7 @@ class CUNet(nn.Module):
         gn = self.conv_out[0]
         if out is None:
             out = torch.empty((b, 1) + grids[0], dtype=torch.float32, device=dev)
-        if self.fuse_gn and tape is None and not self.circular and self.fuse_gn_min_channels <= 1:
+        if self.fuse_gn and tape is None and not self.circular and (self.fuse_gn_narrow and c[0] <= 32 or self.fuse_gn_min_channels <= 1):
             coef = ops.gn_coef(x_stats, gn.weight, gn.bias, gn.num_groups, grids[0][0] * grids[0][1] * grids[0][2], gn.eps,
                                out=ar.get(f"coef.conv_out.{b}", (b, c[0], 2), torch.float32, dev))
             ops.conv3d(x, self._packed("conv_out", self.conv_out[2]), 1, x_plane0=x_plane0, c_in=c[0], out=out, out_fp32=True,
