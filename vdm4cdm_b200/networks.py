@@ -418,10 +418,21 @@ class CUNet(nn.Module):
                 wp, taps = self._packed_poly(name + ".net1", blk.net1[2], c_up, grp, n_par)
                 ops.conv3d(ac, wp, n_par * co, taps=taps, out=part, out_plane0=grp * n_par * (co // 8))
             # the skip channels at the fine resolution; the partial sums come in through the depth-to-space residual
-            a_s = ar.get(f"as.{ci - c_up}.{tag}", (b, (ci - c_up) // 8) + grid + (8,), torch.bfloat16, dev)
-            ops.gn_silu_view(x, ci - c_up, c_up, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a_s, x_plane0=x_plane0 + c_up // 8)
-            ops.conv3d(a_s, self._packed_in_slice(name + ".net1.skiphalf", blk.net1[2], c_up, ci - c_up), co,
-                       residual=part, residual_upsample="d2s", **net1_kw)
+            c_sk = ci - c_up
+            w_sk = self._packed_in_slice(name + ".net1.skiphalf", blk.net1[2], c_up, c_sk)
+            if fuse_ok and (co >= self.fuse_gn_min_channels or (self.fuse_gn_narrow and c_sk <= 32 and co <= 32)):
+                # GroupNorm + SiLU of the skip channels applied by the conv to its input tiles: (a, b) of all ci channels of
+                # the concat norm (groups straddle the two halves), the skip channels' rows handed to the conv
+                coef = ops.gn_coef(x_stats, n1.weight, n1.bias, g, voxels, n1.eps,
+                                   out=ar.get(f"coef1.{name}.{b}", (b, ci, 2), torch.float32, dev))
+                coef_s = ar.get(f"coef1s.{name}.{b}", (b, c_sk, 2), torch.float32, dev)
+                coef_s.copy_(coef[:, c_up:])
+                ops.conv3d(x, w_sk, co, x_plane0=x_plane0 + c_up // 8, c_in=c_sk, residual=part, residual_upsample="d2s",
+                           in_norm=coef_s, **net1_kw)
+            else:
+                a_s = ar.get(f"as.{c_sk}.{tag}", (b, c_sk // 8) + grid + (8,), torch.bfloat16, dev)
+                ops.gn_silu_view(x, c_sk, c_up, ci, g, x_stats, n1.weight, n1.bias, n1.eps, a_s, x_plane0=x_plane0 + c_up // 8)
+                ops.conv3d(a_s, w_sk, co, residual=part, residual_upsample="d2s", **net1_kw)
         else:
             a1 = ar.get(f"{own}a.{ci}.{tag}", (b, ci // 8) + grid + (8,), torch.bfloat16, dev)
             if up_from is None:
