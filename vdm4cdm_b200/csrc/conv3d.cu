@@ -998,22 +998,34 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                              &sh->b_full[0]);
           }
       } else {
+        // This thread has ~768 cycles per weight stage (12 MMAs of N = 128): with twelve 2 KB copies per stage and their address
+        // arithmetic it took longer, and the issuer waited for b_full 27 % of its time (R4p ncu, 128 -> 128).  When the CTA
+        // takes all output channels (n_split == 1) the planes of a channel chunk are contiguous for a tap, in global and in
+        // shared memory alike: ONE copy per tap (three per stage); sizes and strides are loop invariants.
         Ring rb((uint32_t)nsb);
+        const bool whole_rows = p.n_split == 1;
+        const uint32_t stage_tx = plane_copy_bytes * (uint32_t)planes_per_chunk * (uint32_t)tps;
+        const uint32_t tap_bytes = plane_copy_bytes * (uint32_t)planes_per_chunk;
+        const size_t chunk_stride = (size_t)planes_per_chunk * plane_stride;         // elements between channel chunks
+        const uint32_t b_stage_bytes = (uint32_t)p.b_stage_bytes;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           const TileCoord t = decode_tile(p, tile);
-          for (int kc = 0; kc < k_chunks; ++kc) {
+          const __nv_bfloat16* src_c = p.w + (size_t)t.ns * p.n_cta * 8;
+          for (int kc = 0; kc < k_chunks; ++kc, src_c += chunk_stride) {
+            const __nv_bfloat16* src = src_c;
             for (int tap0 = 0; tap0 < n_taps; tap0 += tps, rb.next()) {
-              const int s = (int)rb.s;
+              const uint32_t s = rb.s;
               ptx::mbar_wait(&sh->b_empty[s], rb.ph ^ 1u);
-              ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk * tps);
-              uint8_t* dst = b_smem + (size_t)s * p.b_stage_bytes;
-              const __nv_bfloat16* src = p.w + (size_t)tap0 * tap_stride +
-                                         ((size_t)kc * planes_per_chunk * p.n_pad + (size_t)t.ns * p.n_cta) * 8;
-              for (int q = 0; q < tps; ++q)
+              ptx::mbar_arrive_expect_tx(&sh->b_full[s], stage_tx);
+              uint8_t* dst = b_smem + (size_t)s * b_stage_bytes;
+              if (whole_rows) {
+                for (int q = 0; q < tps; ++q, src += tap_stride, dst += tap_bytes) ptx::bulk_load(dst, src, tap_bytes, &sh->b_full[s]);
+              } else {
+                for (int q = 0; q < tps; ++q, src += tap_stride)
 #pragma unroll
-                for (int pl = 0; pl < planes_per_chunk; ++pl)
-                  ptx::bulk_load(dst + (size_t)(q * planes_per_chunk + pl) * plane_copy_bytes,
-                                 src + (size_t)q * tap_stride + (size_t)pl * plane_stride, plane_copy_bytes, &sh->b_full[s]);
+                  for (int pl = 0; pl < planes_per_chunk; ++pl, dst += plane_copy_bytes)
+                    ptx::bulk_load(dst, src + (size_t)pl * plane_stride, plane_copy_bytes, &sh->b_full[s]);
+              }
             }
           }
         }
