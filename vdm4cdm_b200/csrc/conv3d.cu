@@ -939,9 +939,14 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================== B producer =====================
-    if (lane == 0 && blockIdx.x < (unsigned)p.n_tiles) {
+  } else if (warp == 2 || warp == 3) {
+    // ===================== B producer(s) =====================
+    // Streamed weights: warps 2 AND 3 issue the copies, alternating stages (one thread needed ~900 cycles for the twelve
+    // 1-2 KB copies of a stage the tensor core consumes in 770-1150: R4r ncu, the issuer waited for b_full 29 % of its time
+    // on the 64 -> 64 layers).  Resident weights: warp 2 loads them once.
+    const uint32_t pj = (uint32_t)(warp - 2);
+    const bool streamed = kFold ? p.fold_streamed != 0 : p.b_resident == 0;
+    if (lane == 0 && blockIdx.x < (unsigned)p.n_tiles && (pj == 0 || streamed)) {
       const uint32_t plane_copy_bytes = (uint32_t)p.n_cta * 16u;
       const int tps = p.taps_per_stage, nsb = p.nsb, n_taps = p.n_taps, k_chunks = p.k_chunks;
       const size_t tap_stride = (size_t)p.c_in8 * p.n_pad * 8, plane_stride = (size_t)p.n_pad * 8;
@@ -949,9 +954,11 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
        if (p.fold_streamed) {
         // one ring stage per (tile, chunk, kh, kw): [plane][2 - kd][co] (see issue_fold_stage); n_split == 1
         Ring rb((uint32_t)nsb);
+        uint32_t n_st = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
           for (int kc = 0; kc < k_chunks; ++kc)
-            for (int khw = 0; khw < 9; ++khw, rb.next()) {
+            for (int khw = 0; khw < 9; ++khw, rb.next(), ++n_st) {
+              if ((n_st & 1u) != pj) continue;
               const int s = (int)rb.s;
               ptx::mbar_wait(&sh->b_empty[s], rb.ph ^ 1u);
               ptx::mbar_arrive_expect_tx(&sh->b_full[s], plane_copy_bytes * planes_per_chunk * 3u);
@@ -1008,12 +1015,17 @@ conv3d_planar_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const uint32_t tap_bytes = plane_copy_bytes * (uint32_t)planes_per_chunk;
         const size_t chunk_stride = (size_t)planes_per_chunk * plane_stride;         // elements between channel chunks
         const uint32_t b_stage_bytes = (uint32_t)p.b_stage_bytes;
+        uint32_t n_st = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           const TileCoord t = decode_tile(p, tile);
           const __nv_bfloat16* src_c = p.w + (size_t)t.ns * p.n_cta * 8;
           for (int kc = 0; kc < k_chunks; ++kc, src_c += chunk_stride) {
             const __nv_bfloat16* src = src_c;
-            for (int tap0 = 0; tap0 < n_taps; tap0 += tps, rb.next()) {
+            for (int tap0 = 0; tap0 < n_taps; tap0 += tps, rb.next(), ++n_st) {
+              if ((n_st & 1u) != pj) {
+                src += (size_t)tps * tap_stride;
+                continue;
+              }
               const uint32_t s = rb.s;
               ptx::mbar_wait(&sh->b_empty[s], rb.ph ^ 1u);
               ptx::mbar_arrive_expect_tx(&sh->b_full[s], stage_tx);
