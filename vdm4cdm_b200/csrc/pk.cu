@@ -54,8 +54,13 @@ struct ModeCursor {
   __device__ __forceinline__ int bin(const PkGeom& g, float& weight, float& kmag) const {
     const int f0 = i0 > g.n0 / 2 ? i0 - g.n0 : i0;
     const int f1 = i1 > g.n1 / 2 ? i1 - g.n1 : i1;
-    kmag = sqrtf((float)(f0 * f0 + f1 * f1 + i2 * i2));
-    const int b = (int)ceilf(kmag);
+    const int k2 = f0 * f0 + f1 * f1 + i2 * i2;
+    kmag = sqrtf((float)k2);
+    // ceil(|k|) in integer arithmetic: the smallest b with b^2 >= k2 (what ceil(sqrt(.)) of the reference gives with a
+    // correctly rounded sqrt; independent of how this sqrtf rounds at perfect squares)
+    int b = (int)kmag;
+    while (b * b < k2) ++b;
+    while (b > 0 && (b - 1) * (b - 1) >= k2) --b;
     weight = (i2 == 0 || (g.last_even && i2 == g.n2h - 1)) ? 1.f : 2.f;
     return (b >= 1 && b <= g.kmax) ? b : -1;
   }
