@@ -18,22 +18,27 @@
 // from 27x (per-tap im2col loads, what cuDNN/CUTLASS implicit GEMM do) to (MT+2)/MT*18/16*10/8 ~ 2.1x.
 // (Descriptor semantics verified on hardware by tools/probe_umma.cu, profiles/r01_probe_umma.txt.)
 //
-// Pipeline per persistent CTA (11 warps):
-//   warp 0  A producer : one 4-D TMA load per (tile, channel chunk) -> halo stage (2 stages);
-//                        out-of-range voxels are zero-filled by the TMA unit == Conv3d zero padding
-//   warp 2  B producer : weights -> shared memory, once per CTA when they fit (resident), else a ring of
-//                        (chunk, 3 taps) stages
-//   warp 1  MMA issuer : generic path: chunk, tap, sub-tile s < MT, k16: tcgen05.mma M=128 N=n_cta K=16
-//                        into accumulator s (TMEM, fp32).
-//                        kd-folded path (narrow layers, NF = Cout_pad in {16, 32, 64}): see issue_fold_tile /
-//                        issue_fold_stage; optionally one more channel chunk from a second tensor of which
-//                        only the centre tap is multiplied (the block's 1x1x1 skip conv, issue_skip_chunk).
-//                        2 accumulator sets: the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 3-10 epilogue: tcgen05.ld -> + bias/conditioning row + residual (cp.async ring in shared memory,
-//                        optionally read through a nearest x2 up-sampling) -> bf16 planar (or fp32
-//                        NCDHW) store, per-channel (sum, sumsq) GroupNorm statistics by warp-shuffle
-//                        transpose reduction, kept per CTA in shared memory (fp64) and flushed with fp64
-//                        atomics when the CTA moves to another sample.  Two warps per TMEM lane quarter.
+// Pipeline per persistent CTA (16 warps in four warpgroups, setmaxnreg 64 / 176 / 176 / 88 registers):
+//   warp 0   A producer : one 4-D TMA load per (tile, channel chunk) -> halo stage (2-4 stages);
+//                         out-of-range voxels are zero-filled by the TMA unit == Conv3d zero padding
+//   warp 2,3 B producer : weights -> shared memory, once per CTA when they fit (resident), else a ring of
+//                         (chunk, 3 taps) stages (warp 3 takes every other stage of a streamed ring)
+//   warp 1   MMA issuer : ONE elected lane.  generic path (issue_generic_tiles): chunk, weight stage, tap, sub-tile
+//                         s < MT, k16: tcgen05.mma M=128 N=n_cta K=16 into accumulator s (TMEM, fp32), per-tap 64-bit
+//                         descriptors + immediate per-MMA offsets, ring positions advanced without divisions.
+//                         kd-folded path (narrow layers, NF = Cout_pad in {16, 32, 64}): see issue_fold_tile /
+//                         issue_fold_stage; optionally one more channel chunk from a second tensor of which
+//                         only the centre tap is multiplied (the block's 1x1x1 skip conv, issue_skip_chunk).
+//                         2 accumulator sets: the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 4-11 epilogue : tcgen05.ld -> + bias/conditioning row + residual (cp.async ring in shared memory,
+//                         optionally read through a nearest x2 up-sampling or a depth-to-space shuffle) -> bf16
+//                         planar (or fp32 NCDHW) store, per-channel (sum, sumsq) GroupNorm statistics by warp-shuffle
+//                         transpose reduction, kept per CTA in shared memory (fp64) and flushed with fp64
+//                         atomics when the CTA moves to another sample.  Two warps per TMEM lane quarter.
+//   warps 12-15 input transform (in_norm): GroupNorm + SiLU applied to the landed halo stage in place.
+// Narrow 3x3x3 layers whose input channels are one chunk (Cin, Cout_pad <= 32) do not run this kernel but the
+// d-marching schedule of conv3d_march.cuh (conv3d_march_kernel): one input slice per stage, a TMEM ring of 16 output
+// slices, twelve epilogue warps (or eight + four transform warps).
 //
 // Roofline: tensor-bound; algorithmic FLOPs = 2 * taps * Cin * Cout * B*D*H*W.
 #include <cudaTypedefs.h>
