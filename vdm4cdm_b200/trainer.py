@@ -58,11 +58,33 @@ class FlatBuckets:
     def numel(self) -> int:
         return self.flat_param.numel()
 
-    def zero_grad(self) -> None:
+    def zero_grad(self, detach_small: bool = False) -> None:
+        """Zero the flat gradient bucket and (re-)attach the ``.grad`` views.  With ``detach_small`` the parameters that are
+        not conv filters (biases, GroupNorm affines, the embedding MLPs, the noise schedule: ~115 tensors) get ``.grad =
+        None`` instead: autograd then STORES their gradients instead of launching one in-place add per tensor, and
+        ``collect_small_grads`` moves them into the bucket with a few multi-tensor copies."""
         self.flat_grad.zero_()
         for p, o in zip(self.params, self.offsets):         # re-attach views a caller may have dropped
-            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+            if detach_small and p.dim() <= 2:
+                p.grad = None
+            elif p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+
+    def collect_small_grads(self) -> None:
+        """After backward of a ``zero_grad(detach_small=True)`` step: copy the stored gradients of the small parameters into
+        their bucket slots (``torch._foreach_copy_``: a handful of launches for all of them) and re-attach the views."""
+        dsts, srcs = [], []
+        for p, o in zip(self.params, self.offsets):
+            if p.dim() > 2:
+                continue
+            view = self.flat_grad[o:o + p.numel()].view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                dsts.append(view)
+                srcs.append(p.grad.detach())
+            p.grad = view
+        if dsts:
+            with torch.no_grad():
+                torch._foreach_copy_(dsts, srcs)
 
 
 def allreduce_gradients(buckets: FlatBuckets) -> None:
@@ -183,11 +205,12 @@ class Trainer:
     def _eager_step(self, batch) -> torch.Tensor:
         nvtx = torch.cuda.nvtx.range          # no-ops without a profiler attached
         with nvtx("vdm.train_step"):
-            self.buckets.zero_grad()
+            self.buckets.zero_grad(detach_small=True)
             with nvtx("vdm.forward_loss"):
                 loss = self.model.training_step(batch)
             with nvtx("vdm.backward"):
                 loss.backward()
+                self.buckets.collect_small_grads()
             with nvtx("vdm.allreduce_clip_adamw"):
                 self.optimizer_step()
         return loss.detach()
@@ -197,9 +220,10 @@ class Trainer:
         graph = torch.cuda.CUDAGraph()
         self._nets_changed()                          # the weight re-packing must be part of the graph
         with torch.cuda.graph(graph, stream=self._stream):
-            self.buckets.zero_grad()
+            self.buckets.zero_grad(detach_small=True)
             loss = self.model.training_step(self._static_batch)
             loss.backward()
+            self.buckets.collect_small_grads()
             self._optimizer_kernels()
             self._static_loss = loss.detach()
         self._graph = graph
