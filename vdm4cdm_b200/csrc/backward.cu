@@ -19,6 +19,8 @@ __device__ __forceinline__ float silu_grad(float u) {
   return s * fmaf(u, 1.0f - s, 1.0f);
 }
 
+constexpr int kGnBwdUnroll = 2;      // chunks per loop trip of the GroupNorm backward kernels
+
 struct GnBwdArgs {
   VdmTensor x, dy, add, dx;
   int planes;
@@ -73,19 +75,21 @@ gn_silu_bwd_reduce_kernel(const GnBwdArgs a) {
   const uint64_t seed = a.seed + (a.seed_step ? (uint64_t)(uint32_t)(*a.seed_step) : 0ull);
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t stride = (int64_t)gridDim.x * kEwThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += 2 * stride) {
-    const int64_t i2 = i + stride;
-    const bool two = i2 < a.voxels;
-    const bf16x8 x0 = xp[i], g0 = gp[i];          // four independent 16-byte loads in flight
-    bf16x8 x1 = x0, g1 = g0;
-    if (two) { x1 = xp[i2]; g1 = gp[i2]; }
+  constexpr int U = kGnBwdUnroll;                   // chunks per trip: 2 * U independent 16-byte loads in flight per thread
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += U * stride) {
+    bf16x8 xs[U], gs[U];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k == 1 && !two) break;
-      const int64_t ii = k == 0 ? i : i2;
+    for (int k = 0; k < U; ++k) {
+      const int64_t ii = i + k * stride;
+      if (ii < a.voxels) { xs[k] = xp[ii]; gs[k] = gp[ii]; }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t ii = i + k * stride;
+      if (ii >= a.voxels) break;
       const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, seed, thresh16) : 0xffu;
       float du[8], x[8];
-      chunk_du(k == 0 ? x0 : x1, k == 0 ? g0 : g1, s_scale, s_shift, keep, keep_scale, du, x);
+      chunk_du(xs[k], gs[k], s_scale, s_shift, keep, keep_scale, du, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s1[j] += du[j];
@@ -167,33 +171,35 @@ gn_silu_bwd_apply_kernel(const GnBwdArgs a) {
   const uint64_t seed = a.seed + (a.seed_step ? (uint64_t)(uint32_t)(*a.seed_step) : 0ull);
   float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t stride = (int64_t)gridDim.x * kEwThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += 2 * stride) {
-    const int64_t i2 = i + stride;
-    const bool two = i2 < a.voxels;
-    const bf16x8 x0 = xp[i], g0 = gp[i];
-    bf16x8 x1 = x0, g1 = g0, r0 = x0, r1 = x0;
-    if (ap) r0 = ap[i];
-    if (two) {
-      x1 = xp[i2]; g1 = gp[i2];
-      if (ap) r1 = ap[i2];
+  constexpr int U = kGnBwdUnroll;
+  const bool stream_out = a.voxels * a.planes > ((int64_t)4 << 20);
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < a.voxels; i += U * stride) {
+    bf16x8 xs[U], gs[U], rs[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t ii = i + k * stride;
+      if (ii < a.voxels) {
+        xs[k] = xp[ii]; gs[k] = gp[ii];
+        if (ap) rs[k] = ap[ii];
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k == 1 && !two) break;
-      const int64_t ii = k == 0 ? i : i2;
+    for (int k = 0; k < U; ++k) {
+      const int64_t ii = i + k * stride;
+      if (ii >= a.voxels) break;
       const uint32_t keep = drop ? dropout_keep8(chunk0 + (uint64_t)ii, a.layer_tag, seed, thresh16) : 0xffu;
       float du[8], x[8], o[8];
-      chunk_du(k == 0 ? x0 : x1, k == 0 ? g0 : g1, s_scale, s_shift, keep, keep_scale, du, x);
+      chunk_du(xs[k], gs[k], s_scale, s_shift, keep, keep_scale, du, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = cA[j] * du[j] + cB[j] + cC[j] * x[j];
       if (ap) {
         float r[8];
-        unpack8(k == 0 ? r0 : r1, r);
+        unpack8(rs[k], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += r[j];
       }
       const bf16x8 packed = pack8(o);
-      if (a.voxels * a.planes > ((int64_t)4 << 20)) st_stream(op + ii, packed);
+      if (stream_out) st_stream(op + ii, packed);
       else op[ii] = packed;
       if (a.out_stats) {
         float r[8];

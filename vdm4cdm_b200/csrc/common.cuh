@@ -47,9 +47,10 @@ constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 constexpr uint32_t kStreamTagNoise = 0x56444D34u;    // 'VDM4'
 constexpr uint32_t kStreamTagDropout = 0x44524F50u;  // 'DROP'
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
     const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -58,6 +59,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox4x32<10>(c, k); }
+// Seven rounds (Random123's "Philox4x32-7": the smallest round count that passes BigCrush) for the dropout masks, which are
+// regenerated three times per layer and step (forward, backward reduce, backward apply) and made those kernels ALU-bound
+// (R4z: 3.0 TB/s with dropout vs 4.8 without).  The sampler noise keeps the ten-round generator of oracle/philox_ref.py.
+__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) { return philox4x32<7>(c, k); }
 
 __device__ __forceinline__ float philox_unit(uint32_t w) {
   return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24

@@ -76,7 +76,7 @@ __device__ __forceinline__ void plane_scale_shift(const double* __restrict__ sta
 
 // 8 keep-flags for chunk `chunk` of dropout layer `tag`: bit j set = keep element j.
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t chunk, uint32_t tag, uint64_t seed, uint32_t thresh16) {
-  const uint4 w = philox4x32_10(make_uint4((uint32_t)chunk, (uint32_t)(chunk >> 32), tag, kStreamTagDropout),
+  const uint4 w = philox4x32_7(make_uint4((uint32_t)chunk, (uint32_t)(chunk >> 32), tag, kStreamTagDropout),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const uint32_t r[4] = {w.x, w.y, w.z, w.w};
   uint32_t keep = 0;
