@@ -309,13 +309,13 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
 // tensor WHOLE (so its wait -> LDS -> arithmetic -> STS chain may last four slices: in the tile kernel four warps shared every
 // stage and the chain, not the bandwidth, made the transform slower than the MMAs, R2h); a lane owns one 8-channel plane,
 // its 16 coefficients stay in registers while the sample does not change.  Skip-tensor stages are not transformed.
-template <int KJ, bool SKIP>
+template <int KJ, bool SKIP, int NXW>
 __device__ __forceinline__ void march_transform(const ConvKernelParams& p, MarchShared* sh, uint8_t* a_smem) {
   constexpr int planes = 2 * KJ, S = kMarchStages;
   constexpr int kSliceBytes = (kTileH + 2) * (kTileW + 2) * 16, kStageBytes = planes * kSliceBytes;
   constexpr int lpp = 32 / planes;                         // lanes per plane
   constexpr int nvox = (kTileH + 2) * (kTileW + 2);
-  const int lane = threadIdx.x & 31, j = (threadIdx.x >> 5) - 12;
+  const int lane = threadIdx.x & 31, j = (threadIdx.x >> 5) - (16 - NXW);      // NXW transform warps: warps 16 - NXW .. 15
   const int pl = lane / lpp, l0 = lane % lpp;
   const int skip_chunks = SKIP ? p.skip_chunks : 0;
   float ca[8], cb[8];
@@ -333,21 +333,29 @@ __device__ __forceinline__ void march_transform(const ConvKernelParams& p, March
       }
     }
     for (int i = 0; i < m.len + 2; ++i, ++n_main) {
-      if ((int)(n_main & 3u) == j) {
+      if ((int)(n_main % (uint32_t)NXW) == j) {
         const uint32_t s = it % (uint32_t)S;
         ptx::mbar_wait(&sh->a_full[s], (it / (uint32_t)S) & 1);
         const int dz = m.d0 - 1 + i;
         if (dz >= 0 && dz < p.D) {                         // (a slice beyond the grid is all zero padding: nothing to do)
           uint4* base = reinterpret_cast<uint4*>(a_smem + (size_t)s * kStageBytes + (size_t)pl * kSliceBytes);
           const bool edge = m.h0 == 0 || m.h0 + kTileH >= p.H || m.w0 == 0 || m.w0 + kTileW >= p.W;
-#pragma unroll 4
-          for (int v = l0; v < nvox; v += lpp) {
-            uint4 y = gn_silu8(base[v], ca, cb);
+          auto xf_one = [&](int v, uint4 x) __attribute__((always_inline)) {
+            uint4 y = gn_silu8(x, ca, cb);
             if (edge) {
               const int hy = v / (kTileW + 2), wx = v - hy * (kTileW + 2);
               if ((unsigned)(m.h0 - 1 + hy) >= (unsigned)p.H || (unsigned)(m.w0 - 1 + wx) >= (unsigned)p.W) y = make_uint4(0u, 0u, 0u, 0u);
             }
             base[v] = y;
+          };
+          // eight 16-byte loads in flight per lane (R5d A/B on one box: 4 -> 8 loads, 32->32 convs -1..3 %, conv_out -6 %)
+          constexpr int G = 8;
+          for (int v0 = l0; v0 < nvox; v0 += G * lpp) {
+            uint4 xs[G];
+#pragma unroll
+            for (int g2 = 0; g2 < G; ++g2) if (v0 + g2 * lpp < nvox) xs[g2] = base[v0 + g2 * lpp];
+#pragma unroll
+            for (int g2 = 0; g2 < G; ++g2) if (v0 + g2 * lpp < nvox) xf_one(v0 + g2 * lpp, xs[g2]);
           }
         }
         ptx::fence_proxy_async();
@@ -359,7 +367,7 @@ __device__ __forceinline__ void march_transform(const ConvKernelParams& p, March
       // stage like a_full does (the issuer waits on a_ready for every stage): forward the arrival
       if (i < m.len) {
         for (int c = 0; c < skip_chunks; ++c, ++it, ++n_skip) {
-          if ((int)(n_skip & 3u) == j) {
+          if ((int)(n_skip % (uint32_t)NXW) == j) {
             const uint32_t s = it % (uint32_t)S;
             ptx::mbar_wait(&sh->a_full[s], (it / (uint32_t)S) & 1);
             if (lane == 0) ptx::mbar_arrive(&sh->a_ready[s]);
@@ -590,7 +598,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // warps 12..15 transform): see march_epilogue / march_transform =====================
     ptx::setmaxnreg_inc<kRegsMEpi>();
     if (XF && warp >= 12) {
-      march_transform<KJ, SKIP>(p, sh, a_smem);
+      march_transform<KJ, SKIP, 4>(p, sh, a_smem);
     } else {
       constexpr int EW = XF ? 2 : 3;
       if (p.out_fp32) march_epilogue<NF, kEpiFp32, EW>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
