@@ -315,6 +315,10 @@ __device__ __forceinline__ void march_transform(const ConvKernelParams& p, March
   constexpr int kSliceBytes = (kTileH + 2) * (kTileW + 2) * 16, kStageBytes = planes * kSliceBytes;
   constexpr int lpp = 32 / planes;                         // lanes per plane
   constexpr int nvox = (kTileH + 2) * (kTileW + 2);
+  constexpr int KMAX0 = (nvox + lpp - 1) / lpp;            // voxels per lane: 12 (two planes) or 23 (four)
+  constexpr int G = planes == 2 ? 6 : 8;                   // 16-byte loads in flight per lane (R5d: 4 -> 8, conv_out -6 %)
+  constexpr int KMAX = (KMAX0 + G - 1) / G * G;
+  static_assert(KMAX <= 32, "one bit per voxel of a lane in zmask");
   const int lane = threadIdx.x & 31, j = (threadIdx.x >> 5) - (16 - NXW);      // NXW transform warps: warps 16 - NXW .. 15
   const int pl = lane / lpp, l0 = lane % lpp;
   const int skip_chunks = SKIP ? p.skip_chunks : 0;
@@ -332,6 +336,16 @@ __device__ __forceinline__ void march_transform(const ConvKernelParams& p, March
         ca[2 * j4] = c4.x; cb[2 * j4] = c4.y; ca[2 * j4 + 1] = c4.z; cb[2 * j4 + 1] = c4.w;
       }
     }
+    // voxels of this lane that lie outside the grid in h / w (zero padding applies AFTER the non-linearity): bit k = voxel
+    // l0 + k * lpp of the (kTileH + 2) x (kTileW + 2) halo slice, the same for every slice of the unit
+    uint32_t zmask = 0u;
+    if (m.h0 == 0 || m.h0 + kTileH >= p.H || m.w0 == 0 || m.w0 + kTileW >= p.W) {
+      for (int k = 0; k < KMAX; ++k) {
+        const int v = l0 + k * lpp;
+        const int hy = v / (kTileW + 2), wx = v - hy * (kTileW + 2);
+        if (v < nvox && ((unsigned)(m.h0 - 1 + hy) >= (unsigned)p.H || (unsigned)(m.w0 - 1 + wx) >= (unsigned)p.W)) zmask |= 1u << k;
+      }
+    }
     for (int i = 0; i < m.len + 2; ++i, ++n_main) {
       if ((int)(n_main % (uint32_t)NXW) == j) {
         const uint32_t s = it % (uint32_t)S;
@@ -339,23 +353,22 @@ __device__ __forceinline__ void march_transform(const ConvKernelParams& p, March
         const int dz = m.d0 - 1 + i;
         if (dz >= 0 && dz < p.D) {                         // (a slice beyond the grid is all zero padding: nothing to do)
           uint4* base = reinterpret_cast<uint4*>(a_smem + (size_t)s * kStageBytes + (size_t)pl * kSliceBytes);
-          const bool edge = m.h0 == 0 || m.h0 + kTileH >= p.H || m.w0 == 0 || m.w0 + kTileW >= p.W;
-          auto xf_one = [&](int v, uint4 x) __attribute__((always_inline)) {
-            uint4 y = gn_silu8(x, ca, cb);
-            if (edge) {
-              const int hy = v / (kTileW + 2), wx = v - hy * (kTileW + 2);
-              if ((unsigned)(m.h0 - 1 + hy) >= (unsigned)p.H || (unsigned)(m.w0 - 1 + wx) >= (unsigned)p.W) y = make_uint4(0u, 0u, 0u, 0u);
-            }
-            base[v] = y;
-          };
-          // eight 16-byte loads in flight per lane (R5d A/B on one box: 4 -> 8 loads, 32->32 convs -1..3 %, conv_out -6 %)
-          constexpr int G = 8;
-          for (int v0 = l0; v0 < nvox; v0 += G * lpp) {
+          // BRANCH-FREE body: G independent 16-byte chains per lane that ptxas can interleave (R5g: with a guard and an edge
+          // branch around every voxel the chains ran one after another at ~4.5 cycles per instruction and the four transform
+          // warps were busy 90 % of the time -- they, not the MMA issuer, bounded the fused layers).  Slots past the end of the
+          // slice read whatever follows it in shared memory (the next plane / stage / the weights) and are not stored.
+#pragma unroll 1
+          for (int k0 = 0; k0 < KMAX; k0 += G) {
             uint4 xs[G];
 #pragma unroll
-            for (int g2 = 0; g2 < G; ++g2) if (v0 + g2 * lpp < nvox) xs[g2] = base[v0 + g2 * lpp];
+            for (int g2 = 0; g2 < G; ++g2) xs[g2] = base[l0 + (k0 + g2) * lpp];
 #pragma unroll
-            for (int g2 = 0; g2 < G; ++g2) if (v0 + g2 * lpp < nvox) xf_one(v0 + g2 * lpp, xs[g2]);
+            for (int g2 = 0; g2 < G; ++g2) {
+              const int v = l0 + (k0 + g2) * lpp;
+              uint4 y = gn_silu8(xs[g2], ca, cb);
+              if ((zmask >> (k0 + g2)) & 1u) y = make_uint4(0u, 0u, 0u, 0u);
+              if (v < nvox) base[v] = y;
+            }
           }
         }
         ptx::fence_proxy_async();
