@@ -610,7 +610,15 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ===================== epilogue (12 warps, three per TMEM lane quarter; with the fused input transform eight, and
     // warps 12..15 transform): see march_epilogue / march_transform =====================
     ptx::setmaxnreg_inc<kRegsMEpi>();
-    if (XF && warp >= 12) {
+    // conv_out (16 output columns, one fp32 channel stored): the epilogue is a few instructions per voxel and the layer is
+    // bound by the input transform (R5i: 26 % tensor-pipe activity, transform warps busy ~90 %), so eight warps transform
+    // and four drain.  Only without the fused skip conv: there a warp that takes every EIGHTH main stage would skip a whole
+    // phase of a stage's a_full barrier, and a parity wait cannot tell phase n from phase n + 2.
+    constexpr bool kWideXf = XF && !SKIP && NF == 16;
+    if (kWideXf && p.out_fp32) {
+      if (warp >= 8) march_transform<KJ, SKIP, 8>(p, sh, a_smem);
+      else march_epilogue<NF, kEpiFp32, 1>(p, sh, smem, stat_part, stat_acc, cadd_s, tmem_base);
+    } else if (XF && warp >= 12) {
       march_transform<KJ, SKIP, 4>(p, sh, a_smem);
     } else {
       constexpr int EW = XF ? 2 : 3;
