@@ -413,7 +413,20 @@ __device__ __forceinline__ void transform_tiles(const ConvKernelParams& p, ConvS
       cur_b = t.b;
     }
     const int dlo = t.d0 - p.pad + p.x_shift, hlo = t.h0 - p.pad + p.x_shift, wlo = t.w0 - p.pad + p.x_shift;
-    const bool edge = dlo < 0 || dlo + p.Hd > p.D || hlo < 0 || hlo + p.Hh > p.H || wlo < 0 || wlo + p.Wh > p.W;
+    // Units of this thread that lie outside the grid (zero padding applies AFTER the non-linearity): bit k = unit
+    // part * 32 + lane + k * step, the same for every plane and chunk of the tile (at most 6 * 18 * 10 / 32 = 34 units per
+    // thread).  One mask per tile instead of a branch and two divisions per unit: the loop body below is branch-free, so
+    // ptxas interleaves the units of a group (R5g/R5i: the branchy body of the marching schedule ran at ~4.5 cycles per
+    // instruction and its four warps were the bound of the fused layers).
+    unsigned long long zmask = 0ull;
+    if (dlo < 0 || dlo + p.Hd > p.D || hlo < 0 || hlo + p.Hh > p.H || wlo < 0 || wlo + p.Wh > p.W) {
+      int k = 0;
+      for (int idx = part * 32 + lane; idx < vh; idx += 32 * nparts, ++k) {
+        const bool oob = p.pad ? halo_voxel_oob<kTileH + 2, kTileW + 2>(idx, dlo, hlo, wlo, p.D, p.H, p.W)
+                               : halo_voxel_oob<kTileH, kTileW>(idx, dlo, hlo, wlo, p.D, p.H, p.W);
+        if (oob) zmask |= 1ull << k;
+      }
+    }
     for (int kc = 0; kc < total_chunks; ++kc, ra.next()) {
       const int s = (int)ra.s;
       ptx::mbar_wait(&sh->a_full[s], ra.ph);
@@ -444,27 +457,22 @@ __device__ __forceinline__ void transform_tiles(const ConvKernelParams& p, ConvS
             const int idx = v + g2 * step;
             cur[g2] = idx < vh ? base[idx] : make_uint4(0u, 0u, 0u, 0u);
           }
+          int k = 0;
 #pragma unroll 1
-          for (; v < vh; v += G * step) {
+          for (; v < vh; v += G * step, k += G) {
             const int vn = v + G * step;
 #pragma unroll
             for (int g2 = 0; g2 < G; ++g2) {
               const int idx = vn + g2 * step;
               nxt[g2] = idx < vh ? base[idx] : make_uint4(0u, 0u, 0u, 0u);
             }
+            const unsigned zk = (unsigned)(zmask >> k);
 #pragma unroll
             for (int g2 = 0; g2 < G; ++g2) {
               const int idx = v + g2 * step;
-              if (idx < vh) {
-                uint4 y = VDM_DBG(p, 128) ? cur[g2] : gn_silu8(cur[g2], ca, cb);     // (bring-up 128: copy through)
-                if (VDM_DBG(p, 256)) continue;                                       // (bring-up 256: no stores)
-                if (edge) {
-                  const bool oob = p.pad ? halo_voxel_oob<kTileH + 2, kTileW + 2>(idx, dlo, hlo, wlo, p.D, p.H, p.W)
-                                         : halo_voxel_oob<kTileH, kTileW>(idx, dlo, hlo, wlo, p.D, p.H, p.W);
-                  if (oob) y = make_uint4(0u, 0u, 0u, 0u);
-                }
-                base[idx] = y;
-              }
+              uint4 y = VDM_DBG(p, 128) ? cur[g2] : gn_silu8(cur[g2], ca, cb);     // (bring-up 128: copy through)
+              if ((zk >> g2) & 1u) y = make_uint4(0u, 0u, 0u, 0u);
+              if (idx < vh && !VDM_DBG(p, 256)) base[idx] = y;                       // (bring-up 256: no stores)
             }
 #pragma unroll
             for (int g2 = 0; g2 < G; ++g2) cur[g2] = nxt[g2];
