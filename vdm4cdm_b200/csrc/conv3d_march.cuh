@@ -101,7 +101,8 @@ __device__ __forceinline__ void issue_march_slice(uint64_t a_desc, uint64_t b_de
 template <int NF, int MODE, int EW>
 __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchShared* sh, uint8_t* smem, float* stat_part,
                                                double* stat_acc, float* cadd_s, const uint32_t tmem_base) {
-  // EW = epilogue warps per TMEM lane quarter: 3 (warps 4..15), or 2 (warps 4..11) when warps 12..15 transform the input
+  // EW = epilogue warps per TMEM lane quarter: 3 (warps 4..15), 2 (warps 4..11) when warps 12..15 transform the input, 1 (warps
+  // 4..7) for conv_out, where warps 8..15 transform
   constexpr int kThreadsE = 128 * EW;
   constexpr bool RES = (MODE & kEpiRes) != 0, STATS = (MODE & kEpiStats) != 0, FP32 = (MODE & kEpiFp32) != 0;
   constexpr int R = kMarchBlocks, n_chunks = NF / 16, n_planes = NF / 8;
@@ -309,6 +310,8 @@ __device__ __forceinline__ void march_epilogue(const ConvKernelParams& p, MarchS
 // tensor WHOLE (so its wait -> LDS -> arithmetic -> STS chain may last four slices: in the tile kernel four warps shared every
 // stage and the chain, not the bandwidth, made the transform slower than the MMAs, R2h); a lane owns one 8-channel plane,
 // its 16 coefficients stay in registers while the sample does not change.  Skip-tensor stages are not transformed.
+// NXW = number of transform warps (the last NXW warps of the CTA): 4, or 8 for conv_out (see the role dispatch in the kernel:
+// a warp may not skip a whole phase of a barrier it waits on, which rules NXW = 8 out when skip-tensor stages are interleaved).
 template <int KJ, bool SKIP, int NXW>
 __device__ __forceinline__ void march_transform(const ConvKernelParams& p, MarchShared* sh, uint8_t* a_smem) {
   constexpr int planes = 2 * KJ, S = kMarchStages;
@@ -608,7 +611,7 @@ conv3d_march_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   } else {
     // ===================== epilogue (12 warps, three per TMEM lane quarter; with the fused input transform eight, and
-    // warps 12..15 transform): see march_epilogue / march_transform =====================
+    // warps 12..15 transform; conv_out four, and warps 8..15 transform): see march_epilogue / march_transform =====================
     ptx::setmaxnreg_inc<kRegsMEpi>();
     // conv_out (16 output columns, one fp32 channel stored): the epilogue is a few instructions per voxel and the layer is
     // bound by the input transform (R5i: 26 % tensor-pipe activity, transform warps busy ~90 %), so eight warps transform
