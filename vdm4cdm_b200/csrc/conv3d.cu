@@ -393,6 +393,7 @@ template <int MT, int KJ>
 __device__ __forceinline__ void transform_tiles(const ConvKernelParams& p, ConvShared* sh, uint8_t* a_smem, float* coef) {
   constexpr int planes = 2 * KJ;
   constexpr int nparts = planes >= 4 ? 1 : 4 / planes;        // warps sharing one plane
+  static_assert((MT + 2) * (kTileH + 2) * (kTileW + 2) <= 64 * 32, "zmask: one bit per 16-byte unit of a thread");
   constexpr int pl_step = planes >= 4 ? 4 : planes;
   const int xt = threadIdx.x - kXfFirst, tw = xt >> 5, lane = xt & 31;
   const int pl0 = planes >= 4 ? tw : tw % planes;
