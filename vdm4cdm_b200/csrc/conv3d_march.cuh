@@ -380,7 +380,9 @@ __device__ __forceinline__ void march_transform(const ConvKernelParams& p, March
       }
       ++it;
       // the skip-tensor stages of this output slice are not transformed, but a_ready has to complete one phase per use of a
-      // stage like a_full does (the issuer waits on a_ready for every stage): forward the arrival
+      // stage like a_full does (the issuer waits on a_ready for every stage): forward the arrival.
+      // (With skip stages interleaved, consecutive phases of a stage's a_full belong to different warps; the parity waits here
+      // rely on loads issued >= 3 stages apart landing in order -- see DESIGN.md 3.10a, "known weakness", for the sound form.)
       if (i < m.len) {
         for (int c = 0; c < skip_chunks; ++c, ++it, ++n_skip) {
           if ((int)(n_skip % (uint32_t)NXW) == j) {
